@@ -1,0 +1,343 @@
+/*
+ * vine_b200.h — C ABI of the B200-native Vine5LinkMovingBase hot path.
+ *
+ * The reference (tylerlum/Vine_Robot_IsaacGymEnvs) has no native code and no FFI of its
+ * own: its per-control-step pipeline is Python/torch (isaacgymenvs/tasks/Vine5LinkMovingBase.py,
+ * "V5") on top of the closed Isaac Gym binary (gymapi.simulate & friends) and the
+ * VecTask base class (isaacgymenvs/tasks/base/vec_task.py, "VT").  This header is the
+ * boundary a maintainer would bind (ctypes) to replace that pipeline.
+ * Every entry point cites the reference interface it stands in for.
+ *
+ * Conventions
+ *   - plain C, no torch types; all array arguments are DEVICE pointers unless the
+ *     name ends in `_host`; row-major; the caller (PyTorch) owns every I/O buffer.
+ *   - every function returns 0 (VINE_OK) or a negative VineStatus; no C++ exception,
+ *     exit() or abort() crosses the ABI (contrast VT:297-299 `quit()`).
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*);
+ *     no entry point synchronises the device or allocates after vine_create(), so
+ *     vine_step() is CUDA-graph capturable.
+ *   - one host thread per handle; handles on different devices are independent
+ *     (one per rank; envs never communicate, V5:464).
+ */
+#ifndef VINE_B200_H_
+#define VINE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VINE_ABI_VERSION 1
+
+#define VINE_NUM_DOFS 6          /* 1 prismatic rail cart + 5 revolute links (V5:54,83) */
+#define VINE_NUM_ACTIONS 2       /* u_rail_velocity, u_fpam (V5:171) */
+#define VINE_NUM_REWARDS 13      /* REWARD_NAMES (V5:78-81) */
+#define VINE_NUM_OBJECT_INFO 2   /* target depth, angle (V5:51) */
+#define VINE_MAX_ACTION_DELAY 8
+#define VINE_NUM_METRICS 96
+
+typedef enum VineStatus {
+  VINE_OK = 0,
+  VINE_ERR_INVALID_ARG = -1,
+  VINE_ERR_UNSUPPORTED = -2,     /* e.g. SCALE_OBSERVATIONS with a type V5:267-268 rejects */
+  VINE_ERR_CUDA = -3,
+  VINE_ERR_NOT_BOUND = -4,
+  VINE_ERR_ABI_MISMATCH = -5
+} VineStatus;
+
+/* ObservationType (V5:67-73); widths V5:152-171. */
+typedef enum VineObservationType {
+  VINE_OBS_POS_ONLY = 0,                    /* 14 */
+  VINE_OBS_POS_AND_VEL = 1,                 /* 26 */
+  VINE_OBS_POS_AND_FD_VEL = 2,              /* 26 */
+  VINE_OBS_POS_AND_PREV_POS = 3,            /* 26 */
+  VINE_OBS_POS_AND_FD_VEL_AND_OBJ_INFO = 4, /* 28 */
+  VINE_OBS_TIP_AND_CART_AND_OBJ_INFO = 5    /* 18 */
+} VineObservationType;
+
+/* How the reference's joint torque law tau = -(K q + C qd + b + B u) (V5:1042-1062)
+ * enters the integrator. ZOH = literal reference semantics (efforts frozen for one sim
+ * step, VT:346-356).  IMPLICIT = the spring/damper part is integrated implicitly per
+ * substep (unconditionally stable; see DESIGN.md "R1"). */
+typedef enum VineTorqueLawIntegration {
+  VINE_TORQUE_LAW_ZOH = 0,
+  VINE_TORQUE_LAW_IMPLICIT = 1
+} VineTorqueLawIntegration;
+
+/*
+ * Mirror of the reference's configuration surface for this path:
+ * cfg["env"], cfg["sim"], cfg["task"] of cfg/task/Vine5LinkMovingBase.yaml.
+ * Real-valued knobs are `double` because the reference holds them as Python floats and
+ * rounds to f32 only where they meet a tensor; the library derives its f32 constants the
+ * same way.
+ */
+typedef struct VineConfig {
+  int32_t struct_size;                 /* = sizeof(VineConfig), checked by vine_create */
+  /* sim.* (YT:102-123) */
+  int32_t substeps;
+  double dt;
+  double gravity_z;
+  /* env.* (YT:7-100) */
+  int32_t control_freq_inv;
+  int32_t max_episode_length;
+  double clip_observations;
+  double clip_actions;
+  int32_t observation_type;            /* VineObservationType */
+  int32_t scale_observations;
+  int32_t create_shelf;
+  int32_t create_pipe;
+  int32_t use_smoothed_fpam;
+  int32_t force_u_fpam;
+  int32_t force_u_rail_velocity;
+  int32_t action_delay;
+  double smoothing_alpha_inflate;
+  double smoothing_alpha_deflate;
+  double fpam_min;
+  double fpam_max;
+  double rail_velocity_scale;
+  double damping;                      /* PhysX DOF damping on all 6 DOFs (V5:504) */
+  double stiffness;                    /* PhysX DOF stiffness on revolutes (V5:511) */
+  double rail_soft_limit;
+  double rail_p_gain;
+  double rail_d_gain;
+  double rail_acceleration;
+  int32_t randomize_dof_init;
+  int32_t randomize_targets;
+  double random_init_cart_min_y;
+  double random_init_cart_max_y;
+  double success_dist;
+  double min_target_depth_in_obstacle;
+  double max_target_depth_in_obstacle;
+  double min_target_y;
+  double max_target_y;
+  double min_target_z;
+  double max_target_z;
+  double reward_weights[VINE_NUM_REWARDS];   /* REWARD_NAMES order (V5:186-203) */
+  int32_t use_target_reached_reset;
+  int32_t use_tip_limit_hit_reset;
+  int32_t use_nonzero_contact_force_reset;
+  /* task.* (YT:125-134; ACCEL_TARGET_SCALING_* only on README.md:63) */
+  int32_t vine_randomize;
+  double dynamics_scaling_min;
+  double dynamics_scaling_max;
+  double observation_noise_std;
+  double action_noise_std;
+  double accel_target_scaling_min;
+  double accel_target_scaling_max;
+  /* Simulator-side parameters the reference leaves to Isaac Gym. */
+  int32_t torque_law_integration;      /* VineTorqueLawIntegration */
+  int32_t emulate_stale_body_state;    /* replicate rigid-body staleness after reset (V5:796) */
+  double armature;                     /* added to every revolute joint-space inertia */
+  double revolute_lower;               /* dof_props lower/upper of limit-less joints (V5:778-786) */
+  double revolute_upper;
+  double prismatic_lower;
+  double prismatic_upper;
+  double contact_stiffness;            /* penalty contact, N/m */
+  double contact_damping;              /* N s/m */
+  double contact_rest_offset;          /* YT:117 */
+} VineConfig;
+
+typedef struct VineEnv VineEnv;
+
+/* Version of this header the library was built against. */
+int vine_abi_version(void);
+
+/* Fill `cfg` with the defaults of cfg/task/Vine5LinkMovingBase.yaml (YT:7-134). */
+int vine_config_defaults(VineConfig* cfg);
+
+/* Observation width for a type (V5:152-171); negative on bad type. */
+int vine_num_observations(int observation_type);
+
+/*
+ * Replaces Vine5LinkMovingBase.__init__ / create_sim / _create_envs /
+ * initialize_state_tensors (V5:137-291, 299-362, 364-519) and VecTask.__init__
+ * (VT:169-223): validates the config, bakes the model constants, allocates the private
+ * SoA state for `num_envs` environments on CUDA device `device`.  Envs are numbered
+ * global_env_offset .. global_env_offset+num_envs-1; the Philox key is (seed, global id)
+ * so results do not depend on how envs are sharded over ranks.
+ */
+int vine_create(const VineConfig* cfg, int64_t num_envs, int64_t global_env_offset,
+                int device, uint64_t seed, VineEnv** out);
+
+void vine_destroy(VineEnv* env);
+
+/* Last error text for this handle (or the last vine_create failure when env==NULL). */
+const char* vine_last_error(const VineEnv* env);
+
+/*
+ * Borrow the VecTask buffers (VT:260-283): actions f32[N,2]; obs_buf f32[N,O];
+ * rew_buf f32[N]; reset_buf i64[N]; progress_buf i64[N]; timeout_buf u8[N] (torch.bool);
+ * obs_clamped f32[N,O] = clamp(obs_buf, +-clipObservations) (VT:374), may be NULL.
+ */
+int vine_bind_io(VineEnv* env, const float* actions, float* obs_buf, float* rew_buf,
+                 int64_t* reset_buf, int64_t* progress_buf, uint8_t* timeout_buf,
+                 float* obs_clamped);
+
+/*
+ * One control step == VecTask.step (VT:319-380): clamp actions, pre_physics_step
+ * (V5:922-945), controlFrequencyInv x {forces V5:1028-1106, shelf contact sample
+ * VT:348-351, simulate VT:356}, post_physics_step (V5:1110-1120: progress, deferred
+ * reset_idx, observations, reward, reset), timeout (VT:366), obs clamp (VT:374).
+ * ONE fused kernel launch.
+ */
+int vine_step(VineEnv* env, void* stream);
+
+/*
+ * reset_idx(env_ids) (V5:774-885) outside step, as VecTask.reset_done (VT:412-427)
+ * and the 'R' key (V5:715-718) call it.  `env_ids` i64[n] device pointer, local ids.
+ */
+int vine_reset_idx(VineEnv* env, const int64_t* env_ids, int64_t n, void* stream);
+
+/*
+ * Structure-of-arrays snapshot of the private state, for identical-state parity tests
+ * and for exposing dof_pos etc. as torch tensors. Any pointer may be NULL (skipped).
+ */
+typedef struct VineStateView {
+  float* dof_pos;              /* [N,6]  (V5:303) */
+  float* dof_vel;              /* [N,6]  (V5:304) */
+  float* tip_positions;        /* [N,3]  rigid-body view as of the last simulate (V5:357) */
+  float* cart_body_vel_y;      /* [N]    cart_velocities[:,1] as of the last simulate (V5:362) */
+  float* target_positions;     /* [N,3]  (V5:179) */
+  float* object_info;          /* [N,2]  (V5:238) */
+  float* smoothed_u_fpam;      /* [N]    (V5:224) */
+  float* prev_cart_vel;        /* [N]    (V5:235) */
+  float* prev_cart_vel_error;  /* [N]    (V5:234) */
+  float* shelf_contact_force;  /* [N]    |net contact force on shelf_link| of the last simulate (VT:349-350) */
+  float* actions_history;      /* [N,ACTION_DELAY,2] oldest first (V5:288-291) */
+  float* aggregated_rew_buf;   /* [N]    (V5:183) */
+  int64_t* step_count;         /* [N]    control steps taken (Philox counter) */
+  /* outputs of the last step only (ignored by vine_set_state) */
+  float* u_rail_velocity;      /* [N] */
+  float* u_fpam;               /* [N] */
+  float* prev_u_rail_velocity; /* [N] */
+  float* rail_force;           /* [N] */
+  float* tip_velocities;       /* [N,3] */
+  float* reward_matrix;        /* [N,13] unweighted terms of the last step (V5:1500) */
+} VineStateView;
+
+int vine_get_state(VineEnv* env, const VineStateView* view, void* stream);
+int vine_set_state(VineEnv* env, const VineStateView* view, void* stream);
+
+/* When enabled, vine_step also records the `outputs of the last step` block above. */
+int vine_set_debug_outputs(VineEnv* env, int enabled);
+
+/* ---- function-level entry points (same device code as the fused step; used for parity
+ *      with the reference's own functions on identical inputs) ---- */
+
+/*
+ * compute_observations (V5:1339-1390) + compute_reward (V5:1218-1248, 1272-1278,
+ * compute_reward_jit V5:1470-1537) + compute_reset_jit (V5:1540-1558) + timeout (VT:366).
+ * Inputs are the tensors those functions read.  progress_buf is the value AFTER the
+ * `+= 1` of V5:1111.
+ */
+typedef struct VinePostPhysicsIO {
+  const float* dof_pos;              /* [N,6] */
+  const float* dof_vel;              /* [N,6] */
+  const float* prev_dof_pos;         /* [N,6] */
+  const float* tip_positions;        /* [N,3] */
+  const float* prev_tip_positions;   /* [N,3] */
+  const float* tip_velocities;       /* [N,3] */
+  const float* cart_positions_y;     /* [N] */
+  const float* target_positions;     /* [N,3] */
+  const float* target_velocities;    /* [N,3] */
+  const float* smoothed_u_fpam;      /* [N] */
+  const float* u_fpam;               /* [N] */
+  const float* u_rail_velocity;      /* [N] */
+  const float* prev_u_rail_velocity; /* [N] */
+  const float* object_info;          /* [N,2] */
+  const float* contact_force_norms;  /* [control_freq_inv,N] (VT:351) or NULL */
+  const float* obs_noise;            /* [N,O] standard normals or NULL (V5:1389) */
+  const int64_t* reset_buf_in;       /* [N] */
+  const int64_t* progress_buf;       /* [N] */
+  float* obs_buf;                    /* [N,O] out */
+  float* rew_buf;                    /* [N] out */
+  float* reward_matrix;              /* [N,13] out */
+  int64_t* reset_buf_out;            /* [N] out */
+  uint8_t* timeout_buf;              /* [N] out */
+} VinePostPhysicsIO;
+
+int vine_post_physics(VineEnv* env, const VinePostPhysicsIO* io, void* stream);
+
+/*
+ * pre_physics_step's action path (V5:927-940): raw_actions_to_actions, delay ring,
+ * FORCE_* overrides, pressure smoothing.  action_noise: [N,2] standard normals or NULL.
+ * history_in/out: [N,ACTION_DELAY,2] oldest first.
+ */
+typedef struct VinePrePhysicsIO {
+  const float* actions;          /* [N,2] already clamped (VT:333) */
+  const float* action_noise;     /* [N,2] or NULL */
+  const float* history_in;       /* [N,D,2] */
+  const float* smoothed_in;      /* [N] */
+  float* history_out;            /* [N,D,2] */
+  float* u_rail_velocity;        /* [N] */
+  float* u_fpam;                 /* [N] */
+  float* smoothed_out;           /* [N] */
+} VinePrePhysicsIO;
+
+int vine_pre_physics(VineEnv* env, const VinePrePhysicsIO* io, void* stream);
+
+/*
+ * compute_and_set_dof_actuation_force_tensor (V5:1028-1106).  dynamics_scaling: [N,5,4]
+ * multipliers of (K,C,b,B) per joint or NULL (=1); accel_scaling [N] or NULL.
+ */
+typedef struct VineActuationIO {
+  const float* dof_pos;              /* [N,6] */
+  const float* dof_vel;              /* [N,6] */
+  const float* cart_vel_y;           /* [N] cart_velocities[:,1] */
+  const float* u_rail_velocity;      /* [N] */
+  const float* u_fpam_to_use;        /* [N] smoothed or raw (V5:1059) */
+  const float* prev_cart_vel;        /* [N] */
+  const float* prev_cart_vel_error;  /* [N] */
+  const float* dynamics_scaling;     /* [N,5,4] or NULL */
+  const float* accel_scaling;        /* [N] or NULL */
+  float* dof_efforts;                /* [N,6] out */
+  float* prev_cart_vel_out;          /* [N] out */
+  float* prev_cart_vel_error_out;    /* [N] out */
+} VineActuationIO;
+
+int vine_actuation(VineEnv* env, const VineActuationIO* io, void* stream);
+
+/*
+ * gym.simulate (VT:356) for one sim step (`substeps` substeps of dt/substeps) with the
+ * given efforts held constant; replaces PhysX for this articulation.  obstacle state is
+ * taken from target_positions/object_info.  In/out dof state [N,6]; outputs the
+ * rigid-body views the task reads (tip pos/vel, shelf_link contact norm).
+ */
+typedef struct VineSimulateIO {
+  float* dof_pos;                    /* [N,6] in/out */
+  float* dof_vel;                    /* [N,6] in/out */
+  const float* dof_efforts;          /* [N,6] */
+  const float* dynamics_scaling;     /* [N,5,4] or NULL; used only by IMPLICIT mode */
+  const float* u_fpam_to_use;        /* [N] used only by IMPLICIT mode */
+  const float* target_positions;     /* [N,3] */
+  const float* object_info;          /* [N,2] */
+  float* tip_positions;              /* [N,3] out */
+  float* tip_velocities;             /* [N,3] out */
+  float* shelf_contact_force;        /* [N] out */
+} VineSimulateIO;
+
+int vine_simulate(VineEnv* env, const VineSimulateIO* io, void* stream);
+
+/* Raw Philox4x32-10 stream used for all domain randomization (north_star f):
+ * out u32[n_blocks*4] for counter (gid, site, step, block0+i), key = seed. */
+int vine_philox_debug(uint64_t seed, uint32_t gid, uint32_t site, uint32_t step,
+                      uint32_t block0, int64_t n_blocks, uint32_t* out, void* stream);
+
+/* ---- PPO side (rl_games 1.5.2 A2CAgent pieces; in-repo analogue
+ *      isaacgymenvs/learning/common_agent.py:413-425) ---- */
+
+/*
+ * discount_values: GAE over the horizon. rewards/values/dones f32[T,N] (dones as 0/1),
+ * last_values f32[N], last_dones f32[N]; out advantages f32[T,N], returns f32[T,N].
+ *   delta_t = r_t + gamma V_{t+1} (1-d_{t+1}) - V_t ;  A_t = delta_t + gamma tau (1-d_{t+1}) A_{t+1}
+ */
+int vine_gae(const float* rewards, const float* values, const float* dones,
+             const float* last_values, const float* last_dones, int64_t horizon,
+             int64_t num_envs, double gamma, double tau, float* advantages, float* returns,
+             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VINE_B200_H_ */
