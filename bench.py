@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the Vine5LinkMovingBase hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
+
+Workload (config.workload): the FSTR command line of the reference's README.md:63 (BASELINE
+configs[1] knobs) driven with synthetic U(-1,1)^2 actions, env-step only, ``--num-envs`` envs per
+GPU (default 1,048,576: the top of BASELINE configs[4]'s sweep; state + I/O ~ 400 MB > the 126 MB
+L2, so no L2 flush is needed between steps).  A "step" = one control step of every env = ONE
+fused kernel launch.  Weak scaling: per-GPU env count fixed, envs sharded by contiguous global
+env id, no collective in the step.
+
+Printed JSON (one line, rank 0): the contract keys + ``roofline`` (HBM, SURVEY §8d bytes),
+``roofline_fp32`` (the binding resource: FP32 FMA, against an FFMA peak measured in the same run),
+``cpu_baseline``, ``e2e`` (through the public env class with pinned HOST buffers, H2D + D2H
+every step), ``clocks``, ``gpu_launches``, ``sweep`` (smaller env counts, same kernel).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "env-steps/s (whole box, device-timed)"
+UNIT = "env-steps/s"
+# Algorithmic work per env-step of the FSTR workload (derivations: DESIGN.md §6)
+HBM_BYTES_PER_ENV_STEP = 273.0      # O=18, ACTION_DELAY=1
+FLOPS_PER_ENV_STEP = 27.0e3         # exact count of this kernel's source: 40 substeps x 650 + 1.0 k
+
+
+def fstr_cfg(num_envs, extra=()):
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    return vcfg.compose(vcfg.FSTR_OVERRIDES + [f"num_envs={num_envs}", "headless=True"] + list(extra))
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.stop_flag, self.ok = [], False, True
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), sm, reasons))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self, t0, t1):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
+        nv = self.nv
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        clocks = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": mx, "samples": len(inside),
+                "reasons": [k for k, b in names.items() if bits & b]}
+
+
+def cpu_oracle_rate(num_envs, budget_s, nthreads=0, min_steps=2, max_steps=64, fixed_steps=None, warmup=1):
+    """env-steps/s of the CPU oracle (f32 dynamics, OpenMP over envs) on a bounded FSTR sample."""
+    import numpy as np
+    from oracle import oracle as O
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    vc = vcfg.task_cfg_to_vine_config(fstr_cfg(num_envs)["task"])
+    env = O.OracleEnv(vc, num_envs, seed=42, use_f64=False, nthreads=nthreads)
+    rng = np.random.default_rng(42)
+    acts = rng.uniform(-1, 1, (4, num_envs, 2)).astype(np.float32)
+    for i in range(max(warmup, 1)):
+        env.step(acts[i % 4])
+    t0 = time.perf_counter()
+    env.step(acts[0])
+    one = time.perf_counter() - t0
+    steps = fixed_steps if fixed_steps is not None else int(min(max_steps, max(min_steps, budget_s / max(one, 1e-6))))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        env.step(acts[i % 4])
+    dt = time.perf_counter() - t0
+    return num_envs * steps / dt, steps, dt
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank):
+    """The reference's CPU implementation of the path, timed on the box's host cores.  The reference's
+    own arithmetic for this path is closed PhysX + torch (not installable here), so this arm runs the
+    oracle port (kind "port"), which is pinned bit-exactly to the reference's step logic."""
+    if rank != 0:
+        return
+    cores = host_threads()
+    # size the per-step sample so the whole run ends within ~2 minutes
+    probe_n = 4096
+    rate, _, _ = cpu_oracle_rate(probe_n, 0.0, fixed_steps=2)
+    total_steps = args.steps + args.warmup
+    n = int(max(256, min(args.num_envs, rate * 100.0 / max(total_steps, 1))))
+    n = 1 << (n.bit_length() - 1)
+    value, steps, dt = cpu_oracle_rate(n, 0.0, fixed_steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "FSTR (README.md:63) env step, random actions", "sample_envs_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} envs x {steps} control steps, oracle f32 dynamics, OpenMP x{cores}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def timed_steps(env, lib, pool, steps, use_graph):
+    """Device time (ms) of `steps` control steps, rotating through the action pool."""
+    import torch
+    dev = env.device
+    s = torch.cuda.Stream(dev)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def launch(stream_ptr):
+        for i in range(steps):
+            env._bind(pool[i % len(pool)])
+            env._check(lib.vine_step(env._h, stream_ptr))
+
+    torch.cuda.synchronize(dev)
+    if use_graph:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                launch(C.c_void_p(s.cuda_stream))
+        torch.cuda.synchronize(dev)
+        return g, s, start, end
+    return launch, s, start, end
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import abi
+
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    n = args.num_envs
+    lib = abi.load_library()
+
+    def make_env(num_envs):
+        cfg = fstr_cfg(num_envs, [f"sim_device={dev}", f"rl_device={dev}"])
+        return vine.make(cfg=cfg, global_env_offset=rank * num_envs), cfg
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def measure(num_envs, steps, warmup, sampler=None):
+        env, cfg = make_env(num_envs)
+        gen = torch.Generator(device=dev).manual_seed(42 + rank)
+        pool = [torch.rand(num_envs, 2, device=dev, generator=gen) * 2 - 1 for _ in range(4)]
+        for i in range(max(warmup, 3)):
+            env._bind(pool[i % 4])
+            env._check(lib.vine_step(env._h, env._stream()))
+        runner, s, start, end = timed_steps(env, lib, pool, steps, not args.no_graph)
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s):
+            start.record()
+            if args.no_graph:
+                runner(C.c_void_p(s.cuda_stream))
+            else:
+                runner.replay()
+            end.record()
+        torch.cuda.synchronize(dev)
+        barrier()
+        t1 = time.perf_counter()
+        ms = max_over_ranks(start.elapsed_time(end))
+        assert torch.isfinite(env.obs_buf).all() and torch.isfinite(env.rew_buf).all()
+        env._bind()
+        return env, cfg, ms, (t0, t1)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    env, cfg, ms, window = measure(n, args.steps, args.warmup)
+    clocks = sampler.summary(*window)
+    value = n * world * args.steps / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+
+    # ---- e2e: public env.step() with pinned host buffers, H2D + D2H inside the timed region ----
+    O = env.num_obs
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    a_host = [torch.empty(n, 2).uniform_(-1, 1).pin_memory() for _ in range(4)]
+    obs_h = torch.empty(n, O).pin_memory()
+    rew_h = torch.empty(n).pin_memory()
+    rst_h = torch.empty(n, dtype=torch.long).pin_memory()
+    to_h = torch.empty(n, dtype=torch.bool).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def e2e_step(i):
+        od, rew, rst, extras = env.step(a_host[i % 4])          # H2D of the actions happens inside
+        obs_h.copy_(od["obs"], non_blocking=True)
+        rew_h.copy_(rew, non_blocking=True)
+        rst_h.copy_(rst, non_blocking=True)
+        to_h.copy_(extras["time_outs"], non_blocking=True)
+        stream.synchronize()                                   # a policy needs the result before acting
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n * world * e2e_steps / e2e_s
+    sampler.stop_flag = True
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the (only) kernel in the timed region ----
+    peaks, peaks_kind = measured_peaks()
+    hbm_achieved = HBM_BYTES_PER_ENV_STEP * n / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": hbm_achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks_kind,
+                "kernel": "vine_step_kernel<false>", "note": "kernel is FP32-FMA bound, see roofline_fp32"}
+    traffic_file = os.path.join(REPO, "profiles", "traffic_bytes_per_env_step.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            roofline["traffic"] = json.load(f).get("bytes_per_env_step", 0) * n
+    fp32_peak = None
+    try:
+        pk = C.CDLL(os.path.join(REPO, "vine_robot_isaacgymenvs_b200", "csrc", "libvine_benchpeak.so"))
+        pk.vine_bench_ffma_tflops.restype = C.c_double
+        fp32_peak = pk.vine_bench_ffma_tflops(5)
+    except OSError:
+        pass
+    fp32_achieved = FLOPS_PER_ENV_STEP * n / (ms_per_step * 1e-3) / 1e12
+    roofline_fp32 = {"bound": "fp32_fma", "achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": (fp32_achieved / fp32_peak) if fp32_peak else None,
+                     "peak_source": "FFMA microbenchmark measured in this run (nominal 74.4)"}
+
+    # ---- smaller env counts, same kernel (BASELINE configs[1] literal size and the configs[4] sweep) ----
+    sweep = []
+    if world == 1 and not args.no_sweep:
+        del env
+        torch.cuda.empty_cache()
+        for m in (4096, 65536, 262144):
+            if m >= n:
+                continue
+            _, _, ms_m, _ = measure(m, args.steps, args.warmup)
+            sweep.append({"num_envs": m, "value": m * args.steps / (ms_m * 1e-3), "ms_per_step": ms_m / args.steps,
+                          "l2_resident": True})
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_threads()
+        cn = 65536
+        rate, steps, dt = cpu_oracle_rate(cn, budget_s=12.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cn} envs x {steps} control steps ({dt:.1f} s), oracle f32 dynamics, OpenMP x{cores}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "FSTR (README.md:63 / BASELINE configs[1] knobs) env step, U(-1,1) actions, "
+                               "env-step only", "num_envs_per_gpu": n, "global_envs": n * world,
+                   "obs": cfg["task"]["env"]["OBSERVATION_TYPE"], "substeps_per_step":
+                       cfg["task"]["sim"]["substeps"] * cfg["task"]["env"]["controlFrequencyInv"],
+                   "parallelism": f"env-sharded x{world}, no collective in the step",
+                   "l2": "inputs larger than L2 (no flush)" if n * 400 > 126e6 else "L2-resident",
+                   "cuda_graph": not args.no_graph},
+        "roofline": roofline, "roofline_fp32": roofline_fp32, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 2 * 4,
+                "d2h_bytes_per_step": n * (O * 4 + 4 + 8 + 1), "steps": e2e_steps},
+        "clocks": clocks, "gpu_launches": args.steps, "sweep": sweep,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--num-envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

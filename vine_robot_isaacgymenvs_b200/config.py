@@ -18,6 +18,7 @@ Unknown keys are accepted (the FSTR command line of README.md:63 passes
 import copy
 import ctypes as C
 import os
+import re
 
 import yaml
 
@@ -32,7 +33,9 @@ ROOT_DEFAULTS = {
     "num_envs": "", "horizon_length": "", "minibatch_size": "", "control_frequency_inv": "",
     "vine_randomize": "", "CAPTURE_VIDEO": "", "RAIL_VELOCITY_SCALE": "", "RAIL_SOFT_LIMIT": "",
     "RAIL_P_GAIN": "", "OBSERVATION_TYPE": "", "RAIL_ACCELERATION": "",
-    "enable_viewer_sync_at_start": "",
+    "enable_viewer_sync_at_start": True,
+    "wandb_group": "", "wandb_name": "${train.params.config.name}", "wandb_entity": "",
+    "wandb_project": "isaacgymenvs", "capture_video_freq": 1464, "capture_video_len": 100,
     "seed": 42, "torch_deterministic": False, "max_iterations": "",
     "physics_engine": "physx", "pipeline": "gpu", "sim_device": "cuda:0", "rl_device": "cuda:0",
     "graphics_device_id": 0,
@@ -198,12 +201,30 @@ RESOLVERS = {
 }
 
 
+class _Loader(yaml.SafeLoader):
+    """SafeLoader that reads ``2e-2`` / ``3e-4`` as floats like OmegaConf does (YAML 1.1, which
+    PyYAML implements, demands a dot in the mantissa; the reference's YAMLs rely on OmegaConf)."""
+
+
+_Loader.add_implicit_resolver(
+    "tag:yaml.org,2002:float",
+    re.compile(r"""^(?:[-+]?(?:[0-9][0-9_]*)\.[0-9_]*(?:[eE][-+]?[0-9]+)?
+                   |[-+]?(?:[0-9][0-9_]*)(?:[eE][-+]?[0-9]+)
+                   |\.[0-9_]+(?:[eE][-+][0-9]+)?
+                   |[-+]?\.(?:inf|Inf|INF)|\.(?:nan|NaN|NAN))$""", re.X),
+    list("-+0123456789."))
+
+
+def _yaml_load(stream):
+    return yaml.load(stream, Loader=_Loader)  # noqa: S506 - subclass of SafeLoader
+
+
 def _primitive(text):
     t = text.strip()
     if t == "":
         return ""
     try:
-        v = yaml.safe_load(t)
+        v = _yaml_load(t)
     except yaml.YAMLError:
         return t
     return t if isinstance(v, (dict, list)) else v
@@ -357,16 +378,16 @@ def compose(overrides=None, cfg_dir=None, task="Vine5LinkMovingBase", train=None
             train = o.split("=", 1)[1]
     if cfg_dir is not None:
         with open(os.path.join(cfg_dir, "config.yaml")) as f:
-            root = yaml.safe_load(f)
+            root = _yaml_load(f)
         root.pop("defaults", None)
         root.pop("hydra", None)
         with open(os.path.join(cfg_dir, "task", task + ".yaml")) as f:
-            root["task"] = yaml.safe_load(f)
+            root["task"] = _yaml_load(f)
         tname = train or (task + "PPO")
         tpath = os.path.join(cfg_dir, "train", tname + ".yaml")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                root["train"] = yaml.safe_load(f)
+                root["train"] = _yaml_load(f)
     else:
         if task != "Vine5LinkMovingBase":
             raise ValueError(f"built-in defaults exist only for Vine5LinkMovingBase, not {task!r}")

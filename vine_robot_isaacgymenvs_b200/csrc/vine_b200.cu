@@ -1,0 +1,699 @@
+// vine_b200.cu — kernels and the C ABI (include/vine_b200.h) of the Vine5LinkMovingBase hot path.
+// Target: sm_100a (B200). One fused kernel per control step; one environment per thread with the
+// whole articulation state in registers across controlFrequencyInv x substeps integrator steps.
+//
+// HBM layout (private to the library, structure-of-arrays of 16-byte planes, index = env):
+//   S0 = q0..q3 | S1 = q4,q5,qd0,qd1 | S2 = qd2..qd5
+//   S3 = smoothed_u_fpam, prev_cart_vel, prev_cart_vel_error, |F_shelf_link|
+//   S4 = tip_y, tip_z (rigid-body view), cart body vel y, aggregated reward
+//   S5 = target_y, target_z, object depth, object angle        (target_x == 0, V5:892)
+//   ring[slot][env] = (u_rail, u_fpam) delay ring, slot = step % ACTION_DELAY | ctr[env] = step count
+// VecTask buffers (obs/rew/reset/progress/timeout) are torch-owned row-major tensors (VT:260-283).
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "vine_device.cuh"
+
+#define VINE_BLOCK 128
+#define VINE_DBG_W 20  // u_rail,u_fpam,prev_u_rail,rail_force,tipvel y,z, reward_matrix[13], pad
+
+struct StepArgs {
+  int64_t n, gid0;
+  uint32_t k0, k1;
+  float4 *S0, *S1, *S2, *S3, *S4, *S5;
+  float2* ring;
+  uint32_t* ctr;
+  const float2* actions;
+  float* obs; float* obs_clamped; float* rew;
+  int64_t* reset; int64_t* progress; uint8_t* timeout;
+  float* dbg;  // [N, VINE_DBG_W] or nullptr
+};
+
+struct VineEnv {
+  VineParams p;
+  VineConfig cfg;
+  StepArgs a;
+  int device;
+  int bound;
+  char err[256];
+};
+
+static char g_create_err[256] = "";
+
+#define CUDA_TRY(env, call)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      snprintf((env) ? (env)->err : g_create_err, 256, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+      return VINE_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// coalesced store of a block's observation rows staged in shared memory
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64_t n, float clip,
+                                                float* __restrict__ obs, float* __restrict__ obs_clamped) {
+  const int64_t row0 = (int64_t)blockIdx.x * VINE_BLOCK;
+  const int rows = (int)min((int64_t)VINE_BLOCK, n - row0);
+  const int count2 = rows * O / 2;  // O is even for every ObservationType
+  float2* g = reinterpret_cast<float2*>(obs + row0 * O);
+  float2* gc = obs_clamped ? reinterpret_cast<float2*>(obs_clamped + row0 * O) : nullptr;
+  for (int i = threadIdx.x; i < count2; i += VINE_BLOCK) {
+    const int e0 = 2 * i, r0 = e0 / O, c0 = e0 - r0 * O;  // c0 even, c0+1 < O
+    float2 v;
+    v.x = s_obs[r0 * (VINE_MAX_OBS + 1) + c0];
+    v.y = s_obs[r0 * (VINE_MAX_OBS + 1) + c0 + 1];
+    g[i] = v;
+    if (gc) {  // VT:374 torch.clamp(obs_buf, -clip, clip)
+      v.x = fminf(fmaxf(v.x, -clip), clip); v.y = fminf(fmaxf(v.y, -clip), clip);
+      gc[i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// THE fused control step == VecTask.step (VT:319-380)
+// ------------------------------------------------------------------------------------------
+template <bool CONTACT>
+__global__ void __launch_bounds__(VINE_BLOCK) vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
+  __shared__ float s_obs[VINE_BLOCK * (VINE_MAX_OBS + 1)];
+  const int64_t e = (int64_t)blockIdx.x * VINE_BLOCK + threadIdx.x;
+  if (e < a.n) {
+    const float4 s0 = a.S0[e], s1 = a.S1[e], s2 = a.S2[e], s3 = a.S3[e], s4 = a.S4[e], s5 = a.S5[e];
+    float q[6] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y};
+    float qd[6] = {s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
+    float smoothed = s3.x, prev_cart_vel = s3.y, prev_err = s3.z, lip = s3.w;
+    float tip_y = s4.x, tip_z = s4.y, cart_body_vy = s4.z, agg = s4.w;
+    float target[3] = {0.f, s5.x, s5.y};
+    float obj[2] = {s5.z, s5.w};
+    const uint32_t step = a.ctr[e];
+    const uint32_t gid = (uint32_t)(a.gid0 + e);
+    const float2 act = a.actions[e];
+    int64_t reset_in = a.reset[e];
+    const bool was_reset = reset_in != 0;
+    int64_t progress = a.progress[e];
+
+    // ---- VT:333 + pre_physics_step V5:922-945 ----
+    float a0 = fminf(fmaxf(act.x, -p.clip_act), p.clip_act);
+    float a1 = fminf(fmaxf(act.y, -p.clip_act), p.clip_act);
+    if (p.randomize && p.act_noise != 0.f) {  // V5:930-932 (noise after the clamp)
+      float nz[4];
+      normal4(philox4x32(a.k0, a.k1, gid, VINE_SITE_ACTION_NOISE, step, 0), nz);
+      a0 = __fadd_rn(a0, __fmul_rn(p.act_noise, nz[0]));
+      a1 = __fadd_rn(a1, __fmul_rn(p.act_noise, nz[1]));
+    }
+    float u_rail, u_fpam;
+    rescale_actions(p, a0, a1, u_rail, u_fpam);
+    if (p.D > 0) {  // V5:936-937 FIFO of ACTION_DELAY control steps
+      float2* slot = a.ring + (int64_t)(step % (uint32_t)p.D) * a.n + e;
+      const float2 old = *slot;
+      *slot = make_float2(u_rail, u_fpam);
+      u_rail = old.x; u_fpam = old.y;
+    }
+    apply_overrides_and_smooth(p, u_rail, u_fpam, smoothed);
+    PostIn in;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) in.prev_q[i] = q[i];                       // V5:943
+    in.prev_tip[0] = 0.f; in.prev_tip[1] = tip_y; in.prev_tip[2] = tip_z;  // V5:944
+    in.prev_u_rail = u_rail;                                               // V5:945
+    const float u_use = p.use_smoothed ? smoothed : u_fpam;                // V5:1059
+
+    Obstacles ob;
+    if (CONTACT) build_obstacles(p, target[1], target[2], obj[0], obj[1], ob);
+
+    // ---- controlFrequencyInv x {forces, contact sample, simulate}  VT:338-356 ----
+    Dyn d; rel_to_abs(q, qd, d);
+    float tipb_y = tip_y, tipb_z = tip_z;  // rigid-body tip as of the refresh before the LAST simulate
+    float rail_force = 0.f;
+#pragma unroll
+    for (int i = 0; i < VINE_MAX_CFI; ++i) in.contact[i] = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < p.C; ++i) {
+      if (i > 0 && i == p.C - 1 && reset_in != 0 && p.stale) {  // only needed by V5:797 on reset steps
+        Kin k; link_trig(p, d, k);
+        float vy, vz; tip_fk(d, k, tipb_y, tipb_z, vy, vz);
+      }
+      JointLaw law; joint_law_unscaled(law);
+      float acc_scale = 1.f;
+      if (p.randomize) {  // V5:1053-1055: 20 multipliers re-drawn every sim step (+1 for accel scaling)
+        uint32_t u[24];
+#pragma unroll
+        for (uint32_t b = 0; b < 6; ++b) {
+          const uint4 r = philox4x32(a.k0, a.k1, gid, VINE_SITE_DYNAMICS, step, (uint32_t)i * 8u + b);
+          u[4 * b] = r.x; u[4 * b + 1] = r.y; u[4 * b + 2] = r.z; u[4 * b + 3] = r.w;
+        }
+#pragma unroll
+        for (int j = 0; j < VINE_NL; ++j) {
+          law.K[j] = __fmul_rn(law.K[j], uniform_ab(u[4 * j], p.dyn_min, p.dyn_rng));
+          law.Cd[j] = __fmul_rn(law.Cd[j], uniform_ab(u[4 * j + 1], p.dyn_min, p.dyn_rng));
+          law.b[j] = __fmul_rn(law.b[j], uniform_ab(u[4 * j + 2], p.dyn_min, p.dyn_rng));
+          law.B[j] = __fmul_rn(law.B[j], uniform_ab(u[4 * j + 3], p.dyn_min, p.dyn_rng));
+        }
+        acc_scale = uniform_ab(u[20], p.acc_min, p.acc_rng);
+      }
+      // rigid-body cart velocity: stale on the first sim step after a reset (V5:1069)
+      const float cart_vel = (i == 0) ? cart_body_vy : d.v[0];
+      float efforts[6];
+      efforts[0] = rail_controller(p, cart_vel, u_rail, acc_scale, prev_cart_vel, prev_err);
+      rail_force = efforts[0];
+      if (!p.implicit_law) {
+#pragma unroll
+        for (int j = 0; j < VINE_NL; ++j) {
+          const float th = j == 0 ? d.x[1] : d.x[j + 1] - d.x[j];
+          const float thd = j == 0 ? d.v[1] : d.v[j + 1] - d.v[j];
+          efforts[j + 1] = joint_torque(law, j, th, thd, u_use);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < VINE_NL; ++j) efforts[j + 1] = 0.f;
+      }
+      in.contact[i] = lip;  // VT:348-351: force of the PREVIOUS simulate
+      JointImp J; joint_implicit_consts(p, law, u_use, efforts, J);
+#pragma unroll 1
+      for (int s = 0; s < p.S; ++s) substep<CONTACT>(p, J, rail_force, &ob, d, lip);
+    }
+    float tipvel_y, tipvel_z;
+    {
+      Kin k; link_trig(p, d, k);
+      tip_fk(d, k, tip_y, tip_z, tipvel_y, tipvel_z);
+    }
+    float cart_y_body = d.x[0];
+    cart_body_vy = d.v[0];
+    abs_to_rel(d, q, qd);
+
+    // ---- post_physics_step V5:1110-1120 ----
+    progress += 1;
+    if (reset_in != 0) {  // deferred reset of envs flagged at the end of the previous step (V5:1114-1116)
+      reset_env(p, a.k0, a.k1, gid, step, q, qd, target, obj);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) in.prev_q[i] = q[i];                     // V5:794
+      if (p.stale) {                                                       // V5:796-797 stale rigid-body views
+        in.prev_tip[1] = tipb_y; in.prev_tip[2] = tipb_z;
+      } else {                                                             // "as if FK were done": clean episode boundary
+        Dyn dn; rel_to_abs(q, qd, dn);
+        Kin k; link_trig(p, dn, k);
+        tip_fk(dn, k, tip_y, tip_z, tipvel_y, tipvel_z);
+        in.prev_tip[1] = tip_y; in.prev_tip[2] = tip_z;
+        cart_y_body = q[0]; cart_body_vy = 0.f; lip = 0.f; prev_cart_vel = 0.f;
+#pragma unroll
+        for (int i = 0; i < VINE_MAX_CFI; ++i) in.contact[i] = 0.f;
+      }
+      in.prev_u_rail = 0.f;                                                // V5:798
+      prev_err = 0.f;                                                      // V5:799
+      reset_in = 0; progress = 0; agg = 0.f;                               // V5:807-810
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { in.q[i] = q[i]; in.qd[i] = qd[i]; }
+    in.tip[0] = 0.f; in.tip[1] = tip_y; in.tip[2] = tip_z;
+    in.tipvel[0] = 0.f; in.tipvel[1] = tipvel_y; in.tipvel[2] = tipvel_z;
+    in.target[0] = target[0]; in.target[1] = target[1]; in.target[2] = target[2];
+    in.target_vel[0] = in.target_vel[1] = in.target_vel[2] = 0.f;          // V5:916-918
+    in.obj[0] = obj[0]; in.obj[1] = obj[1];
+    in.cart_y = cart_y_body; in.smoothed = smoothed; in.u_fpam = u_fpam; in.u_rail = u_rail;
+    in.reset_in = reset_in; in.progress = progress;
+    float noise[VINE_MAX_OBS];
+    const bool noisy = p.randomize && p.obs_noise != 0.f;
+    if (noisy) {
+#pragma unroll
+      for (uint32_t b = 0; b < VINE_MAX_OBS / 4; ++b) {
+        if ((int)(4 * b) < p.O) normal4(philox4x32(a.k0, a.k1, gid, VINE_SITE_OBS_NOISE, step, b), &noise[4 * b]);
+      }
+    }
+    PostOut o;
+    post_physics(p, in, noisy ? noise : nullptr, o);
+    agg = __fadd_rn(agg, o.rew);                                           // V5:1278
+
+    // ---- write back ----
+    a.S0[e] = make_float4(q[0], q[1], q[2], q[3]);
+    a.S1[e] = make_float4(q[4], q[5], qd[0], qd[1]);
+    a.S2[e] = make_float4(qd[2], qd[3], qd[4], qd[5]);
+    a.S3[e] = make_float4(smoothed, prev_cart_vel, prev_err, lip);
+    a.S4[e] = make_float4(tip_y, tip_z, cart_body_vy, agg);
+    if (was_reset) a.S5[e] = make_float4(target[1], target[2], obj[0], obj[1]);
+    a.ctr[e] = step + 1u;
+    a.rew[e] = o.rew;
+    a.reset[e] = o.reset;
+    a.progress[e] = progress;
+    a.timeout[e] = o.timeout;
+    float* row = s_obs + threadIdx.x * (VINE_MAX_OBS + 1);
+#pragma unroll
+    for (int i = 0; i < VINE_MAX_OBS; ++i) if (i < p.O) row[i] = o.obs[i];
+    if (a.dbg) {
+      float* dbg = a.dbg + e * VINE_DBG_W;
+      dbg[0] = u_rail; dbg[1] = u_fpam; dbg[2] = in.prev_u_rail; dbg[3] = rail_force;
+      dbg[4] = tipvel_y; dbg[5] = tipvel_z;
+#pragma unroll
+      for (int i = 0; i < VINE_NUM_REWARDS; ++i) dbg[6 + i] = o.r[i];
+    }
+  }
+  __syncthreads();
+  store_obs_block(s_obs, p.O, a.n, p.clip_obs, a.obs, a.obs_clamped);
+}
+
+// ------------------------------------------------------------------------------------------
+// init / reset_idx / get / set state
+// ------------------------------------------------------------------------------------------
+__global__ void vine_init_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n) return;
+  // state right after Vine5LinkMovingBase.__init__ (V5:178-291): q = 0, initial targets (V5:179)
+  uint32_t u[12];
+  for (uint32_t b = 0; b < 3; ++b) {
+    const uint4 r = philox4x32(a.k0, a.k1, (uint32_t)(a.gid0 + e), VINE_SITE_RESET, 0x40000000u, b);
+    u[4 * b] = r.x; u[4 * b + 1] = r.y; u[4 * b + 2] = r.z; u[4 * b + 3] = r.w;
+  }
+  float target[3]; sample_targets(p, u, target);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  a.S0[e] = z; a.S1[e] = z; a.S2[e] = z; a.S3[e] = z;
+  a.S4[e] = make_float4(p.tip0_y, p.tip0_z, 0.f, 0.f);
+  a.S5[e] = make_float4(target[1], target[2], 0.f, 0.f);
+  for (int k = 0; k < p.D; ++k) a.ring[(int64_t)k * a.n + e] = make_float2(0.f, 0.f);
+  a.ctr[e] = 0u;
+}
+
+// reset_idx outside step (VT:412-427 reset_done; 'R' key V5:715-718): rigid-body views untouched
+__global__ void vine_reset_idx_kernel(const __grid_constant__ VineParams p, const StepArgs a, const int64_t* ids, int64_t n_ids) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ids) return;
+  const int64_t e = ids[i];
+  if (e < 0 || e >= a.n) return;
+  float q[6], qd[6], target[3], obj[2];
+  const float4 s5 = a.S5[e];
+  target[0] = 0.f; target[1] = s5.x; target[2] = s5.y; obj[0] = s5.z; obj[1] = s5.w;
+  reset_env(p, a.k0, a.k1, (uint32_t)(a.gid0 + e), a.ctr[e] | 0x80000000u, q, qd, target, obj);
+  float4 s3 = a.S3[e], s4 = a.S4[e];
+  s3.z = 0.f;  // prev_cart_vel_error, V5:799
+  s4.w = 0.f;  // aggregated_rew_buf, V5:810
+  if (!p.stale) {
+    Dyn d; rel_to_abs(q, qd, d);
+    Kin k; link_trig(p, d, k);
+    float vy, vz; tip_fk(d, k, s4.x, s4.y, vy, vz);
+    s4.z = 0.f; s3.w = 0.f; s3.y = 0.f;
+  }
+  a.S0[e] = make_float4(q[0], q[1], q[2], q[3]);
+  a.S1[e] = make_float4(q[4], q[5], 0.f, 0.f);
+  a.S2[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  a.S3[e] = s3; a.S4[e] = s4;
+  a.S5[e] = make_float4(target[1], target[2], obj[0], obj[1]);
+  if (a.reset) a.reset[e] = 0;
+  if (a.progress) a.progress[e] = 0;
+  if (a.rew) a.rew[e] = 0.f;
+}
+
+__global__ void vine_state_kernel(const __grid_constant__ VineParams p, const StepArgs a, const VineStateView v, int set) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.n) return;
+  float4 s0 = a.S0[e], s1 = a.S1[e], s2 = a.S2[e], s3 = a.S3[e], s4 = a.S4[e], s5 = a.S5[e];
+  uint32_t ctr = a.ctr[e];
+  if (set) {
+    if (v.dof_pos) { const float* q = v.dof_pos + 6 * e; s0 = make_float4(q[0], q[1], q[2], q[3]); s1.x = q[4]; s1.y = q[5]; }
+    if (v.dof_vel) { const float* q = v.dof_vel + 6 * e; s1.z = q[0]; s1.w = q[1]; s2 = make_float4(q[2], q[3], q[4], q[5]); }
+    if (v.tip_positions) { s4.x = v.tip_positions[3 * e + 1]; s4.y = v.tip_positions[3 * e + 2]; }
+    if (v.cart_body_vel_y) s4.z = v.cart_body_vel_y[e];
+    if (v.target_positions) { s5.x = v.target_positions[3 * e + 1]; s5.y = v.target_positions[3 * e + 2]; }
+    if (v.object_info) { s5.z = v.object_info[2 * e]; s5.w = v.object_info[2 * e + 1]; }
+    if (v.smoothed_u_fpam) s3.x = v.smoothed_u_fpam[e];
+    if (v.prev_cart_vel) s3.y = v.prev_cart_vel[e];
+    if (v.prev_cart_vel_error) s3.z = v.prev_cart_vel_error[e];
+    if (v.shelf_contact_force) s3.w = v.shelf_contact_force[e];
+    if (v.aggregated_rew_buf) s4.w = v.aggregated_rew_buf[e];
+    if (v.step_count) ctr = (uint32_t)v.step_count[e];
+    if (v.actions_history)
+      for (int k = 0; k < p.D; ++k) {
+        const float* h = v.actions_history + (e * p.D + k) * 2;
+        a.ring[(int64_t)((ctr + (uint32_t)k) % (uint32_t)p.D) * a.n + e] = make_float2(h[0], h[1]);
+      }
+    a.S0[e] = s0; a.S1[e] = s1; a.S2[e] = s2; a.S3[e] = s3; a.S4[e] = s4; a.S5[e] = s5; a.ctr[e] = ctr;
+    return;
+  }
+  if (v.dof_pos) { float* q = v.dof_pos + 6 * e; q[0] = s0.x; q[1] = s0.y; q[2] = s0.z; q[3] = s0.w; q[4] = s1.x; q[5] = s1.y; }
+  if (v.dof_vel) { float* q = v.dof_vel + 6 * e; q[0] = s1.z; q[1] = s1.w; q[2] = s2.x; q[3] = s2.y; q[4] = s2.z; q[5] = s2.w; }
+  if (v.tip_positions) { v.tip_positions[3 * e] = 0.f; v.tip_positions[3 * e + 1] = s4.x; v.tip_positions[3 * e + 2] = s4.y; }
+  if (v.cart_body_vel_y) v.cart_body_vel_y[e] = s4.z;
+  if (v.target_positions) { v.target_positions[3 * e] = 0.f; v.target_positions[3 * e + 1] = s5.x; v.target_positions[3 * e + 2] = s5.y; }
+  if (v.object_info) { v.object_info[2 * e] = s5.z; v.object_info[2 * e + 1] = s5.w; }
+  if (v.smoothed_u_fpam) v.smoothed_u_fpam[e] = s3.x;
+  if (v.prev_cart_vel) v.prev_cart_vel[e] = s3.y;
+  if (v.prev_cart_vel_error) v.prev_cart_vel_error[e] = s3.z;
+  if (v.shelf_contact_force) v.shelf_contact_force[e] = s3.w;
+  if (v.aggregated_rew_buf) v.aggregated_rew_buf[e] = s4.w;
+  if (v.step_count) v.step_count[e] = (int64_t)ctr;
+  if (v.actions_history)
+    for (int k = 0; k < p.D; ++k) {
+      const float2 h = a.ring[(int64_t)((ctr + (uint32_t)k) % (uint32_t)p.D) * a.n + e];
+      v.actions_history[(e * p.D + k) * 2] = h.x; v.actions_history[(e * p.D + k) * 2 + 1] = h.y;
+    }
+  if (a.dbg) {
+    const float* dbg = a.dbg + e * VINE_DBG_W;
+    if (v.u_rail_velocity) v.u_rail_velocity[e] = dbg[0];
+    if (v.u_fpam) v.u_fpam[e] = dbg[1];
+    if (v.prev_u_rail_velocity) v.prev_u_rail_velocity[e] = dbg[2];
+    if (v.rail_force) v.rail_force[e] = dbg[3];
+    if (v.tip_velocities) { v.tip_velocities[3 * e] = 0.f; v.tip_velocities[3 * e + 1] = dbg[4]; v.tip_velocities[3 * e + 2] = dbg[5]; }
+    if (v.reward_matrix) for (int i = 0; i < VINE_NUM_REWARDS; ++i) v.reward_matrix[VINE_NUM_REWARDS * e + i] = dbg[6 + i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// function-level kernels (same device functions as the fused step)
+// ------------------------------------------------------------------------------------------
+__global__ void vine_post_physics_kernel(const __grid_constant__ VineParams p, int64_t n, const VinePostPhysicsIO io) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  PostIn in;
+  for (int i = 0; i < 6; ++i) { in.q[i] = io.dof_pos[6 * e + i]; in.qd[i] = io.dof_vel[6 * e + i]; in.prev_q[i] = io.prev_dof_pos[6 * e + i]; }
+  for (int i = 0; i < 3; ++i) {
+    in.tip[i] = io.tip_positions[3 * e + i]; in.prev_tip[i] = io.prev_tip_positions[3 * e + i];
+    in.tipvel[i] = io.tip_velocities[3 * e + i]; in.target[i] = io.target_positions[3 * e + i];
+    in.target_vel[i] = io.target_velocities[3 * e + i];
+  }
+  in.obj[0] = io.object_info[2 * e]; in.obj[1] = io.object_info[2 * e + 1];
+  in.cart_y = io.cart_positions_y[e]; in.smoothed = io.smoothed_u_fpam[e]; in.u_fpam = io.u_fpam[e];
+  in.u_rail = io.u_rail_velocity[e]; in.prev_u_rail = io.prev_u_rail_velocity[e];
+  for (int i = 0; i < VINE_MAX_CFI; ++i) in.contact[i] = (io.contact_force_norms && i < p.C) ? io.contact_force_norms[(int64_t)i * n + e] : 0.f;
+  in.reset_in = io.reset_buf_in[e]; in.progress = io.progress_buf[e];
+  float noise[VINE_MAX_OBS];
+  const bool noisy = p.randomize && io.obs_noise != nullptr;
+  if (noisy) for (int i = 0; i < p.O; ++i) noise[i] = io.obs_noise[(int64_t)p.O * e + i];
+  PostOut o;
+  post_physics(p, in, noisy ? noise : nullptr, o);
+  for (int i = 0; i < p.O; ++i) io.obs_buf[(int64_t)p.O * e + i] = o.obs[i];
+  io.rew_buf[e] = o.rew;
+  if (io.reward_matrix) for (int i = 0; i < VINE_NUM_REWARDS; ++i) io.reward_matrix[VINE_NUM_REWARDS * e + i] = o.r[i];
+  io.reset_buf_out[e] = o.reset;
+  io.timeout_buf[e] = o.timeout;
+}
+
+__global__ void vine_pre_physics_kernel(const __grid_constant__ VineParams p, int64_t n, const VinePrePhysicsIO io) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float a0 = io.actions[2 * e], a1 = io.actions[2 * e + 1];
+  if (p.randomize && io.action_noise) {
+    a0 = __fadd_rn(a0, __fmul_rn(p.act_noise, io.action_noise[2 * e]));
+    a1 = __fadd_rn(a1, __fmul_rn(p.act_noise, io.action_noise[2 * e + 1]));
+  }
+  float u_rail, u_fpam;
+  rescale_actions(p, a0, a1, u_rail, u_fpam);
+  if (p.D > 0) {
+    const float* hi = io.history_in + (int64_t)2 * p.D * e;
+    float* ho = io.history_out + (int64_t)2 * p.D * e;
+    const float o_rail = hi[0], o_fpam = hi[1];
+    for (int k = 0; k + 1 < p.D; ++k) { ho[2 * k] = hi[2 * k + 2]; ho[2 * k + 1] = hi[2 * k + 3]; }
+    ho[2 * (p.D - 1)] = u_rail; ho[2 * (p.D - 1) + 1] = u_fpam;
+    u_rail = o_rail; u_fpam = o_fpam;
+  }
+  float s = io.smoothed_in[e];
+  apply_overrides_and_smooth(p, u_rail, u_fpam, s);
+  io.u_rail_velocity[e] = u_rail; io.u_fpam[e] = u_fpam; io.smoothed_out[e] = s;
+}
+
+__global__ void vine_actuation_kernel(const __grid_constant__ VineParams p, int64_t n, const VineActuationIO io) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  JointLaw law; joint_law_unscaled(law);
+  if (io.dynamics_scaling) {
+    const float* s = io.dynamics_scaling + 20 * e;
+    for (int j = 0; j < VINE_NL; ++j) {
+      law.K[j] = __fmul_rn(law.K[j], s[4 * j]); law.Cd[j] = __fmul_rn(law.Cd[j], s[4 * j + 1]);
+      law.b[j] = __fmul_rn(law.b[j], s[4 * j + 2]); law.B[j] = __fmul_rn(law.B[j], s[4 * j + 3]);
+    }
+  }
+  float pv = io.prev_cart_vel[e], pe = io.prev_cart_vel_error[e];
+  io.dof_efforts[6 * e] = rail_controller(p, io.cart_vel_y[e], io.u_rail_velocity[e],
+                                          io.accel_scaling ? io.accel_scaling[e] : 1.f, pv, pe);
+  for (int j = 0; j < VINE_NL; ++j)
+    io.dof_efforts[6 * e + j + 1] = joint_torque(law, j, io.dof_pos[6 * e + j + 1], io.dof_vel[6 * e + j + 1], io.u_fpam_to_use[e]);
+  io.prev_cart_vel_out[e] = pv; io.prev_cart_vel_error_out[e] = pe;
+}
+
+template <bool CONTACT>
+__global__ void __launch_bounds__(VINE_BLOCK) vine_simulate_kernel(const __grid_constant__ VineParams p, int64_t n, const VineSimulateIO io) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float q[6], qd[6], efforts[6];
+  for (int i = 0; i < 6; ++i) { q[i] = io.dof_pos[6 * e + i]; qd[i] = io.dof_vel[6 * e + i]; efforts[i] = io.dof_efforts[6 * e + i]; }
+  JointLaw law; joint_law_unscaled(law);
+  if (io.dynamics_scaling) {
+    const float* s = io.dynamics_scaling + 20 * e;
+    for (int j = 0; j < VINE_NL; ++j) {
+      law.K[j] = __fmul_rn(law.K[j], s[4 * j]); law.Cd[j] = __fmul_rn(law.Cd[j], s[4 * j + 1]);
+      law.b[j] = __fmul_rn(law.b[j], s[4 * j + 2]); law.B[j] = __fmul_rn(law.B[j], s[4 * j + 3]);
+    }
+  }
+  const float u_use = io.u_fpam_to_use ? io.u_fpam_to_use[e] : 0.f;
+  Obstacles ob;
+  if (CONTACT) build_obstacles(p, io.target_positions[3 * e + 1], io.target_positions[3 * e + 2],
+                               io.object_info[2 * e], io.object_info[2 * e + 1], ob);
+  Dyn d; rel_to_abs(q, qd, d);
+  JointImp J; joint_implicit_consts(p, law, u_use, efforts, J);
+  float lip = 0.f;
+#pragma unroll 1
+  for (int s = 0; s < p.S; ++s) substep<CONTACT>(p, J, efforts[0], &ob, d, lip);
+  Kin k; link_trig(p, d, k);
+  float ty, tz, vy, vz; tip_fk(d, k, ty, tz, vy, vz);
+  abs_to_rel(d, q, qd);
+  for (int i = 0; i < 6; ++i) { io.dof_pos[6 * e + i] = q[i]; io.dof_vel[6 * e + i] = qd[i]; }
+  if (io.tip_positions) { io.tip_positions[3 * e] = 0.f; io.tip_positions[3 * e + 1] = ty; io.tip_positions[3 * e + 2] = tz; }
+  if (io.tip_velocities) { io.tip_velocities[3 * e] = 0.f; io.tip_velocities[3 * e + 1] = vy; io.tip_velocities[3 * e + 2] = vz; }
+  if (io.shelf_contact_force) io.shelf_contact_force[e] = lip;
+}
+
+__global__ void vine_philox_kernel(uint32_t k0, uint32_t k1, uint32_t gid, uint32_t site, uint32_t step, uint32_t block0,
+                                   int64_t n_blocks, uint32_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_blocks) return;
+  const uint4 r = philox4x32(k0, k1, gid, site, step, block0 + (uint32_t)i);
+  out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+// ------------------------------------------------------------------------------------------
+// GAE over the horizon (rl_games A2CBase.discount_values; analogue learning/common_agent.py:413-425).
+// A_t = delta_t + c_t A_{t+1} is an affine recurrence: each warp owns 32 consecutive envs (coalesced
+// [T,N] rows) and walks the horizon backwards; the f32 operation order is the reference's, so the
+// result is bit-identical to the sequential Python loop.
+// ------------------------------------------------------------------------------------------
+__global__ void vine_gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                                const float* __restrict__ dones, const float* __restrict__ last_values,
+                                const float* __restrict__ last_dones, int64_t T, int64_t N, float gamma, float gt,
+                                float* __restrict__ adv, float* __restrict__ ret) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  float nextv = last_values[e], nonterm = __fsub_rn(1.0f, last_dones[e]), lastgaelam = 0.f;
+  // software prefetch: issue the loads of step t-1 before the dependent math of step t
+  float r = rewards[(T - 1) * N + e], v = values[(T - 1) * N + e], dn = dones[(T - 1) * N + e];
+  for (int64_t t = T - 1; t >= 0; --t) {
+    float r2 = 0.f, v2 = 0.f, d2 = 0.f;
+    if (t > 0) { r2 = rewards[(t - 1) * N + e]; v2 = values[(t - 1) * N + e]; d2 = dones[(t - 1) * N + e]; }
+    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, nextv), nonterm)), v);
+    lastgaelam = __fadd_rn(delta, __fmul_rn(__fmul_rn(gt, nonterm), lastgaelam));
+    adv[t * N + e] = lastgaelam;
+    ret[t * N + e] = __fadd_rn(lastgaelam, v);
+    nextv = v; nonterm = __fsub_rn(1.0f, dn);
+    r = r2; v = v2; dn = d2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" {
+
+int vine_abi_version(void) { return VINE_ABI_VERSION; }
+
+int vine_config_defaults(VineConfig* c) {  // YT:7-134
+  if (!c) return VINE_ERR_INVALID_ARG;
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(*c);
+  c->substeps = 10; c->dt = 0.00833; c->gravity_z = -9.81;
+  c->control_freq_inv = 4; c->max_episode_length = 500;
+  c->clip_observations = 5.0; c->clip_actions = 1.0;
+  c->observation_type = VINE_OBS_POS_AND_FD_VEL_AND_OBJ_INFO; c->scale_observations = 1;
+  c->create_shelf = 0; c->create_pipe = 1;
+  c->use_smoothed_fpam = 1; c->action_delay = 1;
+  c->smoothing_alpha_inflate = 0.81; c->smoothing_alpha_deflate = 0.86;
+  c->fpam_min = -0.1; c->fpam_max = 3.0; c->rail_velocity_scale = 1.0;
+  c->damping = 2e-2; c->stiffness = 0.0;
+  c->rail_soft_limit = 0.3; c->rail_p_gain = 10.0; c->rail_d_gain = 0.0; c->rail_acceleration = 8.0;
+  c->randomize_dof_init = 1; c->randomize_targets = 1;
+  c->random_init_cart_min_y = -0.1 * 0.3; c->random_init_cart_max_y = 0.3;
+  c->success_dist = 0.08;
+  c->min_target_depth_in_obstacle = -0.05; c->max_target_depth_in_obstacle = 0.2;
+  c->min_target_y = -0.48; c->max_target_y = -0.4; c->min_target_z = 0.58; c->max_target_z = 0.67;
+  const double w[VINE_NUM_REWARDS] = {0, 0, 1, 0, 0.1, 0, 0, 0, 0, 1, 0, 0, 0.10};
+  memcpy(c->reward_weights, w, sizeof(w));
+  c->use_target_reached_reset = 1;
+  c->vine_randomize = 1;
+  c->dynamics_scaling_min = 0.999; c->dynamics_scaling_max = 1.001;
+  c->accel_target_scaling_min = 1.0; c->accel_target_scaling_max = 1.0;
+  c->torque_law_integration = VINE_TORQUE_LAW_IMPLICIT;
+  c->emulate_stale_body_state = 1;
+  c->revolute_lower = -3.4e38; c->revolute_upper = 3.4e38;
+  c->prismatic_lower = -3.4e38; c->prismatic_upper = 3.4e38;
+  c->contact_stiffness = 2000.0; c->contact_damping = 2.0; c->contact_rest_offset = 0.001;
+  return VINE_OK;
+}
+
+int vine_num_observations(int t) { const int w = vine_obs_width(t); return w < 0 ? VINE_ERR_INVALID_ARG : w; }
+
+const char* vine_last_error(const VineEnv* env) { return env ? env->err : g_create_err; }
+
+void vine_destroy(VineEnv* env) {
+  if (!env) return;
+  cudaSetDevice(env->device);
+  cudaFree(env->a.S0); cudaFree(env->a.S1); cudaFree(env->a.S2); cudaFree(env->a.S3); cudaFree(env->a.S4);
+  cudaFree(env->a.S5); cudaFree(env->a.ring); cudaFree(env->a.ctr); cudaFree(env->a.dbg);
+  delete env;
+}
+
+int vine_create(const VineConfig* cfg, int64_t num_envs, int64_t global_env_offset, int device, uint64_t seed,
+                VineEnv** out) {
+  if (!cfg || !out || num_envs <= 0 || global_env_offset < 0) { snprintf(g_create_err, 256, "invalid argument"); return VINE_ERR_INVALID_ARG; }
+  if (global_env_offset + num_envs > 0xFFFFFFFFll) { snprintf(g_create_err, 256, "global env id exceeds 32 bits"); return VINE_ERR_INVALID_ARG; }
+  VineParams p; const char* why;
+  const int rc = vine_derive_params(cfg, &p, &why);
+  if (rc != VINE_OK) { snprintf(g_create_err, 256, "%s", why); return rc; }
+  VineEnv* env = new VineEnv();
+  memset(env, 0, sizeof(*env));
+  env->p = p; env->cfg = *cfg; env->device = device;
+  StepArgs& a = env->a;
+  a.n = num_envs; a.gid0 = global_env_offset; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+  cudaError_t e = cudaSetDevice(device);
+  const size_t n = (size_t)num_envs;
+  if (e == cudaSuccess) e = cudaMalloc(&a.S0, n * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(&a.S1, n * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(&a.S2, n * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(&a.S3, n * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(&a.S4, n * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(&a.S5, n * sizeof(float4));
+  if (e == cudaSuccess) e = cudaMalloc(&a.ring, n * sizeof(float2) * (size_t)(p.D > 0 ? p.D : 1));
+  if (e == cudaSuccess) e = cudaMalloc(&a.ctr, n * sizeof(uint32_t));
+  if (e == cudaSuccess) {
+    vine_init_kernel<<<grid_for(num_envs, 256), 256>>>(env->p, env->a);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    snprintf(g_create_err, 256, "vine_create: %s", cudaGetErrorString(e));
+    vine_destroy(env);
+    return VINE_ERR_CUDA;
+  }
+  *out = env;
+  return VINE_OK;
+}
+
+int vine_bind_io(VineEnv* env, const float* actions, float* obs_buf, float* rew_buf, int64_t* reset_buf,
+                 int64_t* progress_buf, uint8_t* timeout_buf, float* obs_clamped) {
+  if (!env) return VINE_ERR_INVALID_ARG;
+  if (!actions || !obs_buf || !rew_buf || !reset_buf || !progress_buf || !timeout_buf) {
+    snprintf(env->err, 256, "vine_bind_io: null buffer"); return VINE_ERR_INVALID_ARG;
+  }
+  if (((uintptr_t)actions | (uintptr_t)obs_buf | (uintptr_t)obs_clamped) & 15u) {
+    snprintf(env->err, 256, "vine_bind_io: actions/obs buffers must be 16-byte aligned"); return VINE_ERR_INVALID_ARG;
+  }
+  env->a.actions = reinterpret_cast<const float2*>(actions);
+  env->a.obs = obs_buf; env->a.obs_clamped = obs_clamped; env->a.rew = rew_buf;
+  env->a.reset = reset_buf; env->a.progress = progress_buf; env->a.timeout = timeout_buf;
+  env->bound = 1;
+  return VINE_OK;
+}
+
+int vine_set_debug_outputs(VineEnv* env, int enabled) {
+  if (!env) return VINE_ERR_INVALID_ARG;
+  if (enabled && !env->a.dbg) {
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    CUDA_TRY(env, cudaMalloc(&env->a.dbg, (size_t)env->a.n * VINE_DBG_W * sizeof(float)));
+    CUDA_TRY(env, cudaMemset(env->a.dbg, 0, (size_t)env->a.n * VINE_DBG_W * sizeof(float)));
+  } else if (!enabled && env->a.dbg) {
+    CUDA_TRY(env, cudaFree(env->a.dbg));
+    env->a.dbg = nullptr;
+  }
+  return VINE_OK;
+}
+
+int vine_step(VineEnv* env, void* stream) {
+  if (!env) return VINE_ERR_INVALID_ARG;
+  if (!env->bound) { snprintf(env->err, 256, "vine_step: call vine_bind_io first"); return VINE_ERR_NOT_BOUND; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = grid_for(env->a.n, VINE_BLOCK);
+  if (env->p.shelf || env->p.pipe) vine_step_kernel<true><<<grid, VINE_BLOCK, 0, st>>>(env->p, env->a);
+  else vine_step_kernel<false><<<grid, VINE_BLOCK, 0, st>>>(env->p, env->a);
+  CUDA_TRY(env, cudaGetLastError());
+  return VINE_OK;
+}
+
+int vine_reset_idx(VineEnv* env, const int64_t* env_ids, int64_t n, void* stream) {
+  if (!env || (n > 0 && !env_ids) || n < 0) return VINE_ERR_INVALID_ARG;
+  if (n == 0) return VINE_OK;
+  vine_reset_idx_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(env->p, env->a, env_ids, n);
+  CUDA_TRY(env, cudaGetLastError());
+  return VINE_OK;
+}
+
+int vine_get_state(VineEnv* env, const VineStateView* view, void* stream) {
+  if (!env || !view) return VINE_ERR_INVALID_ARG;
+  vine_state_kernel<<<grid_for(env->a.n, 256), 256, 0, (cudaStream_t)stream>>>(env->p, env->a, *view, 0);
+  CUDA_TRY(env, cudaGetLastError());
+  return VINE_OK;
+}
+
+int vine_set_state(VineEnv* env, const VineStateView* view, void* stream) {
+  if (!env || !view) return VINE_ERR_INVALID_ARG;
+  vine_state_kernel<<<grid_for(env->a.n, 256), 256, 0, (cudaStream_t)stream>>>(env->p, env->a, *view, 1);
+  CUDA_TRY(env, cudaGetLastError());
+  return VINE_OK;
+}
+
+int vine_post_physics(VineEnv* env, const VinePostPhysicsIO* io, void* stream) {
+  if (!env || !io) return VINE_ERR_INVALID_ARG;
+  vine_post_physics_kernel<<<grid_for(env->a.n, 128), 128, 0, (cudaStream_t)stream>>>(env->p, env->a.n, *io);
+  CUDA_TRY(env, cudaGetLastError());
+  return VINE_OK;
+}
+
+int vine_pre_physics(VineEnv* env, const VinePrePhysicsIO* io, void* stream) {
+  if (!env || !io) return VINE_ERR_INVALID_ARG;
+  vine_pre_physics_kernel<<<grid_for(env->a.n, 128), 128, 0, (cudaStream_t)stream>>>(env->p, env->a.n, *io);
+  CUDA_TRY(env, cudaGetLastError());
+  return VINE_OK;
+}
+
+int vine_actuation(VineEnv* env, const VineActuationIO* io, void* stream) {
+  if (!env || !io) return VINE_ERR_INVALID_ARG;
+  vine_actuation_kernel<<<grid_for(env->a.n, 128), 128, 0, (cudaStream_t)stream>>>(env->p, env->a.n, *io);
+  CUDA_TRY(env, cudaGetLastError());
+  return VINE_OK;
+}
+
+int vine_simulate(VineEnv* env, const VineSimulateIO* io, void* stream) {
+  if (!env || !io) return VINE_ERR_INVALID_ARG;
+  const unsigned grid = grid_for(env->a.n, VINE_BLOCK);
+  if (env->p.shelf || env->p.pipe) vine_simulate_kernel<true><<<grid, VINE_BLOCK, 0, (cudaStream_t)stream>>>(env->p, env->a.n, *io);
+  else vine_simulate_kernel<false><<<grid, VINE_BLOCK, 0, (cudaStream_t)stream>>>(env->p, env->a.n, *io);
+  CUDA_TRY(env, cudaGetLastError());
+  return VINE_OK;
+}
+
+int vine_philox_debug(uint64_t seed, uint32_t gid, uint32_t site, uint32_t step, uint32_t block0, int64_t n_blocks,
+                      uint32_t* out, void* stream) {
+  if (!out || n_blocks <= 0) return VINE_ERR_INVALID_ARG;
+  vine_philox_kernel<<<grid_for(n_blocks, 128), 128, 0, (cudaStream_t)stream>>>((uint32_t)seed, (uint32_t)(seed >> 32), gid, site,
+                                                                                 step, block0, n_blocks, out);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+int vine_gae(const float* rewards, const float* values, const float* dones, const float* last_values,
+             const float* last_dones, int64_t horizon, int64_t num_envs, double gamma, double tau, float* advantages,
+             float* returns, void* stream) {
+  if (!rewards || !values || !dones || !last_values || !last_dones || !advantages || !returns || horizon <= 0 || num_envs <= 0)
+    return VINE_ERR_INVALID_ARG;
+  // Python: `self.gamma * self.tau` is a double product that meets the f32 tensor afterwards
+  vine_gae_kernel<<<grid_for(num_envs, 128), 128, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, last_dones,
+                                                                             horizon, num_envs, (float)gamma, (float)(gamma * tau),
+                                                                             advantages, returns);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+}  // extern "C"

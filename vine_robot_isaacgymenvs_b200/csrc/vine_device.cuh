@@ -1,0 +1,550 @@
+// vine_device.cuh — per-environment device functions of the Vine5LinkMovingBase step.
+// One environment per thread; everything below works on registers.
+//
+// Rounding discipline: the task logic the reference computes with torch f32 kernels (action
+// path, controller, observations, reward, resets) is written with explicit __f*_rn intrinsics in
+// the reference's operation order so nvcc cannot contract it into FMAs — masks stay bit-exact.
+// The dynamics (PhysX in the reference, parity unpinned) uses free-form FMA arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "vine_params.h"
+
+#define VDEV __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11). ctr = (gid, site, step, block), key = seed.
+// ------------------------------------------------------------------------------------------
+VDEV uint4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+VDEV float u01(uint32_t x) { return __fmul_rn((float)(x >> 8), 5.9604644775390625e-08f); }  // [0,1)
+VDEV float uniform_ab(uint32_t x, float lo, float rng) { return __fmaf_rn(u01(x), rng, lo); }
+
+// sin/cos for |x| up to a few thousand (Cody-Waite reduction + Cephes minimax kernels)
+VDEV void vine_sincos(float x, float& s, float& c) {
+  const float j = rintf(x * 0.636619772f);
+  const int q = (int)j;
+  float r = fmaf(j, -1.57079601e+00f, x);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+  const float r2 = r * r;
+  const float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+  const float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f),
+                        r2 * r2, fmaf(-0.5f, r2, 1.0f));
+  const float a = (q & 1) ? cp : sp, b = (q & 1) ? sp : cp;
+  s = (q & 2) ? -a : a;
+  c = ((q + 1) & 2) ? -b : b;
+}
+
+// Box-Muller: 4 u32 -> 4 standard normals
+VDEV void normal4(uint4 r, float out[4]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const float u1 = __fmul_rn((float)((w[2 * p] >> 8) + 1u), 5.9604644775390625e-08f);  // (0,1]
+    const float u2 = u01(w[2 * p + 1]);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    vine_sincos(6.283185307179586f * u2, sn, cs);
+    out[2 * p] = rad * cs; out[2 * p + 1] = rad * sn;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Action path: raw_actions_to_actions V5:984-997, rescale_to_u V5:1458-1459,
+// manual_intervention V5:1023-1026, u_fpam_to_smoothed_u_fpam V5:999-1005.
+// `old_*` is the command popped from the delay ring (== new when ACTION_DELAY = 0).
+// ------------------------------------------------------------------------------------------
+VDEV void rescale_actions(const VineParams& p, float a0, float a1, float& new_rail, float& new_fpam) {
+  new_rail = __fmul_rn(a0, p.rail_scale);
+  new_fpam = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(a1, 1.0f), 2.0f), p.fpam_range), p.fpam_min);
+}
+
+VDEV void apply_overrides_and_smooth(const VineParams& p, float& u_rail, float& u_fpam, float& smoothed) {
+  if (p.force_fpam) u_fpam = 0.0f;
+  if (p.force_rail) u_rail = 0.0f;
+  const float alpha = (u_fpam > smoothed) ? p.alpha_inf : p.alpha_def;
+  smoothed = __fadd_rn(__fmul_rn(alpha, smoothed), __fmul_rn(__fsub_rn(1.0f, alpha), u_fpam));
+}
+
+// ------------------------------------------------------------------------------------------
+// compute_and_set_dof_actuation_force_tensor, V5:1028-1106
+// ------------------------------------------------------------------------------------------
+__constant__ float cTL_K[VINE_NL] = {0.8385f, 1.5400f, 1.5109f, 1.2887f, 0.4347f};  // V5:1045
+__constant__ float cTL_C[VINE_NL] = {0.0178f, 0.0304f, 0.0528f, 0.0367f, 0.0223f};  // V5:1046
+__constant__ float cTL_b[VINE_NL] = {0.0007f, 0.0062f, 0.0402f, 0.0160f, 0.0133f};  // V5:1047
+__constant__ float cTL_B[VINE_NL] = {0.0247f, 0.0616f, 0.0779f, 0.0498f, 0.0268f};  // V5:1048
+
+// scaled torque-law coefficients of one sim step: (K,C,b,B) * U(DYNAMICS_SCALING) (V5:1053-1055)
+struct JointLaw { float K[VINE_NL], Cd[VINE_NL], b[VINE_NL], B[VINE_NL]; };
+
+VDEV void joint_law_unscaled(JointLaw& L) {
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) { L.K[j] = cTL_K[j]; L.Cd[j] = cTL_C[j]; L.b[j] = cTL_b[j]; L.B[j] = cTL_B[j]; }
+}
+
+VDEV float joint_torque(const JointLaw& L, int j, float q, float qd, float u) {  // -(Kq + Cqd + b + Bu)
+  float t = __fmul_rn(L.K[j], q);
+  t = __fadd_rn(t, __fmul_rn(L.Cd[j], qd));
+  t = __fadd_rn(t, L.b[j]);
+  t = __fadd_rn(t, __fmul_rn(L.B[j], u));
+  return -t;
+}
+
+VDEV float rail_controller(const VineParams& p, float cart_vel_y, float u_rail, float acc_scale,
+                           float& prev_cart_vel, float& prev_err) {
+  const float err = __fsub_rn(u_rail, cart_vel_y);
+  float minmax = (err > 0.0f) ? p.rail_force_max : -p.rail_force_max;
+  const float accel = __fdiv_rn(__fsub_rn(cart_vel_y, prev_cart_vel), p.dt);          // V5:1079
+  float accel_target = (err > 0.0f) ? p.rail_accel : -p.rail_accel;
+  accel_target = __fmul_rn(accel_target, acc_scale);                                   // README.md:63 knob
+  minmax = __fadd_rn(minmax, __fmul_rn(0.30f, __fsub_rn(accel_target, accel)));       // V5:1083-1087
+  const float pid = __fadd_rn(__fmul_rn(p.p_gain, err), __fmul_rn(p.d_gain, __fsub_rn(err, prev_err)));
+  prev_err = err; prev_cart_vel = cart_vel_y;                                          // V5:1097-1098
+  return (fabsf(err) > 0.1f) ? minmax : pid;                                           // V5:1094
+}
+
+// ------------------------------------------------------------------------------------------
+// Obstacles: rectangles in the (y,z) plane of motion (custom_shelf.urdf:82-93,139-152 placed by
+// V5:818-829; pipe tube V5:841-885 with the STL's dimensions).
+// ------------------------------------------------------------------------------------------
+struct Rect { float cy, cz, ay, az, ha, hn; };
+struct Obstacles {
+  Rect r[VINE_MAX_RECTS];
+  int n, lip;                        // lip = index of the sensing shelf_link rectangle or -1
+  float lo_y, hi_y, lo_z, hi_z;      // bounding box of all rectangles
+};
+
+VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, float theta, Obstacles& ob) {
+  ob.n = 0; ob.lip = -1;
+  if (p.shelf) {
+    const float ry = ty + (-0.2f + depth), rz = tz - 0.01f;
+    ob.r[0] = {ry - 0.001f, rz, 1.f, 0.f, 0.1995f, 0.005f};
+    ob.r[1] = {ry, rz + 0.2f, 1.f, 0.f, 0.2f, 0.005f};
+    ob.r[2] = {ry + 0.199f, rz, 1.f, 0.f, 0.001f, 0.005f};
+    ob.lip = 2; ob.n = 3;
+  }
+  if (p.pipe) {
+    float st, ct; vine_sincos(theta, st, ct);
+    const float off = 0.0735f - 0.0777f;            // PIPE_RADIUS (V5:88) - mesh centre
+    const float win = 0.07232816f, wout = 0.07758640f;  // sqrt(R^2 - off^2) for R_in, R_out
+    const float ey = ty + depth * ct + off * st, ez = tz + depth * st - off * ct;
+    const float ay = -ct, az = -st, ny = -az, nz = ay;
+    const float mid = 0.5f * (win + wout), hn = 0.5f * (wout - win), ha = 0.5f * 0.34125f;
+    ob.r[ob.n++] = {ey + ay * ha - mid * ny, ez + az * ha - mid * nz, ay, az, ha, hn};
+    ob.r[ob.n++] = {ey + ay * ha + mid * ny, ez + az * ha + mid * nz, ay, az, ha, hn};
+  }
+  ob.lo_y = ob.lo_z = 1e30f; ob.hi_y = ob.hi_z = -1e30f;
+  for (int i = 0; i < ob.n; ++i) {
+    const Rect& R = ob.r[i];
+    const float ey = fabsf(R.ay) * R.ha + fabsf(R.az) * R.hn, ez = fabsf(R.az) * R.ha + fabsf(R.ay) * R.hn;
+    ob.lo_y = fminf(ob.lo_y, R.cy - ey); ob.hi_y = fmaxf(ob.hi_y, R.cy + ey);
+    ob.lo_z = fminf(ob.lo_z, R.cz - ez); ob.hi_z = fmaxf(ob.hi_z, R.cz + ez);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Dynamics state in absolute coordinates: x = (cart y, phi'_0..4), v = d/dt.
+// ------------------------------------------------------------------------------------------
+struct Dyn { float x[6], v[6]; };
+
+VDEV void rel_to_abs(const float q[6], const float qd[6], Dyn& d) {
+  d.x[0] = q[0]; d.v[0] = qd[0];
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) { a += q[j + 1]; b += qd[j + 1]; d.x[j + 1] = a; d.v[j + 1] = b; }
+}
+
+VDEV void abs_to_rel(const Dyn& d, float q[6], float qd[6]) {
+  q[0] = d.x[0]; qd[0] = d.v[0]; q[1] = d.x[1]; qd[1] = d.v[1];
+#pragma unroll
+  for (int j = 1; j < VINE_NL; ++j) { q[j + 1] = d.x[j + 1] - d.x[j]; qd[j + 1] = d.v[j + 1] - d.v[j]; }
+}
+
+struct Kin { float S[VINE_NL], Cc[VINE_NL]; };
+
+VDEV void link_trig(const VineParams& p, const Dyn& d, Kin& k) {
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    float s, c; vine_sincos(d.x[j + 1], s, c);
+    k.S[j] = fmaf(p.s0, c, p.c0 * s); k.Cc[j] = fmaf(p.c0, c, -p.s0 * s);
+  }
+}
+
+// tip position / velocity (the rigid-body views V5:357-362)
+VDEV void tip_fk(const Dyn& d, const Kin& k, float& ty, float& tz, float& tvy, float& tvz) {
+  float py = d.x[0], pz = VINE_PIVOT_Z, vy = d.v[0], vz = 0.f;
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    py = fmaf(-VINE_LINK_LEN, k.S[j], py); pz = fmaf(VINE_LINK_LEN, k.Cc[j], pz);
+    const float lw = VINE_LINK_LEN * d.v[j + 1];
+    vy = fmaf(-lw, k.Cc[j], vy); vz = fmaf(-lw, k.S[j], vz);
+  }
+  ty = py; tz = pz; tvy = vy; tvz = vz;
+}
+
+// ---- penalty contact, frictionless (V5:477,491,499) ----
+struct LinkLoad { float fy, fz, t; };  // net force and torque about the link's proximal joint
+
+VDEV void contact_point(const VineParams& p, float Py, float Pz, float ny, float nz, float dist, float radius,
+                        float jy, float jz, float jvy, float jvz, float w, LinkLoad& L, float& ofy, float& ofz) {
+  const float pen = radius + p.rest - dist;
+  if (!(pen > 0.f)) return;
+  const float ry = Py - jy, rz = Pz - jz;
+  const float vy = jvy - w * rz, vz = jvz + w * ry;
+  const float f = p.kc * pen - p.dc * (vy * ny + vz * nz);
+  if (!(f > 0.f)) return;
+  const float Fy = f * ny, Fz = f * nz;
+  L.fy += Fy; L.fz += Fz; L.t += ry * Fz - rz * Fy;
+  ofy -= Fy; ofz -= Fz;
+}
+
+// capsule (core A-B, radius r) of a link whose proximal joint is at (jy,jz) moving with (jvy,jvz), spin w
+VDEV void capsule_rect(const VineParams& p, const Rect& R, float Ay, float Az, float By, float Bz, float radius,
+                       bool test_a, bool closed_end, float jy, float jz, float jvy, float jvz, float w,
+                       LinkLoad& L, float& ofy, float& ofz) {
+  const float ay = R.ay, az = R.az, ny = -az, nz = ay;
+  // (i) capsule end points against the rectangle's faces
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (e == 0 && !test_a) continue;
+    const float Py = e == 0 ? Ay : By, Pz = e == 0 ? Az : Bz;
+    const float la = (Py - R.cy) * ay + (Pz - R.cz) * az, ln = (Py - R.cy) * ny + (Pz - R.cz) * nz;
+    const float qa = fabsf(la) - R.ha, qn = fabsf(ln) - R.hn;
+    if (qa > 0.f && qn > 0.f) continue;  // corner region: handled by (ii)
+    float dist, gy, gz;
+    if (qa > qn) { dist = qa; const float s = la < 0.f ? -1.f : 1.f; gy = s * ay; gz = s * az; }
+    else { dist = qn; const float s = ln < 0.f ? -1.f : 1.f; gy = s * ny; gz = s * nz; }
+    contact_point(p, Py, Pz, gy, gz, dist, radius, jy, jz, jvy, jvz, w, L, ofy, ofz);
+  }
+  // (ii) rectangle corners against the capsule segment
+  const float ey = By - Ay, ez = Bz - Az;
+  const float inv_ee = __fdividef(1.f, ey * ey + ez * ez);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float sa = (c & 1) ? 1.f : -1.f, sn = (c & 2) ? 1.f : -1.f;
+    const float Vy = R.cy + sa * R.ha * ay + sn * R.hn * ny, Vz = R.cz + sa * R.ha * az + sn * R.hn * nz;
+    float t = ((Vy - Ay) * ey + (Vz - Az) * ez) * inv_ee;
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    if (t >= 1.f && !closed_end) continue;  // shared joint point belongs to the next link
+    const float Py = Ay + t * ey, Pz = Az + t * ez;
+    const float dy = Py - Vy, dz = Pz - Vz;
+    const float d2 = dy * dy + dz * dz;
+    if (!(d2 > 1e-18f)) continue;
+    const float inv = rsqrtf(d2);
+    contact_point(p, Py, Pz, dy * inv, dz * inv, d2 * inv, radius, jy, jz, jvy, jvz, w, L, ofy, ofz);
+  }
+}
+
+// all link-vs-obstacle contacts of one substep; adds generalized forces to f[6], returns |F_lip|
+VDEV float contact_forces(const VineParams& p, const Obstacles& ob, const Dyn& d, const Kin& k, float f[6]) {
+  float py[VINE_NL + 1], pz[VINE_NL + 1], vy[VINE_NL + 1], vz[VINE_NL + 1];
+  py[0] = d.x[0]; pz[0] = VINE_PIVOT_Z; vy[0] = d.v[0]; vz[0] = 0.f;
+  float lo_y = py[0], hi_y = py[0], lo_z = pz[0], hi_z = pz[0];
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    py[j + 1] = fmaf(-VINE_LINK_LEN, k.S[j], py[j]); pz[j + 1] = fmaf(VINE_LINK_LEN, k.Cc[j], pz[j]);
+    const float lw = VINE_LINK_LEN * d.v[j + 1];
+    vy[j + 1] = fmaf(-lw, k.Cc[j], vy[j]); vz[j + 1] = fmaf(-lw, k.S[j], vz[j]);
+    lo_y = fminf(lo_y, py[j + 1]); hi_y = fmaxf(hi_y, py[j + 1]);
+    lo_z = fminf(lo_z, pz[j + 1]); hi_z = fmaxf(hi_z, pz[j + 1]);
+  }
+  // conservative cull: chain inflated by the widest cross-section (FPAM offset + radius + rest)
+  const float m = VINE_FPAM_OFFSET + VINE_FPAM_RADIUS + p.rest + 1e-3f;
+  if (hi_y + m < ob.lo_y || lo_y - m > ob.hi_y || hi_z + m < ob.lo_z || lo_z - m > ob.hi_z) return 0.f;
+
+  LinkLoad L[VINE_NL];
+  float lfy = 0.f, lfz = 0.f;
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    L[j] = {0.f, 0.f, 0.f};
+    const bool last = (j == VINE_NL - 1);
+    // main cylinder URDF:95-99 as a capsule; the last one is shortened so its cap ends at the tip
+    const float By = last ? fmaf(VINE_LINK_RADIUS, k.S[j], py[j + 1]) : py[j + 1];
+    const float Bz = last ? fmaf(-VINE_LINK_RADIUS, k.Cc[j], pz[j + 1]) : pz[j + 1];
+    // FPAM cylinder URDF:110-114, offset along the link's local +y = (cos phi, sin phi)
+    const float oy = VINE_FPAM_OFFSET * k.Cc[j], oz = VINE_FPAM_OFFSET * k.S[j];
+    const float FBy = py[j + 1] + oy + (last ? VINE_FPAM_RADIUS * k.S[j] : 0.f);
+    const float FBz = pz[j + 1] + oz - (last ? VINE_FPAM_RADIUS * k.Cc[j] : 0.f);
+#pragma unroll 1
+    for (int r = 0; r < ob.n; ++r) {
+      float ofy = 0.f, ofz = 0.f;
+      capsule_rect(p, ob.r[r], py[j], pz[j], By, Bz, VINE_LINK_RADIUS, j == 0, last,
+                   py[j], pz[j], vy[j], vz[j], d.v[j + 1], L[j], ofy, ofz);
+      capsule_rect(p, ob.r[r], py[j] + oy, pz[j] + oz, FBy, FBz, VINE_FPAM_RADIUS, true, true,
+                   py[j], pz[j], vy[j], vz[j], d.v[j + 1], L[j], ofy, ofz);
+      if (r == ob.lip) { lfy += ofy; lfz += ofz; }
+    }
+  }
+  // generalized forces: Q_y = sum F;  Q_j = T_j + (p_{j+1} - p_j) x sum_{m>j} F_m
+  float sy = 0.f, sz = 0.f;
+#pragma unroll
+  for (int j = VINE_NL - 1; j >= 0; --j) {
+    const float ry = py[j + 1] - py[j], rz = pz[j + 1] - pz[j];
+    f[j + 1] += L[j].t + (ry * sz - rz * sy);
+    sy += L[j].fy; sz += L[j].fz;
+  }
+  f[0] += sy;
+  return sqrtf(lfy * lfy + lfz * lfz);
+}
+
+// per-sim-step joint constants for the implicit integrator
+struct JointImp { float kk[VINE_NL], dd[VINE_NL], tc[VINE_NL], gam[VINE_NL]; };
+
+VDEV void joint_implicit_consts(const VineParams& p, const JointLaw& law, float u_use, const float efforts[6], JointImp& J) {
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    if (p.implicit_law) {
+      J.kk[j] = p.stiffness + law.K[j]; J.dd[j] = p.damping + law.Cd[j];
+      J.tc[j] = -fmaf(law.B[j], u_use, law.b[j]);
+    } else {
+      J.kk[j] = p.stiffness; J.dd[j] = p.damping; J.tc[j] = efforts[j + 1];
+    }
+    J.gam[j] = fmaf(p.h, J.dd[j], p.h * p.h * J.kk[j]) + p.armature;
+  }
+}
+
+// One substep of the semi-implicit integrator (equations of motion: DESIGN.md §4):
+//   (A + h D + h^2 K + armature) dv = h [ f - D v - K (x - x0) - h K v ],  v += dv,  x += h v   
+template <bool CONTACT>
+VDEV void substep(const VineParams& p, const JointImp& J, float rail_force, const Obstacles* ob, Dyn& d, float& lip) {
+  Kin k; link_trig(p, d, k);
+  float w2[VINE_NL];
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) w2[j] = d.v[j + 1] * d.v[j + 1];
+  // lower triangle of the 6x6 SPD system, rows/cols: 0 = cart, 1..5 = links
+  float M[6][6], f[6];
+  M[0][0] = fmaf(p.h, p.damping, p.mtot);
+  f[0] = fmaf(-p.damping, d.v[0], rail_force);
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    M[j + 1][0] = -p.beta[j] * k.Cc[j];
+    M[j + 1][j + 1] = p.alpha[j];
+    f[0] = fmaf(-p.beta[j] * k.S[j], w2[j], f[0]);
+    float fj = p.g * p.beta[j] * k.S[j];
+#pragma unroll
+    for (int m = 0; m < VINE_NL; ++m) {
+      if (m == j) continue;
+      const float mu = VINE_LINK_LEN * p.beta[m > j ? m : j];
+      if (m < j) M[j + 1][m + 1] = mu * fmaf(k.Cc[j], k.Cc[m], k.S[j] * k.S[m]);
+      fj = fmaf(-mu * fmaf(k.S[j], k.Cc[m], -k.Cc[j] * k.S[m]), w2[m], fj);
+    }
+    f[j + 1] = fj;
+  }
+  // joint torques (relative coordinates) -> absolute: Q_j = t_j - t_{j+1}
+  float t[VINE_NL + 1];
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    const float th = j == 0 ? d.x[1] : d.x[j + 1] - d.x[j];
+    const float thd = j == 0 ? d.v[1] : d.v[j + 1] - d.v[j];
+    t[j] = J.tc[j] - J.kk[j] * th - fmaf(p.h, J.kk[j], J.dd[j]) * thd;
+  }
+  t[VINE_NL] = 0.f;
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    f[j + 1] += t[j] - t[j + 1];
+    M[j + 1][j + 1] += J.gam[j] + (j + 1 < VINE_NL ? J.gam[j + 1] : 0.f);
+    if (j > 0) M[j + 1][j] -= J.gam[j];
+  }
+  if (CONTACT) lip = contact_forces(p, *ob, d, k, f);
+  // LDL^T solve of M dv = h f
+  float dinv[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    float dj = M[j][j];
+#pragma unroll
+    for (int q = 0; q < j; ++q) dj = fmaf(-M[j][q] * M[j][q], M[q][q], dj);
+    M[j][j] = dj; dinv[j] = __fdividef(1.f, dj);
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      float s = M[i][j];
+#pragma unroll
+      for (int q = 0; q < j; ++q) s = fmaf(-M[i][q] * M[j][q], M[q][q], s);
+      M[i][j] = s * dinv[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) f[i] *= p.h;
+#pragma unroll
+  for (int i = 1; i < 6; ++i)
+#pragma unroll
+    for (int q = 0; q < i; ++q) f[i] = fmaf(-M[i][q], f[q], f[i]);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) f[i] *= dinv[i];
+#pragma unroll
+  for (int i = 4; i >= 0; --i)
+#pragma unroll
+    for (int q = i + 1; q < 6; ++q) f[i] = fmaf(-M[q][i], f[q], f[i]);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { d.v[i] += f[i]; d.x[i] = fmaf(p.h, d.v[i], d.x[i]); }
+}
+
+// ------------------------------------------------------------------------------------------
+// compute_observations V5:1339-1390, compute_reward V5:1218-1248 + compute_reward_jit
+// V5:1470-1537, compute_reset_jit V5:1540-1558, timeout VT:366.
+// ------------------------------------------------------------------------------------------
+VDEV float norm3_torch(float x, float y, float z) {  // torch linalg.norm (CPU): nested fma, IEEE sqrt
+  return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
+}
+
+struct PostIn {
+  float q[6], qd[6], prev_q[6];
+  float tip[3], prev_tip[3], tipvel[3], target[3], target_vel[3], obj[2];
+  float cart_y, smoothed, u_fpam, u_rail, prev_u_rail;
+  float contact[VINE_MAX_CFI];
+  int64_t reset_in, progress;
+};
+
+struct PostOut { float obs[VINE_MAX_OBS]; float rew; float r[VINE_NUM_REWARDS]; int64_t reset; unsigned char timeout; };
+
+// raw (unscaled, noise-free) observation row in the order of V5:1354-1378
+VDEV void observation_row(const VineParams& p, const PostIn& in, float raw[VINE_MAX_OBS]) {
+  float fdq[6], fdt[3];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) fdq[i] = __fdiv_rn(__fsub_rn(in.q[i], in.prev_q[i]), p.control_dt);      // V5:1347
+#pragma unroll
+  for (int i = 0; i < 3; ++i) fdt[i] = __fdiv_rn(__fsub_rn(in.tip[i], in.prev_tip[i]), p.control_dt);  // V5:1348
+  const int t = p.obs_type;
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < VINE_MAX_OBS; ++i) raw[i] = 0.f;
+  if (t == VINE_OBS_TIP_AND_CART_AND_OBJ_INFO) {
+    raw[0] = in.q[0]; raw[1] = fdq[0];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { raw[2 + i] = in.tip[i]; raw[5 + i] = fdt[i]; raw[8 + i] = in.target[i]; raw[11 + i] = in.target_vel[i]; }
+    raw[14] = in.smoothed; raw[15] = in.prev_u_rail; raw[16] = in.obj[0]; raw[17] = in.obj[1];
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) raw[i] = in.q[i];
+  k = 6;
+  if (t != VINE_OBS_POS_ONLY) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) raw[6 + i] = t == VINE_OBS_POS_AND_VEL ? in.qd[i] : (t == VINE_OBS_POS_AND_PREV_POS ? in.prev_q[i] : fdq[i]);
+    k = 12;
+  }
+  if (t == VINE_OBS_POS_ONLY) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { raw[6 + i] = in.tip[i]; raw[9 + i] = in.target[i]; }
+    raw[12] = in.smoothed; raw[13] = in.prev_u_rail;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    raw[12 + i] = in.tip[i];
+    raw[15 + i] = t == VINE_OBS_POS_AND_VEL ? in.tipvel[i] : (t == VINE_OBS_POS_AND_PREV_POS ? in.prev_tip[i] : fdt[i]);
+    raw[18 + i] = in.target[i]; raw[21 + i] = in.target_vel[i];
+  }
+  raw[24] = in.smoothed; raw[25] = in.prev_u_rail;
+  if (t == VINE_OBS_POS_AND_FD_VEL_AND_OBJ_INFO) { raw[26] = in.obj[0]; raw[27] = in.obj[1]; }
+  (void)k;
+}
+
+// noise: [O] standard normals or nullptr
+VDEV void post_physics(const VineParams& p, const PostIn& in, const float* noise, PostOut& o) {
+  float raw[VINE_MAX_OBS];
+  observation_row(p, in, raw);
+#pragma unroll
+  for (int i = 0; i < VINE_MAX_OBS; ++i) {
+    float v = __fdiv_rn(raw[i], p.obs_scale[i]);                            // V5:1385
+    if (noise != nullptr && i < p.O) v = __fadd_rn(v, __fmul_rn(p.obs_noise, noise[i]));  // V5:1388-1390
+    o.obs[i] = v;
+  }
+  const float dist = norm3_torch(__fsub_rn(in.tip[0], in.target[0]), __fsub_rn(in.tip[1], in.target[1]),
+                                 __fsub_rn(in.tip[2], in.target[2]));       // V5:1219
+  const bool reached = dist < p.success_dist;                               // V5:1228
+  const bool limit_hit = (in.cart_y > p.soft_limit) || (in.cart_y < -p.soft_limit);  // V5:1232-1233
+  const bool tip_limit_hit = in.tip[1] < in.target[1];                      // V5:1237
+  float contact = 0.f; bool nonzero = false;
+  if (p.shelf) {                                                            // V5:1240-1244 mean over the sim steps
+    float s = in.contact[0];
+#pragma unroll
+    for (int i = 1; i < VINE_MAX_CFI; ++i) if (i < p.C) s = __fadd_rn(s, in.contact[i]);
+    contact = __fdiv_rn(s, (float)p.C);
+    nonzero = contact > 0.f;
+  }
+  float* r = o.r;
+  r[0] = __fsub_rn(0.f, dist);
+  r[1] = -1.f;
+  r[2] = reached ? 1000.f : 0.f;
+  const float vs = norm3_torch(__fsub_rn(in.tipvel[0], in.target_vel[0]), __fsub_rn(in.tipvel[1], in.target_vel[1]),
+                               __fsub_rn(in.tipvel[2], in.target_vel[2]));
+  r[3] = __fsub_rn(0.f, reached ? vs : 0.f);
+  r[4] = norm3_torch(in.tipvel[0], in.tipvel[1], in.tipvel[2]);
+  r[5] = __fsub_rn(0.f, fabsf(in.u_rail));
+  r[6] = __fsub_rn(0.f, fabsf(in.u_fpam));
+  r[7] = __fsub_rn(0.f, fabsf(__fsub_rn(in.u_rail, in.prev_u_rail)));
+  r[8] = __fsub_rn(0.f, fabsf(__fsub_rn(in.u_fpam, in.smoothed)));
+  r[9] = limit_hit ? -100.f : 0.f;
+  r[10] = __fsub_rn(0.f, fabsf(in.cart_y));
+  r[11] = tip_limit_hit ? -100.f : 0.f;
+  r[12] = __fsub_rn(0.f, (contact > 0.f) ? contact : 0.f);
+  // torch.sum(dim=-1) over 13 contiguous f32 (CPU kernel): tail 8..12 first, then lanes 0..7
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 8; i < 13; ++i) acc = __fadd_rn(acc, __fmul_rn(r[i], p.w[i]));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc = __fadd_rn(acc, __fmul_rn(r[i], p.w[i]));
+  o.rew = acc;
+  int64_t reset = (in.progress >= p.max_len_m1) ? 1 : in.reset_in;          // V5:1544
+  if (reached && p.reach_reset) reset = 1;
+  if (tip_limit_hit && p.tip_reset) reset = 1;
+  if (limit_hit) reset = 1;
+  if (nonzero && p.contact_reset) reset = 1;
+  o.reset = reset;
+  o.timeout = (unsigned char)((in.progress >= p.max_len_m1) && (reset != 0));  // VT:366
+}
+
+// ------------------------------------------------------------------------------------------
+// reset_idx V5:774-885 + sample_target_positions V5:887-914.  Draw k of the reference's call
+// order = Philox block k/4, lane k%4: joints 1..5, cart, target x,y,z, shelf depth, pipe depth.
+// ------------------------------------------------------------------------------------------
+VDEV void sample_targets(const VineParams& p, const uint32_t u[12], float target[3]) {
+  if (p.rand_targets) {
+    target[0] = uniform_ab(u[6], 0.f, 0.f);
+    target[1] = uniform_ab(u[7], p.ty_lo, p.ty_rng);
+    target[2] = uniform_ab(u[8], p.tz_lo, p.tz_rng);
+  } else { target[0] = 0.f; target[1] = p.ty_hi; target[2] = p.tz_lo_fixed; }
+}
+
+VDEV void reset_env(const VineParams& p, uint32_t k0, uint32_t k1, uint32_t gid, uint32_t step,
+                    float q[6], float qd[6], float target[3], float obj[2]) {
+  uint32_t u[12];
+#pragma unroll
+  for (uint32_t b = 0; b < 3; ++b) {
+    const uint4 r = philox4x32(k0, k1, gid, VINE_SITE_RESET, step, b);
+    u[4 * b] = r.x; u[4 * b + 1] = r.y; u[4 * b + 2] = r.z; u[4 * b + 3] = r.w;
+  }
+  if (p.rand_dof_init) {
+#pragma unroll
+    for (int j = 0; j < VINE_NL; ++j) q[j + 1] = uniform_ab(u[j], p.rev_lo, p.rev_rng);
+    q[0] = uniform_ab(u[5], p.cart_lo, p.cart_rng);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) q[j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) qd[j] = 0.f;
+  sample_targets(p, u, target);
+  if (p.shelf) obj[0] = uniform_ab(u[9], p.dep_lo, p.dep_rng);              // V5:822-839
+  if (p.pipe) {                                                             // V5:854-885
+    const float ez = __fsub_rn(1.0f, target[2]);
+    // np.polyval with float64 coefficients evaluated on the f32 effective_z (Horner), then f32
+    const double x = (double)ez;
+    double y = 1.0e4 * 1.3199;
+    y = __dadd_rn(__dmul_rn(y, x), 1.0e4 * -1.2276);
+    y = __dadd_rn(__dmul_rn(y, x), 1.0e4 * 0.4045);
+    y = __dadd_rn(__dmul_rn(y, x), 1.0e4 * -0.0447);
+    obj[1] = __fmul_rn((float)y, 0.017453292519943295f);                    // torch.deg2rad
+    obj[0] = uniform_ab(u[p.shelf ? 10 : 9], p.dep_lo, p.dep_rng);          // V5:863
+  }
+}

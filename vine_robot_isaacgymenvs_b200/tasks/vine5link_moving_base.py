@@ -1,0 +1,260 @@
+"""``Vine5LinkMovingBase`` — drop-in for the reference task class
+(isaacgymenvs/tasks/Vine5LinkMovingBase.py, "V5") whose whole per-control-step pipeline runs in
+one fused sm_100a CUDA kernel behind the C ABI of ``include/vine_b200.h``.
+
+Same constructor signature as the reference (``utils/rlgames_utils.py:78-86`` builds it as
+``Task(cfg=..., rl_device=..., sim_device=..., graphics_device_id=..., headless=...,
+virtual_screen_capture=..., force_render=...)``), same ``cfg`` key set (V5:146-291), same buffers.
+Viewer, video capture, wandb logging, keyboard events and .mat replay (V5:593-771, 947-982,
+1122-1216) are outside the hot path and not provided.
+"""
+import ctypes as C
+from enum import Enum
+
+import torch
+
+from .. import abi, config as vcfg
+from .base.vec_task import VecTask
+
+NUM_XYZ = 3
+NUM_OBJECT_INFO = 2       # V5:51
+N_REVOLUTE_DOFS = 5       # V5:54
+N_PRESSURE_ACTIONS = 1    # V5:55
+N_PRISMATIC_DOFS = 1      # V5:83
+REWARD_NAMES = abi.REWARD_NAMES
+
+
+class ObservationType(Enum):  # V5:67-73
+    POS_ONLY = "POS_ONLY"
+    POS_AND_VEL = "POS_AND_VEL"
+    POS_AND_FD_VEL = "POS_AND_FD_VEL"
+    POS_AND_PREV_POS = "POS_AND_PREV_POS"
+    POS_AND_FD_VEL_AND_OBJ_INFO = "POS_AND_FD_VEL_AND_OBJ_INFO"
+    TIP_AND_CART_AND_OBJ_INFO = "TIP_AND_CART_AND_OBJ_INFO"
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Vine5LinkMovingBase(VecTask):
+    def __init__(self, cfg, rl_device, sim_device, graphics_device_id, headless,
+                 virtual_screen_capture=False, force_render=False, *, global_env_offset=0):
+        self.cfg = cfg
+        self.max_episode_length = self.cfg["env"]["maxEpisodeLength"]
+        self.vine_randomize = self.cfg["task"]["vine_randomize"]
+        # numObservations / numActions follow OBSERVATION_TYPE (V5:152-171); KeyError like the reference
+        observation_type = ObservationType[self.cfg["env"]["OBSERVATION_TYPE"]]
+        self.cfg["env"]["numObservations"] = vcfg.num_observations(observation_type.value)
+        self.cfg["env"]["numActions"] = N_PRESSURE_ACTIONS + N_PRISMATIC_DOFS
+        if self.cfg["env"]["SCALE_OBSERVATIONS"] and observation_type not in (
+                ObservationType.POS_AND_FD_VEL_AND_OBJ_INFO, ObservationType.TIP_AND_CART_AND_OBJ_INFO):
+            raise NotImplementedError(f"Observation scaling not implemented for {observation_type}")  # V5:267-268
+        self._seed = int(self.cfg.get("seed", 42))
+        self._global_env_offset = int(global_env_offset)
+        self._lib = abi.load_library()   # raises if the CUDA library is missing: there is no fallback
+        self._h = None
+        self._graph = None
+
+        super().__init__(config=self.cfg, rl_device=rl_device, sim_device=sim_device,
+                         graphics_device_id=graphics_device_id, headless=headless,
+                         virtual_screen_capture=virtual_screen_capture, force_render=force_render)
+
+        self.num_dof = N_REVOLUTE_DOFS + N_PRISMATIC_DOFS
+        self.dt = self.cfg["sim"]["dt"]                       # V5:227
+        self.control_dt = self.dt * self.control_freq_inv     # V5:228
+        self.reward_weights = torch.tensor([[self.cfg["env"][k] for k in abi.REWARD_WEIGHT_KEYS]],
+                                           device=self.device, dtype=torch.float)  # V5:186-203
+        self.obs_scaling = torch.ones(self.num_obs, device=self.device)             # V5:241-266
+        if self.cfg["env"]["SCALE_OBSERVATIONS"]:
+            self.obs_scaling[:] = torch.tensor(_OBS_SCALING[observation_type], device=self.device)
+        self.target_velocities = torch.zeros(self.num_envs, NUM_XYZ, device=self.device)  # V5:916-918
+        self.index_to_view = int(0.1 * self.num_envs)
+        self.num_steps = 0
+
+    # ------------------------------------------------------------------ construction
+    def create_sim(self):
+        """V5:364-519 collapses to: bake constants, allocate the SoA state, bind the VecTask buffers."""
+        self.up_axis = self.cfg["sim"]["up_axis"]
+        assert self.up_axis == "z"                            # V5:441
+        torch.cuda.set_device(self.device)
+        self.vine_config = vcfg.task_cfg_to_vine_config(self.cfg)
+        h = C.c_void_p()
+        rc = self._lib.vine_create(C.byref(self.vine_config), self.num_envs, self._global_env_offset,
+                                   self.device_id, self._seed, C.byref(h))
+        if rc != abi.OK:
+            msg = self._lib.vine_last_error(None).decode()
+            if rc == abi.ERR_UNSUPPORTED:
+                raise NotImplementedError(msg)
+            raise RuntimeError(f"vine_create failed ({rc}): {msg}")
+        self._h = h
+        self.sim = h
+        self.actions = torch.zeros(self.num_envs, self.num_actions, device=self.device, dtype=torch.float)
+        self._obs_clamped = torch.zeros_like(self.obs_buf)
+        self._bind()
+
+    def _bind(self, actions=None):
+        a = self.actions if actions is None else actions
+        self._check(self._lib.vine_bind_io(self._h, _ptr(a), _ptr(self.obs_buf), _ptr(self.rew_buf),
+                                           _ptr(self.reset_buf), _ptr(self.progress_buf),
+                                           _ptr(self.timeout_buf), _ptr(self._obs_clamped)))
+
+    def _check(self, rc):
+        if rc != abi.OK:
+            raise RuntimeError(f"libvine_b200 error {rc}: {self._lib.vine_last_error(self._h).decode()}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                self._lib.vine_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ VecTask contract
+    def pre_physics_step(self, actions):
+        """V5:922-945.  The action path itself runs inside the fused kernel; this stages the actions."""
+        self.actions.copy_(actions, non_blocking=True)
+
+    def post_physics_step(self):
+        """V5:1110-1120 runs inside the fused kernel (progress, deferred reset, obs, reward, resets)."""
+        self.num_steps += 1
+
+    def step(self, actions):
+        """VecTask.step (VT:319-380) as one kernel launch (or one CUDA-graph replay)."""
+        self.pre_physics_step(actions)
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._check(self._lib.vine_step(self._h, self._stream()))
+        self.post_physics_step()
+        self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)      # VT:372
+        self.obs_dict["obs"] = self._obs_clamped.to(self.rl_device)         # VT:374
+        if self.num_states > 0:
+            self.obs_dict["states"] = self.get_state()
+        return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras
+
+    def step_device(self):
+        """Hot loop for callers that write ``self.actions`` in place: launch only, no Python tensors."""
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._check(self._lib.vine_step(self._h, self._stream()))
+
+    def capture_graph(self):
+        """Capture the step into a CUDA graph (the kernel neither allocates nor synchronises)."""
+        torch.cuda.synchronize(self.device)
+        s = torch.cuda.Stream(self.device)
+        g = torch.cuda.CUDAGraph()
+        state = self.get_state_dict()
+        bufs = [b.clone() for b in (self.obs_buf, self.rew_buf, self.reset_buf, self.progress_buf, self.timeout_buf)]
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                self._check(self._lib.vine_step(self._h, C.c_void_p(s.cuda_stream)))
+        torch.cuda.synchronize(self.device)
+        # capture does not execute, but restore anyway so capture_graph() is side-effect free
+        self.set_state_dict(state)
+        for dst, src in zip((self.obs_buf, self.rew_buf, self.reset_buf, self.progress_buf, self.timeout_buf), bufs):
+            dst.copy_(src)
+        self._graph = g
+        return g
+
+    def reset_idx(self, env_ids):
+        """V5:774-885 outside step (reset_done VT:412-427)."""
+        ids = torch.as_tensor(env_ids, device=self.device, dtype=torch.long).contiguous()
+        self._check(self._lib.vine_reset_idx(self._h, _ptr(ids), ids.numel(), self._stream()))
+
+    def compute_observations(self, env_ids=None):
+        """V5:1339: observations are produced by step(); returns the current buffer."""
+        return self.obs_buf
+
+    def compute_reward(self):
+        """V5:1218: rewards are produced by step(); returns the current buffer."""
+        return self.rew_buf
+
+    def refresh_state_tensors(self):
+        """V5:1333-1337: state lives in the library; the properties below read it on demand."""
+        return None
+
+    # ------------------------------------------------------------------ state access
+    _STATE_FIELDS = {
+        "dof_pos": (6,), "dof_vel": (6,), "tip_positions": (3,), "cart_body_vel_y": (), "target_positions": (3,),
+        "object_info": (2,), "smoothed_u_fpam": (), "prev_cart_vel": (), "prev_cart_vel_error": (),
+        "shelf_contact_force": (), "aggregated_rew_buf": (),
+    }
+    _DEBUG_FIELDS = {"u_rail_velocity": (), "u_fpam": (), "prev_u_rail_velocity": (), "rail_force": (),
+                     "tip_velocities": (3,), "reward_matrix": (13,)}
+
+    def get_state_dict(self, debug=False):
+        """Snapshot of the private SoA state as torch tensors named like the reference attributes."""
+        n, dev = self.num_envs, self.device
+        out = {k: torch.zeros((n,) + s, device=dev) for k, s in self._STATE_FIELDS.items()}
+        D = int(self.cfg["env"]["ACTION_DELAY"])
+        out["actions_history"] = torch.zeros(n, max(D, 1), 2, device=dev)
+        out["step_count"] = torch.zeros(n, device=dev, dtype=torch.long)
+        if debug:
+            out.update({k: torch.zeros((n,) + s, device=dev) for k, s in self._DEBUG_FIELDS.items()})
+        view = abi.VineStateView()
+        for name, ftype in view._fields_:
+            if name in out:
+                setattr(view, name, C.cast(out[name].data_ptr(), ftype))
+        self._check(self._lib.vine_get_state(self._h, C.byref(view), self._stream()))
+        return out
+
+    def set_state_dict(self, state):
+        view = abi.VineStateView()
+        keep = []
+        for name, ftype in view._fields_:
+            if name in state and name not in self._DEBUG_FIELDS:
+                want = torch.long if name == "step_count" else torch.float
+                t = state[name].to(device=self.device, dtype=want).contiguous()
+                keep.append(t)
+                setattr(view, name, C.cast(t.data_ptr(), ftype))
+        self._check(self._lib.vine_set_state(self._h, C.byref(view), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
+        del keep
+
+    def enable_debug_outputs(self, enabled=True):
+        self._check(self._lib.vine_set_debug_outputs(self._h, int(enabled)))
+
+    def _get(self, name):
+        return self.get_state_dict(debug=name in self._DEBUG_FIELDS)[name]
+
+    dof_pos = property(lambda s: s._get("dof_pos"), lambda s, v: s.set_state_dict({"dof_pos": v}))
+    dof_vel = property(lambda s: s._get("dof_vel"), lambda s, v: s.set_state_dict({"dof_vel": v}))
+    tip_positions = property(lambda s: s._get("tip_positions"), lambda s, v: s.set_state_dict({"tip_positions": v}))
+    target_positions = property(lambda s: s._get("target_positions"), lambda s, v: s.set_state_dict({"target_positions": v}))
+    object_info = property(lambda s: s._get("object_info"), lambda s, v: s.set_state_dict({"object_info": v}))
+    smoothed_u_fpam = property(lambda s: s._get("smoothed_u_fpam").unsqueeze(-1),
+                               lambda s, v: s.set_state_dict({"smoothed_u_fpam": v.reshape(-1)}))
+    prev_cart_vel = property(lambda s: s._get("prev_cart_vel").unsqueeze(-1))
+    prev_cart_vel_error = property(lambda s: s._get("prev_cart_vel_error").unsqueeze(-1))
+    aggregated_rew_buf = property(lambda s: s._get("aggregated_rew_buf"))
+    u_rail_velocity = property(lambda s: s._get("u_rail_velocity").unsqueeze(-1))
+    u_fpam = property(lambda s: s._get("u_fpam").unsqueeze(-1))
+    prev_u_rail_velocity = property(lambda s: s._get("prev_u_rail_velocity").unsqueeze(-1))
+    rail_force = property(lambda s: s._get("rail_force").unsqueeze(-1))
+    tip_velocities = property(lambda s: s._get("tip_velocities"))
+
+    @property
+    def cart_positions(self):
+        q = self._get("dof_pos")
+        out = torch.zeros(self.num_envs, 3, device=self.device)
+        out[:, 1] = q[:, 0]
+        out[:, 2] = 0.975  # URDF:275
+        return out
+
+
+_OBS_SCALING = {  # V5:246-266
+    ObservationType.POS_AND_FD_VEL_AND_OBJ_INFO: [0.12, 0.269, 0.148, 0.249, 0.148, 0.344,
+                                                  0.67, 2.22, 1.47, 1.14, 0.903, 0.716,
+                                                  0.0656, 0.238, 0.0656, 0.732, 2.0, 0.732,
+                                                  0.02, 0.0235, 0.02, 0.732, 2.0, 0.732,
+                                                  0.845, 0.86, 0.0385, 0.5],
+    ObservationType.TIP_AND_CART_AND_OBJ_INFO: [0.12, 0.67, 0.0656, 0.238, 0.0656, 0.732, 2.0, 0.732,
+                                                0.02, 0.0235, 0.02, 0.732, 2.0, 0.732,
+                                                0.845, 0.86, 0.0385, 0.5],
+}
