@@ -123,16 +123,16 @@ __global__ void __launch_bounds__(VINE_BLOCK) vine_step_kernel(const __grid_cons
     if (CONTACT) build_obstacles(p, target[1], target[2], obj[0], obj[1], ob);
 
     // ---- controlFrequencyInv x {forces, contact sample, simulate}  VT:338-356 ----
-    Dyn d; rel_to_abs(q, qd, d);
+    Dyn d; rel_to_abs(p, q, qd, d);
     float tipb_y = tip_y, tipb_z = tip_z;  // rigid-body tip as of the refresh before the LAST simulate
     float rail_force = 0.f;
 #pragma unroll
     for (int i = 0; i < VINE_MAX_CFI; ++i) in.contact[i] = 0.f;
 #pragma unroll 1
     for (int i = 0; i < p.C; ++i) {
+      if (i > 0) refresh_trig(p, d);  // exact sin/cos once per sim step; substeps rotate incrementally
       if (i > 0 && i == p.C - 1 && reset_in != 0 && p.stale) {  // only needed by V5:797 on reset steps
-        Kin k; link_trig(p, d, k);
-        float vy, vz; tip_fk(d, k, tipb_y, tipb_z, vy, vz);
+        float vy, vz; tip_fk(d, tipb_y, tipb_z, vy, vz);
       }
       JointLaw law; joint_law_unscaled(law);
       float acc_scale = 1.f;
@@ -174,10 +174,7 @@ __global__ void __launch_bounds__(VINE_BLOCK) vine_step_kernel(const __grid_cons
       for (int s = 0; s < p.S; ++s) substep<CONTACT>(p, J, rail_force, &ob, d, lip);
     }
     float tipvel_y, tipvel_z;
-    {
-      Kin k; link_trig(p, d, k);
-      tip_fk(d, k, tip_y, tip_z, tipvel_y, tipvel_z);
-    }
+    tip_fk(d, tip_y, tip_z, tipvel_y, tipvel_z);
     float cart_y_body = d.x[0];
     cart_body_vy = d.v[0];
     abs_to_rel(d, q, qd);
@@ -191,9 +188,8 @@ __global__ void __launch_bounds__(VINE_BLOCK) vine_step_kernel(const __grid_cons
       if (p.stale) {                                                       // V5:796-797 stale rigid-body views
         in.prev_tip[1] = tipb_y; in.prev_tip[2] = tipb_z;
       } else {                                                             // "as if FK were done": clean episode boundary
-        Dyn dn; rel_to_abs(q, qd, dn);
-        Kin k; link_trig(p, dn, k);
-        tip_fk(dn, k, tip_y, tip_z, tipvel_y, tipvel_z);
+        Dyn dn; rel_to_abs(p, q, qd, dn);
+        tip_fk(dn, tip_y, tip_z, tipvel_y, tipvel_z);
         in.prev_tip[1] = tip_y; in.prev_tip[2] = tip_z;
         cart_y_body = q[0]; cart_body_vy = 0.f; lip = 0.f; prev_cart_vel = 0.f;
 #pragma unroll
@@ -286,9 +282,8 @@ __global__ void vine_reset_idx_kernel(const __grid_constant__ VineParams p, cons
   s3.z = 0.f;  // prev_cart_vel_error, V5:799
   s4.w = 0.f;  // aggregated_rew_buf, V5:810
   if (!p.stale) {
-    Dyn d; rel_to_abs(q, qd, d);
-    Kin k; link_trig(p, d, k);
-    float vy, vz; tip_fk(d, k, s4.x, s4.y, vy, vz);
+    Dyn d; rel_to_abs(p, q, qd, d);
+    float vy, vz; tip_fk(d, s4.x, s4.y, vy, vz);
     s4.z = 0.f; s3.w = 0.f; s3.y = 0.f;
   }
   a.S0[e] = make_float4(q[0], q[1], q[2], q[3]);
@@ -445,13 +440,12 @@ __global__ void __launch_bounds__(VINE_BLOCK) vine_simulate_kernel(const __grid_
   Obstacles ob;
   if (CONTACT) build_obstacles(p, io.target_positions[3 * e + 1], io.target_positions[3 * e + 2],
                                io.object_info[2 * e], io.object_info[2 * e + 1], ob);
-  Dyn d; rel_to_abs(q, qd, d);
+  Dyn d; rel_to_abs(p, q, qd, d);
   JointImp J; joint_implicit_consts(p, law, u_use, efforts, J);
   float lip = 0.f;
 #pragma unroll 1
   for (int s = 0; s < p.S; ++s) substep<CONTACT>(p, J, efforts[0], &ob, d, lip);
-  Kin k; link_trig(p, d, k);
-  float ty, tz, vy, vz; tip_fk(d, k, ty, tz, vy, vz);
+  float ty, tz, vy, vz; tip_fk(d, ty, tz, vy, vz);
   abs_to_rel(d, q, qd);
   for (int i = 0; i < 6; ++i) { io.dof_pos[6 * e + i] = q[i]; io.dof_vel[6 * e + i] = qd[i]; }
   if (io.tip_positions) { io.tip_positions[3 * e] = 0.f; io.tip_positions[3 * e + 1] = ty; io.tip_positions[3 * e + 2] = tz; }

@@ -155,13 +155,24 @@ VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, 
 // ------------------------------------------------------------------------------------------
 // Dynamics state in absolute coordinates: x = (cart y, phi'_0..4), v = d/dt.
 // ------------------------------------------------------------------------------------------
-struct Dyn { float x[6], v[6]; };
+// S/C = sin/cos of the absolute link angles phi_k = 3.1415 + phi'_k, carried in registers: refreshed
+// exactly once per sim step (refresh_trig) and rotated incrementally by h*w_k in every substep.
+struct Dyn { float x[6], v[6], S[VINE_NL], C[VINE_NL]; };
 
-VDEV void rel_to_abs(const float q[6], const float qd[6], Dyn& d) {
+VDEV void refresh_trig(const VineParams& p, Dyn& d) {
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    float s, c; vine_sincos(d.x[j + 1], s, c);
+    d.S[j] = fmaf(p.s0, c, p.c0 * s); d.C[j] = fmaf(p.c0, c, -p.s0 * s);
+  }
+}
+
+VDEV void rel_to_abs(const VineParams& p, const float q[6], const float qd[6], Dyn& d) {
   d.x[0] = q[0]; d.v[0] = qd[0];
   float a = 0.f, b = 0.f;
 #pragma unroll
   for (int j = 0; j < VINE_NL; ++j) { a += q[j + 1]; b += qd[j + 1]; d.x[j + 1] = a; d.v[j + 1] = b; }
+  refresh_trig(p, d);
 }
 
 VDEV void abs_to_rel(const Dyn& d, float q[6], float qd[6]) {
@@ -170,24 +181,14 @@ VDEV void abs_to_rel(const Dyn& d, float q[6], float qd[6]) {
   for (int j = 1; j < VINE_NL; ++j) { q[j + 1] = d.x[j + 1] - d.x[j]; qd[j + 1] = d.v[j + 1] - d.v[j]; }
 }
 
-struct Kin { float S[VINE_NL], Cc[VINE_NL]; };
-
-VDEV void link_trig(const VineParams& p, const Dyn& d, Kin& k) {
-#pragma unroll
-  for (int j = 0; j < VINE_NL; ++j) {
-    float s, c; vine_sincos(d.x[j + 1], s, c);
-    k.S[j] = fmaf(p.s0, c, p.c0 * s); k.Cc[j] = fmaf(p.c0, c, -p.s0 * s);
-  }
-}
-
 // tip position / velocity (the rigid-body views V5:357-362)
-VDEV void tip_fk(const Dyn& d, const Kin& k, float& ty, float& tz, float& tvy, float& tvz) {
+VDEV void tip_fk(const Dyn& d, float& ty, float& tz, float& tvy, float& tvz) {
   float py = d.x[0], pz = VINE_PIVOT_Z, vy = d.v[0], vz = 0.f;
 #pragma unroll
   for (int j = 0; j < VINE_NL; ++j) {
-    py = fmaf(-VINE_LINK_LEN, k.S[j], py); pz = fmaf(VINE_LINK_LEN, k.Cc[j], pz);
+    py = fmaf(-VINE_LINK_LEN, d.S[j], py); pz = fmaf(VINE_LINK_LEN, d.C[j], pz);
     const float lw = VINE_LINK_LEN * d.v[j + 1];
-    vy = fmaf(-lw, k.Cc[j], vy); vz = fmaf(-lw, k.S[j], vz);
+    vy = fmaf(-lw, d.C[j], vy); vz = fmaf(-lw, d.S[j], vz);
   }
   ty = py; tz = pz; tvy = vy; tvz = vz;
 }
@@ -246,15 +247,15 @@ VDEV void capsule_rect(const VineParams& p, const Rect& R, float Ay, float Az, f
 }
 
 // all link-vs-obstacle contacts of one substep; adds generalized forces to f[6], returns |F_lip|
-VDEV float contact_forces(const VineParams& p, const Obstacles& ob, const Dyn& d, const Kin& k, float f[6]) {
+VDEV float contact_forces(const VineParams& p, const Obstacles& ob, const Dyn& d, float f[6]) {
   float py[VINE_NL + 1], pz[VINE_NL + 1], vy[VINE_NL + 1], vz[VINE_NL + 1];
   py[0] = d.x[0]; pz[0] = VINE_PIVOT_Z; vy[0] = d.v[0]; vz[0] = 0.f;
   float lo_y = py[0], hi_y = py[0], lo_z = pz[0], hi_z = pz[0];
 #pragma unroll
   for (int j = 0; j < VINE_NL; ++j) {
-    py[j + 1] = fmaf(-VINE_LINK_LEN, k.S[j], py[j]); pz[j + 1] = fmaf(VINE_LINK_LEN, k.Cc[j], pz[j]);
+    py[j + 1] = fmaf(-VINE_LINK_LEN, d.S[j], py[j]); pz[j + 1] = fmaf(VINE_LINK_LEN, d.C[j], pz[j]);
     const float lw = VINE_LINK_LEN * d.v[j + 1];
-    vy[j + 1] = fmaf(-lw, k.Cc[j], vy[j]); vz[j + 1] = fmaf(-lw, k.S[j], vz[j]);
+    vy[j + 1] = fmaf(-lw, d.C[j], vy[j]); vz[j + 1] = fmaf(-lw, d.S[j], vz[j]);
     lo_y = fminf(lo_y, py[j + 1]); hi_y = fmaxf(hi_y, py[j + 1]);
     lo_z = fminf(lo_z, pz[j + 1]); hi_z = fmaxf(hi_z, pz[j + 1]);
   }
@@ -269,12 +270,12 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, const Dyn& d
     L[j] = {0.f, 0.f, 0.f};
     const bool last = (j == VINE_NL - 1);
     // main cylinder URDF:95-99 as a capsule; the last one is shortened so its cap ends at the tip
-    const float By = last ? fmaf(VINE_LINK_RADIUS, k.S[j], py[j + 1]) : py[j + 1];
-    const float Bz = last ? fmaf(-VINE_LINK_RADIUS, k.Cc[j], pz[j + 1]) : pz[j + 1];
+    const float By = last ? fmaf(VINE_LINK_RADIUS, d.S[j], py[j + 1]) : py[j + 1];
+    const float Bz = last ? fmaf(-VINE_LINK_RADIUS, d.C[j], pz[j + 1]) : pz[j + 1];
     // FPAM cylinder URDF:110-114, offset along the link's local +y = (cos phi, sin phi)
-    const float oy = VINE_FPAM_OFFSET * k.Cc[j], oz = VINE_FPAM_OFFSET * k.S[j];
-    const float FBy = py[j + 1] + oy + (last ? VINE_FPAM_RADIUS * k.S[j] : 0.f);
-    const float FBz = pz[j + 1] + oz - (last ? VINE_FPAM_RADIUS * k.Cc[j] : 0.f);
+    const float oy = VINE_FPAM_OFFSET * d.C[j], oz = VINE_FPAM_OFFSET * d.S[j];
+    const float FBy = py[j + 1] + oy + (last ? VINE_FPAM_RADIUS * d.S[j] : 0.f);
+    const float FBz = pz[j + 1] + oz - (last ? VINE_FPAM_RADIUS * d.C[j] : 0.f);
 #pragma unroll 1
     for (int r = 0; r < ob.n; ++r) {
       float ofy = 0.f, ofz = 0.f;
@@ -297,81 +298,102 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, const Dyn& d
   return sqrtf(lfy * lfy + lfz * lfz);
 }
 
-// per-sim-step joint constants for the implicit integrator
-struct JointImp { float kk[VINE_NL], dd[VINE_NL], tc[VINE_NL], gam[VINE_NL]; };
+// per-sim-step joint constants for the implicit integrator:
+//   t_j = tc_j - kk_j theta_j - ek_j thetadot_j  (ek = dd + h kk),  gam_j = h dd_j + h^2 kk_j + armature,
+//   diag_j = alpha_j + gam_j + gam_{j+1} (constant part of the system matrix diagonal)
+struct JointImp { float kk[VINE_NL], ek[VINE_NL], tc[VINE_NL], gam[VINE_NL], diag[VINE_NL], m00; };
 
 VDEV void joint_implicit_consts(const VineParams& p, const JointLaw& law, float u_use, const float efforts[6], JointImp& J) {
 #pragma unroll
   for (int j = 0; j < VINE_NL; ++j) {
+    float dd;
     if (p.implicit_law) {
-      J.kk[j] = p.stiffness + law.K[j]; J.dd[j] = p.damping + law.Cd[j];
+      J.kk[j] = p.stiffness + law.K[j]; dd = p.damping + law.Cd[j];
       J.tc[j] = -fmaf(law.B[j], u_use, law.b[j]);
     } else {
-      J.kk[j] = p.stiffness; J.dd[j] = p.damping; J.tc[j] = efforts[j + 1];
+      J.kk[j] = p.stiffness; dd = p.damping; J.tc[j] = efforts[j + 1];
     }
-    J.gam[j] = fmaf(p.h, J.dd[j], p.h * p.h * J.kk[j]) + p.armature;
+    J.ek[j] = fmaf(p.h, J.kk[j], dd);
+    J.gam[j] = fmaf(p.h, dd, p.h * p.h * J.kk[j]) + p.armature;
   }
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) J.diag[j] = p.alpha[j] + J.gam[j] + (j + 1 < VINE_NL ? J.gam[j + 1] : 0.f);
+  J.m00 = fmaf(p.h, p.damping, p.mtot);
 }
 
 // One substep of the semi-implicit integrator (equations of motion: DESIGN.md §4):
-//   (A + h D + h^2 K + armature) dv = h [ f - D v - K (x - x0) - h K v ],  v += dv,  x += h v   
+//   (A + h D + h^2 K + armature) dv = h [ f - D v - K (x - x0) - h K v ],  v += dv,  x += h v
+// Velocity-product terms in O(n): with a_m = C_m w_m^2, b_m = S_m w_m^2,
+//   P_j = sum_{m>j} L beta_m a_m + L beta_j sum_{m<j} a_m  (Q_j likewise with b):
+//   f_j = S_j (g beta_j - P_j) + C_j Q_j ,   f_y = F - D v_y - (1/L) sum_m L beta_m b_m
 template <bool CONTACT>
 VDEV void substep(const VineParams& p, const JointImp& J, float rail_force, const Obstacles* ob, Dyn& d, float& lip) {
-  Kin k; link_trig(p, d, k);
-  float w2[VINE_NL];
+  float a[VINE_NL], b[VINE_NL], As[VINE_NL], Bs[VINE_NL];
 #pragma unroll
-  for (int j = 0; j < VINE_NL; ++j) w2[j] = d.v[j + 1] * d.v[j + 1];
-  // lower triangle of the 6x6 SPD system, rows/cols: 0 = cart, 1..5 = links
-  float M[6][6], f[6];
-  M[0][0] = fmaf(p.h, p.damping, p.mtot);
-  f[0] = fmaf(-p.damping, d.v[0], rail_force);
+  for (int j = 0; j < VINE_NL; ++j) { const float w2 = d.v[j + 1] * d.v[j + 1]; a[j] = d.C[j] * w2; b[j] = d.S[j] * w2; }
+  As[VINE_NL - 1] = 0.f; Bs[VINE_NL - 1] = 0.f;
 #pragma unroll
-  for (int j = 0; j < VINE_NL; ++j) {
-    M[j + 1][0] = -p.beta[j] * k.Cc[j];
-    M[j + 1][j + 1] = p.alpha[j];
-    f[0] = fmaf(-p.beta[j] * k.S[j], w2[j], f[0]);
-    float fj = p.g * p.beta[j] * k.S[j];
+  for (int j = VINE_NL - 2; j >= 0; --j) {
+    As[j] = fmaf(p.Lbeta[j + 1], a[j + 1], As[j + 1]);
+    Bs[j] = fmaf(p.Lbeta[j + 1], b[j + 1], Bs[j + 1]);
+  }
+  float f[6];
+  f[0] = fmaf(-p.inv_L, fmaf(p.Lbeta[0], b[0], Bs[0]), fmaf(-p.damping, d.v[0], rail_force));
+  {
+    float Ap = 0.f, Bp = 0.f;
 #pragma unroll
-    for (int m = 0; m < VINE_NL; ++m) {
-      if (m == j) continue;
-      const float mu = VINE_LINK_LEN * p.beta[m > j ? m : j];
-      if (m < j) M[j + 1][m + 1] = mu * fmaf(k.Cc[j], k.Cc[m], k.S[j] * k.S[m]);
-      fj = fmaf(-mu * fmaf(k.S[j], k.Cc[m], -k.Cc[j] * k.S[m]), w2[m], fj);
+    for (int j = 0; j < VINE_NL; ++j) {
+      const float P = fmaf(p.Lbeta[j], Ap, As[j]), Q = fmaf(p.Lbeta[j], Bp, Bs[j]);
+      f[j + 1] = fmaf(d.C[j], Q, d.S[j] * (p.gbeta[j] - P));
+      Ap += a[j]; Bp += b[j];
     }
-    f[j + 1] = fj;
   }
   // joint torques (relative coordinates) -> absolute: Q_j = t_j - t_{j+1}
-  float t[VINE_NL + 1];
+  {
+    float tn = 0.f;
 #pragma unroll
-  for (int j = 0; j < VINE_NL; ++j) {
-    const float th = j == 0 ? d.x[1] : d.x[j + 1] - d.x[j];
-    const float thd = j == 0 ? d.v[1] : d.v[j + 1] - d.v[j];
-    t[j] = J.tc[j] - J.kk[j] * th - fmaf(p.h, J.kk[j], J.dd[j]) * thd;
-  }
-  t[VINE_NL] = 0.f;
-#pragma unroll
-  for (int j = 0; j < VINE_NL; ++j) {
-    f[j + 1] += t[j] - t[j + 1];
-    M[j + 1][j + 1] += J.gam[j] + (j + 1 < VINE_NL ? J.gam[j + 1] : 0.f);
-    if (j > 0) M[j + 1][j] -= J.gam[j];
-  }
-  if (CONTACT) lip = contact_forces(p, *ob, d, k, f);
-  // LDL^T solve of M dv = h f
-  float dinv[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    float dj = M[j][j];
-#pragma unroll
-    for (int q = 0; q < j; ++q) dj = fmaf(-M[j][q] * M[j][q], M[q][q], dj);
-    M[j][j] = dj; dinv[j] = __fdividef(1.f, dj);
-#pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
-      float s = M[i][j];
-#pragma unroll
-      for (int q = 0; q < j; ++q) s = fmaf(-M[i][q] * M[j][q], M[q][q], s);
-      M[i][j] = s * dinv[j];
+    for (int j = VINE_NL - 1; j >= 0; --j) {
+      const float th = j == 0 ? d.x[1] : d.x[j + 1] - d.x[j];
+      const float thd = j == 0 ? d.v[1] : d.v[j + 1] - d.v[j];
+      const float t = fmaf(-J.ek[j], thd, fmaf(-J.kk[j], th, J.tc[j]));
+      f[j + 1] += t - tn;
+      tn = t;
     }
   }
+  if (CONTACT) lip = contact_forces(p, *ob, d, f);
+  // lower triangle of the SPD system matrix; rows/cols: 0 = cart, 1..5 = links
+  float M[6][6];
+  M[0][0] = J.m00;
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    M[j + 1][0] = -p.beta[j] * d.C[j];
+    M[j + 1][j + 1] = J.diag[j];
+#pragma unroll
+    for (int m = 0; m < j; ++m) {
+      const float c = p.Lbeta[j] * fmaf(d.C[j], d.C[m], d.S[j] * d.S[m]);
+      M[j + 1][m + 1] = (m == j - 1) ? c - J.gam[j] : c;
+    }
+  }
+  // LDL^T (row-wise): u_q = A_jq - sum_{r<q} u_r L_qr ; L_jq = u_q / d_q ; d_j = A_jj - sum_q u_q L_jq
+  float dinv[6];
+  dinv[0] = __fdividef(1.f, M[0][0]);
+#pragma unroll
+  for (int j = 1; j < 6; ++j) {
+    float u[5];
+    float dj = M[j][j];
+#pragma unroll
+    for (int q = 0; q < j; ++q) {
+      float uq = M[j][q];
+#pragma unroll
+      for (int r = 0; r < q; ++r) uq = fmaf(-u[r], M[q][r], uq);
+      u[q] = uq;
+      const float l = uq * dinv[q];
+      M[j][q] = l;
+      dj = fmaf(-uq, l, dj);
+    }
+    dinv[j] = __fdividef(1.f, dj);
+  }
+  // solve M dv = h f
 #pragma unroll
   for (int i = 0; i < 6; ++i) f[i] *= p.h;
 #pragma unroll
@@ -384,8 +406,20 @@ VDEV void substep(const VineParams& p, const JointImp& J, float rail_force, cons
   for (int i = 4; i >= 0; --i)
 #pragma unroll
     for (int q = i + 1; q < 6; ++q) f[i] = fmaf(-M[q][i], f[q], f[i]);
+  d.v[0] += f[0]; d.x[0] = fmaf(p.h, d.v[0], d.x[0]);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { d.v[i] += f[i]; d.x[i] = fmaf(p.h, d.v[i], d.x[i]); }
+  for (int j = 0; j < VINE_NL; ++j) {
+    d.v[j + 1] += f[j + 1];
+    const float dl = p.h * d.v[j + 1];
+    d.x[j + 1] += dl;
+    // rotate (S,C) by dl: sin dl ~ dl (1 - dl^2/6), cos dl ~ 1 - dl^2/2 + dl^4/24  (|dl| << 1)
+    const float d2 = dl * dl;
+    const float sd = dl * fmaf(-0.16666667f, d2, 1.f);
+    const float cd = fmaf(d2, fmaf(0.041666668f, d2, -0.5f), 1.f);
+    const float s = d.S[j], c = d.C[j];
+    d.S[j] = fmaf(s, cd, c * sd);
+    d.C[j] = fmaf(c, cd, -s * sd);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -46,6 +46,7 @@ struct VineParams {
   float h, g, damping, stiffness, armature;
   float kc, dc, rest;            // penalty contact
   float beta[VINE_NL], alpha[VINE_NL], mtot;
+  float Lbeta[VINE_NL], gbeta[VINE_NL], inv_L;  // L*beta_j, g*beta_j, 1/L (hoisted products)
   float s0, c0;                  // sin/cos of the URDF base angle 3.1415 (URDF:289)
   float tip0_y, tip0_z;          // tip pose at q = 0
 };
@@ -140,6 +141,8 @@ static inline int vine_derive_params(const VineConfig* c, VineParams* p, const c
     tail += kLinkMass[j];
   }
   p->mtot = (float)(kCartMass + tail);
+  for (int j = 0; j < VINE_NL; ++j) { p->Lbeta[j] = (float)kLinkLen * p->beta[j]; p->gbeta[j] = p->g * p->beta[j]; }
+  p->inv_L = (float)(1.0 / kLinkLen);
   p->s0 = (float)sin(kBaseAngle); p->c0 = (float)cos(kBaseAngle);
   p->tip0_y = (float)(-5.0 * kLinkLen * sin(kBaseAngle)); p->tip0_z = (float)(kPivotZ + 5.0 * kLinkLen * cos(kBaseAngle));
   return VINE_OK;
