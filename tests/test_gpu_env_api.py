@@ -1,0 +1,135 @@
+"""GPU: the VecTask contract of the env class, CUDA-graph replay, and size-independent
+properties at BASELINE's full sizes (sharding invariance, determinism, delay-ring semantics)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def fstr_env(n, extra=(), **kw):
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    cfg = vcfg.compose(vcfg.FSTR_OVERRIDES + [f"num_envs={n}", "headless=True"] + list(extra))
+    return vine.make(cfg=cfg, **kw)
+
+
+def test_vectask_contract():
+    n = 512
+    env = fstr_env(n)
+    assert (env.num_envs, env.num_obs, env.num_acts, env.num_states, env.num_agents) == (n, 18, 2, 0, 1)
+    assert env.observation_space.shape == (18,) and env.action_space.shape == (2,)
+    assert env.control_freq_inv == 4 and env.max_episode_length == 100 and env.clip_obs == 5.0 and env.clip_actions == 1.0
+    assert abs(env.control_dt - 0.00833 * 4) < 1e-12 and env.reward_weights.shape == (1, 13) and env.obs_scaling.shape == (18,)
+    for name, dt, shape in (("obs_buf", torch.float32, (n, 18)), ("states_buf", torch.float32, (n, 0)),
+                            ("rew_buf", torch.float32, (n,)), ("reset_buf", torch.int64, (n,)),
+                            ("progress_buf", torch.int64, (n,)), ("randomize_buf", torch.int64, (n,))):
+        t = getattr(env, name)
+        assert t.dtype == dt and tuple(t.shape) == shape and t.is_cuda, name
+    assert bool((env.reset_buf == 1).all())                               # VT:275
+    obs = env.reset()["obs"]                                              # VT:398-410: zeros before the first step
+    assert tuple(obs.shape) == (n, 18) and float(obs.abs().max()) == 0.0
+    assert tuple(env.zero_actions().shape) == (n, 2) and tuple(env.get_state().shape) == (n, 0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(5):
+        od, rew, reset, extras = env.step(torch.rand(n, 2, device="cuda", generator=g) * 4 - 2)
+        assert od["obs"].dtype == torch.float32 and tuple(od["obs"].shape) == (n, 18)
+        assert torch.equal(od["obs"], torch.clamp(env.obs_buf, -5.0, 5.0))   # VT:374
+        assert float(od["obs"].abs().max()) <= 5.0 and float(env.obs_buf.abs().max()) > 5.0   # quirk D.11
+        assert rew.dtype == torch.float32 and reset.dtype == torch.int64 and extras["time_outs"].dtype == torch.bool
+        assert set(reset.unique().tolist()) <= {0, 1}
+    # every env was reset during the first step (quirk D.4), so progress counts from there
+    assert int(env.progress_buf.max()) <= 4
+    for name, shape in (("dof_pos", (n, 6)), ("dof_vel", (n, 6)), ("tip_positions", (n, 3)), ("cart_positions", (n, 3)),
+                        ("target_positions", (n, 3)), ("target_velocities", (n, 3)), ("object_info", (n, 2)),
+                        ("smoothed_u_fpam", (n, 1)), ("aggregated_rew_buf", (n,))):
+        assert tuple(getattr(env, name).shape) == shape, name
+    # reset_done (VT:412-427)
+    env.reset_buf[::7] = 1
+    od, ids = env.reset_done()
+    assert ids.numel() >= n // 7 and bool((env.reset_buf[ids] == 0).all()) and bool((env.progress_buf[ids] == 0).all())
+    q = env.dof_pos
+    assert float(q[ids, 1:].abs().max()) <= np.radians(10) + 1e-6 and float(env.dof_vel[ids].abs().max()) == 0.0
+    t = env.target_positions[ids]
+    assert float(t[:, 1].min()) >= -0.4 and float(t[:, 1].max()) <= 0.4 and float(t[:, 2].min()) >= 0.55
+
+
+def test_config_errors_match_the_reference():
+    import vine_robot_isaacgymenvs_b200 as vine
+    with pytest.raises(KeyError):
+        vine.make(num_envs=8, overrides=["OBSERVATION_TYPE=NOPE"])
+    with pytest.raises(NotImplementedError):                       # V5:267-268
+        vine.make(num_envs=8, overrides=["OBSERVATION_TYPE=POS_AND_FD_VEL"])
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        vine.make(num_envs=8, sim_device="cpu", overrides=["sim_device=cpu"])
+
+
+def test_cuda_graph_replay_equals_eager_launches():
+    n = 2048
+    a, b = fstr_env(n), fstr_env(n)
+    b.capture_graph()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(25):
+        act = torch.rand(n, 2, device="cuda", generator=g) * 2 - 1
+        a.step(act); b.step(act)
+        for k in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "timeout_buf"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (k, t)
+    sa, sb = a.get_state_dict(), b.get_state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+
+
+def test_sharding_invariance_and_determinism_at_full_size():
+    """Philox keyed by the GLOBAL env id: 1 x 1,048,576 envs == 2 x 524,288 envs, bit for bit."""
+    n = 1 << 20
+    dr = ["task.task.randomization_parameters.OBSERVATION_NOISE_STD=0.01",
+          "task.task.randomization_parameters.DYNAMICS_SCALING_MIN=0.9",
+          "task.task.randomization_parameters.DYNAMICS_SCALING_MAX=1.1", "task.env.maxEpisodeLength=3"]
+    whole = fstr_env(n, dr)
+    lo = fstr_env(n // 2, dr, global_env_offset=0)
+    hi = fstr_env(n // 2, dr, global_env_offset=n // 2)
+    again = fstr_env(n, dr)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for t in range(5):
+        act = torch.rand(n, 2, device="cuda", generator=g) * 2.4 - 1.2
+        whole.step(act); again.step(act)
+        lo.step(act[: n // 2]); hi.step(act[n // 2:])
+        for k in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "timeout_buf"):
+            w = getattr(whole, k)
+            assert torch.equal(w, getattr(again, k)), ("determinism", k, t)
+            assert torch.equal(w[: n // 2], getattr(lo, k)) and torch.equal(w[n // 2:], getattr(hi, k)), ("sharding", k, t)
+        assert bool(torch.isfinite(whole.obs_buf).all())
+    assert int(whole.reset_buf.sum()) > 0
+
+
+@pytest.mark.parametrize("delay", [0, 1, 3])
+def test_action_delay_is_exactly_k_control_steps(delay):
+    n = 256
+    env = fstr_env(n, [f"task.env.ACTION_DELAY={delay}", "vine_randomize=False", "task.env.maxEpisodeLength=1000",
+                       "task.env.USE_TARGET_REACHED_RESET=False"])
+    env.enable_debug_outputs(True)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    sent = []
+    for t in range(8):
+        act = torch.rand(n, 2, device="cuda", generator=g) * 2 - 1
+        sent.append(act.clone())
+        env.step(act)
+        u_rail = env.u_rail_velocity.reshape(-1)
+        expect = sent[t - delay][:, 0] * 1.0 if t - delay >= 0 else torch.zeros(n, device="cuda")   # V5:288-291
+        assert torch.equal(u_rail, expect), t
+
+
+def test_long_random_rollout_stays_physical():
+    n = 4096
+    env = fstr_env(n)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    resets = timeouts = 0
+    for t in range(300):
+        od, rew, reset, extras = env.step(torch.rand(n, 2, device="cuda", generator=g) * 2 - 1)
+        resets += int(reset.sum()); timeouts += int(extras["time_outs"].sum())
+    assert bool(torch.isfinite(env.obs_buf).all()) and bool(torch.isfinite(env.rew_buf).all())
+    assert int(env.progress_buf.max()) <= 99                                   # maxEpisodeLength 100
+    assert resets > n and 0 < timeouts < resets                               # limit hits + successes + timeouts
+    assert float(env.dof_vel.abs().max()) < 200.0 and float(env.dof_pos[:, 1:].abs().max()) < 3.2
+    tip = env.tip_positions
+    assert float(tip[:, 2].max()) < 1.42 and float(tip[:, 2].min()) > 0.5      # within the chain's reach of the pivot

@@ -1,0 +1,82 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL on GPUs, gloo in CPU tests).
+
+The env step needs no collective: envs shard by contiguous *global* env-id ranges and the Philox
+streams are keyed by the global id, so any sharding reproduces the single-GPU result bit for bit.
+Collectives exist only on the PPO side (the reference reaches them through rl_games' Horovod
+wrapper: ``hvd.setup_algo / sync_stats / average_value``, learning/common_agent.py:125-138,219):
+  * gradient all-reduce (+ the KL scalar packed into the same buffer),
+  * running mean/std sufficient statistics (observations, values) and advantage sums.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_from_env(backend=None, device=None):
+    """Initialise the default process group from torchrun's env vars (no-op when WORLD_SIZE == 1)."""
+    rank, world, local_rank = rank_world()
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device(device or f"cuda:{local_rank}")
+        dist.init_process_group(backend, **kw)
+    return rank, world, local_rank
+
+
+def env_shard(total_envs, rank, world):
+    """Contiguous global env-id range [start, start+count) owned by ``rank`` (remainder to low ranks)."""
+    base, rem = divmod(int(total_envs), int(world))
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+def max_over_ranks(value, device="cpu"):
+    """max of a python float over ranks (bench timing: the slowest rank defines the step time)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def allreduce_mean_(flat, extra_scalars=None):
+    """In-place mean over ranks of a flat gradient buffer; ``extra_scalars`` (e.g. the KL estimate
+    needed by the adaptive-LR schedule, Vine5LinkMovingBasePPO.yaml:64-66) ride in the same
+    collective so one minibatch costs exactly one all-reduce."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat, extra_scalars
+    world = dist.get_world_size()
+    if extra_scalars is not None:
+        packed = torch.cat([flat.reshape(-1), extra_scalars.reshape(-1).to(flat.dtype)])
+        dist.all_reduce(packed)
+        packed /= world
+        flat.copy_(packed[: flat.numel()].view_as(flat))
+        extra_scalars = packed[flat.numel():].clone()
+    else:
+        dist.all_reduce(flat)
+        flat /= world
+    return flat, extra_scalars
+
+
+def merge_moments(count, mean, m2):
+    """All-reduce running-mean/std sufficient statistics (Chan et al. parallel update):
+    every rank passes its (count, mean[D], M2[D]); returns the statistics of the union."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return count, mean, m2
+    c = torch.as_tensor(count, dtype=torch.float64, device=mean.device).reshape(1)
+    s1 = mean.double() * c
+    packed = torch.cat([c, s1.reshape(-1)])
+    dist.all_reduce(packed)
+    tot = packed[0]
+    gmean = packed[1:].view_as(mean) / tot
+    # M2_total = sum_r [ M2_r + n_r (mean_r - gmean)^2 ]
+    local = m2.double() + c * (mean.double() - gmean) ** 2
+    dist.all_reduce(local)
+    return tot.to(torch.float64), gmean.to(mean.dtype), local.to(m2.dtype)
