@@ -32,7 +32,7 @@ METRIC = "env-steps/s (whole box, device-timed)"
 UNIT = "env-steps/s"
 # Algorithmic work per env-step of the FSTR workload (derivations: DESIGN.md §6)
 HBM_BYTES_PER_ENV_STEP = 273.0      # O=18, ACTION_DELAY=1
-FLOPS_PER_ENV_STEP = 27.0e3         # exact count of this kernel's source: 40 substeps x 650 + 1.0 k
+FLOPS_PER_ENV_STEP = 18.67e3        # ncu ffma*2+fmul+fadd thread-inst per env-step (profiles/README.md); SASS: 40 x 426 + 4 x 383 + 0.5 k
 
 
 def fstr_cfg(num_envs, extra=()):
@@ -103,7 +103,8 @@ def cpu_oracle_rate(num_envs, budget_s, nthreads=0, min_steps=2, max_steps=64, f
     from oracle import oracle as O
     from vine_robot_isaacgymenvs_b200 import config as vcfg
     vc = vcfg.task_cfg_to_vine_config(fstr_cfg(num_envs)["task"])
-    env = O.OracleEnv(vc, num_envs, seed=42, use_f64=False, nthreads=nthreads)
+    # explicit thread count: torchrun exports OMP_NUM_THREADS=1, which would silently serialise the CPU arm
+    env = O.OracleEnv(vc, num_envs, seed=42, use_f64=False, nthreads=nthreads or host_threads())
     rng = np.random.default_rng(42)
     acts = rng.uniform(-1, 1, (4, num_envs, 2)).astype(np.float32)
     for i in range(max(warmup, 1)):

@@ -178,7 +178,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("VINE_B200_LIB") or LIB_PATH   # env override: kernel-variant experiments
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} not found: the Vine5LinkMovingBase hot path is CUDA-only (sm_100a) and has no "
