@@ -184,6 +184,14 @@ int vine_bind_io(VineEnv* env, const float* actions, float* obs_buf, float* rew_
 int vine_step(VineEnv* env, void* stream);
 
 /*
+ * The same step for the env sub-range [first, first+count) only (first a multiple of 128).
+ * Envs are independent (V5:464), so a step may be issued as several range launches on different
+ * streams to overlap host<->device copies of one chunk with the compute of another; the union of
+ * ranges covering 0..num_envs is bit-identical to one vine_step.
+ */
+int vine_step_range(VineEnv* env, int64_t first, int64_t count, void* stream);
+
+/*
  * reset_idx(env_ids) (V5:774-885) outside step, as VecTask.reset_done (VT:412-427)
  * and the 'R' key (V5:715-718) call it.  `env_ids` i64[n] device pointer, local ids.
  */

@@ -79,6 +79,23 @@ def test_cuda_graph_replay_equals_eager_launches():
         assert torch.equal(sa[k], sb[k]), k
 
 
+def test_pipelined_host_step_equals_plain_step():
+    """env.step_host (chunked vine_step_range launches on several streams, pinned host I/O) must be
+    bit-identical to env.step: envs are independent and Philox is keyed by the global env id."""
+    n = 50_000                                     # not a multiple of the chunk / CTA size on purpose
+    a, b = fstr_env(n), fstr_env(n)
+    obs_h = torch.empty(n, 18).pin_memory(); rew_h = torch.empty(n).pin_memory()
+    rst_h = torch.empty(n, dtype=torch.long).pin_memory(); to_h = torch.empty(n, dtype=torch.bool).pin_memory()
+    g = torch.Generator().manual_seed(5)
+    for t in range(12):
+        act_h = (torch.rand(n, 2, generator=g) * 2 - 1).pin_memory()
+        od, rew, rst, extras = a.step(act_h.cuda())
+        b.step_host(act_h, obs_h, rew_h, rst_h, to_h, chunks=5)
+        assert torch.equal(od["obs"].cpu(), obs_h) and torch.equal(rew.cpu(), rew_h), t
+        assert torch.equal(rst.cpu(), rst_h) and torch.equal(extras["time_outs"].cpu(), to_h), t
+        assert torch.equal(a.obs_buf, b.obs_buf) and torch.equal(a.progress_buf, b.progress_buf)
+
+
 def test_sharding_invariance_and_determinism_at_full_size():
     """Philox keyed by the GLOBAL env id: 1 x 1,048,576 envs == 2 x 524,288 envs, bit for bit."""
     n = 1 << 20

@@ -19,6 +19,7 @@
 
 struct StepArgs {
   int64_t n, gid0;
+  int64_t first, end;  // env range [first, end) of this launch (vine_step: 0..n; vine_step_range: a chunk)
   uint32_t k0, k1;
   float4 *S0, *S1, *S2, *S3, *S4, *S5;
   float2* ring;
@@ -52,10 +53,10 @@ static char g_create_err[256] = "";
 // ------------------------------------------------------------------------------------------
 // coalesced store of a block's observation rows staged in shared memory
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64_t n, float clip,
+__device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64_t first, int64_t end, float clip,
                                                 float* __restrict__ obs, float* __restrict__ obs_clamped) {
-  const int64_t row0 = (int64_t)blockIdx.x * VINE_BLOCK;
-  const int rows = (int)min((int64_t)VINE_BLOCK, n - row0);
+  const int64_t row0 = first + (int64_t)blockIdx.x * VINE_BLOCK;
+  const int rows = (int)min((int64_t)VINE_BLOCK, end - row0);
   const int count2 = rows * O / 2;  // O is even for every ObservationType
   float2* g = reinterpret_cast<float2*>(obs + row0 * O);
   float2* gc = obs_clamped ? reinterpret_cast<float2*>(obs_clamped + row0 * O) : nullptr;
@@ -78,8 +79,8 @@ __device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64
 template <bool CONTACT>
 __global__ void __launch_bounds__(VINE_BLOCK) vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
   __shared__ float s_obs[VINE_BLOCK * (VINE_MAX_OBS + 1)];
-  const int64_t e = (int64_t)blockIdx.x * VINE_BLOCK + threadIdx.x;
-  if (e < a.n) {
+  const int64_t e = a.first + (int64_t)blockIdx.x * VINE_BLOCK + threadIdx.x;
+  if (e < a.end) {
     const float4 s0 = a.S0[e], s1 = a.S1[e], s2 = a.S2[e], s3 = a.S3[e], s4 = a.S4[e], s5 = a.S5[e];
     float q[6] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y};
     float qd[6] = {s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(VINE_BLOCK) vine_step_kernel(const __grid_cons
     }
   }
   __syncthreads();
-  store_obs_block(s_obs, p.O, a.n, p.clip_obs, a.obs, a.obs_clamped);
+  store_obs_block(s_obs, p.O, a.first, a.end, p.clip_obs, a.obs, a.obs_clamped);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -553,7 +554,7 @@ int vine_create(const VineConfig* cfg, int64_t num_envs, int64_t global_env_offs
   memset(env, 0, sizeof(*env));
   env->p = p; env->cfg = *cfg; env->device = device;
   StepArgs& a = env->a;
-  a.n = num_envs; a.gid0 = global_env_offset; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
+  a.n = num_envs; a.first = 0; a.end = num_envs; a.gid0 = global_env_offset; a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32);
   cudaError_t e = cudaSetDevice(device);
   const size_t n = (size_t)num_envs;
   if (e == cudaSuccess) e = cudaMalloc(&a.S0, n * sizeof(float4));
@@ -614,6 +615,22 @@ int vine_step(VineEnv* env, void* stream) {
   const unsigned grid = grid_for(env->a.n, VINE_BLOCK);
   if (env->p.shelf || env->p.pipe) vine_step_kernel<true><<<grid, VINE_BLOCK, 0, st>>>(env->p, env->a);
   else vine_step_kernel<false><<<grid, VINE_BLOCK, 0, st>>>(env->p, env->a);
+  CUDA_TRY(env, cudaGetLastError());
+  return VINE_OK;
+}
+
+int vine_step_range(VineEnv* env, int64_t first, int64_t count, void* stream) {
+  if (!env) return VINE_ERR_INVALID_ARG;
+  if (!env->bound) { snprintf(env->err, 256, "vine_step_range: call vine_bind_io first"); return VINE_ERR_NOT_BOUND; }
+  if (first < 0 || count <= 0 || first + count > env->a.n || (first % VINE_BLOCK) != 0) {
+    snprintf(env->err, 256, "vine_step_range: need 0 <= first, first %% %d == 0, first + count <= num_envs", VINE_BLOCK);
+    return VINE_ERR_INVALID_ARG;
+  }
+  StepArgs a = env->a;
+  a.first = first; a.end = first + count;
+  const unsigned grid = grid_for(count, VINE_BLOCK);
+  if (env->p.shelf || env->p.pipe) vine_step_kernel<true><<<grid, VINE_BLOCK, 0, (cudaStream_t)stream>>>(env->p, a);
+  else vine_step_kernel<false><<<grid, VINE_BLOCK, 0, (cudaStream_t)stream>>>(env->p, a);
   CUDA_TRY(env, cudaGetLastError());
   return VINE_OK;
 }

@@ -144,6 +144,44 @@ class Vine5LinkMovingBase(VecTask):
         else:
             self._check(self._lib.vine_step(self._h, self._stream()))
 
+    def step_host(self, actions_host, obs_host, rew_host, reset_host, timeout_host, chunks=8):
+        """``step`` for callers whose policy lives on the HOST: pinned ``actions_host`` in, pinned
+        ``obs_host`` (clamped, VT:374) / ``rew_host`` / ``reset_host`` / ``timeout_host`` out.
+
+        The env range is cut into ``chunks`` pieces; each piece runs H2D(actions) -> fused step ->
+        D2H(results) on its own stream, so the three phases of different pieces overlap (both copy
+        engines and the SMs busy at once).  Envs are independent, so the result is bit-identical to
+        ``step``.  Returns after everything has landed in the host buffers.
+        """
+        n = self.num_envs
+        per = -(-n // max(int(chunks), 1))
+        per = max(128, -(-per // 128) * 128)          # vine_step_range wants starts on CTA boundaries
+        if not hasattr(self, "_chunk_streams"):
+            self._chunk_streams = [torch.cuda.Stream(self.device) for _ in range(4)]
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        first, k = 0, 0
+        while first < n:
+            cnt = min(per, n - first)
+            s = self._chunk_streams[k % len(self._chunk_streams)]
+            sl = slice(first, first + cnt)
+            with torch.cuda.stream(s):
+                if k < len(self._chunk_streams):
+                    s.wait_event(ready)
+                self.actions[sl].copy_(actions_host[sl], non_blocking=True)
+                self._check(self._lib.vine_step_range(self._h, first, cnt, C.c_void_p(s.cuda_stream)))
+                obs_host[sl].copy_(self._obs_clamped[sl], non_blocking=True)
+                rew_host[sl].copy_(self.rew_buf[sl], non_blocking=True)
+                reset_host[sl].copy_(self.reset_buf[sl], non_blocking=True)
+                timeout_host[sl].copy_(self.timeout_buf[sl], non_blocking=True)
+            first += cnt
+            k += 1
+        for s in self._chunk_streams:
+            cur.wait_stream(s)
+            s.synchronize()
+        self.num_steps += 1
+
     def capture_graph(self):
         """Capture the step into a CUDA graph (the kernel neither allocates nor synchronises)."""
         torch.cuda.synchronize(self.device)
