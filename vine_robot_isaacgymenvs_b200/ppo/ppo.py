@@ -9,8 +9,12 @@ In-repo analogue of the same math: isaacgymenvs/learning/common_agent.py:257-314
 :319-435 (update), :482-517 (losses).  rl_games itself is not vendored in the reference
 (setup.py:22) and not installed here: PARITY UNPINNED, checked by learning curves only.
 
-Multi-GPU: one process per GPU, envs sharded; per minibatch ONE all-reduce carrying the flattened
-gradients plus the KL scalar; per epoch one all-reduce of the running-statistics moments.
+The whole iteration is free of host synchronisation (episode statistics, KL and the learning
+rate live on the device), so the rollout (16 x {policy, fused env step} + GAE) and the update
+(mini_epochs x minibatches of forward/backward/Adam) are each captured into ONE CUDA graph
+(``use_graphs=True``, single GPU).  Multi-GPU: one process per GPU, envs sharded; per minibatch ONE
+all-reduce carrying the flattened gradients plus the KL scalar; per epoch one all-reduce of the
+running-statistics moments.
 """
 import ctypes as C
 import math
@@ -90,7 +94,7 @@ def policy_kl(p0_mu, p0_sigma, p1_mu, p1_sigma):
 
 
 class PPOAgent:
-    def __init__(self, env, train_cfg, device=None, seed=42):
+    def __init__(self, env, train_cfg, device=None, seed=42, use_graphs=False):
         c = train_cfg["params"]["config"]
         self.env, self.c = env, c
         self.device = device or env.device
@@ -103,7 +107,7 @@ class PPOAgent:
         self.batch = self.n * self.T
         self.minibatch = min(int(c["minibatch_size"]), self.batch)
         assert self.batch % self.minibatch == 0, "batch must be a multiple of minibatch_size"
-        self.lr, self.kl_threshold = float(c["learning_rate"]), float(c["kl_threshold"])
+        self.kl_threshold = float(c["kl_threshold"])
         self.adaptive = c.get("lr_schedule") == "adaptive"
         self.reward_scale = float(c.get("reward_shaper", {}).get("scale_value", 1.0))
         self.value_bootstrap = bool(c.get("value_bootstrap", False))
@@ -113,27 +117,37 @@ class PPOAgent:
         self.bf16 = bool(c.get("mixed_precision", False))
         units = train_cfg["params"]["network"]["mlp"]["units"]
         torch.manual_seed(seed)
-        self.model = ActorCritic(self.O, self.A, units).to(self.device)
-        self.obs_rms = RunningMeanStd((self.O,)).to(self.device)
-        self.val_rms = RunningMeanStd(()).to(self.device)
+        dev = self.device
+        self.model = ActorCritic(self.O, self.A, units).to(dev)
+        self.obs_rms = RunningMeanStd((self.O,)).to(dev)
+        self.val_rms = RunningMeanStd(()).to(dev)
         self.world = vd.rank_world()[1]
         if self.world > 1:  # hvd.setup_algo equivalent: identical parameters on every rank
             for p in self.model.parameters():
                 torch.distributed.broadcast(p.data, 0)
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr, eps=1e-8)
+        self.use_graphs = bool(use_graphs) and self.world == 1
+        self.lr_t = torch.tensor(float(c["learning_rate"]), device=dev)   # device-side: no sync in the schedule
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t, eps=1e-8, capturable=True)
         self._lib = abi.load_library()
-        T, n, dev = self.T, self.n, self.device
+        T, n = self.T, self.n
         f = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
         self.b_obs, self.b_act, self.b_mu = f(T, n, self.O), f(T, n, self.A), f(T, n, self.A)
         self.b_nlp, self.b_val, self.b_rew, self.b_done = f(T, n), f(T, n), f(T, n), f(T, n)
         self.b_adv, self.b_ret = f(T, n), f(T, n)
         self.obs = env.reset()["obs"].clone()
         self.dones = torch.ones(n, device=dev)
+        self.last_value = f(n)
         self.epoch = 0
         self.frames = 0
-        self.stats = {"episodes": 0, "successes": 0, "return_sum": 0.0, "len_sum": 0}
-        self.ep_ret = torch.zeros(n, device=dev)
-        self.ep_len = torch.zeros(n, device=dev)
+        # device-side statistics: [episodes, successes, return_sum, length_sum] and [a_loss, c_loss, kl, n]
+        self.ep_stats = torch.zeros(4, device=dev, dtype=torch.float64)
+        self.loss_stats = torch.zeros(4, device=dev, dtype=torch.float64)
+        self.ep_ret, self.ep_len = f(n), f(n)
+        self._g_rollout = self._g_update = None
+
+    @property
+    def lr(self):
+        return float(self.lr_t)
 
     # ------------------------------------------------------------------ acting
     @torch.no_grad()
@@ -147,7 +161,7 @@ class PPOAgent:
         return mu, logstd, value
 
     @torch.no_grad()
-    def play_steps(self):
+    def _rollout(self):
         env = self.env
         for t in range(self.T):
             mu, logstd, value = self._policy(self.obs)
@@ -155,66 +169,69 @@ class PPOAgent:
             action = mu + sigma * torch.randn_like(mu)
             self.b_obs[t], self.b_act[t], self.b_mu[t] = self.obs, action, mu
             self.b_nlp[t], self.b_val[t], self.b_done[t] = neglogp(action, mu, sigma, logstd), value, self.dones
-            od, rew, dones, infos = env.step(torch.clamp(action, -1.0, 1.0))   # rl_games preprocess_actions
+            env.actions.copy_(torch.clamp(action, -1.0, 1.0))                  # rl_games preprocess_actions
+            env.step_device()                                                  # ONE fused kernel launch
+            rew, dones, timeouts = env.rew_buf, env.reset_buf, env.timeout_buf
             shaped = rew * self.reward_scale
             if self.value_bootstrap:                                           # Vine5LinkMovingBasePPO.yaml:56
-                shaped = shaped + self.gamma * value * infos["time_outs"].float()
+                shaped = shaped + self.gamma * value * timeouts.float()
             self.b_rew[t] = shaped
-            # episode statistics: success == the 1000-point "Position Success" term fired (V5:1507)
+            # episode statistics; success == the 1000-point "Position Success" term fired (V5:1507)
             self.ep_ret += rew
             self.ep_len += 1
-            d = dones.bool()
-            if bool(d.any()):
-                self.stats["episodes"] += int(d.sum())
-                self.stats["successes"] += int((d & (rew > 500.0)).sum())
-                self.stats["return_sum"] += float(self.ep_ret[d].sum())
-                self.stats["len_sum"] += int(self.ep_len[d].sum())
-                self.ep_ret[d] = 0
-                self.ep_len[d] = 0
-            self.obs = od["obs"].clone()
-            self.dones = dones.float()
+            d = dones.to(torch.float32)
+            self.ep_stats += torch.stack([d.sum(), (d * (rew > 500.0)).sum(), (d * self.ep_ret).sum(),
+                                          (d * self.ep_len).sum()]).double()
+            self.ep_ret *= 1.0 - d
+            self.ep_len *= 1.0 - d
+            self.obs.copy_(env._obs_clamped)
+            self.dones.copy_(d)
         _, _, last_value = self._policy(self.obs)
+        self.last_value.copy_(last_value)
         p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
-        rc = self._lib.vine_gae(p(self.b_rew), p(self.b_val), p(self.b_done), p(last_value.contiguous()),
-                                p(self.dones), self.T, self.n, self.gamma, self.tau, p(self.b_adv), p(self.b_ret),
+        rc = self._lib.vine_gae(p(self.b_rew), p(self.b_val), p(self.b_done), p(self.last_value), p(self.dones),
+                                self.T, self.n, self.gamma, self.tau, p(self.b_adv), p(self.b_ret),
                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0
+
+    def play_steps(self):
+        if self._g_rollout is not None:
+            self._g_rollout.replay()
+        else:
+            self._rollout()
         self.frames += self.T * self.n * self.world
 
     # ------------------------------------------------------------------ learning
     def _update_lr(self, kl):
         if not self.adaptive:
             return
-        if kl > 2.0 * self.kl_threshold:
-            self.lr = max(self.lr / 1.5, 1e-6)
-        if kl < 0.5 * self.kl_threshold:
-            self.lr = min(self.lr * 1.5, 1e-2)
-        for g in self.opt.param_groups:
-            g["lr"] = self.lr
+        lr = self.lr_t
+        lr = torch.where(kl > 2.0 * self.kl_threshold, torch.clamp(lr / 1.5, min=1e-6), lr)
+        lr = torch.where(kl < 0.5 * self.kl_threshold, torch.clamp(lr * 1.5, max=1e-2), lr)
+        self.lr_t.copy_(lr)
 
-    def train_epoch(self):
-        self.play_steps()
+    def _update(self):
         B = self.batch
         obs, act, mu_old = self.b_obs.view(B, self.O), self.b_act.view(B, self.A), self.b_mu.view(B, self.A)
         nlp_old, val_old, ret = self.b_nlp.view(B), self.b_val.view(B), self.b_ret.view(B)
         adv = ret - val_old
-        if self.normalize_input:
-            self.obs_rms.update(obs)
-            obs = self.obs_rms(obs)
-        if self.normalize_value:
-            self.val_rms.update(torch.cat([val_old, ret]))
-            val_old, ret = self.val_rms(val_old), self.val_rms(ret)
-        if self.normalize_advantage:
-            s = torch.stack([adv.sum(), (adv * adv).sum(), torch.tensor(float(B), device=adv.device)]).double()
-            if self.world > 1:
-                torch.distributed.all_reduce(s)
-            mean = s[0] / s[2]
-            std = torch.sqrt(torch.clamp((s[1] - s[2] * mean * mean) / (s[2] - 1.0), min=0.0))
-            adv = (adv - mean.float()) / (std.float() + 1e-8)
-        sigma_old = torch.exp(self.model.sigma.detach()).expand(B, -1).clone()
+        with torch.no_grad():
+            if self.normalize_input:
+                self.obs_rms.update(obs)
+                obs = self.obs_rms(obs)
+            if self.normalize_value:
+                self.val_rms.update(torch.cat([val_old, ret]))
+                val_old, ret = self.val_rms(val_old), self.val_rms(ret)
+            if self.normalize_advantage:
+                s = torch.stack([adv.sum(), (adv * adv).sum()]).double()
+                cnt = float(B * self.world)
+                if self.world > 1:
+                    torch.distributed.all_reduce(s)
+                mean = s[0] / cnt
+                std = torch.sqrt(torch.clamp((s[1] - cnt * mean * mean) / (cnt - 1.0), min=0.0))
+                adv = (adv - mean.float()) / (std.float() + 1e-8)
+            sigma_old = torch.exp(self.model.sigma.detach()).expand(B, -1).clone()
         params = [p for p in self.model.parameters()]
-        info = {"a_loss": 0.0, "c_loss": 0.0, "kl": 0.0}
-        nmb = 0
         for _ in range(self.mini_epochs):
             for i in range(0, B, self.minibatch):
                 sl = slice(i, i + self.minibatch)
@@ -231,7 +248,7 @@ class PPOAgent:
                 b_loss = (torch.clamp_min(mu - 1.1, 0.0) ** 2 + torch.clamp_max(mu + 1.1, 0.0) ** 2).sum(-1).mean()
                 entropy = (0.5 + 0.5 * math.log(2 * math.pi) + logstd).sum(-1).mean()
                 loss = a_loss + 0.5 * c_loss * self.critic_coef - self.entropy_coef * entropy + b_loss * self.bounds_coef
-                self.opt.zero_grad(set_to_none=True)
+                self.opt.zero_grad(set_to_none=False)
                 loss.backward()
                 with torch.no_grad():
                     kl = policy_kl(mu.detach(), sigma.detach(), mu_old[sl], sigma_old[sl])
@@ -246,32 +263,60 @@ class PPOAgent:
                     if self.truncate_grads:
                         nn.utils.clip_grad_norm_(params, self.grad_norm)
                 self.opt.step()
-                klv = float(kl)
-                self._update_lr(klv)
-                info["a_loss"] += float(a_loss); info["c_loss"] += float(c_loss); info["kl"] += klv
-                nmb += 1
+                with torch.no_grad():
+                    self._update_lr(kl)
+                    self.loss_stats += torch.stack([a_loss.detach(), c_loss.detach(), kl,
+                                                    torch.ones((), device=kl.device)]).double()
+
+    def capture_graphs(self, warmup=3):
+        """Warm up eagerly on a side stream, then capture the rollout and the update as two graphs."""
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._rollout()
+                self._update()
+                self.frames += self.T * self.n
+                self.epoch += 1
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self._g_rollout, self._g_update = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_rollout):
+            self._rollout()
+        with torch.cuda.graph(self._g_update):
+            self._update()
+        torch.cuda.synchronize(self.device)
+
+    def train_epoch(self):
+        if self.use_graphs and self._g_rollout is None:
+            self.capture_graphs()
+        self.play_steps()
+        if self._g_update is not None:
+            self._g_update.replay()
+        else:
+            self._update()
         self.epoch += 1
-        return {k: v / nmb for k, v in info.items()}
 
     def pop_stats(self):
-        s = self.stats
-        eps = max(s["episodes"], 1)
-        out = {"episodes": s["episodes"], "success_rate": s["successes"] / eps, "mean_return": s["return_sum"] / eps,
-               "mean_length": s["len_sum"] / eps}
-        self.stats = {"episodes": 0, "successes": 0, "return_sum": 0.0, "len_sum": 0}
-        return out
+        e = self.ep_stats.tolist()
+        l = self.loss_stats.tolist()
+        self.ep_stats.zero_()
+        self.loss_stats.zero_()
+        eps, nmb = max(e[0], 1.0), max(l[3], 1.0)
+        return {"episodes": int(e[0]), "success_rate": e[1] / eps, "mean_return": e[2] / eps, "mean_length": e[3] / eps,
+                "a_loss": l[0] / nmb, "c_loss": l[1] / nmb, "kl": l[2] / nmb}
 
     def train(self, max_epochs, log_every=25, log=print):
-        t0 = time.perf_counter()
         hist = []
+        torch.cuda.synchronize(self.device)
+        t0, f0 = time.perf_counter(), self.frames
         for ep in range(max_epochs):
-            info = self.train_epoch()
+            self.train_epoch()
             if (ep + 1) % log_every == 0 or ep == max_epochs - 1:
-                torch.cuda.synchronize()
+                torch.cuda.synchronize(self.device)
                 st = self.pop_stats()
-                st.update(info)
-                st.update({"epoch": ep + 1, "frames": self.frames, "lr": self.lr,
-                           "fps_total": self.frames / (time.perf_counter() - t0)})
+                st.update({"epoch": self.epoch, "frames": self.frames, "lr": self.lr,
+                           "fps_total": (self.frames - f0) / (time.perf_counter() - t0)})
                 hist.append(st)
                 if log:
                     log(" ".join(f"{k}={v:.4g}" if isinstance(v, float) else f"{k}={v}" for k, v in st.items()))
@@ -290,4 +335,5 @@ class PPOAgent:
         self.val_rms.load_state_dict(sd["reward_mean_std"])
         if "optimizer" in sd:
             self.opt.load_state_dict(sd["optimizer"])
-        self.epoch, self.frames, self.lr = sd.get("epoch", 0), sd.get("frame", 0), sd.get("last_lr", self.lr)
+        self.epoch, self.frames = sd.get("epoch", 0), sd.get("frame", 0)
+        self.lr_t.fill_(float(sd.get("last_lr", self.lr)))
