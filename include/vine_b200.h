@@ -345,6 +345,24 @@ int vine_gae(const float* rewards, const float* values, const float* dones,
              int64_t num_envs, double gamma, double tau, float* advantages, float* returns,
              void* stream);
 
+/*
+ * Actor-critic MLP of cfg/train/Vine5LinkMovingBasePPO.yaml:10-30 (rl_games `actor_critic` network:
+ * shared MLP [256,128,64] ELU, mu head [2], value head [1]) as ONE fused tcgen05/TMEM kernel for
+ * rollout inference (rl_games A2CAgent.get_action_values; in-repo analogue
+ * learning/common_agent.py:257-314).  Weights are nn.Linear layout f32 [out,in]; vine_mlp_pack
+ * converts them to bf16 in the tensor-core operand layout (call it after every optimizer step).
+ *   x = clamp((obs - obs_mean) * obs_inv_std, +-5);  mu f32[N,2];  value f32[N] de-normalised as
+ *   clamp(v, +-5) * value_stats[1] + value_stats[0]  (rl_games RunningMeanStd, normalize_input /
+ *   normalize_value; value_stats = device pointer to {mean, std} so a captured CUDA graph sees updates).
+ */
+#define VINE_MLP_PACKED_BYTES 102208
+int vine_mlp_pack(const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                  const float* b3, const float* w_mu, const float* b_mu, const float* w_v, const float* b_v,
+                  int num_obs, void* packed, void* stream);
+int vine_mlp_forward(const void* packed, const float* obs, const float* obs_mean, const float* obs_inv_std,
+                     int64_t n, int num_obs, const float* value_stats, float* mu, float* value,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,7 +134,9 @@ EXPORTED_SYMBOLS = [
     "vine_destroy", "vine_last_error", "vine_bind_io", "vine_step", "vine_step_range", "vine_reset_idx",
     "vine_get_state", "vine_set_state", "vine_set_debug_outputs", "vine_post_physics",
     "vine_pre_physics", "vine_actuation", "vine_simulate", "vine_philox_debug", "vine_gae",
+    "vine_mlp_pack", "vine_mlp_forward",
 ]
+MLP_PACKED_BYTES = 102208
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libvine_b200.so")
@@ -167,6 +169,8 @@ def _declare(lib):
                                       C.c_int64, vp, vp]
     lib.vine_gae.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_double, C.c_double,
                              vp, vp, vp]
+    lib.vine_mlp_pack.argtypes = [vp] * 10 + [C.c_int, vp, vp]
+    lib.vine_mlp_forward.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("vine_destroy", "vine_last_error"):

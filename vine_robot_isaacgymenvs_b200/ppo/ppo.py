@@ -94,7 +94,7 @@ def policy_kl(p0_mu, p0_sigma, p1_mu, p1_sigma):
 
 
 class PPOAgent:
-    def __init__(self, env, train_cfg, device=None, seed=42, use_graphs=False):
+    def __init__(self, env, train_cfg, device=None, seed=42, use_graphs=False, use_fused_policy=True):
         c = train_cfg["params"]["config"]
         self.env, self.c = env, c
         self.device = device or env.device
@@ -144,6 +144,29 @@ class PPOAgent:
         self.loss_stats = torch.zeros(4, device=dev, dtype=torch.float64)
         self.ep_ret, self.ep_len = f(n), f(n)
         self._g_rollout = self._g_update = None
+        # fused tcgen05/TMEM policy forward for the rollout (vine_mlp_forward); the update keeps autograd
+        self.fused = (bool(use_fused_policy) and list(units) == [256, 128, 64] and self.A == 2 and self.O <= 32
+                      and self.normalize_input and self.normalize_value)
+        if self.fused:
+            self._packed = torch.zeros(abi.MLP_PACKED_BYTES, dtype=torch.uint8, device=dev)
+            self._obs_mean_f, self._obs_inv_std_f = f(self.O), f(self.O)
+            self._val_stats = f(2)
+            self._mu_buf, self._val_buf = f(n, self.A), f(n)
+            self._refresh_fused()
+
+    @torch.no_grad()
+    def _refresh_fused(self):
+        """Re-pack the current weights (bf16, tensor-core operand layout) and normalisation statistics."""
+        m = self.model
+        self._obs_mean_f.copy_(self.obs_rms.running_mean.float())
+        self._obs_inv_std_f.copy_(torch.rsqrt(self.obs_rms.running_var.float() + self.obs_rms.eps))
+        self._val_stats.copy_(torch.stack([self.val_rms.running_mean.float(),
+                                           torch.sqrt(self.val_rms.running_var.float() + self.val_rms.eps)]))
+        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        lin = [m.mlp[0], m.mlp[2], m.mlp[4], m.mu, m.value]
+        args = [p(t) for l in lin for t in (l.weight, l.bias)]
+        rc = self._lib.vine_mlp_pack(*args, self.O, p(self._packed), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
 
     @property
     def lr(self):
@@ -152,6 +175,13 @@ class PPOAgent:
     # ------------------------------------------------------------------ acting
     @torch.no_grad()
     def _policy(self, obs):
+        if self.fused and obs.shape[0] == self.n:
+            p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+            rc = self._lib.vine_mlp_forward(p(self._packed), p(obs), p(self._obs_mean_f), p(self._obs_inv_std_f), self.n,
+                                            self.O, p(self._val_stats), p(self._mu_buf), p(self._val_buf),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            assert rc == 0
+            return self._mu_buf, self.model.sigma.detach().expand(self.n, -1), self._val_buf
         x = self.obs_rms(obs) if self.normalize_input else obs
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.bf16):
             mu, logstd, value = self.model(x)
@@ -267,6 +297,8 @@ class PPOAgent:
                     self._update_lr(kl)
                     self.loss_stats += torch.stack([a_loss.detach(), c_loss.detach(), kl,
                                                     torch.ones((), device=kl.device)]).double()
+        if self.fused:
+            self._refresh_fused()
 
     def capture_graphs(self, warmup=3):
         """Warm up eagerly on a side stream, then capture the rollout and the update as two graphs."""
