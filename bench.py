@@ -275,6 +275,46 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = time_e2e(e2e_step_pipelined)
     sampler.stop_flag = True
 
+    # ---- PPO frames/s (second half of BASELINE.json's metric): BASELINE configs[1] literally ----
+    # FSTR, 4096 envs per GPU, horizon 16, minibatch 32768, 4 mini-epochs; one iteration = rollout
+    # (16 x {policy, fused env step}) + GAE + update; frames = T * N * ranks per iteration.
+    def measure_ppo(num_envs, iters, warmup, extra, use_graphs=True):
+        from vine_robot_isaacgymenvs_b200.ppo.ppo import PPOAgent
+        pcfg = fstr_cfg(num_envs, [f"sim_device={dev}", f"rl_device={dev}"] + list(extra))
+        penv = vine.make(cfg=pcfg, global_env_offset=rank * num_envs)
+        agent = PPOAgent(penv, pcfg["train"], device=dev, seed=42 + rank, use_graphs=use_graphs)
+        for _ in range(max(warmup, 3)):
+            agent.train_epoch()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            agent.train_epoch()
+        e1.record()
+        barrier()
+        ms_it = max_over_ranks(e0.elapsed_time(e1)) / iters
+        stats = agent.pop_stats()
+        assert all(x == x for x in (stats["a_loss"], stats["c_loss"], stats["kl"])), stats
+        return {"value": agent.T * num_envs * world / (ms_it * 1e-3), "unit": "frames/s", "ms_per_iteration": ms_it,
+                "num_envs_per_gpu": num_envs, "horizon": agent.T, "minibatch": agent.minibatch,
+                "mini_epochs": agent.mini_epochs, "iterations": iters,
+                "network": "mlp[256,128,64]+lstm256+ln" if agent.has_rnn else "mlp[256,128,64]",
+                "cuda_graphs": agent.use_graphs,
+                "collectives": "none" if world == 1 else "NCCL all-reduce: grads+KL per minibatch, running stats per iteration"}
+
+    ppo = None
+    if not args.no_ppo:
+        del env
+        env = None
+        torch.cuda.empty_cache()
+        ppo = {"config": "BASELINE configs[1]: FSTR num_envs=4096 rollout+PPO",
+               "reference_network": measure_ppo(4096, args.ppo_iters, 5, []),
+               "mlp_only": measure_ppo(4096, args.ppo_iters, 5, ["train.params.network.rnn=null"])}
+        if not args.no_sweep:
+            ppo["mlp_only_65536_envs"] = measure_ppo(65536, max(3, args.ppo_iters // 4), 3,
+                                                     ["train.params.network.rnn=null",
+                                                      "train.params.config.minibatch_size=131072"])
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -305,7 +345,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- smaller env counts, same kernel (BASELINE configs[1] literal size and the configs[4] sweep) ----
     sweep = []
     if world == 1 and not args.no_sweep:
-        del env
+        env = None
         torch.cuda.empty_cache()
         for m in (4096, 65536, 262144):
             if m >= n:
@@ -340,7 +380,7 @@ def run_ours(args, rank, world, local_rank):
                 "api": f"env.step_host(pinned host buffers, chunks={args.e2e_chunks}): H2D, step and D2H of different "
                        "env chunks overlap on separate streams; returns after all results are on the host",
                 "unpipelined_value": e2e_simple},
-        "clocks": clocks, "gpu_launches": args.steps, "sweep": sweep,
+        "clocks": clocks, "gpu_launches": args.steps, "sweep": sweep, "ppo": ppo,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -359,6 +399,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--ppo-iters", type=int, default=20)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

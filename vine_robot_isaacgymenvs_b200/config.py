@@ -230,6 +230,9 @@ def _primitive(text):
     return t if isinstance(v, (dict, list)) else v
 
 
+_ROOT = object()   # sentinel: "start at the root" (None is a legal node value, e.g. ``rnn=null``)
+
+
 class _Resolver:
     def __init__(self, root):
         self.root = root
@@ -340,8 +343,8 @@ class _Resolver:
             return self.resolve_node(base + keys)
         return self.resolve_node(ref.split("."))
 
-    def resolve_all(self, node=None, path=()):
-        node = self.root if node is None else node
+    def resolve_all(self, node=_ROOT, path=()):
+        node = self.root if node is _ROOT else node
         if isinstance(node, dict):
             return {k: self.resolve_all(v, path + (k,)) for k, v in node.items()}
         if isinstance(node, list):

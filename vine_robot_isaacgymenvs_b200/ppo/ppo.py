@@ -63,24 +63,72 @@ class RunningMeanStd(nn.Module):
         return torch.clamp((x - mean) / std, -5.0, 5.0)
 
 
-class ActorCritic(nn.Module):
-    """``actor_critic`` network of Vine5LinkMovingBasePPO.yaml:10-30: shared MLP [256,128,64] ELU,
-    mu head, value head, state-independent learnable log-std initialised to 0 (fixed_sigma: True)."""
+class _RnnHolder(nn.Module):
+    """Parameter holder named like rl_games' LSTMWithDones wrapper (checkpoint key ``rnn.rnn.weight_ih_l0``)."""
 
-    def __init__(self, num_obs, num_actions, units=(256, 128, 64)):
+    def __init__(self, input_size, hidden):
+        super().__init__()
+        self.rnn = nn.LSTM(input_size, hidden, 1)
+
+
+class ActorCritic(nn.Module):
+    """``actor_critic`` network of Vine5LinkMovingBasePPO.yaml:10-40 (rl_games A2CBuilder, separate: False):
+    shared MLP [256,128,64] ELU -> (rnn: lstm 256, before_mlp False, concat_input True, layer_norm True)
+    -> mu head, value head; state-independent learnable log-std initialised to 0 (fixed_sigma: True).
+    Sub-module names follow rl_games' ``a2c_network`` so checkpoints map key for key.
+
+    With the LSTM the training forward is truncated BPTT over ``seq_len`` steps; the hidden state is
+    multiplied by (1 - done_t) before consuming observation t, which is what rl_games' rollout does
+    when it zeroes the states of finished envs (a2c_common.play_steps_rnn)."""
+
+    def __init__(self, num_obs, num_actions, units=(256, 128, 64), rnn=None):
         super().__init__()
         layers, d = [], num_obs
         for u in units:
             layers += [nn.Linear(d, u), nn.ELU()]
             d = u
-        self.mlp = nn.Sequential(*layers)
+        self.actor_mlp = nn.Sequential(*layers)
+        self.has_rnn = bool(rnn) and str(rnn.get("name", "lstm")).lower() not in ("none", "")
+        if self.has_rnn:
+            if str(rnn["name"]).lower() != "lstm" or int(rnn.get("layers", 1)) != 1 or rnn.get("before_mlp", False):
+                raise ValueError("only the reference's rnn block is supported: lstm, 1 layer, before_mlp False")
+            self.concat_input = bool(rnn.get("concat_input", False))
+            self.rnn_units = int(rnn["units"])
+            self.rnn = _RnnHolder(d + (num_obs if self.concat_input else 0), self.rnn_units)
+            d = self.rnn_units
+            self.layer_norm = nn.LayerNorm(d) if rnn.get("layer_norm", False) else nn.Identity()
         self.mu = nn.Linear(d, num_actions)
         self.value = nn.Linear(d, 1)
         self.sigma = nn.Parameter(torch.zeros(num_actions))
 
-    def forward(self, obs):
-        h = self.mlp(obs)
-        return self.mu(h), self.sigma.expand(obs.shape[0], -1), self.value(h)
+    def forward(self, obs, states=None, not_done=None):
+        """obs [L, S, O] (or [S, O] == L=1); states (h, c) each [S, H]; not_done [L, S] or None.
+        Returns mu [L*S, A], logstd, value [L*S, 1], new states."""
+        if not self.has_rnn:
+            x = obs.reshape(-1, obs.shape[-1])
+            h = self.actor_mlp(x)
+            return self.mu(h), self.sigma.expand(x.shape[0], -1), self.value(h), None
+        if obs.dim() == 2:
+            obs = obs.unsqueeze(0)
+        L, S, O = obs.shape
+        x = obs.reshape(L * S, O)
+        m = self.actor_mlp(x)
+        inp = torch.cat([m, x.to(m.dtype)], -1) if self.concat_input else m
+        r = self.rnn.rnn
+        gi = torch.nn.functional.linear(inp, r.weight_ih_l0, r.bias_ih_l0 + r.bias_hh_l0).view(L, S, -1)
+        h, c = states
+        outs = []
+        for t in range(L):
+            if not_done is not None:
+                nd = not_done[t].unsqueeze(-1)
+                h, c = h * nd, c * nd
+            g = gi[t] + torch.nn.functional.linear(h.to(gi.dtype), r.weight_hh_l0)
+            i, f, gg, o = g.float().chunk(4, -1)                         # torch gate order: i, f, g, o
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            outs.append(h)
+        out = self.layer_norm(torch.stack(outs).reshape(L * S, -1))
+        return self.mu(out), self.sigma.expand(L * S, -1), self.value(out), (h, c)
 
 
 def neglogp(x, mean, std, logstd):
@@ -96,6 +144,7 @@ def policy_kl(p0_mu, p0_sigma, p1_mu, p1_sigma):
 class PPOAgent:
     def __init__(self, env, train_cfg, device=None, seed=42, use_graphs=False, use_fused_policy=True):
         c = train_cfg["params"]["config"]
+        net = train_cfg["params"]["network"]
         self.env, self.c = env, c
         self.device = device or env.device
         self.n, self.T = env.num_envs, int(c["horizon_length"])
@@ -107,6 +156,9 @@ class PPOAgent:
         self.batch = self.n * self.T
         self.minibatch = min(int(c["minibatch_size"]), self.batch)
         assert self.batch % self.minibatch == 0, "batch must be a multiple of minibatch_size"
+        # rl_games flattens the rollout env-major (swap_and_flatten01), so a minibatch is a slice of envs x all T steps
+        assert self.minibatch % self.T == 0, "minibatch_size must be a multiple of horizon_length"
+        self.mb_envs = self.minibatch // self.T
         self.kl_threshold = float(c["kl_threshold"])
         self.adaptive = c.get("lr_schedule") == "adaptive"
         self.reward_scale = float(c.get("reward_shaper", {}).get("scale_value", 1.0))
@@ -115,10 +167,13 @@ class PPOAgent:
         self.normalize_advantage = bool(c["normalize_advantage"])
         self.truncate_grads, self.grad_norm = bool(c.get("truncate_grads", False)), float(c.get("grad_norm", 1.0))
         self.bf16 = bool(c.get("mixed_precision", False))
-        units = train_cfg["params"]["network"]["mlp"]["units"]
+        units = net["mlp"]["units"]
         torch.manual_seed(seed)
         dev = self.device
-        self.model = ActorCritic(self.O, self.A, units).to(dev)
+        self.model = ActorCritic(self.O, self.A, units, rnn=net.get("rnn")).to(dev)
+        self.has_rnn = self.model.has_rnn
+        self.seq_len = int(c.get("seq_len", 4)) if self.has_rnn else 1
+        assert self.T % self.seq_len == 0, "horizon_length must be a multiple of seq_len"
         self.obs_rms = RunningMeanStd((self.O,)).to(dev)
         self.val_rms = RunningMeanStd(()).to(dev)
         self.world = vd.rank_world()[1]
@@ -134,6 +189,10 @@ class PPOAgent:
         self.b_obs, self.b_act, self.b_mu = f(T, n, self.O), f(T, n, self.A), f(T, n, self.A)
         self.b_nlp, self.b_val, self.b_rew, self.b_done = f(T, n), f(T, n), f(T, n), f(T, n)
         self.b_adv, self.b_ret = f(T, n), f(T, n)
+        if self.has_rnn:   # LSTM state of every env, and its snapshots at the start of every seq_len chunk
+            H = self.model.rnn_units
+            self.rnn_h, self.rnn_c = f(n, H), f(n, H)
+            self.b_h, self.b_c = f(T // self.seq_len, n, H), f(T // self.seq_len, n, H)
         self.obs = env.reset()["obs"].clone()
         self.dones = torch.ones(n, device=dev)
         self.last_value = f(n)
@@ -145,8 +204,8 @@ class PPOAgent:
         self.ep_ret, self.ep_len = f(n), f(n)
         self._g_rollout = self._g_update = None
         # fused tcgen05/TMEM policy forward for the rollout (vine_mlp_forward); the update keeps autograd
-        self.fused = (bool(use_fused_policy) and list(units) == [256, 128, 64] and self.A == 2 and self.O <= 32
-                      and self.normalize_input and self.normalize_value)
+        self.fused = (bool(use_fused_policy) and not self.has_rnn and list(units) == [256, 128, 64] and self.A == 2
+                      and self.O <= 32 and self.normalize_input and self.normalize_value)
         if self.fused:
             self._packed = torch.zeros(abi.MLP_PACKED_BYTES, dtype=torch.uint8, device=dev)
             self._obs_mean_f, self._obs_inv_std_f = f(self.O), f(self.O)
@@ -163,7 +222,7 @@ class PPOAgent:
         self._val_stats.copy_(torch.stack([self.val_rms.running_mean.float(),
                                            torch.sqrt(self.val_rms.running_var.float() + self.val_rms.eps)]))
         p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
-        lin = [m.mlp[0], m.mlp[2], m.mlp[4], m.mu, m.value]
+        lin = [m.actor_mlp[0], m.actor_mlp[2], m.actor_mlp[4], m.mu, m.value]
         args = [p(t) for l in lin for t in (l.weight, l.bias)]
         rc = self._lib.vine_mlp_pack(*args, self.O, p(self._packed), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0
@@ -174,27 +233,33 @@ class PPOAgent:
 
     # ------------------------------------------------------------------ acting
     @torch.no_grad()
-    def _policy(self, obs):
+    def _policy(self, obs, states=None):
+        """mu, logstd, de-normalised value and the next LSTM state for one observation per env."""
         if self.fused and obs.shape[0] == self.n:
             p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
             rc = self._lib.vine_mlp_forward(p(self._packed), p(obs), p(self._obs_mean_f), p(self._obs_inv_std_f), self.n,
                                             self.O, p(self._val_stats), p(self._mu_buf), p(self._val_buf),
                                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
             assert rc == 0
-            return self._mu_buf, self.model.sigma.detach().expand(self.n, -1), self._val_buf
+            return self._mu_buf, self.model.sigma.detach().expand(self.n, -1), self._val_buf, None
         x = self.obs_rms(obs) if self.normalize_input else obs
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.bf16):
-            mu, logstd, value = self.model(x)
+            mu, logstd, value, states = self.model(x, states)
         mu, logstd, value = mu.float(), logstd.float(), value.float().squeeze(-1)
         if self.normalize_value:
             value = self.val_rms(value, unnorm=True)
-        return mu, logstd, value
+        return mu, logstd, value, states
 
     @torch.no_grad()
     def _rollout(self):
         env = self.env
         for t in range(self.T):
-            mu, logstd, value = self._policy(self.obs)
+            states = None
+            if self.has_rnn:
+                if t % self.seq_len == 0:
+                    self.b_h[t // self.seq_len], self.b_c[t // self.seq_len] = self.rnn_h, self.rnn_c
+                states = (self.rnn_h, self.rnn_c)
+            mu, logstd, value, states = self._policy(self.obs, states)
             sigma = torch.exp(logstd)
             action = mu + sigma * torch.randn_like(mu)
             self.b_obs[t], self.b_act[t], self.b_mu[t] = self.obs, action, mu
@@ -214,9 +279,13 @@ class PPOAgent:
                                           (d * self.ep_len).sum()]).double()
             self.ep_ret *= 1.0 - d
             self.ep_len *= 1.0 - d
+            if self.has_rnn:   # finished envs start their next episode from a zero state
+                nd = (1.0 - d).unsqueeze(-1)
+                self.rnn_h.copy_(states[0] * nd)
+                self.rnn_c.copy_(states[1] * nd)
             self.obs.copy_(env._obs_clamped)
             self.dones.copy_(d)
-        _, _, last_value = self._policy(self.obs)
+        _, _, last_value, _ = self._policy(self.obs, (self.rnn_h, self.rnn_c) if self.has_rnn else None)
         self.last_value.copy_(last_value)
         p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
         rc = self._lib.vine_gae(p(self.b_rew), p(self.b_val), p(self.b_done), p(self.last_value), p(self.dones),
@@ -241,54 +310,69 @@ class PPOAgent:
         self.lr_t.copy_(lr)
 
     def _update(self):
-        B = self.batch
-        obs, act, mu_old = self.b_obs.view(B, self.O), self.b_act.view(B, self.A), self.b_mu.view(B, self.A)
-        nlp_old, val_old, ret = self.b_nlp.view(B), self.b_val.view(B), self.b_ret.view(B)
+        T, n, L = self.T, self.n, self.seq_len
+        obs, act, mu_old = self.b_obs, self.b_act, self.b_mu                  # [T, n, .]
+        nlp_old, val_old, ret = self.b_nlp, self.b_val, self.b_ret            # [T, n]
         adv = ret - val_old
         with torch.no_grad():
             if self.normalize_input:
-                self.obs_rms.update(obs)
+                self.obs_rms.update(obs.reshape(T * n, self.O))
                 obs = self.obs_rms(obs)
             if self.normalize_value:
-                self.val_rms.update(torch.cat([val_old, ret]))
+                self.val_rms.update(torch.cat([val_old.reshape(-1), ret.reshape(-1)]))
                 val_old, ret = self.val_rms(val_old), self.val_rms(ret)
             if self.normalize_advantage:
                 s = torch.stack([adv.sum(), (adv * adv).sum()]).double()
-                cnt = float(B * self.world)
+                cnt = float(T * n * self.world)
                 if self.world > 1:
                     torch.distributed.all_reduce(s)
                 mean = s[0] / cnt
                 std = torch.sqrt(torch.clamp((s[1] - cnt * mean * mean) / (cnt - 1.0), min=0.0))
                 adv = (adv - mean.float()) / (std.float() + 1e-8)
-            sigma_old = torch.exp(self.model.sigma.detach()).expand(B, -1).clone()
+            sigma_old = torch.exp(self.model.sigma.detach()).clone()
+            not_done = 1.0 - self.b_done
         params = [p for p in self.model.parameters()]
+        E = self.mb_envs
+
+        def mb(x, e0):
+            """[T, n, ...] -> minibatch rows ordered (chunk, step-in-chunk, env): [L, (T/L)*E, ...] flattened."""
+            y = x[:, e0:e0 + E]
+            y = y.reshape(T // L, L, E, *x.shape[2:]).transpose(0, 1)
+            return y.reshape(L, (T // L) * E, *x.shape[2:])
+
         for _ in range(self.mini_epochs):
-            for i in range(0, B, self.minibatch):
-                sl = slice(i, i + self.minibatch)
+            for e0 in range(0, n, E):
+                o_mb = mb(obs, e0)                                             # [L, S, O]
+                flat = lambda x: mb(x, e0).reshape(L * (T // L) * E, *x.shape[2:])  # noqa: E731
+                states = nd = None
+                if self.has_rnn:
+                    H = self.model.rnn_units
+                    states = (self.b_h[:, e0:e0 + E].reshape(-1, H), self.b_c[:, e0:e0 + E].reshape(-1, H))
+                    nd = mb(not_done, e0)
                 with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.bf16):
-                    mu, logstd, value = self.model(obs[sl])
+                    mu, logstd, value, _ = self.model(o_mb, states, nd)
                 mu, logstd, value = mu.float(), logstd.float(), value.float().squeeze(-1)
                 sigma = torch.exp(logstd)
-                nlp = neglogp(act[sl], mu, sigma, logstd)
-                ratio = torch.exp(nlp_old[sl] - nlp)
-                a = adv[sl]
+                nlp = neglogp(flat(act), mu, sigma, logstd)
+                ratio = torch.exp(flat(nlp_old) - nlp)
+                a, vo, r = flat(adv), flat(val_old), flat(ret)
                 a_loss = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - self.e_clip, 1.0 + self.e_clip)).mean()
-                v_clip = val_old[sl] + (value - val_old[sl]).clamp(-self.e_clip, self.e_clip)
-                c_loss = torch.max((value - ret[sl]) ** 2, (v_clip - ret[sl]) ** 2).mean()
+                v_clip = vo + (value - vo).clamp(-self.e_clip, self.e_clip)
+                c_loss = torch.max((value - r) ** 2, (v_clip - r) ** 2).mean()
                 b_loss = (torch.clamp_min(mu - 1.1, 0.0) ** 2 + torch.clamp_max(mu + 1.1, 0.0) ** 2).sum(-1).mean()
                 entropy = (0.5 + 0.5 * math.log(2 * math.pi) + logstd).sum(-1).mean()
                 loss = a_loss + 0.5 * c_loss * self.critic_coef - self.entropy_coef * entropy + b_loss * self.bounds_coef
                 self.opt.zero_grad(set_to_none=False)
                 loss.backward()
                 with torch.no_grad():
-                    kl = policy_kl(mu.detach(), sigma.detach(), mu_old[sl], sigma_old[sl])
+                    kl = policy_kl(mu.detach(), sigma.detach(), flat(mu_old), sigma_old.expand_as(mu))
                     if self.world > 1:  # ONE collective per minibatch: gradients + KL
-                        flat = torch.cat([p.grad.reshape(-1) for p in params])
-                        flat, extra = vd.allreduce_mean_(flat, kl.reshape(1))
+                        g = torch.cat([p.grad.reshape(-1) for p in params])
+                        g, extra = vd.allreduce_mean_(g, kl.reshape(1))
                         kl = extra[0]
                         o = 0
                         for p in params:
-                            p.grad.copy_(flat[o:o + p.numel()].view_as(p))
+                            p.grad.copy_(g[o:o + p.numel()].view_as(p))
                             o += p.numel()
                     if self.truncate_grads:
                         nn.utils.clip_grad_norm_(params, self.grad_norm)
@@ -354,18 +438,34 @@ class PPOAgent:
                     log(" ".join(f"{k}={v:.4g}" if isinstance(v, float) else f"{k}={v}" for k, v in st.items()))
         return hist
 
-    # checkpoint layout follows what the reference's deployment loader reads
-    # (isaacgymenvs/vine_robot_test_model.py:135-139: keys 'model' and 'running_mean_std')
+    # ------------------------------------------------------------------ checkpoints
+    # Layout of rl-games 1.5.2 ``A2CBase.get_full_state_weights`` -- what the reference's train.py saves under
+    # runs/<name>/nn/*.pth and what isaacgymenvs/vine_robot_test_model.py:135-139 reads back: ``model`` holds the
+    # network under ``a2c_network.*`` plus the input/value normalisers as ``running_mean_std.*`` / ``value_mean_std.*``.
+    def rlgames_model_state(self):
+        sd = {"a2c_network." + k: v.detach().clone() for k, v in self.model.state_dict().items()}
+        for name, rms in (("running_mean_std", self.obs_rms), ("value_mean_std", self.val_rms)):
+            for k, v in rms.state_dict().items():
+                sd[f"{name}.{k}"] = v.detach().clone()
+        return sd
+
     def state_dict(self):
-        return {"model": self.model.state_dict(), "running_mean_std": self.obs_rms.state_dict(),
-                "reward_mean_std": self.val_rms.state_dict(), "optimizer": self.opt.state_dict(),
-                "epoch": self.epoch, "frame": self.frames, "last_lr": self.lr}
+        return {"model": self.rlgames_model_state(), "optimizer": self.opt.state_dict(), "epoch": self.epoch,
+                "frame": self.frames, "last_lr": self.lr, "last_mean_rewards": 0.0, "env_state": None}
 
     def load_state_dict(self, sd):
-        self.model.load_state_dict(sd["model"])
-        self.obs_rms.load_state_dict(sd["running_mean_std"])
-        self.val_rms.load_state_dict(sd["reward_mean_std"])
-        if "optimizer" in sd:
+        model = sd["model"]
+        net = {k[len("a2c_network."):]: v for k, v in model.items() if k.startswith("a2c_network.")}
+        self.model.load_state_dict(net)
+        for name, rms in (("running_mean_std", self.obs_rms), ("value_mean_std", self.val_rms)):
+            sub = {k[len(name) + 1:]: v for k, v in model.items() if k.startswith(name + ".")}
+            if not sub and name in sd:          # older layout: normalisers stored beside 'model'
+                sub = sd[name]
+            if sub:
+                rms.load_state_dict({k: v.to(rms.running_mean.dtype) for k, v in sub.items()})
+        if sd.get("optimizer"):
             self.opt.load_state_dict(sd["optimizer"])
         self.epoch, self.frames = sd.get("epoch", 0), sd.get("frame", 0)
         self.lr_t.fill_(float(sd.get("last_lr", self.lr)))
+        if self.fused:
+            self._refresh_fused()
