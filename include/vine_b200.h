@@ -363,6 +363,58 @@ int vine_mlp_forward(const void* packed, const float* obs, const float* obs_mean
                      int64_t n, int num_obs, const float* value_stats, float* mu, float* value,
                      void* stream);
 
+/*
+ * PPO minibatch update of the same network as ONE fused tcgen05/TMEM kernel: forward, the PPO losses of
+ * Vine5LinkMovingBasePPO.yaml:46-81 (e_clip actor loss, clipped value loss x critic_coef / 2, bounds loss,
+ * entropy), backward and weight gradients (rl_games A2CAgent.calc_gradients + autograd; in-repo analogue
+ * learning/common_agent.py:319-435, 482-517), then the gradient reduction and torch.optim.Adam.
+ *
+ * Parameters live in ONE flat f32 vector in torch layouts, in this order:
+ *   W1[256,O] b1[256] W2[128,256] b2[128] W3[64,128] b3[64] Wmu[2,64] bmu[2] Wv[1,64] bv[1] logstd[2]
+ * (vine_ppo_num_params(O) floats); `packed` is their tensor-core copy (vine_mlp_pack format), which
+ * vine_ppo_adam rewrites in place, so vine_mlp_forward always sees the current policy.
+ *
+ * A minibatch is rl_games' env-major slice: envs [env_begin, env_begin+env_count) x all `horizon` steps of the
+ * [T, N] rollout buffers.  values_old / returns are value-normalised, advantages are batch-normalised (both
+ * done by the caller once per iteration), obs is raw and normalised inside like vine_mlp_forward.
+ *
+ * state (device, >= 16 floats): [0] learning rate, [1] Adam step count, [2] KL of the last minibatch,
+ * [3] "KL pending" flag, [4..7] running sums of a_loss, c_loss, kl, b_loss, [8] minibatches summed.
+ * With adaptive_lr the `legacy` schedule of rl_games (lr /= 1.5 if kl > 2 kl_threshold, lr *= 1.5 if
+ * kl < kl_threshold / 2, clamped to [lr_min, lr_max]) is applied on the device between optimiser steps:
+ * no host synchronisation anywhere, the whole update is CUDA-graph capturable.
+ */
+#define VINE_PPO_WS_FLOATS 49664   /* floats per CTA gradient partial */
+typedef struct VinePpoMinibatch {
+  const void* packed;            /* VINE_MLP_PACKED_BYTES */
+  const float* obs;              /* [T, N, O] raw observations */
+  const float* actions;          /* [T, N, 2] */
+  const float* mu_old;           /* [T, N, 2] */
+  const float* neglogp_old;      /* [T, N] */
+  const float* values_old;       /* [T, N] normalised */
+  const float* returns;          /* [T, N] normalised */
+  const float* advantages;       /* [T, N] normalised */
+  const float* obs_mean;         /* [O] */
+  const float* obs_inv_std;      /* [O] */
+  const float* logstd;           /* [2] current (points into the flat parameter vector) */
+  const float* logstd_old;       /* [2] at rollout time */
+  float* workspace;              /* [workspace_ctas][VINE_PPO_WS_FLOATS] gradient partials, 16-B aligned */
+  float* state;                  /* device optimiser state, see above */
+  float* debug_out;              /* NULL or [T*env_count, 4]: mu0, mu1, normalised value, neglogp per sample */
+  int32_t horizon, num_envs, env_begin, env_count, num_obs, workspace_ctas, adaptive_lr, reserved;
+  float e_clip, critic_coef, entropy_coef, bounds_loss_coef, kl_threshold, lr_min, lr_max, reserved_f;
+} VinePpoMinibatch;
+
+int vine_ppo_num_params(int num_obs);
+int vine_ppo_max_ctas(void);     /* upper bound of gradient partials one vine_ppo_minibatch call writes */
+/* returns the number of partials written (> 0) or a negative error */
+int vine_ppo_minibatch(const VinePpoMinibatch* batch, void* stream);
+/* flat[p] = sum of the partials in parameter order, flat[P..P+3] = a_loss, c_loss, kl, b_loss (means) */
+int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* flat, void* stream);
+/* Adam step with g = flat * grad_scale (1/world after an all-reduce); updates params, moments, packed, state */
+int vine_ppo_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq,
+                  void* packed, float* state, int num_obs, float beta1, float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,8 +135,21 @@ EXPORTED_SYMBOLS = [
     "vine_get_state", "vine_set_state", "vine_set_debug_outputs", "vine_post_physics",
     "vine_pre_physics", "vine_actuation", "vine_simulate", "vine_philox_debug", "vine_gae",
     "vine_mlp_pack", "vine_mlp_forward",
+    "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
 ]
 MLP_PACKED_BYTES = 102208
+PPO_WS_FLOATS = 49664
+PPO_STATE_FLOATS = 16
+
+
+class VinePpoMinibatch(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in (
+        "packed", "obs", "actions", "mu_old", "neglogp_old", "values_old", "returns", "advantages", "obs_mean",
+        "obs_inv_std", "logstd", "logstd_old", "workspace", "state", "debug_out")]
+        + [(n, C.c_int32) for n in ("horizon", "num_envs", "env_begin", "env_count", "num_obs", "workspace_ctas",
+                                    "adaptive_lr", "reserved")]
+        + [(n, C.c_float) for n in ("e_clip", "critic_coef", "entropy_coef", "bounds_loss_coef", "kl_threshold",
+                                    "lr_min", "lr_max", "reserved_f")])
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libvine_b200.so")
@@ -171,6 +184,11 @@ def _declare(lib):
                              vp, vp, vp]
     lib.vine_mlp_pack.argtypes = [vp] * 10 + [C.c_int, vp, vp]
     lib.vine_mlp_forward.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp]
+    lib.vine_ppo_num_params.argtypes = [C.c_int]
+    lib.vine_ppo_max_ctas.argtypes = []
+    lib.vine_ppo_minibatch.argtypes = [C.POINTER(VinePpoMinibatch), vp]
+    lib.vine_ppo_reduce.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    lib.vine_ppo_adam.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("vine_destroy", "vine_last_error"):

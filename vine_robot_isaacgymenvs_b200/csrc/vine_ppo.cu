@@ -1,0 +1,543 @@
+// vine_ppo.cu — the PPO minibatch update of the actor-critic MLP as ONE fused tcgen05/TMEM kernel (sm_100a),
+// plus the gradient reduction and the Adam step that re-packs the weights for the tensor cores.
+//
+// What it replaces (rl-games 1.5.2 A2CAgent.calc_gradients + torch autograd + torch.optim.Adam for the network of
+// cfg/train/Vine5LinkMovingBasePPO.yaml:10-30; in-repo analogue isaacgymenvs/learning/common_agent.py:319-435,482-517):
+//   forward  x -> ELU(W1 x+b1) -> ELU(W2 .+b2) -> ELU(W3 .+b3) -> (mu, v)
+//   loss     clipped-ratio actor loss + clipped value loss * critic_coef/2 + bound loss - entropy (YP:61-81)
+//   backward d(loss)/d(every parameter)
+// One CTA owns a tile of 128 samples.  Weights (bf16, UMMA layout, 100 KB) and ALL activations of the tile
+// (x, h1, h2, h3: 120 KB) stay resident in shared memory; every GEMM of the tile is a tcgen05.mma sequence:
+//   forward      h_l   = h_{l-1} W_l^T        A = activations (K-major),  B = W_l (K-major)
+//   backward     dh_l-1 = dz_l W_l            A = dz_l (K-major),         B = W_l (MN-major: same bytes, no W^T copy)
+//   weight grad  dW_l += dz_l^T h_{l-1}       A = dz_l (MN-major),        B = h_{l-1} (MN-major): reduction over the
+//                                             128 samples of the tile, accumulated in TMEM across the CTA's tiles
+// dz_l overwrites h_l in place (ELU' is a function of the output), so nothing is ever written to HBM except the
+// per-CTA gradient partials at the end.  TMEM: 128 columns of working accumulator + 384 columns of persistent
+// weight-gradient accumulators (dW2 256, dW1 2x32, dW3^T 64) = all 512.  HBM traffic per sample: 72 B of observations
+// + 32 B of rollout scalars in, nothing out.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vine_b200.h"
+#include "vine_umma.cuh"
+
+namespace {
+using namespace vine_umma;
+
+constexpr int H1 = 256, H2 = 128, H3 = 64, NH = 16, K1 = 32;
+constexpr int TILE = 128, THREADS = 256;
+// packed parameter block: identical to vine_mlp.cu (vine_mlp_pack / vine_mlp_forward share it)
+constexpr int OFF_W1 = 0;
+constexpr int OFF_W2 = OFF_W1 + H1 * K1 * 2;
+constexpr int OFF_W3 = OFF_W2 + H2 * H1 * 2;
+constexpr int OFF_W4 = OFF_W3 + H3 * H2 * 2;
+constexpr int OFF_B = OFF_W4 + NH * H3 * 2;  // f32: b1[256] b2[128] b3[64] bh[16]
+constexpr int PACKED_BYTES = OFF_B + (H1 + H2 + H3 + NH) * 4;
+static_assert(PACKED_BYTES == VINE_MLP_PACKED_BYTES, "header constant out of date");
+// shared-memory map
+constexpr int OFF_X = 102400;                      // x   [128 x 32]  bf16 (column 31 == 1: carries db1 through dW1)
+constexpr int OFF_A1 = OFF_X + TILE * K1 * 2;      // h1 / dz1 [128 x 256]
+constexpr int OFF_A2 = OFF_A1 + TILE * H1 * 2;     // h2 / dz2 [128 x 128]
+constexpr int OFF_A3 = OFF_A2 + TILE * H2 * 2;     // h3 / dz3 [128 x 64]
+constexpr int OFF_DZH = OFF_A3 + TILE * H3 * 2;    // d(mu0,mu1,v) [128 x 16] bf16
+constexpr int OFF_DZHF = OFF_DZH + TILE * NH * 2;  // the same in f32 [128][4] for the CUDA-core head gradient
+constexpr int OFF_RED = OFF_DZHF + TILE * 4 * 4;   // block-reduction scratch
+constexpr int OFF_BAR = OFF_RED + 256;
+constexpr int SMEM_BYTES = OFF_BAR + 64;
+static_assert(PACKED_BYTES <= OFF_X && SMEM_BYTES <= 232448, "shared-memory budget");
+// TMEM columns
+constexpr uint32_t TM_DATA = 0, TM_DW2 = 128, TM_DW1 = 384, TM_DW3T = 448;
+// per-CTA gradient partial (floats)
+constexpr int WS_W2 = 0;                  // [128 out][256 in]
+constexpr int WS_W1 = WS_W2 + H2 * H1;    // [256 out][32 in], column 31 = db1
+constexpr int WS_W3T = WS_W1 + H1 * K1;   // [128 in][64 out]
+constexpr int WS_WH = WS_W3T + H2 * H3;   // [3][64]: mu0, mu1, v
+constexpr int WS_BH = WS_WH + 3 * H3;     // [3] (+1 pad)
+constexpr int WS_B2 = WS_BH + 4;
+constexpr int WS_B3 = WS_B2 + H2;
+constexpr int WS_STATS = WS_B3 + H3;      // a_loss, c_loss, kl, b_loss, dlogstd0, dlogstd1, -, -
+constexpr int WS_FLOATS = 49664;
+static_assert(WS_STATS + 8 <= WS_FLOATS && WS_FLOATS == VINE_PPO_WS_FLOATS, "workspace layout");
+// device-resident optimiser state (floats): see include/vine_b200.h
+constexpr int ST_LR = 0, ST_STEP = 1, ST_KL = 2, ST_PENDING = 3, ST_SUMS = 4 /* a,c,kl,b */, ST_COUNT = 8;
+
+struct MbArgs {
+  const uint8_t* packed;
+  const float *obs, *act, *mu_old, *nlp_old, *val_old, *ret, *adv, *obs_mean, *obs_inv_std, *logstd, *logstd_old;
+  float *ws, *state, *debug;
+  int T, N, e0, E, O;
+  float e_clip, critic_coef, entropy_coef, bounds_coef, inv_B, kl_threshold, lr_min, lr_max;
+  int adaptive;
+};
+
+__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+
+// accumulator columns [taddr, taddr+ncols) -> bias + ELU -> bf16 -> tile columns [c_out, c_out+ncols) of row `row`
+template <int KL>
+__device__ __forceinline__ void fwd_epilogue(uint32_t taddr, int ncols, int c_out, const float* bias, uint8_t* tile, int row) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c0, r);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c_out + c0 + g * 8 + 2 * i;
+        w[i] = pack_bf16(elu(__uint_as_float(r[g * 8 + 2 * i]) + bias[c]), elu(__uint_as_float(r[g * 8 + 2 * i + 1]) + bias[c + 1]));
+      }
+      *reinterpret_cast<uint4*>(tile + tile_offset(row, c_out + c0 + g * 8, KL)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// dz = dh * ELU'(h) with ELU'(h) = h > 0 ? 1 : h + 1, written over h in place
+template <int KL>
+__device__ __forceinline__ void bwd_epilogue(uint32_t taddr, int ncols, int c_out, uint8_t* tile, int row) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c0, r);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4* p = reinterpret_cast<uint4*>(tile + tile_offset(row, c_out + c0 + g * 8, KL));
+      const uint4 hv = *p;
+      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 h = unpack_bf16(hw[i]);
+        const float d0 = __uint_as_float(r[g * 8 + 2 * i]) * (h.x > 0.f ? 1.f : h.x + 1.f);
+        const float d1 = __uint_as_float(r[g * 8 + 2 * i + 1]) * (h.y > 0.f ? 1.f : h.y + 1.f);
+        w[i] = pack_bf16(d0, d1);
+      }
+      *p = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+__device__ __forceinline__ float bf16_at(const uint8_t* tile, int row, int col, int KL) {
+  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + tile_offset(row, col, KL)));
+}
+
+__global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const MbArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const uint32_t bar_w = smem_u32(smem + OFF_BAR), bar_mma = bar_w + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
+  const float* biases = reinterpret_cast<const float*>(smem + OFF_B);
+  float* dzhf = reinterpret_cast<float*>(smem + OFF_DZHF);
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar_w, PACKED_BYTES);
+    bulk_g2s(smem_u32(smem), a.packed, PACKED_BYTES, bar_w);   // ONE bulk TMA copy: all weights and biases
+    if (blockIdx.x == 0) {
+      // the adaptive-KL learning-rate schedule (rl_games `legacy`) acts between optimiser steps: apply the KL of the
+      // previous minibatch now, then count this step.  The Adam kernel that follows in the stream reads both.
+      if (a.state[ST_PENDING] != 0.f) {
+        if (a.adaptive) {
+          const float kl = a.state[ST_KL];
+          float lr = a.state[ST_LR];
+          if (kl > 2.f * a.kl_threshold) lr = fmaxf(lr / 1.5f, a.lr_min);
+          if (kl < 0.5f * a.kl_threshold) lr = fminf(lr * 1.5f, a.lr_max);
+          a.state[ST_LR] = lr;
+        }
+        a.state[ST_PENDING] = 0.f;
+      }
+      a.state[ST_STEP] += 1.f;
+    }
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 TMEM lanes
+  mbar_wait(bar_w, 0);
+
+  uint8_t *x_t = smem + OFF_X, *a1_t = smem + OFF_A1, *a2_t = smem + OFF_A2, *a3_t = smem + OFF_A3, *dzh_t = smem + OFF_DZH;
+  const uint32_t sW1 = smem_u32(smem + OFF_W1), sW2 = smem_u32(smem + OFF_W2), sW3 = smem_u32(smem + OFF_W3),
+                 sW4 = smem_u32(smem + OFF_W4);
+  const uint32_t sX = smem_u32(x_t), sA1 = smem_u32(a1_t), sA2 = smem_u32(a2_t), sA3 = smem_u32(a3_t), sDZH = smem_u32(dzh_t);
+  uint32_t phase = 0;
+
+  // One step of the tile's dependency chain: make this thread's smem writes visible to the tensor core, join the
+  // CTA, let ONE thread issue the MMAs, optionally do CUDA-core work while they run, then wait for their completion.
+  auto mma_step = [&](auto&& issue, auto&& overlap) {
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue();
+      mma_commit(bar_mma);
+    }
+    overlap();
+    mbar_wait(bar_mma, phase);
+    phase ^= 1;
+    fence_after_sync();
+  };
+  auto nothing = [] {};
+
+  // persistent per-thread accumulators
+  float db = 0.f;                 // tid < 128: db2[tid];  128 <= tid < 192: db3[tid-128]
+  float gh = 0.f;                 // tid < 192: dWh[tid/64][tid%64];  192 <= tid < 195: dbh[tid-192]
+  float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // a_loss, c_loss, kl, b_loss, dlogstd0, dlogstd1 (half 0 threads)
+
+  const int64_t B = (int64_t)a.T * a.E;
+  const int64_t ntiles = (B + TILE - 1) / TILE;
+  const float ls0 = a.logstd[0], ls1 = a.logstd[1], lso0 = a.logstd_old[0], lso1 = a.logstd_old[1];
+  const float sig0 = __expf(ls0), sig1 = __expf(ls1), sigo0 = __expf(lso0), sigo1 = __expf(lso1);
+  bool first = true;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
+    const int64_t s = tile * TILE + row;
+    const bool valid = s < B;
+    const int64_t grow = valid ? (s / a.E) * (int64_t)a.N + a.e0 + (s % a.E) : 0;   // row in the [T, N] rollout buffers
+    // rollout scalars of this sample (half 0 threads own the loss of their row)
+    float act0 = 0.f, act1 = 0.f, muo0 = 0.f, muo1 = 0.f, nlpo = 0.f, vo = 0.f, ret = 0.f, adv = 0.f;
+    if (half == 0 && valid) {
+      const float2 av = *reinterpret_cast<const float2*>(a.act + 2 * grow);
+      const float2 mv = *reinterpret_cast<const float2*>(a.mu_old + 2 * grow);
+      act0 = av.x, act1 = av.y, muo0 = mv.x, muo1 = mv.y;
+      nlpo = a.nlp_old[grow], vo = a.val_old[grow], ret = a.ret[grow], adv = a.adv[grow];
+    }
+    // ---- x tile: normalised observation, bf16, zero padded to K1; column 31 is the constant 1 (bias gradient) ----
+    {
+      const int k0 = half * 16;
+      float x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = k0 + i;
+        float v = 0.f;
+        if (valid && k < a.O) v = fminf(fmaxf((a.obs[grow * a.O + k] - a.obs_mean[k]) * a.obs_inv_std[k], -5.f), 5.f);
+        if (valid && k == K1 - 1) v = 1.f;
+        x[i] = v;
+      }
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        *reinterpret_cast<uint4*>(x_t + tile_offset(row, k0 + g * 8, K1)) =
+            make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]),
+                       pack_bf16(x[g * 8 + 4], x[g * 8 + 5]), pack_bf16(x[g * 8 + 6], x[g * 8 + 7]));
+    }
+    // =============================== forward ===============================
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {   // layer 1 in two halves of 128 output features (working accumulator = 128 columns)
+      mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sX, K1), k_major(sW1, K1, h * 128), instr_desc(128, false, false), K1 / 16, false); },
+               nothing);
+      fwd_epilogue<H1>(lane_base + TM_DATA + half * 64, 64, h * 128 + half * 64, biases, a1_t, row);
+    }
+    mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA1, H1), k_major(sW2, H1), instr_desc(H2, false, false), H1 / 16, false); }, nothing);
+    fwd_epilogue<H2>(lane_base + TM_DATA + half * 64, 64, half * 64, biases + H1, a2_t, row);
+    mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA2, H2), k_major(sW3, H2), instr_desc(H3, false, false), H2 / 16, false); }, nothing);
+    fwd_epilogue<H3>(lane_base + TM_DATA + half * 32, 32, half * 32, biases + H1 + H2, a3_t, row);
+    mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA3, H3), k_major(sW4, H3), instr_desc(NH, false, false), H3 / 16, false); }, nothing);
+    // =============================== loss ===============================
+    if (half == 0) {
+      uint32_t r[16];
+      tmem_ld16(lane_base + TM_DATA, r);
+      const float* bh = biases + H1 + H2 + H3;
+      const float mu0 = __uint_as_float(r[0]) + bh[0], mu1 = __uint_as_float(r[1]) + bh[1], v = __uint_as_float(r[2]) + bh[2];
+      float dmu0 = 0.f, dmu1 = 0.f, dv = 0.f;
+      if (valid) {
+        const float d0 = (act0 - mu0) / sig0, d1 = (act1 - mu1) / sig1;
+        const float nlp = 0.5f * (d0 * d0 + d1 * d1) + 1.8378770664093453f + ls0 + ls1;
+        const float ratio = __expf(nlpo - nlp);
+        const float lo = 1.f - a.e_clip, hi = 1.f + a.e_clip;
+        const float t1 = -adv * ratio, t2 = -adv * fminf(fmaxf(ratio, lo), hi);
+        const bool inside = ratio >= lo && ratio <= hi;
+        const float g_nlp = ((inside || t1 > t2) ? -adv : 0.f) * (-ratio);
+        dmu0 = g_nlp * (-d0 / sig0);
+        dmu1 = g_nlp * (-d1 / sig1);
+        float dls0 = g_nlp * (1.f - d0 * d0) - a.entropy_coef, dls1 = g_nlp * (1.f - d1 * d1) - a.entropy_coef;
+        // clipped value loss (clip_value: True), both on normalised values
+        const float dvo = v - vo, vclip = vo + fminf(fmaxf(dvo, -a.e_clip), a.e_clip);
+        const float e1 = v - ret, e2 = vclip - ret, c1 = e1 * e1, c2 = e2 * e2;
+        const float pass2 = (fabsf(dvo) <= a.e_clip) ? 1.f : 0.f;
+        const float dvc = c1 > c2 ? 2.f * e1 : (c2 > c1 ? 2.f * e2 * pass2 : e1 + e2 * pass2);
+        dv = 0.5f * a.critic_coef * dvc;
+        // bound loss on mu (soft bound 1.1)
+        const float bh0 = fmaxf(mu0 - 1.1f, 0.f), bl0 = fminf(mu0 + 1.1f, 0.f), bh1 = fmaxf(mu1 - 1.1f, 0.f), bl1 = fminf(mu1 + 1.1f, 0.f);
+        dmu0 += a.bounds_coef * 2.f * (bh0 + bl0);
+        dmu1 += a.bounds_coef * 2.f * (bh1 + bl1);
+        // KL(old || new) of the diagonal Gaussians, rl_games policy_kl
+        const float m0 = mu0 - muo0, m1 = mu1 - muo1;
+        const float kl = __logf(sig0 / sigo0 + 1e-5f) + (sigo0 * sigo0 + m0 * m0) / (2.f * (sig0 * sig0 + 1e-5f)) - 0.5f +
+                         __logf(sig1 / sigo1 + 1e-5f) + (sigo1 * sigo1 + m1 * m1) / (2.f * (sig1 * sig1 + 1e-5f)) - 0.5f;
+        st[0] += fmaxf(t1, t2) * a.inv_B;
+        st[1] += fmaxf(c1, c2) * a.inv_B;
+        st[2] += kl * a.inv_B;
+        st[3] += (bh0 * bh0 + bl0 * bl0 + bh1 * bh1 + bl1 * bl1) * a.inv_B;
+        st[4] += dls0 * a.inv_B;
+        st[5] += dls1 * a.inv_B;
+        dmu0 *= a.inv_B, dmu1 *= a.inv_B, dv *= a.inv_B;
+        if (a.debug) {
+          float* d = a.debug + 4 * s;
+          d[0] = mu0, d[1] = mu1, d[2] = v, d[3] = nlp;
+        }
+      }
+      *reinterpret_cast<uint4*>(dzh_t + tile_offset(row, 0, NH)) = make_uint4(pack_bf16(dmu0, dmu1), pack_bf16(dv, 0.f), 0u, 0u);
+      *reinterpret_cast<uint4*>(dzh_t + tile_offset(row, 8, NH)) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<float4*>(dzhf + 4 * row) = make_float4(dmu0, dmu1, dv, 0.f);
+    }
+    // =============================== backward ===============================
+    // heads: dh3 = dzh Wh (reduction over the 16 padded head rows); meanwhile dWh, dbh on CUDA cores (3 x 64 outputs)
+    mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sDZH, NH), mn_major(sW4, H3), instr_desc(H3, false, true), NH / 16, false); },
+             [&] {
+               if (tid < 3 * H3) {
+                 const int r_ = tid >> 6;
+                 const int c_ = tid & 63;
+                 float acc = 0.f;
+#pragma unroll 4
+                 for (int s_ = 0; s_ < TILE; ++s_) acc = fmaf(dzhf[4 * s_ + r_], bf16_at(a3_t, s_, c_, H3), acc);
+                 gh += acc;
+               } else if (tid < 3 * H3 + 3) {
+                 float acc = 0.f;
+                 for (int s_ = 0; s_ < TILE; ++s_) acc += dzhf[4 * s_ + (tid - 3 * H3)];
+                 gh += acc;
+               }
+               __syncthreads();   // h3 is overwritten in place next
+             });
+    bwd_epilogue<H3>(lane_base + TM_DATA + half * 32, 32, half * 32, a3_t, row);   // dz3 over h3
+    // layer 3: dW3^T += h2^T dz3 (persistent), dh2 = dz3 W3; meanwhile db3 = column sums of dz3
+    mma_step(
+        [&] {
+          mma_sequence(tmem + TM_DW3T, mn_major(sA2, H2), mn_major(sA3, H3), instr_desc(H3, true, true), TILE / 16, !first);
+          mma_sequence(tmem + TM_DATA, k_major(sA3, H3), mn_major(sW3, H2), instr_desc(H2, false, true), H3 / 16, false);
+        },
+        [&] {
+          if (tid >= 128 && tid < 128 + H3) {
+            float acc = 0.f;
+#pragma unroll 4
+            for (int s_ = 0; s_ < TILE; ++s_) acc += bf16_at(a3_t, s_, tid - 128, H3);
+            db += acc;
+          }
+        });
+    bwd_epilogue<H2>(lane_base + TM_DATA + half * 64, 64, half * 64, a2_t, row);   // dz2 over h2
+    // layer 2: dW2 += dz2^T h1 (persistent), dh1[:, 0:128] = dz2 W2[:, 0:128]; meanwhile db2
+    mma_step(
+        [&] {
+          mma_sequence(tmem + TM_DW2, mn_major(sA2, H2), mn_major(sA1, H1), instr_desc(H1, true, true), TILE / 16, !first);
+          mma_sequence(tmem + TM_DATA, k_major(sA2, H2), mn_major(sW2, H1, 0), instr_desc(128, false, true), H2 / 16, false);
+        },
+        [&] {
+          if (tid < H2) {
+            float acc = 0.f;
+#pragma unroll 4
+            for (int s_ = 0; s_ < TILE; ++s_) acc += bf16_at(a2_t, s_, tid, H2);
+            db += acc;
+          }
+        });
+    bwd_epilogue<H1>(lane_base + TM_DATA + half * 64, 64, half * 64, a1_t, row);           // dz1[:, 0:128] over h1
+    mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA2, H2), mn_major(sW2, H1, 128), instr_desc(128, false, true), H2 / 16, false); },
+             nothing);
+    bwd_epilogue<H1>(lane_base + TM_DATA + half * 64, 64, 128 + half * 64, a1_t, row);     // dz1[:, 128:256]
+    // layer 1: dW1 += dz1^T x (two halves of 128 output features; x column 31 == 1 gives db1)
+    mma_step(
+        [&] {
+          mma_sequence(tmem + TM_DW1, mn_major(sA1, H1, 0), mn_major(sX, K1), instr_desc(K1, true, true), TILE / 16, !first);
+          mma_sequence(tmem + TM_DW1 + K1, mn_major(sA1, H1, 128), mn_major(sX, K1), instr_desc(K1, true, true), TILE / 16, !first);
+        },
+        nothing);
+  }
+
+  // ---- per-CTA gradient partial: TMEM accumulators + register accumulators -> workspace ----
+  float* ws = a.ws + (size_t)blockIdx.x * WS_FLOATS;
+  {
+    uint32_t r[32];
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {   // dW2: lane = output feature, 256 columns, this thread's half
+      tmem_ld32(lane_base + TM_DW2 + half * 128 + c0, r);
+      float4* dst = reinterpret_cast<float4*>(ws + WS_W2 + row * H1 + half * 128 + c0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+    }
+    tmem_ld32(lane_base + TM_DW1 + half * K1, r);   // dW1: half h holds output features h*128 + lane
+    {
+      float4* dst = reinterpret_cast<float4*>(ws + WS_W1 + (half * 128 + row) * K1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+    }
+    tmem_ld32(lane_base + TM_DW3T + half * 32, r);  // dW3^T: lane = input feature, 64 columns
+    {
+      float4* dst = reinterpret_cast<float4*>(ws + WS_W3T + row * H3 + half * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+    }
+  }
+  if (tid < H2) ws[WS_B2 + tid] = db;
+  else if (tid < H2 + H3) ws[WS_B3 + tid - H2] = db;
+  if (tid < 3 * H3) ws[WS_WH + tid] = gh;
+  else if (tid < 3 * H3 + 3) ws[WS_BH + tid - 3 * H3] = gh;
+  // loss statistics + d(logstd): reduce over the 128 sample-owning threads
+  float* red = reinterpret_cast<float*>(smem + OFF_RED);
+  if (half == 0) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      float v = st[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0) red[warp * 8 + j] = v;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (tid < 6) ws[WS_STATS + tid] = red[tid] + red[8 + tid] + red[16 + tid] + red[24 + tid];
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// flat parameter vector (torch layouts): W1[256,O] b1[256] W2[128,256] b2[128] W3[64,128] b3[64] Wmu[2,64] bmu[2]
+// Wv[1,64] bv[1] logstd[2].  For parameter p: where its gradient sits in a CTA partial, and where its tensor-core
+// copy sits in the packed block (bf16 weight / f32 bias; -1 = none).
+__host__ __device__ inline int num_params(int O) { return H1 * O + H1 + H2 * H1 + H2 + H3 * H2 + H3 + 2 * H3 + 2 + H3 + 1 + 2; }
+
+__device__ inline void param_map(int p, int O, int& ws_off, int& pk_off, bool& pk_is_f32) {
+  pk_is_f32 = false;
+  int q = p;
+  if (q < H1 * O) { const int o = q / O, i = q % O; ws_off = WS_W1 + o * K1 + i; pk_off = OFF_W1 + tile_offset(o, i, K1); return; }
+  q -= H1 * O;
+  if (q < H1) { ws_off = WS_W1 + q * K1 + (K1 - 1); pk_off = OFF_B + 4 * q; pk_is_f32 = true; return; }
+  q -= H1;
+  if (q < H2 * H1) { const int o = q / H1, i = q % H1; ws_off = WS_W2 + o * H1 + i; pk_off = OFF_W2 + tile_offset(o, i, H1); return; }
+  q -= H2 * H1;
+  if (q < H2) { ws_off = WS_B2 + q; pk_off = OFF_B + 4 * (H1 + q); pk_is_f32 = true; return; }
+  q -= H2;
+  if (q < H3 * H2) { const int o = q / H2, i = q % H2; ws_off = WS_W3T + i * H3 + o; pk_off = OFF_W3 + tile_offset(o, i, H2); return; }
+  q -= H3 * H2;
+  if (q < H3) { ws_off = WS_B3 + q; pk_off = OFF_B + 4 * (H1 + H2 + q); pk_is_f32 = true; return; }
+  q -= H3;
+  if (q < 2 * H3) { ws_off = WS_WH + q; pk_off = OFF_W4 + tile_offset(q / H3, q % H3, H3); return; }
+  q -= 2 * H3;
+  if (q < 2) { ws_off = WS_BH + q; pk_off = OFF_B + 4 * (H1 + H2 + H3 + q); pk_is_f32 = true; return; }
+  q -= 2;
+  if (q < H3) { ws_off = WS_WH + 2 * H3 + q; pk_off = OFF_W4 + tile_offset(2, q, H3); return; }
+  q -= H3;
+  if (q < 1) { ws_off = WS_BH + 2; pk_off = OFF_B + 4 * (H1 + H2 + H3 + 2); pk_is_f32 = true; return; }
+  q -= 1;
+  ws_off = WS_STATS + 4 + q;
+  pk_off = -1;
+}
+
+// flat[p] = sum over CTA partials; flat[P + j] = loss statistics j (a_loss, c_loss, kl, b_loss)
+__global__ void vine_ppo_reduce_kernel(const float* __restrict__ ws, int n_partials, int O, float* __restrict__ flat) {
+  const int P = num_params(O);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P + 4) return;
+  int ws_off, pk_off;
+  bool f32;
+  if (p < P) param_map(p, O, ws_off, pk_off, f32);
+  else ws_off = WS_STATS + (p - P);
+  float acc = 0.f;
+  for (int k = 0; k < n_partials; ++k) acc += ws[(size_t)k * WS_FLOATS + ws_off];
+  flat[p] = acc;
+}
+
+// torch.optim.Adam (no weight decay, no amsgrad) on the flat parameter vector + re-pack for the tensor cores
+__global__ void vine_ppo_adam_kernel(const float* __restrict__ flat, float scale, float* __restrict__ params, float* __restrict__ m,
+                                     float* __restrict__ v, uint8_t* __restrict__ packed, float* __restrict__ state, int O,
+                                     float beta1, float beta2, float eps) {
+  const int P = num_params(O);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) {
+    if (p == P) {   // bookkeeping by exactly one thread
+      for (int j = 0; j < 4; ++j) state[ST_SUMS + j] += flat[P + j] * scale;
+      state[ST_COUNT] += 1.f;
+      state[ST_KL] = flat[P + 2] * scale;
+      state[ST_PENDING] = 1.f;
+    }
+    return;
+  }
+  const float lr = state[ST_LR], step = state[ST_STEP];
+  const float g = flat[p] * scale;
+  const float mn = beta1 * m[p] + (1.f - beta1) * g;
+  const float vn = beta2 * v[p] + (1.f - beta2) * g * g;
+  m[p] = mn;
+  v[p] = vn;
+  const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
+  const float w = params[p] - (lr / bc1) * mn / (sqrtf(vn) / sqrtf(bc2) + eps);
+  params[p] = w;
+  int ws_off, pk_off;
+  bool f32;
+  param_map(p, O, ws_off, pk_off, f32);
+  if (pk_off >= 0) {
+    if (f32) *reinterpret_cast<float*>(packed + pk_off) = w;
+    else *reinterpret_cast<__nv_bfloat16*>(packed + pk_off) = __float2bfloat16_rn(w);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int vine_ppo_num_params(int num_obs) { return (num_obs < 1 || num_obs >= K1) ? VINE_ERR_INVALID_ARG : num_params(num_obs); }
+
+int vine_ppo_max_ctas(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return VINE_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return VINE_ERR_CUDA;
+  return sms;
+}
+
+int vine_ppo_minibatch(const VinePpoMinibatch* b, void* stream) {
+  if (!b || !b->packed || !b->obs || !b->actions || !b->mu_old || !b->neglogp_old || !b->values_old || !b->returns ||
+      !b->advantages || !b->obs_mean || !b->obs_inv_std || !b->logstd || !b->logstd_old || !b->workspace || !b->state)
+    return VINE_ERR_INVALID_ARG;
+  if (b->horizon < 1 || b->num_envs < 1 || b->env_count < 1 || b->env_begin < 0 || b->env_begin + b->env_count > b->num_envs ||
+      b->num_obs < 1 || b->num_obs >= K1 || (((uintptr_t)b->packed) & 15u) || (((uintptr_t)b->workspace) & 15u))
+    return VINE_ERR_INVALID_ARG;
+  static int configured = -1;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return VINE_ERR_CUDA;
+  if (configured != dev) {
+    if (cudaFuncSetAttribute(vine_ppo_minibatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+      return VINE_ERR_CUDA;
+    configured = dev;
+  }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t B = (int64_t)b->horizon * b->env_count;
+  const int64_t ntiles = (B + TILE - 1) / TILE;
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  if (b->workspace_ctas < grid) return VINE_ERR_INVALID_ARG;
+  MbArgs a;
+  a.packed = (const uint8_t*)b->packed;
+  a.obs = b->obs, a.act = b->actions, a.mu_old = b->mu_old, a.nlp_old = b->neglogp_old, a.val_old = b->values_old;
+  a.ret = b->returns, a.adv = b->advantages, a.obs_mean = b->obs_mean, a.obs_inv_std = b->obs_inv_std;
+  a.logstd = b->logstd, a.logstd_old = b->logstd_old, a.ws = b->workspace, a.state = b->state, a.debug = b->debug_out;
+  a.T = b->horizon, a.N = b->num_envs, a.e0 = b->env_begin, a.E = b->env_count, a.O = b->num_obs;
+  a.e_clip = b->e_clip, a.critic_coef = b->critic_coef, a.entropy_coef = b->entropy_coef, a.bounds_coef = b->bounds_loss_coef;
+  a.inv_B = 1.0f / (float)B, a.kl_threshold = b->kl_threshold, a.lr_min = b->lr_min, a.lr_max = b->lr_max, a.adaptive = b->adaptive_lr;
+  vine_ppo_minibatch_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  if (cudaGetLastError() != cudaSuccess) return VINE_ERR_CUDA;
+  return grid;   // number of gradient partials written (>= 1)
+}
+
+int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* flat, void* stream) {
+  if (!workspace || !flat || n_partials < 1 || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
+  const int n = num_params(num_obs) + 4;
+  vine_ppo_reduce_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, n_partials, num_obs, flat);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+int vine_ppo_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq, void* packed,
+                  float* state, int num_obs, float beta1, float beta2, float eps, void* stream) {
+  if (!flat || !params || !exp_avg || !exp_avg_sq || !packed || !state || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
+  const int n = num_params(num_obs) + 1;
+  vine_ppo_adam_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(flat, grad_scale, params, exp_avg, exp_avg_sq,
+                                                                         (uint8_t*)packed, state, num_obs, beta1, beta2, eps);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+}  // extern "C"

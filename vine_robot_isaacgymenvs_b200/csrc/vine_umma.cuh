@@ -1,0 +1,125 @@
+// vine_umma.cuh — thin inline-PTX layer over the sm_100a tensor-core path (tcgen05 + TMEM + mbarrier + bulk TMA).
+//
+// Operand tiles live in shared memory in the UMMA "interleaved" (no-swizzle) canonical layout: 8 x 16-byte core
+// matrices stored contiguously (128 B).  A tile of R rows x K bf16 columns is stored "row-blocked":
+//   offset(row, k) = (row/8) * (K/8)*128  +  (k/8) * 128  +  (row%8) * 16  +  (k%8) * 2
+// The SAME bytes can be consumed by tcgen05.mma in two ways (cute/arch/mma_sm100_desc.hpp, make_umma_desc):
+//   * K-major  (reduction runs along k):    LBO = 128 (next 8 k), SBO = (K/8)*128 (next 8 rows), 16 k per MMA = +256 B
+//   * MN-major (reduction runs along rows): SBO = 128 (next 8 k == next 8 M/N), LBO = (K/8)*128 (next 8 rows),
+//                                           16 rows per MMA = + 2*LBO
+// which is what lets one resident copy of the activations / weights serve forward, backward-data and weight-gradient
+// GEMMs without any transposed copy.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vine_umma {
+
+__host__ __device__ constexpr int tile_offset(int row, int k, int K) {
+  return (row >> 3) * ((K >> 3) * 128) + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+
+// one operand of an MMA sequence: base address + how the descriptor advances per K=16 step
+struct Operand {
+  uint32_t addr, lbo, sbo, kstep;
+};
+// tile of R rows x K columns (row-blocked), reduction along its columns, starting at row `row0`
+__device__ __forceinline__ Operand k_major(uint32_t tile, int K, int row0 = 0) {
+  const uint32_t sbo = (uint32_t)(K >> 3) * 128u;
+  return Operand{tile + (uint32_t)(row0 >> 3) * sbo, 128u, sbo, 256u};
+}
+// same tile, reduction along its rows; M/N index = column, starting at column `col0`
+__device__ __forceinline__ Operand mn_major(uint32_t tile, int K, int col0 = 0) {
+  const uint32_t lbo = (uint32_t)(K >> 3) * 128u;
+  return Operand{tile + (uint32_t)(col0 >> 3) * 128u, lbo, 128u, 2u * lbo};
+}
+
+// instruction descriptor: D=f32, A=B=bf16, M=128, N; a_mn / b_mn select MN-major operands
+__device__ __forceinline__ uint32_t instr_desc(int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk TMA: global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[128 x N] (+)= A * B over `ksteps` steps of K=16; issued by ONE thread
+__device__ __forceinline__ void mma_sequence(uint32_t tmem_d, Operand a, Operand b, uint32_t idesc, int ksteps, bool accumulate) {
+  for (int ks = 0; ks < ksteps; ++ks)
+    mma_bf16(tmem_d, smem_desc(a.addr + ks * a.kstep, a.lbo, a.sbo), smem_desc(b.addr + ks * b.kstep, b.lbo, b.sbo), idesc,
+             (accumulate || ks > 0) ? 1u : 0u);
+}
+// mbarrier arrives when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core / TMA reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+
+}  // namespace vine_umma
