@@ -278,11 +278,12 @@ def run_ours(args, rank, world, local_rank):
     # ---- PPO frames/s (second half of BASELINE.json's metric): BASELINE configs[1] literally ----
     # FSTR, 4096 envs per GPU, horizon 16, minibatch 32768, 4 mini-epochs; one iteration = rollout
     # (16 x {policy, fused env step}) + GAE + update; frames = T * N * ranks per iteration.
-    def measure_ppo(num_envs, iters, warmup, extra, use_graphs=True):
+    def measure_ppo(num_envs, iters, warmup, extra, use_graphs=True, fused_update=True):
         from vine_robot_isaacgymenvs_b200.ppo.ppo import PPOAgent
         pcfg = fstr_cfg(num_envs, [f"sim_device={dev}", f"rl_device={dev}"] + list(extra))
         penv = vine.make(cfg=pcfg, global_env_offset=rank * num_envs)
-        agent = PPOAgent(penv, pcfg["train"], device=dev, seed=42 + rank, use_graphs=use_graphs)
+        agent = PPOAgent(penv, pcfg["train"], device=dev, seed=42 + rank, use_graphs=use_graphs,
+                         use_fused_update=fused_update)
         for _ in range(max(warmup, 3)):
             agent.train_epoch()
         barrier()
@@ -300,6 +301,9 @@ def run_ours(args, rank, world, local_rank):
                 "mini_epochs": agent.mini_epochs, "iterations": iters,
                 "network": "mlp[256,128,64]+lstm256+ln" if agent.has_rnn else "mlp[256,128,64]",
                 "cuda_graphs": agent.use_graphs,
+                "update": "vine_ppo_minibatch/reduce/adam (tcgen05, hand-written)" if agent.fused_update
+                          else "torch autograd + cuBLAS/cuDNN + torch Adam",
+                "policy_forward": "vine_mlp_forward (tcgen05)" if agent.fused else "torch",
                 "collectives": "none" if world == 1 else "NCCL all-reduce: grads+KL per minibatch, running stats per iteration"}
 
     ppo = None
@@ -309,7 +313,9 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         ppo = {"config": "BASELINE configs[1]: FSTR num_envs=4096 rollout+PPO",
                "reference_network": measure_ppo(4096, args.ppo_iters, 5, []),
-               "mlp_only": measure_ppo(4096, args.ppo_iters, 5, ["train.params.network.rnn=null"])}
+               "mlp_only": measure_ppo(4096, args.ppo_iters, 5, ["train.params.network.rnn=null"]),
+               "mlp_only_torch_update": measure_ppo(4096, args.ppo_iters, 5, ["train.params.network.rnn=null"],
+                                                    fused_update=False)}
         if not args.no_sweep:
             ppo["mlp_only_65536_envs"] = measure_ppo(65536, max(3, args.ppo_iters // 4), 3,
                                                      ["train.params.network.rnn=null",

@@ -10,18 +10,23 @@ from vine_robot_isaacgymenvs_b200.ppo.ppo import PPOAgent
 pytestmark = pytest.mark.gpu
 
 
-def make_agent(extra, graphs, n=512):
+def make_agent(extra, graphs, n=512, **kw):
     cfg = vcfg.compose(vcfg.FSTR_OVERRIDES + [f"num_envs={n}", "headless=True", "train.params.config.minibatch_size=4096"]
                        + extra)
     env = vine.make(cfg=cfg)
-    return PPOAgent(env, cfg["train"], seed=1, use_graphs=graphs)
+    return PPOAgent(env, cfg["train"], seed=1, use_graphs=graphs, **kw)
 
 
-@pytest.mark.parametrize("rnn", [True, False], ids=["lstm", "mlp"])
+MLP = ["train.params.network.rnn=null"]
+
+
+@pytest.mark.parametrize("variant", ["lstm", "mlp_fused", "mlp_torch"])
 @pytest.mark.parametrize("graphs", [False, True], ids=["eager", "graphs"])
-def test_ppo_iterations_are_finite_and_learn_something(rnn, graphs):
-    agent = make_agent([] if rnn else ["train.params.network.rnn=null"], graphs)
+def test_ppo_iterations_are_finite_and_learn_something(variant, graphs):
+    rnn = variant == "lstm"
+    agent = make_agent([] if rnn else MLP, graphs, use_fused_update=variant == "mlp_fused")
     assert agent.has_rnn == rnn and agent.seq_len == (4 if rnn else 1)
+    assert agent.fused_update == (variant == "mlp_fused") and agent.fused == (not rnn)
     before = [p.detach().clone() for p in agent.model.parameters()]
     for _ in range(6):
         agent.train_epoch()
@@ -31,6 +36,30 @@ def test_ppo_iterations_are_finite_and_learn_something(rnn, graphs):
     assert all(torch.isfinite(p).all() for p in agent.model.parameters())
     assert any(not torch.equal(a, b) for a, b in zip(before, agent.model.parameters()))
     assert float(agent.obs_rms.count) > 1.0 and agent.frames == (6 + (3 if graphs else 0)) * 16 * 512  # +3: graph warm-up
+
+
+def test_fused_update_moves_the_parameters_like_the_torch_update():
+    """Same rollout, one minibatch, one Adam step: hand-written kernels vs torch autograd + torch.optim.Adam."""
+    one = ["train.params.config.mini_epochs=1", "train.params.config.minibatch_size=8192"]
+    a = make_agent(MLP + one, False, use_fused_update=True)
+    b = make_agent(MLP + one, False, use_fused_update=False)
+    b.load_state_dict(a.state_dict())
+    start = a.flat.clone()
+    a._rollout()
+    for name in ("b_obs", "b_act", "b_mu", "b_nlp", "b_val", "b_ret", "b_adv", "b_done"):
+        getattr(b, name).copy_(getattr(a, name))
+    a._update_any()
+    b._update_any()
+    torch.cuda.synchronize()
+    after_b = torch.cat([p.detach().reshape(-1) for p in b._param_order()])
+    da, db = a.flat - start, after_b - start
+    cos = float((da * db).sum() / (da.norm() * db.norm()))
+    assert cos > 0.97, cos                                  # Adam's first step is sign(g) * lr: agreement of signs
+    assert abs(float(da.abs().max()) - 3e-4) < 1e-5 and abs(float(db.abs().max()) - 3e-4) < 1e-5
+    sa, sb = a.pop_stats(), b.pop_stats()
+    for k in ("a_loss", "c_loss", "kl"):
+        assert abs(sa[k] - sb[k]) <= 3e-2 * abs(sb[k]) + 1e-4, (k, sa[k], sb[k])
+    assert torch.equal(a.obs_rms.running_mean, b.obs_rms.running_mean)
 
 
 def test_checkpoint_roundtrip_uses_rl_games_layout(tmp_path):
@@ -45,3 +74,11 @@ def test_checkpoint_roundtrip_uses_rl_games_layout(tmp_path):
     for pa, pb in zip(a.model.parameters(), b.model.parameters()):
         assert torch.equal(pa, pb)
     assert torch.equal(a.obs_rms.running_mean, b.obs_rms.running_mean) and b.epoch == 1
+    # fused-update agents: parameters are views of one flat vector, optimiser moments travel too
+    c = make_agent(MLP, False)
+    c.train_epoch()
+    torch.save(c.state_dict(), tmp_path / "ck2.pth")
+    d = make_agent(MLP, False)
+    d.load_state_dict(torch.load(tmp_path / "ck2.pth", map_location="cuda:0"))
+    assert torch.equal(c.flat, d.flat) and torch.equal(c.adam_m, d.adam_m) and torch.equal(c._packed, d._packed)
+    assert float(d.ppo_state[1]) == float(c.ppo_state[1]) > 0 and abs(d.lr - c.lr) < 1e-12

@@ -142,7 +142,8 @@ def policy_kl(p0_mu, p0_sigma, p1_mu, p1_sigma):
 
 
 class PPOAgent:
-    def __init__(self, env, train_cfg, device=None, seed=42, use_graphs=False, use_fused_policy=True):
+    def __init__(self, env, train_cfg, device=None, seed=42, use_graphs=False, use_fused_policy=True,
+                 use_fused_update=True):
         c = train_cfg["params"]["config"]
         net = train_cfg["params"]["network"]
         self.env, self.c = env, c
@@ -181,9 +182,18 @@ class PPOAgent:
             for p in self.model.parameters():
                 torch.distributed.broadcast(p.data, 0)
         self.use_graphs = bool(use_graphs) and self.world == 1
-        self.lr_t = torch.tensor(float(c["learning_rate"]), device=dev)   # device-side: no sync in the schedule
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t, eps=1e-8, capturable=True)
         self._lib = abi.load_library()
+        # The MLP-only network runs entirely on hand-written sm_100a kernels: vine_mlp_forward for the rollout and
+        # vine_ppo_minibatch / vine_ppo_reduce / vine_ppo_adam for the update (tcgen05/TMEM); anything else (the LSTM
+        # variant) falls back to torch autograd + cuBLAS/cuDNN for the update.
+        self.fused = (bool(use_fused_policy) and not self.has_rnn and list(units) == [256, 128, 64] and self.A == 2
+                      and self.O <= 31 and self.normalize_input and self.normalize_value)
+        self.fused_update = self.fused and bool(use_fused_update) and not self.truncate_grads
+        if self.fused_update:
+            self._init_fused_update(float(c["learning_rate"]))
+        else:
+            self.lr_t = torch.tensor(float(c["learning_rate"]), device=dev)   # device-side: no sync in the schedule
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t, eps=1e-8, capturable=True)
         T, n = self.T, self.n
         f = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
         self.b_obs, self.b_act, self.b_mu = f(T, n, self.O), f(T, n, self.A), f(T, n, self.A)
@@ -203,29 +213,55 @@ class PPOAgent:
         self.loss_stats = torch.zeros(4, device=dev, dtype=torch.float64)
         self.ep_ret, self.ep_len = f(n), f(n)
         self._g_rollout = self._g_update = None
-        # fused tcgen05/TMEM policy forward for the rollout (vine_mlp_forward); the update keeps autograd
-        self.fused = (bool(use_fused_policy) and not self.has_rnn and list(units) == [256, 128, 64] and self.A == 2
-                      and self.O <= 32 and self.normalize_input and self.normalize_value)
-        if self.fused:
+        if self.fused:   # fused tcgen05/TMEM policy forward for the rollout (vine_mlp_forward)
             self._packed = torch.zeros(abi.MLP_PACKED_BYTES, dtype=torch.uint8, device=dev)
             self._obs_mean_f, self._obs_inv_std_f = f(self.O), f(self.O)
             self._val_stats = f(2)
             self._mu_buf, self._val_buf = f(n, self.A), f(n)
-            self._refresh_fused()
+            self._refresh_fused(pack=True)
+
+    def _param_order(self):
+        """The flat parameter order of include/vine_b200.h (vine_ppo_*)."""
+        m = self.model
+        return [m.actor_mlp[0].weight, m.actor_mlp[0].bias, m.actor_mlp[2].weight, m.actor_mlp[2].bias,
+                m.actor_mlp[4].weight, m.actor_mlp[4].bias, m.mu.weight, m.mu.bias, m.value.weight, m.value.bias, m.sigma]
 
     @torch.no_grad()
-    def _refresh_fused(self):
-        """Re-pack the current weights (bf16, tensor-core operand layout) and normalisation statistics."""
-        m = self.model
+    def _init_fused_update(self, lr):
+        dev, lib = self.device, self._lib
+        order = self._param_order()
+        P = lib.vine_ppo_num_params(self.O)
+        self.flat = torch.cat([p.detach().reshape(-1) for p in order]).contiguous()
+        assert self.flat.numel() == P
+        o = 0
+        for p in order:   # the torch modules become views of the flat vector the kernels update
+            p.data = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.adam_m, self.adam_v = torch.zeros(P, device=dev), torch.zeros(P, device=dev)
+        self.ppo_state = torch.zeros(abi.PPO_STATE_FLOATS, device=dev)
+        self.ppo_state[0] = lr
+        self.lr_t = self.ppo_state[0]                                      # 0-dim view: the device-side learning rate
+        self._ctas = lib.vine_ppo_max_ctas()
+        self._ws = torch.empty(self._ctas, abi.PPO_WS_FLOATS, device=dev)
+        self._flat_grads = torch.zeros(P + 4, device=dev)
+        self._logstd_old = torch.zeros(2, device=dev)
+        z = lambda: torch.zeros(self.T, self.n, device=dev)  # noqa: E731
+        self._val_old_n, self._ret_n, self._adv_n = z(), z(), z()
+        self._mb_structs = None
+
+    @torch.no_grad()
+    def _refresh_fused(self, pack=False):
+        """Refresh the normalisation statistics the kernels read; ``pack``: also re-pack the weights (bf16, tensor-core
+        operand layout) -- only needed when something other than vine_ppo_adam changed them."""
         self._obs_mean_f.copy_(self.obs_rms.running_mean.float())
         self._obs_inv_std_f.copy_(torch.rsqrt(self.obs_rms.running_var.float() + self.obs_rms.eps))
         self._val_stats.copy_(torch.stack([self.val_rms.running_mean.float(),
                                            torch.sqrt(self.val_rms.running_var.float() + self.val_rms.eps)]))
-        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
-        lin = [m.actor_mlp[0], m.actor_mlp[2], m.actor_mlp[4], m.mu, m.value]
-        args = [p(t) for l in lin for t in (l.weight, l.bias)]
-        rc = self._lib.vine_mlp_pack(*args, self.O, p(self._packed), C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        assert rc == 0
+        if pack:
+            p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+            args = [p(t) for t in self._param_order()[:10]]
+            rc = self._lib.vine_mlp_pack(*args, self.O, p(self._packed), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            assert rc == 0
 
     @property
     def lr(self):
@@ -382,7 +418,52 @@ class PPOAgent:
                     self.loss_stats += torch.stack([a_loss.detach(), c_loss.detach(), kl,
                                                     torch.ones((), device=kl.device)]).double()
         if self.fused:
-            self._refresh_fused()
+            self._refresh_fused(pack=True)
+
+    @torch.no_grad()
+    def _update_fused(self):
+        """The update on hand-written kernels only: per minibatch ONE fused tcgen05 launch (forward, losses, backward,
+        weight gradients), the partial-gradient reduction, [one NCCL all-reduce of grads + loss statistics], Adam."""
+        T, n, lib = self.T, self.n, self._lib
+        val_old, ret = self.b_val, self.b_ret
+        adv = ret - val_old
+        self.obs_rms.update(self.b_obs.reshape(T * n, self.O))
+        self.val_rms.update(torch.cat([val_old.reshape(-1), ret.reshape(-1)]))
+        self._val_old_n.copy_(self.val_rms(val_old))
+        self._ret_n.copy_(self.val_rms(ret))
+        if self.normalize_advantage:
+            s = torch.stack([adv.sum(), (adv * adv).sum()]).double()
+            cnt = float(T * n * self.world)
+            if self.world > 1:
+                torch.distributed.all_reduce(s)
+            mean = s[0] / cnt
+            std = torch.sqrt(torch.clamp((s[1] - cnt * mean * mean) / (cnt - 1.0), min=0.0))
+            adv = (adv - mean.float()) / (std.float() + 1e-8)
+        self._adv_n.copy_(adv)
+        self._refresh_fused()
+        self._logstd_old.copy_(self.model.sigma)
+        if self._mb_structs is None:
+            ptr = lambda x: x.data_ptr()  # noqa: E731
+            self._mb_structs = [abi.VinePpoMinibatch(
+                packed=ptr(self._packed), obs=ptr(self.b_obs), actions=ptr(self.b_act), mu_old=ptr(self.b_mu),
+                neglogp_old=ptr(self.b_nlp), values_old=ptr(self._val_old_n), returns=ptr(self._ret_n),
+                advantages=ptr(self._adv_n), obs_mean=ptr(self._obs_mean_f), obs_inv_std=ptr(self._obs_inv_std_f),
+                logstd=ptr(self.model.sigma), logstd_old=ptr(self._logstd_old), workspace=ptr(self._ws),
+                state=ptr(self.ppo_state), debug_out=None, horizon=T, num_envs=n, env_begin=e0, env_count=self.mb_envs,
+                num_obs=self.O, workspace_ctas=self._ctas, adaptive_lr=int(self.adaptive), e_clip=self.e_clip,
+                critic_coef=self.critic_coef, entropy_coef=self.entropy_coef, bounds_loss_coef=self.bounds_coef,
+                kl_threshold=self.kl_threshold, lr_min=1e-6, lr_max=1e-2) for e0 in range(0, n, self.mb_envs)]
+        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for _ in range(self.mini_epochs):
+            for mb in self._mb_structs:
+                n_part = lib.vine_ppo_minibatch(C.byref(mb), stream)
+                assert n_part > 0, n_part
+                assert lib.vine_ppo_reduce(p(self._ws), n_part, self.O, p(self._flat_grads), stream) == 0
+                if self.world > 1:   # ONE collective per minibatch: gradients + loss statistics (incl. the KL)
+                    torch.distributed.all_reduce(self._flat_grads)
+                assert lib.vine_ppo_adam(p(self._flat_grads), 1.0 / self.world, p(self.flat), p(self.adam_m), p(self.adam_v),
+                                         p(self._packed), p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, stream) == 0
 
     def capture_graphs(self, warmup=3):
         """Warm up eagerly on a side stream, then capture the rollout and the update as two graphs."""
@@ -391,7 +472,7 @@ class PPOAgent:
         with torch.cuda.stream(s):
             for _ in range(warmup):
                 self._rollout()
-                self._update()
+                self._update_any()
                 self.frames += self.T * self.n
                 self.epoch += 1
         torch.cuda.current_stream(self.device).wait_stream(s)
@@ -400,7 +481,7 @@ class PPOAgent:
         with torch.cuda.graph(self._g_rollout):
             self._rollout()
         with torch.cuda.graph(self._g_update):
-            self._update()
+            self._update_any()
         torch.cuda.synchronize(self.device)
 
     def train_epoch(self):
@@ -410,14 +491,25 @@ class PPOAgent:
         if self._g_update is not None:
             self._g_update.replay()
         else:
-            self._update()
+            self._update_any()
         self.epoch += 1
+
+    def _update_any(self):
+        if self.fused_update:
+            self._update_fused()
+        else:
+            self._update()
 
     def pop_stats(self):
         e = self.ep_stats.tolist()
-        l = self.loss_stats.tolist()
+        if self.fused_update:   # the Adam kernel keeps the running sums: a_loss, c_loss, kl, b_loss, count
+            st = self.ppo_state.tolist()
+            l = [st[4], st[5], st[6], st[8]]
+            self.ppo_state[4:9] = 0.0
+        else:
+            l = self.loss_stats.tolist()
+            self.loss_stats.zero_()
         self.ep_stats.zero_()
-        self.loss_stats.zero_()
         eps, nmb = max(e[0], 1.0), max(l[3], 1.0)
         return {"episodes": int(e[0]), "success_rate": e[1] / eps, "mean_return": e[2] / eps, "mean_length": e[3] / eps,
                 "a_loss": l[0] / nmb, "c_loss": l[1] / nmb, "kl": l[2] / nmb}
@@ -449,23 +541,38 @@ class PPOAgent:
                 sd[f"{name}.{k}"] = v.detach().clone()
         return sd
 
+    def _optimizer_state(self):
+        if self.fused_update:
+            return {"fused_adam": {"exp_avg": self.adam_m.clone(), "exp_avg_sq": self.adam_v.clone(),
+                                   "step": float(self.ppo_state[1])}}
+        return self.opt.state_dict()
+
     def state_dict(self):
-        return {"model": self.rlgames_model_state(), "optimizer": self.opt.state_dict(), "epoch": self.epoch,
+        return {"model": self.rlgames_model_state(), "optimizer": self._optimizer_state(), "epoch": self.epoch,
                 "frame": self.frames, "last_lr": self.lr, "last_mean_rewards": 0.0, "env_state": None}
 
     def load_state_dict(self, sd):
         model = sd["model"]
         net = {k[len("a2c_network."):]: v for k, v in model.items() if k.startswith("a2c_network.")}
-        self.model.load_state_dict(net)
+        with torch.no_grad():   # copy in place: with the fused update the parameters are views of one flat vector
+            own = self.model.state_dict()
+            assert set(own) == set(net), (sorted(set(own) ^ set(net)))
+            for k, v in own.items():
+                v.copy_(net[k])
         for name, rms in (("running_mean_std", self.obs_rms), ("value_mean_std", self.val_rms)):
             sub = {k[len(name) + 1:]: v for k, v in model.items() if k.startswith(name + ".")}
             if not sub and name in sd:          # older layout: normalisers stored beside 'model'
                 sub = sd[name]
             if sub:
                 rms.load_state_dict({k: v.to(rms.running_mean.dtype) for k, v in sub.items()})
-        if sd.get("optimizer"):
-            self.opt.load_state_dict(sd["optimizer"])
+        opt = sd.get("optimizer")
+        if opt and self.fused_update and "fused_adam" in opt:
+            self.adam_m.copy_(opt["fused_adam"]["exp_avg"])
+            self.adam_v.copy_(opt["fused_adam"]["exp_avg_sq"])
+            self.ppo_state[1] = float(opt["fused_adam"]["step"])
+        elif opt and not self.fused_update and "fused_adam" not in opt:
+            self.opt.load_state_dict(opt)
         self.epoch, self.frames = sd.get("epoch", 0), sd.get("frame", 0)
         self.lr_t.fill_(float(sd.get("last_lr", self.lr)))
         if self.fused:
-            self._refresh_fused()
+            self._refresh_fused(pack=True)

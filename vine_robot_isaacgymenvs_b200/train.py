@@ -28,7 +28,8 @@ def launch(overrides):
     n = int(cfg["task"]["env"]["numEnvs"])
     env = make(cfg=cfg, seed=int(cfg["seed"]), multi_gpu=multi, global_env_offset=rank * n if multi else 0)
     agent = PPOAgent(env, cfg["train"], device=dev, seed=seed, use_graphs=bool(cfg.get("use_graphs", True)),
-                     use_fused_policy=bool(cfg.get("use_fused_policy", True)))
+                     use_fused_policy=bool(cfg.get("use_fused_policy", True)),
+                     use_fused_update=bool(cfg.get("use_fused_update", True)))
     name = cfg["train"]["params"]["config"]["name"]
     out_dir = os.path.join("runs", name, "nn")
     if cfg.get("checkpoint"):
