@@ -364,6 +364,83 @@ int vine_mlp_forward(const void* packed, const float* obs, const float* obs_mean
                      void* stream);
 
 /*
+ * One rollout step of the policy in ONE launch (rl_games A2CAgent.get_action_values + the buffer writes of
+ * play_steps; in-repo analogue learning/common_agent.py:257-314): vine_mlp_forward's network, then
+ *   action = mu + exp(logstd) * N(0,1)   Philox4x32-10, key = seed, counter = (global env id, 16, *rng_counter, 0)
+ *   neglogp = 0.5 sum(eps^2) + log(2 pi) + sum(logstd);   env_actions = clamp(action, +-1)  (preprocess_actions)
+ * and a copy of the raw observation row.  Every output pointer is optional (NULL = skip); with actions == NULL
+ * the call is pure inference (== vine_mlp_forward).  The Philox stream is keyed by the GLOBAL env id, so sampled
+ * actions do not depend on how envs are sharded over GPUs.
+ */
+typedef struct VinePolicyAct {
+  const void* packed;            /* VINE_MLP_PACKED_BYTES */
+  const float* obs;              /* [n, O] */
+  const float* obs_mean;         /* [O] */
+  const float* obs_inv_std;      /* [O] */
+  const float* value_stats;      /* {mean, std} */
+  float* mu;                     /* [n, 2] */
+  float* value;                  /* [n] de-normalised */
+  const float* logstd;           /* [2]; required when sampling */
+  const uint32_t* rng_counter;   /* device word, advanced by vine_rollout_post */
+  float* actions;                /* [n, 2] raw sampled actions; NULL = no sampling */
+  float* neglogp;                /* [n] */
+  float* obs_copy;               /* [n, O] */
+  float* env_actions;            /* [n, 2] clamped to [-1, 1] */
+  int64_t n;
+  int32_t num_obs, reserved;
+  uint64_t seed;
+  int64_t global_env_offset;
+} VinePolicyAct;
+int vine_policy_act(const VinePolicyAct* args, void* stream);
+
+/*
+ * After the env step (rl_games play_steps tail): shaped = reward * reward_scale (YP:58-59)
+ * [+ gamma * value on time-outs, value_bootstrap YP:56], dones, per-env episode return/length and the
+ * device-side episode statistics ep_stats f64[4] += {episodes, successes, sum return, sum length}.
+ */
+typedef struct VineRolloutPost {
+  const float* rewards;          /* env rew_buf [n] */
+  const int64_t* resets;         /* env reset_buf [n] */
+  const uint8_t* timeouts;       /* env timeout_buf [n] (bool) */
+  const float* values;           /* [n] value estimates of this step */
+  float* shaped_rewards;         /* [n] out */
+  float* dones_next;             /* [n] out, 0/1 */
+  float* ep_return;              /* [n] in/out */
+  float* ep_length;              /* [n] in/out */
+  double* ep_stats;              /* [4] accumulated */
+  uint32_t* rng_counter;         /* incremented once per call (may be NULL) */
+  int64_t n;
+  float reward_scale, gamma;
+  int32_t value_bootstrap;
+  float success_reward_threshold;
+} VineRolloutPost;
+int vine_rollout_post(const VineRolloutPost* args, void* stream);
+
+/*
+ * Update prologue (once per PPO iteration): rl_games RunningMeanStd updates of observations and values
+ * (values and returns pooled), advantage mean/std, then values_n/returns_n = clamp((x - mean)/std, +-5) and
+ * advantages_n = ((returns - values) - mean) / (std + 1e-8).  vine_ppo_moments accumulates f64 sufficient
+ * statistics into `moments` (2*O + 4 doubles, zero on first use; all-reduce it across ranks and set `world`),
+ * vine_ppo_finalize merges them into the running statistics (f64, in place), writes the f32 copies the
+ * kernels read, normalises, and clears `moments`.
+ */
+typedef struct VinePpoPrologue {
+  const float* obs;              /* [count, O] */
+  const float* values;           /* [count] */
+  const float* returns;          /* [count] */
+  double* moments;               /* [2*O + 4] */
+  double *obs_mean, *obs_var, *obs_count;     /* [O], [O], [1] */
+  double *val_mean, *val_var, *val_count;     /* scalars */
+  float *obs_mean_f, *obs_inv_std_f;          /* [O] out */
+  float *value_stats, *adv_stats;             /* {mean, std}, {mean, 1/(std+1e-8)} out */
+  float *values_n, *returns_n, *advantages_n; /* [count] out */
+  int64_t count;
+  int32_t num_obs, world, normalize_advantage, reserved;
+} VinePpoPrologue;
+int vine_ppo_moments(const VinePpoPrologue* args, void* stream);
+int vine_ppo_finalize(const VinePpoPrologue* args, void* stream);
+
+/*
  * PPO minibatch update of the same network as ONE fused tcgen05/TMEM kernel: forward, the PPO losses of
  * Vine5LinkMovingBasePPO.yaml:46-81 (e_clip actor loss, clipped value loss x critic_coef / 2, bounds loss,
  * entropy), backward and weight gradients (rl_games A2CAgent.calc_gradients + autograd; in-repo analogue

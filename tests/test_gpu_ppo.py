@@ -59,7 +59,7 @@ def test_fused_update_moves_the_parameters_like_the_torch_update():
     sa, sb = a.pop_stats(), b.pop_stats()
     for k in ("a_loss", "c_loss", "kl"):
         assert abs(sa[k] - sb[k]) <= 3e-2 * abs(sb[k]) + 1e-4, (k, sa[k], sb[k])
-    assert torch.equal(a.obs_rms.running_mean, b.obs_rms.running_mean)
+    assert torch.allclose(a.obs_rms.running_mean, b.obs_rms.running_mean, atol=1e-6)
 
 
 def test_checkpoint_roundtrip_uses_rl_games_layout(tmp_path):

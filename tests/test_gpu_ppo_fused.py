@@ -151,3 +151,113 @@ def test_adam_kernel_matches_torch_adam_and_repacks_the_weights():
     assert lib.vine_mlp_pack(*[p(w.contiguous()) for w in Wn[:10]], O, p(packed_ref), None) == 0
     torch.cuda.synchronize()
     assert torch.equal(packed, packed_ref)
+
+
+def _act_problem(n, O, seed=3):
+    lib = abi.load_library()
+    W, buf, mean, inv_std, _ = make_problem(1, n, O, seed=seed)
+    packed = torch.zeros(abi.MLP_PACKED_BYTES, dtype=torch.uint8, device="cuda")
+    assert lib.vine_mlp_pack(*[p(w.contiguous()) for w in W[:10]], O, p(packed), None) == 0
+    return lib, W, buf["obs"][0].contiguous(), mean, inv_std, packed
+
+
+def _act(lib, packed, obs, mean, inv_std, logstd, counter, n, O, offset=0, seed=1234):
+    vstats = torch.tensor([0.3, 1.7], device="cuda")
+    out = dict(mu=torch.zeros(n, 2, device="cuda"), value=torch.zeros(n, device="cuda"), actions=torch.zeros(n, 2, device="cuda"),
+               neglogp=torch.zeros(n, device="cuda"), obs_copy=torch.zeros(n, O, device="cuda"),
+               env_actions=torch.zeros(n, 2, device="cuda"))
+    a = abi.VinePolicyAct(packed=packed.data_ptr(), obs=obs.data_ptr(), obs_mean=mean.data_ptr(), obs_inv_std=inv_std.data_ptr(),
+                          value_stats=vstats.data_ptr(), logstd=logstd.data_ptr(), rng_counter=counter.data_ptr(), n=n, num_obs=O,
+                          seed=seed, global_env_offset=offset, **{k: v.data_ptr() for k, v in out.items()})
+    assert lib.vine_policy_act(C.byref(a), None) == 0
+    torch.cuda.synchronize()
+    return out
+
+
+def test_policy_act_samples_gaussian_actions_keyed_by_global_env_id():
+    n, O = 20000, 18
+    lib, W, obs, mean, inv_std, packed = _act_problem(n, O)
+    logstd = torch.tensor([-0.3, 0.2], device="cuda")
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    o = _act(lib, packed, obs, mean, inv_std, logstd, counter, n, O)
+    # the network part equals the inference entry point
+    mu2, val2 = torch.zeros(n, 2, device="cuda"), torch.zeros(n, device="cuda")
+    vstats = torch.tensor([0.3, 1.7], device="cuda")
+    assert lib.vine_mlp_forward(p(packed), p(obs), p(mean), p(inv_std), n, O, p(vstats), p(mu2), p(val2), None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(o["mu"], mu2) and torch.equal(o["value"], val2) and torch.equal(o["obs_copy"], obs)
+    z = (o["actions"] - o["mu"]) / torch.exp(logstd)
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02 and abs(float((z[:, 0] * z[:, 1]).mean())) < 0.02
+    nlp = 0.5 * (z ** 2).sum(-1) + math.log(2 * math.pi) + logstd.sum()
+    assert torch.allclose(o["neglogp"], nlp, atol=2e-4, rtol=1e-4)
+    assert torch.equal(o["env_actions"], o["actions"].clamp(-1, 1))
+    # same counter -> same noise; next counter -> fresh noise; a shard with the matching global offset -> the same slice
+    o2 = _act(lib, packed, obs, mean, inv_std, logstd, counter, n, O)
+    assert torch.equal(o2["actions"], o["actions"])
+    shard = _act(lib, packed, obs[5000:9000].contiguous(), mean, inv_std, logstd, counter, 4000, O, offset=5000)
+    assert torch.equal(shard["actions"], o["actions"][5000:9000])
+    counter += 1
+    o3 = _act(lib, packed, obs, mean, inv_std, logstd, counter, n, O)
+    assert not torch.equal(o3["actions"], o["actions"]) and torch.equal(o3["mu"], o["mu"])
+
+
+def test_rollout_post_matches_torch():
+    lib = abi.load_library()
+    n = 5000
+    g = torch.Generator(device="cuda").manual_seed(1)
+    rew = torch.randn(n, device="cuda", generator=g) * 400 + 300
+    resets = (torch.rand(n, device="cuda", generator=g) < 0.3).long()
+    timeouts = (torch.rand(n, device="cuda", generator=g) < 0.5) & (resets != 0)
+    values = torch.randn(n, device="cuda", generator=g)
+    ep_ret, ep_len = torch.randn(n, device="cuda", generator=g) * 10, torch.randint(0, 50, (n,), device="cuda").float()
+    ep_ret0, ep_len0 = ep_ret.clone(), ep_len.clone()
+    shaped, dones = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    stats = torch.zeros(4, dtype=torch.float64, device="cuda")
+    counter = torch.full((1,), 7, dtype=torch.int32, device="cuda")
+    a = abi.VineRolloutPost(rewards=rew.data_ptr(), resets=resets.data_ptr(), timeouts=timeouts.data_ptr(), values=values.data_ptr(),
+                            shaped_rewards=shaped.data_ptr(), dones_next=dones.data_ptr(), ep_return=ep_ret.data_ptr(),
+                            ep_length=ep_len.data_ptr(), ep_stats=stats.data_ptr(), rng_counter=counter.data_ptr(), n=n,
+                            reward_scale=0.01, gamma=0.99, value_bootstrap=1, success_reward_threshold=500.0)
+    assert lib.vine_rollout_post(C.byref(a), None) == 0
+    torch.cuda.synchronize()
+    d = resets.float()
+    assert torch.allclose(shaped, rew * 0.01 + 0.99 * values * timeouts.float(), atol=1e-6) and torch.equal(dones, d)
+    er, el = ep_ret0 + rew, ep_len0 + 1
+    assert torch.equal(ep_ret, er * (1 - d)) and torch.equal(ep_len, el * (1 - d)) and int(counter) == 8
+    want = torch.stack([d.sum(), (d * (rew > 500)).sum(), (d * er).double().sum(), (d * el).sum()]).double()
+    assert torch.allclose(stats, want, rtol=1e-6)
+
+
+def test_update_prologue_matches_running_mean_std():
+    from vine_robot_isaacgymenvs_b200.ppo.ppo import RunningMeanStd
+    lib = abi.load_library()
+    count, O = 16 * 1000, 18
+    g = torch.Generator(device="cuda").manual_seed(2)
+    f = lambda *s: torch.zeros(*s, device="cuda")  # noqa: E731
+    obs_rms, val_rms = RunningMeanStd((O,)).cuda(), RunningMeanStd(()).cuda()
+    ref_obs, ref_val = RunningMeanStd((O,)).cuda(), RunningMeanStd(()).cuda()
+    moments = torch.zeros(2 * O + 4, dtype=torch.float64, device="cuda")
+    mean_f, inv_f, vstats, astats, vn, rn, an = f(O), f(O), f(2), f(2), f(count), f(count), f(count)
+    for it in range(3):
+        obs = torch.randn(count, O, device="cuda", generator=g) * (1 + it) + it
+        val, ret = torch.randn(count, device="cuda", generator=g) * 3 + 1, torch.randn(count, device="cuda", generator=g) * 2
+        a = abi.VinePpoPrologue(
+            obs=obs.data_ptr(), values=val.data_ptr(), returns=ret.data_ptr(), moments=moments.data_ptr(),
+            obs_mean=obs_rms.running_mean.data_ptr(), obs_var=obs_rms.running_var.data_ptr(), obs_count=obs_rms.count.data_ptr(),
+            val_mean=val_rms.running_mean.data_ptr(), val_var=val_rms.running_var.data_ptr(), val_count=val_rms.count.data_ptr(),
+            obs_mean_f=mean_f.data_ptr(), obs_inv_std_f=inv_f.data_ptr(), value_stats=vstats.data_ptr(), adv_stats=astats.data_ptr(),
+            values_n=vn.data_ptr(), returns_n=rn.data_ptr(), advantages_n=an.data_ptr(), count=count, num_obs=O, world=1,
+            normalize_advantage=1)
+        assert lib.vine_ppo_moments(C.byref(a), None) == 0 and lib.vine_ppo_finalize(C.byref(a), None) == 0
+        torch.cuda.synchronize()
+        ref_obs.update(obs)
+        ref_val.update(torch.cat([val, ret]))
+        assert torch.allclose(obs_rms.running_mean, ref_obs.running_mean, atol=1e-5)
+        assert torch.allclose(obs_rms.running_var, ref_obs.running_var, rtol=1e-5)
+        assert torch.allclose(val_rms.running_var, ref_val.running_var, rtol=1e-5) and float(obs_rms.count) == float(ref_obs.count)
+        assert torch.allclose(vn, ref_val(val), atol=1e-5) and torch.allclose(rn, ref_val(ret), atol=1e-5)
+        adv = ret - val
+        assert torch.allclose(an, (adv - adv.mean()) / (adv.std() + 1e-8), atol=1e-4)
+        assert torch.allclose(mean_f, ref_obs.running_mean.float(), atol=1e-5)
+        assert torch.allclose(inv_f, torch.rsqrt(ref_obs.running_var.float() + 1e-5), rtol=1e-5)
+        assert float(moments.abs().max()) == 0.0

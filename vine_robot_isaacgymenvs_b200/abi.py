@@ -136,10 +136,35 @@ EXPORTED_SYMBOLS = [
     "vine_pre_physics", "vine_actuation", "vine_simulate", "vine_philox_debug", "vine_gae",
     "vine_mlp_pack", "vine_mlp_forward",
     "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
+    "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
 ]
 MLP_PACKED_BYTES = 102208
 PPO_WS_FLOATS = 49664
 PPO_STATE_FLOATS = 16
+
+
+class VinePolicyAct(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in (
+        "packed", "obs", "obs_mean", "obs_inv_std", "value_stats", "mu", "value", "logstd", "rng_counter", "actions",
+        "neglogp", "obs_copy", "env_actions")]
+        + [("n", C.c_int64), ("num_obs", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64),
+           ("global_env_offset", C.c_int64)])
+
+
+class VineRolloutPost(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in (
+        "rewards", "resets", "timeouts", "values", "shaped_rewards", "dones_next", "ep_return", "ep_length", "ep_stats",
+        "rng_counter")]
+        + [("n", C.c_int64), ("reward_scale", C.c_float), ("gamma", C.c_float), ("value_bootstrap", C.c_int32),
+           ("success_reward_threshold", C.c_float)])
+
+
+class VinePpoPrologue(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in (
+        "obs", "values", "returns", "moments", "obs_mean", "obs_var", "obs_count", "val_mean", "val_var", "val_count",
+        "obs_mean_f", "obs_inv_std_f", "value_stats", "adv_stats", "values_n", "returns_n", "advantages_n")]
+        + [("count", C.c_int64), ("num_obs", C.c_int32), ("world", C.c_int32), ("normalize_advantage", C.c_int32),
+           ("reserved", C.c_int32)])
 
 
 class VinePpoMinibatch(C.Structure):
@@ -184,6 +209,10 @@ def _declare(lib):
                              vp, vp, vp]
     lib.vine_mlp_pack.argtypes = [vp] * 10 + [C.c_int, vp, vp]
     lib.vine_mlp_forward.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp]
+    lib.vine_policy_act.argtypes = [C.POINTER(VinePolicyAct), vp]
+    lib.vine_rollout_post.argtypes = [C.POINTER(VineRolloutPost), vp]
+    lib.vine_ppo_moments.argtypes = [C.POINTER(VinePpoPrologue), vp]
+    lib.vine_ppo_finalize.argtypes = [C.POINTER(VinePpoPrologue), vp]
     lib.vine_ppo_num_params.argtypes = [C.c_int]
     lib.vine_ppo_max_ctas.argtypes = []
     lib.vine_ppo_minibatch.argtypes = [C.POINTER(VinePpoMinibatch), vp]

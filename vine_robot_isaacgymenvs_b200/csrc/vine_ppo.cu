@@ -20,33 +20,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/vine_b200.h"
-#include "vine_umma.cuh"
+#include "vine_mlp_common.cuh"
 
 namespace {
-using namespace vine_umma;
+using namespace vine_mlp;
 
-constexpr int H1 = 256, H2 = 128, H3 = 64, NH = 16, K1 = 32;
-constexpr int TILE = 128, THREADS = 256;
-// packed parameter block: identical to vine_mlp.cu (vine_mlp_pack / vine_mlp_forward share it)
-constexpr int OFF_W1 = 0;
-constexpr int OFF_W2 = OFF_W1 + H1 * K1 * 2;
-constexpr int OFF_W3 = OFF_W2 + H2 * H1 * 2;
-constexpr int OFF_W4 = OFF_W3 + H3 * H2 * 2;
-constexpr int OFF_B = OFF_W4 + NH * H3 * 2;  // f32: b1[256] b2[128] b3[64] bh[16]
-constexpr int PACKED_BYTES = OFF_B + (H1 + H2 + H3 + NH) * 4;
-static_assert(PACKED_BYTES == VINE_MLP_PACKED_BYTES, "header constant out of date");
 // shared-memory map
-constexpr int OFF_X = 102400;                      // x   [128 x 32]  bf16 (column 31 == 1: carries db1 through dW1)
-constexpr int OFF_A1 = OFF_X + TILE * K1 * 2;      // h1 / dz1 [128 x 256]
-constexpr int OFF_A2 = OFF_A1 + TILE * H1 * 2;     // h2 / dz2 [128 x 128]
-constexpr int OFF_A3 = OFF_A2 + TILE * H2 * 2;     // h3 / dz3 [128 x 64]
-constexpr int OFF_DZH = OFF_A3 + TILE * H3 * 2;    // d(mu0,mu1,v) [128 x 16] bf16
+// (x column 31 == 1 carries db1 through dW1; dz_l overwrites h_l in place)
+constexpr int OFF_DZH = OFF_END;                   // d(mu0,mu1,v) [128 x 16] bf16
 constexpr int OFF_DZHF = OFF_DZH + TILE * NH * 2;  // the same in f32 [128][4] for the CUDA-core head gradient
 constexpr int OFF_RED = OFF_DZHF + TILE * 4 * 4;   // block-reduction scratch
 constexpr int OFF_BAR = OFF_RED + 256;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
-static_assert(PACKED_BYTES <= OFF_X && SMEM_BYTES <= 232448, "shared-memory budget");
+static_assert(SMEM_BYTES <= 232448, "shared-memory budget");
 // TMEM columns
 constexpr uint32_t TM_DATA = 0, TM_DW2 = 128, TM_DW1 = 384, TM_DW3T = 448;
 // per-CTA gradient partial (floats)
@@ -71,57 +57,6 @@ struct MbArgs {
   float e_clip, critic_coef, entropy_coef, bounds_coef, inv_B, kl_threshold, lr_min, lr_max;
   int adaptive;
 };
-
-__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
-
-// accumulator columns [taddr, taddr+ncols) -> bias + ELU -> bf16 -> tile columns [c_out, c_out+ncols) of row `row`
-template <int KL>
-__device__ __forceinline__ void fwd_epilogue(uint32_t taddr, int ncols, int c_out, const float* bias, uint8_t* tile, int row) {
-#pragma unroll 1
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(taddr + c0, r);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint32_t w[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = c_out + c0 + g * 8 + 2 * i;
-        w[i] = pack_bf16(elu(__uint_as_float(r[g * 8 + 2 * i]) + bias[c]), elu(__uint_as_float(r[g * 8 + 2 * i + 1]) + bias[c + 1]));
-      }
-      *reinterpret_cast<uint4*>(tile + tile_offset(row, c_out + c0 + g * 8, KL)) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-  }
-}
-
-// dz = dh * ELU'(h) with ELU'(h) = h > 0 ? 1 : h + 1, written over h in place
-template <int KL>
-__device__ __forceinline__ void bwd_epilogue(uint32_t taddr, int ncols, int c_out, uint8_t* tile, int row) {
-#pragma unroll 1
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(taddr + c0, r);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint4* p = reinterpret_cast<uint4*>(tile + tile_offset(row, c_out + c0 + g * 8, KL));
-      const uint4 hv = *p;
-      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-      uint32_t w[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 h = unpack_bf16(hw[i]);
-        const float d0 = __uint_as_float(r[g * 8 + 2 * i]) * (h.x > 0.f ? 1.f : h.x + 1.f);
-        const float d1 = __uint_as_float(r[g * 8 + 2 * i + 1]) * (h.y > 0.f ? 1.f : h.y + 1.f);
-        w[i] = pack_bf16(d0, d1);
-      }
-      *p = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-  }
-}
-
-__device__ __forceinline__ float bf16_at(const uint8_t* tile, int row, int col, int KL) {
-  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + tile_offset(row, col, KL)));
-}
 
 __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const MbArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -212,23 +147,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
       nlpo = a.nlp_old[grow], vo = a.val_old[grow], ret = a.ret[grow], adv = a.adv[grow];
     }
     // ---- x tile: normalised observation, bf16, zero padded to K1; column 31 is the constant 1 (bias gradient) ----
-    {
-      const int k0 = half * 16;
-      float x[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int k = k0 + i;
-        float v = 0.f;
-        if (valid && k < a.O) v = fminf(fmaxf((a.obs[grow * a.O + k] - a.obs_mean[k]) * a.obs_inv_std[k], -5.f), 5.f);
-        if (valid && k == K1 - 1) v = 1.f;
-        x[i] = v;
-      }
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-        *reinterpret_cast<uint4*>(x_t + tile_offset(row, k0 + g * 8, K1)) =
-            make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]),
-                       pack_bf16(x[g * 8 + 4], x[g * 8 + 5]), pack_bf16(x[g * 8 + 6], x[g * 8 + 7]));
-    }
+    build_x_tile(x_t, row, half, valid, a.obs + grow * a.O, a.obs_mean, a.obs_inv_std, a.O, true, nullptr);
     // =============================== forward ===============================
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {   // layer 1 in two halves of 128 output features (working accumulator = 128 columns)

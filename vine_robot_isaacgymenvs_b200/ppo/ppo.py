@@ -205,6 +205,9 @@ class PPOAgent:
             self.b_h, self.b_c = f(T // self.seq_len, n, H), f(T // self.seq_len, n, H)
         self.obs = env.reset()["obs"].clone()
         self.dones = torch.ones(n, device=dev)
+        if self.fused_update:   # [T+1, n]: dones seen before step t; row T carries over to the next rollout's row 0
+            self._done_ext = torch.ones(T + 1, n, device=dev)
+            self.b_done, self.dones = self._done_ext[:T], self._done_ext[T]
         self.last_value = f(n)
         self.epoch = 0
         self.frames = 0
@@ -247,7 +250,10 @@ class PPOAgent:
         self._logstd_old = torch.zeros(2, device=dev)
         z = lambda: torch.zeros(self.T, self.n, device=dev)  # noqa: E731
         self._val_old_n, self._ret_n, self._adv_n = z(), z(), z()
-        self._mb_structs = None
+        self._mb_structs = self._roll_structs = None
+        self._rng_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._moments = torch.zeros(2 * self.O + 4, dtype=torch.float64, device=dev)
+        self._adv_stats = torch.zeros(2, device=dev)
 
     @torch.no_grad()
     def _refresh_fused(self, pack=False):
@@ -287,7 +293,45 @@ class PPOAgent:
         return mu, logstd, value, states
 
     @torch.no_grad()
+    def _rollout_fused(self):
+        """The rollout on hand-written kernels only: per control step vine_policy_act (normalise, MLP on tcgen05,
+        sample, neglogp, all rollout-buffer writes), the fused env step, vine_rollout_post; then the last value and GAE."""
+        env, lib, T, n = self.env, self._lib, self.T, self.n
+        if self._roll_structs is None:
+            ptr = lambda x: x.data_ptr()  # noqa: E731
+            common = dict(packed=ptr(self._packed), obs=ptr(env._obs_clamped), obs_mean=ptr(self._obs_mean_f),
+                          obs_inv_std=ptr(self._obs_inv_std_f), value_stats=ptr(self._val_stats), n=n, num_obs=self.O,
+                          seed=int(env._seed) ^ 0x5DEECE66D, global_env_offset=int(env._global_env_offset))
+            acts = [abi.VinePolicyAct(mu=ptr(self.b_mu[t]), value=ptr(self.b_val[t]), logstd=ptr(self.model.sigma),
+                                      rng_counter=ptr(self._rng_counter), actions=ptr(self.b_act[t]),
+                                      neglogp=ptr(self.b_nlp[t]), obs_copy=ptr(self.b_obs[t]), env_actions=ptr(env.actions),
+                                      **common) for t in range(T)]
+            posts = [abi.VineRolloutPost(rewards=ptr(env.rew_buf), resets=ptr(env.reset_buf), timeouts=ptr(env.timeout_buf),
+                                         values=ptr(self.b_val[t]), shaped_rewards=ptr(self.b_rew[t]),
+                                         dones_next=ptr(self._done_ext[t + 1]), ep_return=ptr(self.ep_ret),
+                                         ep_length=ptr(self.ep_len), ep_stats=ptr(self.ep_stats),
+                                         rng_counter=ptr(self._rng_counter), n=n, reward_scale=self.reward_scale,
+                                         gamma=self.gamma, value_bootstrap=int(self.value_bootstrap),
+                                         success_reward_threshold=500.0) for t in range(T)]
+            last = abi.VinePolicyAct(mu=ptr(self._mu_buf), value=ptr(self.last_value), **common)
+            self._roll_structs = (acts, posts, last)
+        acts, posts, last = self._roll_structs
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._done_ext[0].copy_(self._done_ext[T])
+        for t in range(T):
+            assert lib.vine_policy_act(C.byref(acts[t]), stream) == 0
+            env.step_device()
+            assert lib.vine_rollout_post(C.byref(posts[t]), stream) == 0
+        assert lib.vine_policy_act(C.byref(last), stream) == 0
+        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        rc = lib.vine_gae(p(self.b_rew), p(self.b_val), p(self.b_done), p(self.last_value), p(self.dones),
+                          T, n, self.gamma, self.tau, p(self.b_adv), p(self.b_ret), stream)
+        assert rc == 0
+
+    @torch.no_grad()
     def _rollout(self):
+        if self.fused_update:
+            return self._rollout_fused()
         env = self.env
         for t in range(self.T):
             states = None
@@ -425,22 +469,23 @@ class PPOAgent:
         """The update on hand-written kernels only: per minibatch ONE fused tcgen05 launch (forward, losses, backward,
         weight gradients), the partial-gradient reduction, [one NCCL all-reduce of grads + loss statistics], Adam."""
         T, n, lib = self.T, self.n, self._lib
-        val_old, ret = self.b_val, self.b_ret
-        adv = ret - val_old
-        self.obs_rms.update(self.b_obs.reshape(T * n, self.O))
-        self.val_rms.update(torch.cat([val_old.reshape(-1), ret.reshape(-1)]))
-        self._val_old_n.copy_(self.val_rms(val_old))
-        self._ret_n.copy_(self.val_rms(ret))
-        if self.normalize_advantage:
-            s = torch.stack([adv.sum(), (adv * adv).sum()]).double()
-            cnt = float(T * n * self.world)
-            if self.world > 1:
-                torch.distributed.all_reduce(s)
-            mean = s[0] / cnt
-            std = torch.sqrt(torch.clamp((s[1] - cnt * mean * mean) / (cnt - 1.0), min=0.0))
-            adv = (adv - mean.float()) / (std.float() + 1e-8)
-        self._adv_n.copy_(adv)
-        self._refresh_fused()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self._mb_structs is None:
+            ptr = lambda x: x.data_ptr()  # noqa: E731
+            self._prologue = abi.VinePpoPrologue(
+                obs=ptr(self.b_obs), values=ptr(self.b_val), returns=ptr(self.b_ret), moments=ptr(self._moments),
+                obs_mean=ptr(self.obs_rms.running_mean), obs_var=ptr(self.obs_rms.running_var),
+                obs_count=ptr(self.obs_rms.count), val_mean=ptr(self.val_rms.running_mean),
+                val_var=ptr(self.val_rms.running_var), val_count=ptr(self.val_rms.count),
+                obs_mean_f=ptr(self._obs_mean_f), obs_inv_std_f=ptr(self._obs_inv_std_f), value_stats=ptr(self._val_stats),
+                adv_stats=ptr(self._adv_stats), values_n=ptr(self._val_old_n), returns_n=ptr(self._ret_n),
+                advantages_n=ptr(self._adv_n), count=T * n, num_obs=self.O, world=self.world,
+                normalize_advantage=int(self.normalize_advantage))
+        # running statistics + normalised targets: f64 sufficient statistics, [one all-reduce], finalize
+        assert lib.vine_ppo_moments(C.byref(self._prologue), stream) == 0
+        if self.world > 1:
+            torch.distributed.all_reduce(self._moments)
+        assert lib.vine_ppo_finalize(C.byref(self._prologue), stream) == 0
         self._logstd_old.copy_(self.model.sigma)
         if self._mb_structs is None:
             ptr = lambda x: x.data_ptr()  # noqa: E731
@@ -454,7 +499,6 @@ class PPOAgent:
                 critic_coef=self.critic_coef, entropy_coef=self.entropy_coef, bounds_loss_coef=self.bounds_coef,
                 kl_threshold=self.kl_threshold, lr_min=1e-6, lr_max=1e-2) for e0 in range(0, n, self.mb_envs)]
         p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for _ in range(self.mini_epochs):
             for mb in self._mb_structs:
                 n_part = lib.vine_ppo_minibatch(C.byref(mb), stream)
