@@ -28,47 +28,100 @@ static_assert(PACKED_BYTES <= OFF_X, "packed block overlaps the activation tiles
 
 __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
-// accumulator columns [taddr, taddr+ncols) -> bias + ELU -> bf16 -> tile columns [c_out, c_out+ncols) of row `row`
+// 32 accumulator columns (already in registers) -> bias + ELU -> bf16 -> tile columns [c_out, c_out+32) of row `row`
+template <int KL>
+__device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int c_out, const float* bias, uint8_t* tile, int row) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c_out + g * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + c_out + g * 8 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      w[i] = pack_bf16(elu(__uint_as_float(r[g * 8 + 2 * i]) + bb[2 * i]), elu(__uint_as_float(r[g * 8 + 2 * i + 1]) + bb[2 * i + 1]));
+    *reinterpret_cast<uint4*>(tile + tile_offset(row, c_out + g * 8, KL)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// accumulator columns [taddr, taddr+ncols) -> tile columns [c_out, c_out+ncols); ncols = 32 or 64 (both TMEM loads in flight)
 template <int KL>
 __device__ __forceinline__ void fwd_epilogue(uint32_t taddr, int ncols, int c_out, const float* bias, uint8_t* tile, int row) {
-#pragma unroll 1
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(taddr + c0, r);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint32_t w[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = c_out + c0 + g * 8 + 2 * i;
-        w[i] = pack_bf16(elu(__uint_as_float(r[g * 8 + 2 * i]) + bias[c]), elu(__uint_as_float(r[g * 8 + 2 * i + 1]) + bias[c + 1]));
-      }
-      *reinterpret_cast<uint4*>(tile + tile_offset(row, c_out + c0 + g * 8, KL)) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+  uint32_t r0[32], r1[32];
+  tmem_ld32_async(taddr, r0);
+  if (ncols > 32) {
+    tmem_ld32_async(taddr + 32, r1);
+    tmem_wait(r1);
   }
+  tmem_wait(r0);
+  fwd_chunk<KL>(r0, c_out, bias, tile, row);
+  if (ncols > 32) fwd_chunk<KL>(r1, c_out + 32, bias, tile, row);
 }
 
 // dz = dh * ELU'(h) with ELU'(h) = h > 0 ? 1 : h + 1, written over h in place
 template <int KL>
+__device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], int c_out, uint8_t* tile, int row) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4* p = reinterpret_cast<uint4*>(tile + tile_offset(row, c_out + g * 8, KL));
+    const uint4 hv = *p;
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 h = unpack_bf16(hw[i]);
+      const float d0 = __uint_as_float(r[g * 8 + 2 * i]) * (h.x > 0.f ? 1.f : h.x + 1.f);
+      const float d1 = __uint_as_float(r[g * 8 + 2 * i + 1]) * (h.y > 0.f ? 1.f : h.y + 1.f);
+      w[i] = pack_bf16(d0, d1);
+    }
+    *p = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+template <int KL>
 __device__ __forceinline__ void bwd_epilogue(uint32_t taddr, int ncols, int c_out, uint8_t* tile, int row) {
-#pragma unroll 1
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(taddr + c0, r);
+  uint32_t r0[32], r1[32];
+  tmem_ld32_async(taddr, r0);
+  if (ncols > 32) {
+    tmem_ld32_async(taddr + 32, r1);
+    tmem_wait(r1);
+  }
+  tmem_wait(r0);
+  bwd_chunk<KL>(r0, c_out, tile, row);
+  if (ncols > 32) bwd_chunk<KL>(r1, c_out + 32, tile, row);
+}
+
+// Reductions over the 128 rows of a row-blocked [128 x NC] bf16 tile by the 8 warps of the CTA: a warp owns whole
+// 8-column groups (NC/64 of them); its lanes are 8 rows of a core matrix (128 contiguous bytes: conflict-free 16-byte
+// loads) x 4 row-group phases, so one butterfly over the warp finishes the sum and lane 0 is the only writer of the
+// result -- no shared-memory float atomics (those are CAS loops).
+__device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint4* p = reinterpret_cast<uint4*>(tile + tile_offset(row, c_out + c0 + g * 8, KL));
-      const uint4 hv = *p;
-      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-      uint32_t w[4];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out[c] += sum over rows of tile[row][c]   (out: shared, f32, owned by this CTA)
+template <int NC>
+__device__ __forceinline__ void column_sums(const uint8_t* tile, float* out, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, r8 = lane & 7, ph = lane >> 3;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 h = unpack_bf16(hw[i]);
-        const float d0 = __uint_as_float(r[g * 8 + 2 * i]) * (h.x > 0.f ? 1.f : h.x + 1.f);
-        const float d1 = __uint_as_float(r[g * 8 + 2 * i + 1]) * (h.y > 0.f ? 1.f : h.y + 1.f);
-        w[i] = pack_bf16(d0, d1);
+  for (int j = 0; j < NC / 64; ++j) {
+    const int cg = warp * (NC / 64) + j;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int rg = ph; rg < TILE / 8; rg += 4) {
+      const uint4 v = *reinterpret_cast<const uint4*>(tile + tile_offset(rg * 8 + r8, cg * 8, NC));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16(w[k]);
+        acc[2 * k] += f.x, acc[2 * k + 1] += f.y;
       }
-      *p = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float t = warp_sum_f(acc[k]);
+      if (lane == 0) out[cg * 8 + k] += t;
     }
   }
 }

@@ -28,8 +28,9 @@ using namespace vine_mlp;
 // shared-memory map
 // (x column 31 == 1 carries db1 through dW1; dz_l overwrites h_l in place)
 constexpr int OFF_DZH = OFF_END;                   // d(mu0,mu1,v) [128 x 16] bf16
-constexpr int OFF_DZHF = OFF_DZH + TILE * NH * 2;  // the same in f32 [128][4] for the CUDA-core head gradient
-constexpr int OFF_RED = OFF_DZHF + TILE * 4 * 4;   // block-reduction scratch
+constexpr int OFF_ACC = OFF_DZH + TILE * NH * 2;   // f32 accumulators over the CTA's tiles: db2[128] db3[64] dWh[3][64] dbh[3]
+constexpr int ACC_B2 = 0, ACC_B3 = H2, ACC_WH = H2 + H3, ACC_BH = H2 + H3 + 3 * H3, ACC_FLOATS = 512;
+constexpr int OFF_RED = OFF_ACC + ACC_FLOATS * 4;  // block-reduction scratch
 constexpr int OFF_BAR = OFF_RED + 256;
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 static_assert(SMEM_BYTES <= 232448, "shared-memory budget");
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
   const uint32_t bar_w = smem_u32(smem + OFF_BAR), bar_mma = bar_w + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
   const float* biases = reinterpret_cast<const float*>(smem + OFF_B);
-  float* dzhf = reinterpret_cast<float*>(smem + OFF_DZHF);
+  float* acc_s = reinterpret_cast<float*>(smem + OFF_ACC);
+  for (int i = tid; i < ACC_FLOATS; i += THREADS) acc_s[i] = 0.f;
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
@@ -124,8 +126,6 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
   auto nothing = [] {};
 
   // persistent per-thread accumulators
-  float db = 0.f;                 // tid < 128: db2[tid];  128 <= tid < 192: db3[tid-128]
-  float gh = 0.f;                 // tid < 192: dWh[tid/64][tid%64];  192 <= tid < 195: dbh[tid-192]
   float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // a_loss, c_loss, kl, b_loss, dlogstd0, dlogstd1 (half 0 threads)
 
   const int64_t B = (int64_t)a.T * a.E;
@@ -206,23 +206,49 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
       }
       *reinterpret_cast<uint4*>(dzh_t + tile_offset(row, 0, NH)) = make_uint4(pack_bf16(dmu0, dmu1), pack_bf16(dv, 0.f), 0u, 0u);
       *reinterpret_cast<uint4*>(dzh_t + tile_offset(row, 8, NH)) = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<float4*>(dzhf + 4 * row) = make_float4(dmu0, dmu1, dv, 0.f);
     }
     // =============================== backward ===============================
-    // heads: dh3 = dzh Wh (reduction over the 16 padded head rows); meanwhile dWh, dbh on CUDA cores (3 x 64 outputs)
+    // heads: dh3 = dzh Wh (reduction over the 16 padded head rows); meanwhile dWh = dzh^T h3 and dbh on CUDA cores
     mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sDZH, NH), mn_major(sW4, H3), instr_desc(H3, false, true), NH / 16, false); },
-             [&] {
-               if (tid < 3 * H3) {
-                 const int r_ = tid >> 6;
-                 const int c_ = tid & 63;
-                 float acc = 0.f;
-#pragma unroll 4
-                 for (int s_ = 0; s_ < TILE; ++s_) acc = fmaf(dzhf[4 * s_ + r_], bf16_at(a3_t, s_, c_, H3), acc);
-                 gh += acc;
-               } else if (tid < 3 * H3 + 3) {
-                 float acc = 0.f;
-                 for (int s_ = 0; s_ < TILE; ++s_) acc += dzhf[4 * s_ + (tid - 3 * H3)];
-                 gh += acc;
+             [&] {   // warp w owns columns [8w, 8w+8) of h3; lanes = 8 rows x 4 row-group phases (see column_sums)
+               const int lane = tid & 31, r8 = lane & 7, ph = lane >> 3;
+               float acc[3][8];
+#pragma unroll
+               for (int j = 0; j < 3; ++j)
+#pragma unroll
+                 for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+               float bsum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+               for (int rg = ph; rg < TILE / 8; rg += 4) {
+                 const int r_ = rg * 8 + r8;
+                 const uint4 hv = *reinterpret_cast<const uint4*>(a3_t + tile_offset(r_, warp * 8, H3));
+                 const uint2 dv = *reinterpret_cast<const uint2*>(dzh_t + tile_offset(r_, 0, NH));
+                 const float2 d01 = unpack_bf16(dv.x), d2_ = unpack_bf16(dv.y);
+                 const float d[3] = {d01.x, d01.y, d2_.x};
+                 const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                 for (int k = 0; k < 4; ++k) {
+                   const float2 h = unpack_bf16(hw[k]);
+#pragma unroll
+                   for (int j = 0; j < 3; ++j) {
+                     acc[j][2 * k] = fmaf(d[j], h.x, acc[j][2 * k]);
+                     acc[j][2 * k + 1] = fmaf(d[j], h.y, acc[j][2 * k + 1]);
+                   }
+                 }
+#pragma unroll
+                 for (int j = 0; j < 3; ++j) bsum[j] += d[j];
+               }
+#pragma unroll
+               for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                 for (int k = 0; k < 8; ++k) {
+                   const float t = warp_sum_f(acc[j][k]);
+                   if (lane == 0) acc_s[ACC_WH + j * H3 + warp * 8 + k] += t;
+                 }
+                 if (warp == 0) {   // every warp sees all 128 rows of dzh; one of them records the bias gradient
+                   const float t = warp_sum_f(bsum[j]);
+                   if (lane == 0) acc_s[ACC_BH + j] += t;
+                 }
                }
                __syncthreads();   // h3 is overwritten in place next
              });
@@ -233,14 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
           mma_sequence(tmem + TM_DW3T, mn_major(sA2, H2), mn_major(sA3, H3), instr_desc(H3, true, true), TILE / 16, !first);
           mma_sequence(tmem + TM_DATA, k_major(sA3, H3), mn_major(sW3, H2), instr_desc(H2, false, true), H3 / 16, false);
         },
-        [&] {
-          if (tid >= 128 && tid < 128 + H3) {
-            float acc = 0.f;
-#pragma unroll 4
-            for (int s_ = 0; s_ < TILE; ++s_) acc += bf16_at(a3_t, s_, tid - 128, H3);
-            db += acc;
-          }
-        });
+        [&] { column_sums<H3>(a3_t, acc_s + ACC_B3, tid); });
     bwd_epilogue<H2>(lane_base + TM_DATA + half * 64, 64, half * 64, a2_t, row);   // dz2 over h2
     // layer 2: dW2 += dz2^T h1 (persistent), dh1[:, 0:128] = dz2 W2[:, 0:128]; meanwhile db2
     mma_step(
@@ -248,14 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
           mma_sequence(tmem + TM_DW2, mn_major(sA2, H2), mn_major(sA1, H1), instr_desc(H1, true, true), TILE / 16, !first);
           mma_sequence(tmem + TM_DATA, k_major(sA2, H2), mn_major(sW2, H1, 0), instr_desc(128, false, true), H2 / 16, false);
         },
-        [&] {
-          if (tid < H2) {
-            float acc = 0.f;
-#pragma unroll 4
-            for (int s_ = 0; s_ < TILE; ++s_) acc += bf16_at(a2_t, s_, tid, H2);
-            db += acc;
-          }
-        });
+        [&] { column_sums<H2>(a2_t, acc_s + ACC_B2, tid); });
     bwd_epilogue<H1>(lane_base + TM_DATA + half * 64, 64, half * 64, a1_t, row);           // dz1[:, 0:128] over h1
     mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA2, H2), mn_major(sW2, H1, 128), instr_desc(128, false, true), H2 / 16, false); },
              nothing);
@@ -296,10 +308,11 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
         dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
     }
   }
-  if (tid < H2) ws[WS_B2 + tid] = db;
-  else if (tid < H2 + H3) ws[WS_B3 + tid - H2] = db;
-  if (tid < 3 * H3) ws[WS_WH + tid] = gh;
-  else if (tid < 3 * H3 + 3) ws[WS_BH + tid - 3 * H3] = gh;
+  __syncthreads();   // the last tile's shared-memory atomics
+  if (tid < H2) ws[WS_B2 + tid] = acc_s[ACC_B2 + tid];
+  else if (tid < H2 + H3) ws[WS_B3 + tid - H2] = acc_s[ACC_B3 + tid - H2];
+  if (tid < 3 * H3) ws[WS_WH + tid] = acc_s[ACC_WH + tid];
+  else if (tid < 3 * H3 + 3) ws[WS_BH + tid - 3 * H3] = acc_s[ACC_BH + tid - 3 * H3];
   // loss statistics + d(logstd): reduce over the 128 sample-owning threads
   float* red = reinterpret_cast<float*>(smem + OFF_RED);
   if (half == 0) {
@@ -350,18 +363,45 @@ __device__ inline void param_map(int p, int O, int& ws_off, int& pk_off, bool& p
   pk_off = -1;
 }
 
-// flat[p] = sum over CTA partials; flat[P + j] = loss statistics j (a_loss, c_loss, kl, b_loss)
-__global__ void vine_ppo_reduce_kernel(const float* __restrict__ ws, int n_partials, int O, float* __restrict__ flat) {
+// inverse of param_map: which parameter (or statistic, as P + j) a workspace slot carries; -1 = padding
+__device__ inline int ws_to_param(int w, int O) {
   const int P = num_params(O);
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P + 4) return;
-  int ws_off, pk_off;
-  bool f32;
-  if (p < P) param_map(p, O, ws_off, pk_off, f32);
-  else ws_off = WS_STATS + (p - P);
-  float acc = 0.f;
-  for (int k = 0; k < n_partials; ++k) acc += ws[(size_t)k * WS_FLOATS + ws_off];
-  flat[p] = acc;
+  const int bW1 = 0, bb1 = H1 * O, bW2 = bb1 + H1, bb2 = bW2 + H2 * H1, bW3 = bb2 + H2, bb3 = bW3 + H3 * H2, bWmu = bb3 + H3,
+            bbmu = bWmu + 2 * H3, bWv = bbmu + 2, bbv = bWv + H3;
+  if (w < WS_W1) return bW2 + w;
+  if (w < WS_W3T) { const int r = w - WS_W1, o = r / K1, i = r % K1; return i < O ? bW1 + o * O + i : (i == K1 - 1 ? bb1 + o : -1); }
+  if (w < WS_WH) { const int r = w - WS_W3T, i = r / H3, o = r % H3; return bW3 + o * H2 + i; }
+  if (w < WS_BH) { const int r = w - WS_WH; return r < 2 * H3 ? bWmu + r : bWv + (r - 2 * H3); }
+  if (w < WS_B2) { const int r = w - WS_BH; return r < 2 ? bbmu + r : (r == 2 ? bbv : -1); }
+  if (w < WS_B3) return bb2 + (w - WS_B2);
+  if (w < WS_STATS) return bb3 + (w - WS_B3);
+  const int r = w - WS_STATS;
+  return r < 4 ? P + r : (r < 6 ? P - 2 + (r - 4) : -1);
+}
+
+// flat[p] = sum over CTA partials (parameter order); flat[P + j] = loss statistics j (a_loss, c_loss, kl, b_loss).
+// One workspace slot per (x) thread so the partial reads are coalesced, RED_SPLIT threads share a slot's partials.
+constexpr int RED_SLOTS = 64, RED_SPLIT = 4;
+__global__ void __launch_bounds__(RED_SLOTS* RED_SPLIT) vine_ppo_reduce_kernel(const float* __restrict__ ws, int n_partials, int O,
+                                                                               float* __restrict__ flat) {
+  __shared__ float part[RED_SPLIT][RED_SLOTS];
+  const int lane = threadIdx.x % RED_SLOTS, grp = threadIdx.x / RED_SLOTS;
+  const int w = blockIdx.x * RED_SLOTS + lane;
+  float acc0 = 0.f, acc1 = 0.f;
+  if (w < WS_STATS + 8) {
+    int k = grp;
+    for (; k + RED_SPLIT < n_partials; k += 2 * RED_SPLIT) {
+      acc0 += ws[(size_t)k * WS_FLOATS + w];
+      acc1 += ws[(size_t)(k + RED_SPLIT) * WS_FLOATS + w];
+    }
+    if (k < n_partials) acc0 += ws[(size_t)k * WS_FLOATS + w];
+  }
+  part[grp][lane] = acc0 + acc1;
+  __syncthreads();
+  if (grp == 0 && w < WS_STATS + 8) {
+    const int p = ws_to_param(w, O);
+    if (p >= 0) flat[p] = part[0][lane] + part[1][lane] + part[2][lane] + part[3][lane];
+  }
 }
 
 // torch.optim.Adam (no weight decay, no amsgrad) on the flat parameter vector + re-pack for the tensor cores
@@ -445,8 +485,9 @@ int vine_ppo_minibatch(const VinePpoMinibatch* b, void* stream) {
 
 int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* flat, void* stream) {
   if (!workspace || !flat || n_partials < 1 || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
-  const int n = num_params(num_obs) + 4;
-  vine_ppo_reduce_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, n_partials, num_obs, flat);
+  const int slots = WS_STATS + 8;
+  vine_ppo_reduce_kernel<<<(slots + RED_SLOTS - 1) / RED_SLOTS, RED_SLOTS * RED_SPLIT, 0, (cudaStream_t)stream>>>(workspace, n_partials,
+                                                                                                          num_obs, flat);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
