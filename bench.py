@@ -28,6 +28,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+OUT = sys.stdout
 METRIC = "env-steps/s (whole box, device-timed)"
 UNIT = "env-steps/s"
 # Algorithmic work per env-step of the FSTR workload (derivations: DESIGN.md §6)
@@ -151,7 +152,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def timed_steps(env, lib, pool, steps, use_graph):
@@ -388,12 +389,23 @@ def run_ours(args, rank, world, local_rank):
                 "unpipelined_value": e2e_simple},
         "clocks": clocks, "gpu_launches": args.steps, "sweep": sweep, "ppo": ppo,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout: libraries that write to fd 1 (NCCL prints its version banner or its
+    NCCL_DEBUG log there) are sent to stderr; the returned stream is the real stdout for the JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global OUT
+    OUT = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -71,12 +71,12 @@ def merge_moments(count, mean, m2):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return count, mean, m2
     c = torch.as_tensor(count, dtype=torch.float64, device=mean.device).reshape(1)
-    s1 = mean.double() * c
+    s1 = mean.double() * c[0]
     packed = torch.cat([c, s1.reshape(-1)])
     dist.all_reduce(packed)
     tot = packed[0]
     gmean = packed[1:].view_as(mean) / tot
     # M2_total = sum_r [ M2_r + n_r (mean_r - gmean)^2 ]
-    local = m2.double() + c * (mean.double() - gmean) ** 2
+    local = m2.double() + c[0] * (mean.double() - gmean) ** 2   # c[0]: keeps 0-dim statistics 0-dim
     dist.all_reduce(local)
     return tot.to(torch.float64), gmean.to(mean.dtype), local.to(m2.dtype)

@@ -181,7 +181,7 @@ class PPOAgent:
         if self.world > 1:  # hvd.setup_algo equivalent: identical parameters on every rank
             for p in self.model.parameters():
                 torch.distributed.broadcast(p.data, 0)
-        self.use_graphs = bool(use_graphs) and self.world == 1
+        self._want_graphs = bool(use_graphs)
         self._lib = abi.load_library()
         # The MLP-only network runs entirely on hand-written sm_100a kernels: vine_mlp_forward for the rollout and
         # vine_ppo_minibatch / vine_ppo_reduce / vine_ppo_adam for the update (tcgen05/TMEM); anything else (the LSTM
@@ -189,6 +189,8 @@ class PPOAgent:
         self.fused = (bool(use_fused_policy) and not self.has_rnn and list(units) == [256, 128, 64] and self.A == 2
                       and self.O <= 31 and self.normalize_input and self.normalize_value)
         self.fused_update = self.fused and bool(use_fused_update) and not self.truncate_grads
+        # CUDA graphs: single GPU always; multi-GPU only for the kernel-only path (its NCCL all-reduces are captured too)
+        self.use_graphs = self._want_graphs and (self.world == 1 or (self.fused_update and bool(c.get("graph_nccl", True))))
         if self.fused_update:
             self._init_fused_update(float(c["learning_rate"]))
         else:
