@@ -295,11 +295,25 @@ def run_ours(args, rank, world, local_rank):
         e1.record()
         barrier()
         ms_it = max_over_ranks(e0.elapsed_time(e1)) / iters
+        # split of one iteration, timed separately (same graphs / launches): rollout+GAE vs update
+        parts = {}
+        for name, fn in (("rollout_ms", agent.play_steps), ("update_ms", (agent._g_update.replay if agent._g_update is not None
+                                                                          else agent._update_any))):
+            barrier()
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            barrier()
+            parts[name] = max_over_ranks(e0.elapsed_time(e1)) / iters
         stats = agent.pop_stats()
         assert all(x == x for x in (stats["a_loss"], stats["c_loss"], stats["kl"])), stats
         return {"value": agent.T * num_envs * world / (ms_it * 1e-3), "unit": "frames/s", "ms_per_iteration": ms_it,
                 "num_envs_per_gpu": num_envs, "horizon": agent.T, "minibatch": agent.minibatch,
-                "mini_epochs": agent.mini_epochs, "iterations": iters,
+                "mini_epochs": agent.mini_epochs, "iterations": iters, **parts,
+                # algorithmic tensor work of the update: 3 x forward MACs x 2 per sample per mini-epoch (MLP: 18*256+256*128+128*64+64*3 = 45,760 MAC)
+                "update_tflops": (6 * 45760 * agent.T * num_envs * agent.mini_epochs / (parts["update_ms"] * 1e-3) / 1e12
+                                  if not agent.has_rnn else None),
                 "network": "mlp[256,128,64]+lstm256+ln" if agent.has_rnn else "mlp[256,128,64]",
                 "cuda_graphs": agent.use_graphs,
                 "update": "vine_ppo_minibatch/reduce/adam (tcgen05, hand-written)" if agent.fused_update
