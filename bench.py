@@ -192,8 +192,10 @@ def run_ours(args, rank, world, local_rank):
     n = args.num_envs
     lib = abi.load_library()
 
-    def make_env(num_envs):
-        cfg = fstr_cfg(num_envs, [f"sim_device={dev}", f"rl_device={dev}"])
+    def make_env(num_envs, preset=None):
+        from vine_robot_isaacgymenvs_b200 import config as vcfg
+        extra = [f"sim_device={dev}", f"rl_device={dev}"]
+        cfg = fstr_cfg(num_envs, extra) if preset is None else vcfg.compose(preset + [f"num_envs={num_envs}", "headless=True"] + extra)
         return vine.make(cfg=cfg, global_env_offset=rank * num_envs), cfg
 
     def barrier():
@@ -208,8 +210,8 @@ def run_ours(args, rank, world, local_rank):
             return float(t.item())
         return x
 
-    def measure(num_envs, steps, warmup, sampler=None):
-        env, cfg = make_env(num_envs)
+    def measure(num_envs, steps, warmup, sampler=None, preset=None):
+        env, cfg = make_env(num_envs, preset)
         gen = torch.Generator(device=dev).manual_seed(42 + rank)
         pool = [torch.rand(num_envs, 2, device=dev, generator=gen) * 2 - 1 for _ in range(4)]
         for i in range(max(warmup, 3)):
@@ -374,6 +376,14 @@ def run_ours(args, rank, world, local_rank):
             _, _, ms_m, _ = measure(m, args.steps, args.warmup)
             sweep.append({"num_envs": m, "value": m * args.steps / (ms_m * 1e-3), "ms_per_step": ms_m / args.steps,
                           "l2_resident": True})
+
+        # the contact kernels (same fused launch, CONTACT=true template): BASELINE configs[2] and [3] at their env counts
+        from vine_robot_isaacgymenvs_b200 import config as vcfg
+        for label, preset, m in (("configs[2] shelf, contact-force resets", vcfg.SHELF_OVERRIDES, 16384),
+                                 ("configs[3] pipe + full DR (per-GPU share of 65536)", vcfg.PIPE_DR_OVERRIDES, 8192),
+                                 ("shelf", vcfg.SHELF_OVERRIDES, 1 << 20), ("pipe + full DR", vcfg.PIPE_DR_OVERRIDES, 1 << 20)):
+            _, _, ms_m, _ = measure(m, args.steps, args.warmup, preset=preset)
+            sweep.append({"workload": label, "num_envs": m, "value": m * args.steps / (ms_m * 1e-3), "ms_per_step": ms_m / args.steps})
 
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only ----
     cpu = None

@@ -150,3 +150,35 @@ def test_long_random_rollout_stays_physical():
     assert float(env.dof_vel.abs().max()) < 200.0 and float(env.dof_pos[:, 1:].abs().max()) < 3.2
     tip = env.tip_positions
     assert float(tip[:, 2].max()) < 1.42 and float(tip[:, 2].min()) > 0.5      # within the chain's reach of the pivot
+
+
+@pytest.mark.parametrize("preset,n", [("SHELF_OVERRIDES", 16384), ("PIPE_DR_OVERRIDES", 65536)], ids=["configs2_shelf", "configs3_pipe_dr"])
+def test_contact_configs_at_baseline_sizes_are_deterministic_shard_invariant_and_physical(preset, n):
+    """BASELINE configs[2] / configs[3] at their full env counts, through size-independent properties: bit-identical
+    reruns, bit-identical under 4-way sharding by global env id (the 8-GPU layout of configs[3]), finite and bounded
+    state after a random rollout that pushes half the envs into the obstacles."""
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    ov = getattr(vcfg, preset) + ["headless=True", "task.env.maxEpisodeLength=40"]
+    make = lambda m, off=0: vine.make(cfg=vcfg.compose(ov + [f"num_envs={m}"]), global_env_offset=off)  # noqa: E731
+    whole, again = make(n), make(n)
+    shards = [make(n // 4, k * (n // 4)) for k in range(4)]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    early_resets = 0
+    for t in range(60):
+        act = torch.rand(n, 2, device="cuda", generator=g) * 2.4 - 1.2
+        act[: n // 2, 1] = act[: n // 2, 1].abs()                   # half the envs inflate: pushes the tip into the obstacles
+        whole.step(act); again.step(act)
+        for k, sh in enumerate(shards):
+            sh.step(act[k * (n // 4):(k + 1) * (n // 4)])
+        if t % 10 == 9 or t < 3:
+            for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "timeout_buf"):
+                w = getattr(whole, name)
+                assert torch.equal(w, getattr(again, name)), ("determinism", name, t)
+                assert torch.equal(w, torch.cat([getattr(sh, name) for sh in shards])), ("sharding", name, t)
+        early_resets += int(((whole.reset_buf != 0) & (whole.progress_buf < 39)).sum())    # success / rail limit / contact
+    assert bool(torch.isfinite(whole.obs_buf).all()) and bool(torch.isfinite(whole.rew_buf).all())
+    assert float(whole.dof_vel.abs().max()) < 400.0 and float(whole.obs_dict["obs"].abs().max()) <= 5.0      # VT:374 clamp
+    tip = whole.tip_positions
+    assert float(tip[:, 2].max()) < 1.42 and float(tip[:, 2].min()) > 0.5
+    assert early_resets > 0

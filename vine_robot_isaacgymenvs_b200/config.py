@@ -175,6 +175,25 @@ FSTR_OVERRIDES = [
     "max_iterations=600",
 ]
 
+# BASELINE configs[2]: shelf target reaching (README.md:71 + contact-force resets on), SURVEY §8(d) C3
+SHELF_OVERRIDES = [
+    "task=Vine5LinkMovingBase", "wandb_activate=False", "task.env.CREATE_SHELF=True", "task.env.CREATE_PIPE=False",
+    "task.env.MIN_TARGET_DEPTH_IN_OBSTACLE=-0.05", "task.env.MAX_TARGET_DEPTH_IN_OBSTACLE=0.2",
+    "task.env.USE_NONZERO_CONTACT_FORCE_RESET=True", "vine_randomize=True",
+    "task.task.randomization_parameters.ACTION_NOISE_STD=0.01",
+]
+# BASELINE configs[3]: pipe obstacle with full domain randomization (widened ranges), SURVEY §8(d) C4
+PIPE_DR_OVERRIDES = [
+    "task=Vine5LinkMovingBase", "wandb_activate=False", "task.env.CREATE_SHELF=False", "task.env.CREATE_PIPE=True",
+    "vine_randomize=True",
+    "task.task.randomization_parameters.DYNAMICS_SCALING_MIN=0.9",
+    "task.task.randomization_parameters.DYNAMICS_SCALING_MAX=1.1",
+    "task.task.randomization_parameters.ACTION_NOISE_STD=0.01",
+    "task.task.randomization_parameters.OBSERVATION_NOISE_STD=0.01",
+    "+task.task.randomization_parameters.ACCEL_TARGET_SCALING_MIN=0.9",
+    "+task.task.randomization_parameters.ACCEL_TARGET_SCALING_MAX=1.1",
+]
+
 
 # --------------------------------------------------------------------------------------------
 # Interpolation engine (OmegaConf subset)

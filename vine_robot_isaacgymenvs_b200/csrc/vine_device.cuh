@@ -276,8 +276,17 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, const Dyn& d
     const float oy = VINE_FPAM_OFFSET * d.C[j], oz = VINE_FPAM_OFFSET * d.S[j];
     const float FBy = py[j + 1] + oy + (last ? VINE_FPAM_RADIUS * d.S[j] : 0.f);
     const float FBz = pz[j + 1] + oz - (last ? VINE_FPAM_RADIUS * d.C[j] : 0.f);
+    // per (link, rectangle) cull in the rectangle's frame: everything of this link (both capsules + rest offset) lies
+    // within `reach` of the link's midpoint, so a pair farther than that from the rectangle contributes exactly zero
+    const float my = 0.5f * (py[j] + py[j + 1]), mz = 0.5f * (pz[j] + pz[j + 1]);
+    const float reach = 0.09f + p.rest;   // sqrt(0.04425^2 + 0.055^2) + 0.0169 = 0.0875 (FPAM side), 0.0824 (main)
 #pragma unroll 1
     for (int r = 0; r < ob.n; ++r) {
+      {
+        const Rect& R = ob.r[r];
+        const float dy = my - R.cy, dz = mz - R.cz;
+        if (fabsf(dy * R.ay + dz * R.az) > R.ha + reach || fabsf(dz * R.ay - dy * R.az) > R.hn + reach) continue;
+      }
       float ofy = 0.f, ofz = 0.f;
       capsule_rect(p, ob.r[r], py[j], pz[j], By, Bz, VINE_LINK_RADIUS, j == 0, last,
                    py[j], pz[j], vy[j], vz[j], d.v[j + 1], L[j], ofy, ofz);
