@@ -230,6 +230,23 @@ int vine_set_state(VineEnv* env, const VineStateView* view, void* stream);
 /* When enabled, vine_step also records the `outputs of the last step` block above. */
 int vine_set_debug_outputs(VineEnv* env, int enabled);
 
+/*
+ * The aggregate entries of the reference's per-step wandb dict (compute_reward, V5:1250-1322) in ONE reduction
+ * launch, no host synchronisation (the reference calls `.item()` ~100 times per step).  Needs
+ * vine_set_debug_outputs(env, 1).  Over all envs of this handle:
+ *   sums f64[VINE_METRIC_SUMS]:  [0..15] dist_tip_to_target, target_reached, limit_hit, tip_limit_hit, abs_tip_y,
+ *     tip_z, tip_velocities, u_rail_velocity, prev_u_rail_velocity, rail_force, u_fpam, smoothed_u_fpam,
+ *     tip_target_velocity_difference, progress_buf, contact_forces, nonzero_contact_force;
+ *     [16..28] the 13 reward terms (REWARD_NAMES order, V5:78-81); [29..41] the same weighted; [42] total reward;
+ *     [43] aggregated reward; [44] aggregated reward squared.   (divide by num_envs for the means)
+ *   maxes f32[VINE_METRIC_MAXES]: [0] max_abs_tip_y, [1] max_tip_z, [2] tip_velocities_max, [3..15] max reward
+ *     terms, [16..28] max weighted terms, [29] max total reward.
+ * Multi-GPU: all-reduce sums (SUM) and maxes (MAX) across ranks.
+ */
+#define VINE_METRIC_SUMS 45
+#define VINE_METRIC_MAXES 30
+int vine_metrics(VineEnv* env, double* sums, float* maxes, void* stream);
+
 /* ---- function-level entry points (same device code as the fused step; used for parity
  *      with the reference's own functions on identical inputs) ---- */
 

@@ -182,3 +182,64 @@ def test_contact_configs_at_baseline_sizes_are_deterministic_shard_invariant_and
     tip = whole.tip_positions
     assert float(tip[:, 2].max()) < 1.42 and float(tip[:, 2].min()) > 0.5
     assert early_resets > 0
+
+
+def test_metrics_kernel_matches_the_reference_wandb_formulas():
+    """vine_metrics vs the formulas of compute_reward's wandb_dict (V5:1250-1322) evaluated with torch on the exposed state."""
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    from vine_robot_isaacgymenvs_b200.tasks.vine5link_moving_base import REWARD_NAMES
+    n = 3000
+    env = vine.make(cfg=vcfg.compose(vcfg.SHELF_OVERRIDES + [f"num_envs={n}", "headless=True", "task.env.maxEpisodeLength=50"]))
+    env.enable_debug_outputs(True)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    for t in range(25):
+        act = torch.rand(n, 2, device="cuda", generator=g) * 2.4 - 1.2
+        act[: n // 2, 1] = act[: n // 2, 1].abs()
+        env.step(act)
+    got = env.metrics()
+    st = env.get_state_dict(debug=True)
+    R, w = st["reward_matrix"], env.reward_weights.reshape(-1)
+    tip, tipvel = st["tip_positions"], st["tip_velocities"]
+    want = {
+        "dist_tip_to_target": (-R[:, 0]).mean(), "target_reached": (R[:, 2] != 0).float().mean(),
+        "limit_hit": (R[:, 9] != 0).float().mean(), "abs_tip_y": tip[:, 1].abs().mean(), "tip_z": tip[:, 2].mean(),
+        "max_abs_tip_y": tip[:, 1].abs().max(), "max_tip_z": tip[:, 2].max(), "tip_velocities": tipvel.norm(dim=-1).mean(),
+        "tip_velocities_max": tipvel.norm(dim=-1).max(), "u_rail_velocity": st["u_rail_velocity"].abs().mean(),
+        "rail_force": st["rail_force"].abs().mean(), "u_fpam": st["u_fpam"].abs().mean(),
+        "smoothed_u_fpam": st["smoothed_u_fpam"].abs().mean(), "progress_buf": env.progress_buf.float().mean(),
+        "contact_forces": (-R[:, 12]).mean(), "nonzero_contact_force": (R[:, 12] != 0).float().mean(),
+        "Mean Total Reward": env.rew_buf.mean(), "Max Total Reward": env.rew_buf.max(),
+        "Aggregated Reward": st["aggregated_rew_buf"].mean(),
+        "Aggregated Reward 1 Std Up": st["aggregated_rew_buf"].mean() + st["aggregated_rew_buf"].std(),
+    }
+    for i, name in enumerate(REWARD_NAMES):
+        want[f"Mean {name} Reward"], want[f"Max {name} Reward"] = R[:, i].mean(), R[:, i].max()
+        want[f"Weighted Mean {name} Reward"], want[f"Weighted Max {name} Reward"] = (R[:, i] * w[i]).mean(), (R[:, i] * w[i]).max()
+    assert set(want) <= set(got)
+    for k, v in want.items():
+        assert abs(got[k] - float(v)) <= 1e-4 * abs(float(v)) + 1e-5, (k, got[k], float(v))
+    assert got["contact_forces"] > 0 and got["target_reached"] >= 0
+
+
+def test_mat_trajectory_replay_overwrites_state_like_the_reference(tmp_path):
+    """overwrite_with_mat (V5:947-982): every env gets the recorded DOF positions / target / tip of step num_steps % T."""
+    import numpy as np
+    import scipy.io
+    T = 7
+    rng = np.random.default_rng(0)
+    mat = {"cart_pos": rng.uniform(-0.2, 0.2, (1, T)), "Q": rng.uniform(-0.3, 0.3, (5, T)),
+           "moving_target_pos": np.stack([np.zeros(T), rng.uniform(-0.4, 0.4, T), rng.uniform(0.55, 0.7, T)]),
+           "target_vel": np.zeros((3, 1)), "tip_pos": rng.uniform(0.4, 0.6, (3, T)), "tip_vel": np.zeros((3, T))}
+    path = str(tmp_path / "traj.mat")
+    scipy.io.savemat(path, mat)
+    env = fstr_env(64, [f"task.env.MAT_FILE={path}"])
+    env.step(torch.zeros(64, 2, device="cuda"))
+    env.step(torch.zeros(64, 2, device="cuda"))
+    i = env.overwrite_with_mat()
+    assert i == 2
+    q = env.dof_pos
+    assert torch.allclose(q[:, 0], torch.full((64,), float(mat["cart_pos"][0, i]), device="cuda"))
+    assert torch.allclose(q[:, 1:], torch.tensor(mat["Q"][:, i], dtype=torch.float32, device="cuda").expand(64, 5))
+    assert float(env.dof_vel.abs().max()) == 0.0
+    assert torch.allclose(env.target_positions[:, 1:], torch.tensor(mat["moving_target_pos"][1:, i], dtype=torch.float32, device="cuda").expand(64, 2))

@@ -132,12 +132,16 @@ class VineSimulateIO(C.Structure):
 EXPORTED_SYMBOLS = [
     "vine_abi_version", "vine_config_defaults", "vine_num_observations", "vine_create",
     "vine_destroy", "vine_last_error", "vine_bind_io", "vine_step", "vine_step_range", "vine_reset_idx",
-    "vine_get_state", "vine_set_state", "vine_set_debug_outputs", "vine_post_physics",
+    "vine_get_state", "vine_set_state", "vine_set_debug_outputs", "vine_metrics", "vine_post_physics",
     "vine_pre_physics", "vine_actuation", "vine_simulate", "vine_philox_debug", "vine_gae",
     "vine_mlp_pack", "vine_mlp_forward",
     "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
     "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
 ]
+METRIC_SUMS, METRIC_MAXES = 45, 30
+METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limit_hit", "abs_tip_y", "tip_z", "tip_velocities",
+                  "u_rail_velocity", "prev_u_rail_velocity", "rail_force", "u_fpam", "smoothed_u_fpam",
+                  "tip_target_velocity_difference", "progress_buf", "contact_forces", "nonzero_contact_force"]
 MLP_PACKED_BYTES = 102208
 PPO_WS_FLOATS = 49664
 PPO_STATE_FLOATS = 16
@@ -199,6 +203,7 @@ def _declare(lib):
     lib.vine_get_state.argtypes = [vp, C.POINTER(VineStateView), vp]
     lib.vine_set_state.argtypes = [vp, C.POINTER(VineStateView), vp]
     lib.vine_set_debug_outputs.argtypes = [vp, C.c_int]
+    lib.vine_metrics.argtypes = [vp, vp, vp, vp]
     lib.vine_post_physics.argtypes = [vp, C.POINTER(VinePostPhysicsIO), vp]
     lib.vine_pre_physics.argtypes = [vp, C.POINTER(VinePrePhysicsIO), vp]
     lib.vine_actuation.argtypes = [vp, C.POINTER(VineActuationIO), vp]

@@ -611,6 +611,114 @@ int vine_set_debug_outputs(VineEnv* env, int enabled) {
   return VINE_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Metrics of the reference's per-step wandb dict (V5:1250-1322) as ONE reduction launch over the
+// debug plane + state planes (the reference issues ~100 `.item()` syncs per step for the same numbers).
+// sums f64[VINE_METRIC_SUMS], maxes f32[VINE_METRIC_MAXES]; layouts: include/vine_b200.h.
+// ------------------------------------------------------------------------------------------
+#define MS_SCALARS 16
+#define MS_NSUM (MS_SCALARS + 2 * VINE_NUM_REWARDS + 1 + 2)      /* = VINE_METRIC_SUMS */
+#define MS_NMAX (3 + 2 * VINE_NUM_REWARDS + 1)                   /* = VINE_METRIC_MAXES */
+static_assert(MS_NSUM == VINE_METRIC_SUMS && MS_NMAX == VINE_METRIC_MAXES, "metric layout");
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  v = __fadd_rn(v, 0.f);   // -0.0 -> +0.0 (its bit pattern would order below every negative number)
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void vine_metrics_init_kernel(double* sums, float* maxes) {
+  const int i = threadIdx.x;
+  if (i < MS_NSUM) sums[i] = 0.0;
+  if (i < MS_NMAX) maxes[i] = __int_as_float(0xff800000);   // -inf
+}
+
+__global__ void __launch_bounds__(256) vine_metrics_kernel(const __grid_constant__ VineParams p, const StepArgs a, double* sums,
+                                                           float* maxes) {
+  float s[MS_NSUM], m[MS_NMAX];
+#pragma unroll
+  for (int i = 0; i < MS_NSUM; ++i) s[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < MS_NMAX; ++i) m[i] = __int_as_float(0xff800000);
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (int64_t)gridDim.x * blockDim.x) {
+    const float* d = a.dbg + e * VINE_DBG_W;
+    const float4 s3 = a.S3[e], s4 = a.S4[e];
+    const float* r = d + 6;
+    const float tipvel = sqrtf(d[4] * d[4] + d[5] * d[5]);
+    const float v[MS_SCALARS] = {
+        -r[0],                                  // dist_tip_to_target (Position reward = -dist, V5:1480)
+        r[2] != 0.f ? 1.f : 0.f,                // target_reached
+        r[9] != 0.f ? 1.f : 0.f,                // limit_hit
+        r[11] != 0.f ? 1.f : 0.f,               // tip_limit_hit
+        fabsf(s4.x), s4.y,                      // abs_tip_y, tip_z (rigid-body view)
+        tipvel,                                 // tip_velocities
+        fabsf(d[0]), fabsf(d[2]), fabsf(d[3]),  // u_rail_velocity, prev_u_rail_velocity, rail_force
+        fabsf(d[1]), fabsf(s3.x),               // u_fpam, smoothed_u_fpam
+        tipvel,                                 // tip_target_velocity_difference (target velocity == 0, V5:916-918)
+        (float)a.progress[e],                   // progress_buf
+        -r[12],                                 // contact_forces (Contact Force reward = -contact [contact > 0])
+        r[12] != 0.f ? 1.f : 0.f};              // nonzero_contact_force
+#pragma unroll
+    for (int i = 0; i < MS_SCALARS; ++i) s[i] += v[i];
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < VINE_NUM_REWARDS; ++i) {
+      const float wr = r[i] * p.w[i];
+      s[MS_SCALARS + i] += r[i];
+      s[MS_SCALARS + VINE_NUM_REWARDS + i] += wr;
+      m[3 + i] = fmaxf(m[3 + i], r[i]);
+      m[3 + VINE_NUM_REWARDS + i] = fmaxf(m[3 + VINE_NUM_REWARDS + i], wr);
+    }
+    tot = a.rew[e];
+    s[MS_SCALARS + 2 * VINE_NUM_REWARDS] += tot;
+    s[MS_SCALARS + 2 * VINE_NUM_REWARDS + 1] += s4.w;            // aggregated reward
+    s[MS_SCALARS + 2 * VINE_NUM_REWARDS + 2] += s4.w * s4.w;
+    m[0] = fmaxf(m[0], fabsf(s4.x)); m[1] = fmaxf(m[1], s4.y); m[2] = fmaxf(m[2], tipvel);
+    m[3 + 2 * VINE_NUM_REWARDS] = fmaxf(m[3 + 2 * VINE_NUM_REWARDS], tot);
+  }
+  __shared__ double rs[8][MS_NSUM];
+  __shared__ float rm[8][MS_NMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < MS_NSUM; ++i) {
+    double t = (double)s[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) rs[warp][i] = t;
+  }
+#pragma unroll
+  for (int i = 0; i < MS_NMAX; ++i) {
+    float t = m[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (lane == 0) rm[warp][i] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < MS_NSUM) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += rs[w][threadIdx.x];
+    atomicAdd(sums + threadIdx.x, t);
+  }
+  if (threadIdx.x < MS_NMAX) {
+    float t = rm[0][threadIdx.x];
+    for (int w = 1; w < 8; ++w) t = fmaxf(t, rm[w][threadIdx.x]);
+    atomic_max_float(maxes + threadIdx.x, t);
+  }
+}
+
+int vine_metrics(VineEnv* env, double* sums, float* maxes, void* stream) {
+  if (!env || !sums || !maxes) return VINE_ERR_INVALID_ARG;
+  if (!env->bound) { snprintf(env->err, 256, "vine_metrics: call vine_bind_io first"); return VINE_ERR_NOT_BOUND; }
+  if (!env->a.dbg) { snprintf(env->err, 256, "vine_metrics: enable vine_set_debug_outputs first"); return VINE_ERR_INVALID_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  vine_metrics_init_kernel<<<1, 64, 0, st>>>(sums, maxes);
+  int64_t blocks = (env->a.n + 255) / 256;
+  if (blocks > 592) blocks = 592;
+  vine_metrics_kernel<<<(unsigned)blocks, 256, 0, st>>>(env->p, env->a, sums, maxes);
+  CUDA_TRY(env, cudaGetLastError());
+  return VINE_OK;
+}
+
 int vine_step(VineEnv* env, void* stream) {
   if (!env) return VINE_ERR_INVALID_ARG;
   if (!env->bound) { snprintf(env->err, 256, "vine_step: call vine_bind_io first"); return VINE_ERR_NOT_BOUND; }

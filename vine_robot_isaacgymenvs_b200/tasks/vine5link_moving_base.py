@@ -123,6 +123,31 @@ class Vine5LinkMovingBase(VecTask):
         """V5:1110-1120 runs inside the fused kernel (progress, deferred reset, obs, reward, resets)."""
         self.num_steps += 1
 
+    # ------------------------------------------------------------------ .mat trajectory replay (V5:281-297, 947-982)
+    def read_mat_file(self, filename):
+        """MAT_FILE of a recorded hardware run: cart_pos (1,T), Q (5,T), moving_target_pos (3,T), tip_pos (3,T), ..."""
+        import scipy.io
+        self.mat = scipy.io.loadmat(filename)
+        return self.mat
+
+    def overwrite_with_mat(self):
+        """Overwrite every env's DOF positions (velocities 0), target and rigid-body tip with step
+        ``num_steps % T`` of the recorded trajectory, like the reference's viewer replay (V5:947-982)."""
+        if getattr(self, "mat", None) is None:
+            self.read_mat_file(self.cfg["env"]["MAT_FILE"])
+        m, n = self.mat, self.num_envs
+        total = m["cart_pos"].shape[1]
+        assert m["cart_pos"].shape == (1, total) and m["Q"].shape == (5, total)
+        i = self.num_steps % total
+        row = lambda a: torch.as_tensor(a, dtype=torch.float32, device=self.device).reshape(1, -1).repeat(n, 1)  # noqa: E731
+        state = {"dof_pos": torch.cat([row(m["cart_pos"][:, i]), row(m["Q"][:, i])], dim=1),
+                 "dof_vel": torch.zeros(n, 6, device=self.device),
+                 "target_positions": row(m["moving_target_pos"][:, i])}
+        if "tip_pos" in m:
+            state["tip_positions"] = row(m["tip_pos"][:, i])
+        self.set_state_dict(state)
+        return i
+
     def step(self, actions):
         """VecTask.step (VT:319-380) as one kernel launch (or one CUDA-graph replay)."""
         self.pre_physics_step(actions)
@@ -257,6 +282,47 @@ class Vine5LinkMovingBase(VecTask):
 
     def enable_debug_outputs(self, enabled=True):
         self._check(self._lib.vine_set_debug_outputs(self._h, int(enabled)))
+        self._debug_enabled = bool(enabled)
+
+    def metrics_async(self):
+        """Launch the metrics reduction (vine_metrics) for the state after the last step; returns pinned host tensors
+        (sums f64[45], maxes f32[30]) and a CUDA event that fires when they are filled -- no host synchronisation."""
+        if not getattr(self, "_debug_enabled", False):
+            self.enable_debug_outputs(True)
+            raise RuntimeError("metrics need the debug plane: enabled now, call again after the next step()")
+        if not hasattr(self, "_metric_bufs"):
+            self._metric_bufs = (torch.zeros(abi.METRIC_SUMS, dtype=torch.float64, device=self.device),
+                                 torch.zeros(abi.METRIC_MAXES, dtype=torch.float32, device=self.device),
+                                 torch.zeros(abi.METRIC_SUMS, dtype=torch.float64).pin_memory(),
+                                 torch.zeros(abi.METRIC_MAXES, dtype=torch.float32).pin_memory())
+        sums, maxes, sums_h, maxes_h = self._metric_bufs
+        self._check(self._lib.vine_metrics(self._h, C.c_void_p(sums.data_ptr()), C.c_void_p(maxes.data_ptr()), self._stream()))
+        sums_h.copy_(sums, non_blocking=True)
+        maxes_h.copy_(maxes, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return sums_h, maxes_h, ev
+
+    def metrics(self):
+        """The aggregate keys of the reference's ``wandb_dict`` (compute_reward, V5:1250-1322) with the same names."""
+        sums_h, maxes_h, ev = self.metrics_async()
+        ev.synchronize()
+        n = float(self.num_envs)
+        s, m = sums_h.tolist(), maxes_h.tolist()
+        out = {k: s[i] / n for i, k in enumerate(abi.METRIC_SCALARS)}
+        out.update({"max_abs_tip_y": m[0], "max_tip_z": m[1], "tip_velocities_max": m[2]})
+        R = len(REWARD_NAMES)
+        for i, name in enumerate(REWARD_NAMES):
+            out[f"Mean {name} Reward"] = s[16 + i] / n
+            out[f"Max {name} Reward"] = m[3 + i]
+            out[f"Weighted Mean {name} Reward"] = s[16 + R + i] / n
+            out[f"Weighted Max {name} Reward"] = m[3 + R + i]
+        out["Mean Total Reward"], out["Max Total Reward"] = s[16 + 2 * R] / n, m[3 + 2 * R]
+        mean = s[17 + 2 * R] / n
+        std = max(s[18 + 2 * R] - n * mean * mean, 0.0) / max(n - 1.0, 1.0)
+        out["Aggregated Reward"] = mean
+        out["Aggregated Reward 1 Std Up"], out["Aggregated Reward 1 Std Down"] = mean + std ** 0.5, mean - std ** 0.5
+        return out
 
     def _get(self, name):
         return self.get_state_dict(debug=name in self._DEBUG_FIELDS)[name]
