@@ -458,6 +458,21 @@ int vine_ppo_moments(const VinePpoPrologue* args, void* stream);
 int vine_ppo_finalize(const VinePpoPrologue* args, void* stream);
 
 /*
+ * Pointwise half of the LSTM layer of the reference's network (Vine5LinkMovingBasePPO.yaml:32-38; rl_games
+ * LSTMWithDones, torch gate order i,f,g,o), one fused launch per time step and direction.  `gates` bf16 [S, 4H] are
+ * the pre-activations (input projection + recurrent GEMM + biases); not_done [S] multiplies the incoming state
+ * (hidden state zeroed where an episode ended before this observation).  Forward writes c, h (f32), the bf16
+ * h * not_done_next that feeds the next recurrent GEMM, and the activated gates (bf16 [S, 4H]) for backward.
+ * Backward takes dh_out (f32, from the layers above), the raw recurrent dh of step t+1 (bf16, = dG_{t+1} W_hh, masked
+ * here with not_done_next) and dc_next, and writes dG (bf16 [S, 4H]) and dc_prev.  Optional pointers may be NULL.
+ */
+int vine_lstm_cell_fwd(const void* gates_bf16, const float* c_prev, const float* not_done, const float* not_done_next,
+                       int64_t num_seqs, int hidden, float* c, float* h, void* h_next_bf16, void* acts_bf16, void* stream);
+int vine_lstm_cell_bwd(const void* acts_bf16, const float* c_prev, const float* c, const float* not_done, const float* dh_out,
+                       const void* dh_rec_bf16, const float* not_done_next, const float* dc_next, int64_t num_seqs, int hidden,
+                       void* dgates_bf16, float* dc_prev, void* stream);
+
+/*
  * PPO minibatch update of the same network as ONE fused tcgen05/TMEM kernel: forward, the PPO losses of
  * Vine5LinkMovingBasePPO.yaml:46-81 (e_clip actor loss, clipped value loss x critic_coef / 2, bounds loss,
  * entropy), backward and weight gradients (rl_games A2CAgent.calc_gradients + autograd; in-repo analogue

@@ -82,3 +82,38 @@ def test_checkpoint_roundtrip_uses_rl_games_layout(tmp_path):
     d.load_state_dict(torch.load(tmp_path / "ck2.pth", map_location="cuda:0"))
     assert torch.equal(c.flat, d.flat) and torch.equal(c.adam_m, d.adam_m) and torch.equal(c._packed, d._packed)
     assert float(d.ppo_state[1]) == float(c.ppo_state[1]) > 0 and abs(d.lr - c.lr) < 1e-12
+
+
+def test_fused_lstm_cell_kernels_match_the_torch_restatement():
+    """csrc/vine_lstm.cu + bf16 GEMMs (ppo/lstm_ops.py) vs the pure-torch fp32 loop of the same module: outputs, final
+    state and every gradient (tolerance: bf16 GEMM operands, relative Frobenius error <= 2e-2)."""
+    from vine_robot_isaacgymenvs_b200.ppo.ppo import ActorCritic
+    rnn = {"name": "lstm", "units": 256, "layers": 1, "before_mlp": False, "concat_input": True, "layer_norm": True}
+    torch.manual_seed(3)
+    m = ActorCritic(18, 2, (256, 128, 64), rnn=rnn).cuda()
+    L, S = 4, 2048
+    obs = torch.randn(L, S, 18, device="cuda")
+    h0 = (torch.randn(S, 256, device="cuda") * 0.5).requires_grad_(True)
+    c0 = (torch.randn(S, 256, device="cuda") * 0.5).requires_grad_(True)
+    nd = (torch.rand(L, S, device="cuda") > 0.2).float()
+    wts = torch.randn(L * S, 3, device="cuda")
+
+    def run(fused):
+        m.fused_cell = fused
+        m.zero_grad()
+        for t in (h0, c0):
+            t.grad = None
+        mu, _, v, (h, c) = m(obs, (h0, c0), nd)
+        loss = (mu * wts[:, :2]).sum() + (v.squeeze(-1) * wts[:, 2]).sum() + 0.3 * h.sum() - 0.2 * c.sum()
+        loss.backward()
+        grads = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        grads["h0"], grads["c0"] = h0.grad.clone(), c0.grad.clone()
+        return mu.detach(), v.detach(), h.detach(), c.detach(), grads
+
+    mu_r, v_r, h_r, c_r, g_r = run(False)
+    mu_f, v_f, h_f, c_f, g_f = run(True)
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-12))  # noqa: E731
+    assert rel(mu_f, mu_r) < 2e-2 and rel(v_f, v_r) < 2e-2 and rel(h_f, h_r) < 1e-2 and rel(c_f, c_r) < 1e-2
+    assert set(g_f) == set(g_r)
+    errs = {k: rel(g_f[k], g_r[k]) for k in g_r}
+    assert max(errs.values()) < 2e-2, errs

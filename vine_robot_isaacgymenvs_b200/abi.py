@@ -137,6 +137,7 @@ EXPORTED_SYMBOLS = [
     "vine_mlp_pack", "vine_mlp_forward",
     "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
     "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
+    "vine_lstm_cell_fwd", "vine_lstm_cell_bwd",
 ]
 METRIC_SUMS, METRIC_MAXES = 45, 30
 METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limit_hit", "abs_tip_y", "tip_z", "tip_velocities",
@@ -218,6 +219,8 @@ def _declare(lib):
     lib.vine_rollout_post.argtypes = [C.POINTER(VineRolloutPost), vp]
     lib.vine_ppo_moments.argtypes = [C.POINTER(VinePpoPrologue), vp]
     lib.vine_ppo_finalize.argtypes = [C.POINTER(VinePpoPrologue), vp]
+    lib.vine_lstm_cell_fwd.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp, vp]
+    lib.vine_lstm_cell_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp]
     lib.vine_ppo_num_params.argtypes = [C.c_int]
     lib.vine_ppo_max_ctas.argtypes = []
     lib.vine_ppo_minibatch.argtypes = [C.POINTER(VinePpoMinibatch), vp]

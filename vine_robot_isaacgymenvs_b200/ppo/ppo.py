@@ -89,6 +89,7 @@ class ActorCritic(nn.Module):
             d = u
         self.actor_mlp = nn.Sequential(*layers)
         self.has_rnn = bool(rnn) and str(rnn.get("name", "lstm")).lower() not in ("none", "")
+        self.fused_cell = True    # CUDA only: fused pointwise LSTM kernels (False = the pure-torch restatement)
         if self.has_rnn:
             if str(rnn["name"]).lower() != "lstm" or int(rnn.get("layers", 1)) != 1 or rnn.get("before_mlp", False):
                 raise ValueError("only the reference's rnn block is supported: lstm, 1 layer, before_mlp False")
@@ -115,8 +116,13 @@ class ActorCritic(nn.Module):
         m = self.actor_mlp(x)
         inp = torch.cat([m, x.to(m.dtype)], -1) if self.concat_input else m
         r = self.rnn.rnn
-        gi = torch.nn.functional.linear(inp, r.weight_ih_l0, r.bias_ih_l0 + r.bias_hh_l0).view(L, S, -1)
         h, c = states
+        if self.fused_cell and inp.is_cuda:   # pointwise work in csrc/vine_lstm.cu, GEMMs in bf16
+            from .lstm_ops import lstm_seq
+            hs, (h, c) = lstm_seq(inp.view(L, S, -1), r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0 + r.bias_hh_l0, h, c, not_done)
+            out = self.layer_norm(hs.reshape(L * S, -1))
+            return self.mu(out), self.sigma.expand(L * S, -1), self.value(out), (h, c)
+        gi = torch.nn.functional.linear(inp, r.weight_ih_l0, r.bias_ih_l0 + r.bias_hh_l0).view(L, S, -1)
         outs = []
         for t in range(L):
             if not_done is not None:
