@@ -407,6 +407,9 @@ typedef struct VinePolicyAct {
   int32_t num_obs, reserved;
   uint64_t seed;
   int64_t global_env_offset;
+  void* u_out;                   /* NULL, or [ceil(n/128)] tiles [128 x 128] bf16 (UMMA row-blocked): the LSTM input
+                                    [MLP output (64) | normalised obs (32, col 31 == 1) | 0]; heads and sampling are
+                                    skipped (they follow the LSTM: vine_lstm_step / vine_lstm_head) */
 } VinePolicyAct;
 int vine_policy_act(const VinePolicyAct* args, void* stream);
 
@@ -456,6 +459,56 @@ typedef struct VinePpoPrologue {
 } VinePpoPrologue;
 int vine_ppo_moments(const VinePpoPrologue* args, void* stream);
 int vine_ppo_finalize(const VinePpoPrologue* args, void* stream);
+
+/*
+ * The recurrent half of the reference's network (Vine5LinkMovingBasePPO.yaml:32-40: lstm 256, concat_input,
+ * layer_norm; rl_games A2CBuilder.Network.forward) on hand-written kernels.  Activations live in HBM as 128-row
+ * tiles in the UMMA row-blocked layout (one bulk-TMA copy per GEMM operand): u / hm / hh = [tiles][...] as described
+ * in csrc/vine_lstm_net.cu; c = f32 [n, 256] row-major.
+ *   vine_lstm_pack : torch-layout f32 parameters (W_ih [1024, 64+O], W_hh [1024, 256], b_ih, b_hh, LayerNorm gamma/beta,
+ *                    W_mu [2,256], b_mu, W_v [1,256], b_v) -> the packed block (bf16 weight pieces + f32 vectors).
+ *   vine_lstm_step : one time step: gates = u W_ih^T + hm W_hh^T + b (tcgen05, TMEM accumulator), c = f c_prev*nd + i g,
+ *                    h = o tanh(c); writes c, hh (bf16 tiles), optionally hm_next = hh * not_done_next and the activated
+ *                    gates (for backward).  Grid = (tiles, 8 slices of 32 hidden units).
+ *   vine_lstm_mask : hm = hh * not_done (rollout: the done flag arrives after the step has run).
+ *   vine_lstm_head : LayerNorm + mu/value heads per row (+ Philox Gaussian sampling, neglogp, clamped env action: the
+ *                    same outputs and Philox keying as vine_policy_act).
+ */
+#define VINE_LSTM_PACKED_BYTES 795664
+typedef struct VineLstmStep {
+  const void* params;            /* VINE_LSTM_PACKED_BYTES */
+  const void* u;                 /* [tiles][128 x 128] bf16 */
+  const void* hm;                /* [tiles][2][128 x 128] bf16: not_done * h_prev */
+  const float* c_prev;           /* [n, 256] */
+  const float* not_done;         /* [n] mask of c_prev (NULL = 1) */
+  const float* not_done_next;    /* [n] mask for hm_next (NULL = 1) */
+  float* c;                      /* [n, 256] out */
+  void* hh;                      /* [tiles][2][128 x 128] bf16 out */
+  void* hm_next;                 /* NULL or like hh */
+  void* act;                     /* NULL or [tiles][16][128 x 64] bf16 activated gates */
+  int64_t n;
+} VineLstmStep;
+typedef struct VineLstmHead {
+  const void* params;
+  const void* hh;
+  const float* value_stats;      /* {mean, std} */
+  float* mu;                     /* [n, 2] or NULL */
+  float* value;                  /* [n] de-normalised, or NULL */
+  const float* logstd;           /* [2]; required when sampling */
+  const uint32_t* rng_counter;
+  float* actions;                /* [n, 2] or NULL (no sampling) */
+  float* neglogp;                /* [n] */
+  float* env_actions;            /* [n, 2] clamped */
+  int64_t n;
+  uint64_t seed;
+  int64_t global_env_offset;
+} VineLstmHead;
+int vine_lstm_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* ln_gamma,
+                   const float* ln_beta, const float* w_mu, const float* b_mu, const float* w_v, const float* b_v,
+                   int num_obs, void* packed, void* stream);
+int vine_lstm_step(const VineLstmStep* args, void* stream);
+int vine_lstm_mask(const void* hh, const float* not_done, int64_t n, void* hm, void* stream);
+int vine_lstm_head(const VineLstmHead* args, void* stream);
 
 /*
  * Pointwise half of the LSTM layer of the reference's network (Vine5LinkMovingBasePPO.yaml:32-38; rl_games

@@ -137,13 +137,15 @@ EXPORTED_SYMBOLS = [
     "vine_mlp_pack", "vine_mlp_forward",
     "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
     "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
-    "vine_lstm_cell_fwd", "vine_lstm_cell_bwd",
+    "vine_lstm_cell_fwd", "vine_lstm_cell_bwd", "vine_lstm_pack", "vine_lstm_step", "vine_lstm_mask", "vine_lstm_head",
 ]
 METRIC_SUMS, METRIC_MAXES = 45, 30
 METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limit_hit", "abs_tip_y", "tip_z", "tip_velocities",
                   "u_rail_velocity", "prev_u_rail_velocity", "rail_force", "u_fpam", "smoothed_u_fpam",
                   "tip_target_velocity_difference", "progress_buf", "contact_forces", "nonzero_contact_force"]
 MLP_PACKED_BYTES = 102208
+LSTM_PACKED_BYTES = 795664
+LSTM_TILE_BYTES = 32768          # one [128 x 128] bf16 activation tile
 PPO_WS_FLOATS = 49664
 PPO_STATE_FLOATS = 16
 
@@ -153,7 +155,18 @@ class VinePolicyAct(C.Structure):
         "packed", "obs", "obs_mean", "obs_inv_std", "value_stats", "mu", "value", "logstd", "rng_counter", "actions",
         "neglogp", "obs_copy", "env_actions")]
         + [("n", C.c_int64), ("num_obs", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64),
-           ("global_env_offset", C.c_int64)])
+           ("global_env_offset", C.c_int64), ("u_out", C.c_void_p)])
+
+
+class VineLstmStep(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("params", "u", "hm", "c_prev", "not_done", "not_done_next", "c", "hh", "hm_next",
+                                          "act")] + [("n", C.c_int64)]
+
+
+class VineLstmHead(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("params", "hh", "value_stats", "mu", "value", "logstd", "rng_counter", "actions",
+                                           "neglogp", "env_actions")]
+                + [("n", C.c_int64), ("seed", C.c_uint64), ("global_env_offset", C.c_int64)])
 
 
 class VineRolloutPost(C.Structure):
@@ -221,6 +234,10 @@ def _declare(lib):
     lib.vine_ppo_finalize.argtypes = [C.POINTER(VinePpoPrologue), vp]
     lib.vine_lstm_cell_fwd.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp, vp, vp]
     lib.vine_lstm_cell_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp]
+    lib.vine_lstm_pack.argtypes = [vp] * 10 + [C.c_int, vp, vp]
+    lib.vine_lstm_step.argtypes = [C.POINTER(VineLstmStep), vp]
+    lib.vine_lstm_mask.argtypes = [vp, vp, C.c_int64, vp, vp]
+    lib.vine_lstm_head.argtypes = [C.POINTER(VineLstmHead), vp]
     lib.vine_ppo_num_params.argtypes = [C.c_int]
     lib.vine_ppo_max_ctas.argtypes = []
     lib.vine_ppo_minibatch.argtypes = [C.POINTER(VinePpoMinibatch), vp]

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_policy_act_kernel(const VineP
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t e = tile * TILE + row;
     const bool valid = e < a.n;
-    build_x_tile(x_t, row, half, valid, a.obs + e * O, a.obs_mean, a.obs_inv_std, O, false,
+    build_x_tile(x_t, row, half, valid, a.obs + e * O, a.obs_mean, a.obs_inv_std, O, a.u_out != nullptr,
                  (valid && a.obs_copy) ? a.obs_copy + e * O : nullptr);
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
@@ -88,6 +88,21 @@ __global__ void __launch_bounds__(THREADS, 1) vine_policy_act_kernel(const VineP
     fwd_epilogue<H2>(lane_base + half * 64, 64, half * 64, biases + H1, a2_t, row);
     mma_step([&] { mma_sequence(tmem, k_major(sA2, H2), k_major(sW3, H2), instr_desc(H3, false, false), H2 / 16, false); });
     fwd_epilogue<H3>(lane_base + half * 32, 32, half * 32, biases + H1 + H2, a3_t, row);
+    if (a.u_out) {
+      // recurrent network: emit the LSTM input tile U = [h3 (64) | x (32) | 0 (32)] (row-blocked [128 x 128] bf16) and stop;
+      // LayerNorm and the heads follow the LSTM (vine_lstm_step / vine_lstm_head)
+      __syncthreads();   // both column halves of h3 are in shared memory
+      uint8_t* ut = reinterpret_cast<uint8_t*>(a.u_out) + (size_t)tile * (TILE * 128 * 2);
+#pragma unroll
+      for (int q = half * 8; q < half * 8 + 8; ++q) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (q < 8) v = *reinterpret_cast<const uint4*>(a3_t + tile_offset(row, 8 * q, H3));
+        else if (q < 12) v = *reinterpret_cast<const uint4*>(x_t + tile_offset(row, 8 * (q - 8), K1));
+        *reinterpret_cast<uint4*>(ut + tile_offset(row, 8 * q, 128)) = v;
+      }
+      __syncthreads();   // x / h3 tiles are rewritten by the next tile
+      continue;
+    }
     mma_step([&] { mma_sequence(tmem, k_major(sA3, H3), k_major(sW4, H3), instr_desc(NH, false, false), H3 / 16, false); });
     if (half == 0) {
       uint32_t r[16];
@@ -249,7 +264,8 @@ int vine_policy_act(const VinePolicyAct* a, void* stream) {
       a->num_obs > K1 || (((uintptr_t)a->packed) & 15u))
     return VINE_ERR_INVALID_ARG;
   if (a->actions && !a->logstd) return VINE_ERR_INVALID_ARG;
-  if (!a->actions && !a->mu && !a->value) return VINE_ERR_INVALID_ARG;
+  if (!a->actions && !a->mu && !a->value && !a->u_out) return VINE_ERR_INVALID_ARG;
+  if (a->u_out && (a->num_obs >= K1 || (((uintptr_t)a->u_out) & 15u))) return VINE_ERR_INVALID_ARG;
   static int configured = -1;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return VINE_ERR_CUDA;
