@@ -511,6 +511,60 @@ int vine_lstm_mask(const void* hh, const float* not_done, int64_t n, void* hm, v
 int vine_lstm_head(const VineLstmHead* args, void* stream);
 
 /*
+ * Training counterpart of vine_lstm_head over all rows of a minibatch (rows = [step][sequence]): LayerNorm + heads,
+ * the PPO losses of vine_ppo_minibatch (same formulas), and the backward down to dh (bf16 tiles like hh).
+ * scalars f32 [n, 8] per row: action0, action1, mu_old0, mu_old1, neglogp_old, value_old (normalised), return
+ * (normalised), advantage (normalised).  grads f32[VINE_LSTM_HEAD_GRAD_FLOATS] must be zero on entry and receives
+ * d(LayerNorm gamma)[256], d(beta)[256], d(W_mu0, W_mu1, W_v)[3][256], d(b)[3] (+1 pad), d(logstd)[2],
+ * loss statistics a_loss, c_loss, kl, b_loss (means), padding.
+ */
+#define VINE_LSTM_HEAD_GRAD_FLOATS 1296
+typedef struct VineLstmHeadTrain {
+  const void* params;
+  const void* hh;                /* [tiles][2][128 x 128] bf16 */
+  const float* scalars;          /* [n, 8] */
+  const float* logstd;           /* [2] */
+  const float* logstd_old;       /* [2] */
+  void* dh;                      /* out, tiles like hh */
+  float* grads;                  /* [VINE_LSTM_HEAD_GRAD_FLOATS] accumulated */
+  float* debug_out;              /* NULL or [n, 4]: mu0, mu1, normalised value, neglogp */
+  int64_t n;
+  float e_clip, critic_coef, entropy_coef, bounds_loss_coef, inv_B, reserved_f;
+} VineLstmHeadTrain;
+int vine_lstm_head_train(const VineLstmHeadTrain* args, void* stream);
+
+/*
+ * Backward through one LSTM time step of a minibatch (truncated BPTT, steps visited in reverse):
+ *   vine_lstm_cell_bwd_tiles : pointwise; from the activated gates, c_prev, c, dh (from the head) [+ dh_rec from the
+ *       following step, already masked] and dc_next -> dG (bf16 tiles like act) and dc_prev.
+ *   vine_lstm_bwd_gemm : d[u(:, 0:64) | hm] = dG W (tcgen05; the 1024 gate rows streamed as 16 pieces through a 3-stage
+ *       ring of bulk-TMA copies; the forward weight pieces are read as MN-major operands): dh3 f32 [n, 64] = gradient of
+ *       the MLP output, dh_rec = not_done * d(hm) as bf16 tiles for the previous step (NULL at the first step).
+ */
+typedef struct VineLstmCellBwd {
+  const void* act;               /* [tiles][16][128 x 64] bf16 */
+  const float* c_prev;           /* [n, 256] */
+  const float* c;                /* [n, 256] */
+  const float* not_done;         /* [n] or NULL */
+  const void* dh;                /* tiles like hh: dh from the head */
+  const void* dh_rec;            /* tiles like hh or NULL */
+  const float* dc_next;          /* [n, 256] or NULL */
+  void* dg;                      /* out, tiles like act */
+  float* dc_prev;                /* out [n, 256] */
+  int64_t n;
+} VineLstmCellBwd;
+typedef struct VineLstmBwdGemm {
+  const void* params;
+  const void* dg;
+  const float* not_done;         /* [n] mask applied to dh_rec (NULL = 1) */
+  float* dh3;                    /* out [n, 64] */
+  void* dh_rec;                  /* out tiles like hh, or NULL */
+  int64_t n;
+} VineLstmBwdGemm;
+int vine_lstm_cell_bwd_tiles(const VineLstmCellBwd* args, void* stream);
+int vine_lstm_bwd_gemm(const VineLstmBwdGemm* args, void* stream);
+
+/*
  * Pointwise half of the LSTM layer of the reference's network (Vine5LinkMovingBasePPO.yaml:32-38; rl_games
  * LSTMWithDones, torch gate order i,f,g,o), one fused launch per time step and direction.  `gates` bf16 [S, 4H] are
  * the pre-activations (input projection + recurrent GEMM + biases); not_done [S] multiplies the incoming state

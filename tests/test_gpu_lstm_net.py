@@ -114,3 +114,102 @@ def test_lstm_head_sampling_matches_policy_act_conventions():
     assert abs(float(zz.mean())) < 0.05 and abs(float(zz.std()) - 1) < 0.05
     assert torch.allclose(out["neglogp"], 0.5 * (zz ** 2).sum(-1) + math.log(2 * math.pi) + logstd.sum(), atol=2e-4)
     assert torch.equal(out["env_actions"], out["actions"].clamp(-1, 1))
+
+
+def _packed_gate_perm():
+    """index tensor: packed gate row R -> torch gate row (piece p row g*16+k = gate g of unit 16p+k)."""
+    R = torch.arange(1024)
+    p_, r = R // 64, R % 64
+    return (r // 16) * 256 + 16 * p_ + (r % 16)
+
+
+def test_native_lstm_step_backward_chain_matches_autograd():
+    """head_train -> cell_bwd_tiles -> bwd_gemm for one time step vs torch autograd of the same step (fp32 math on the
+    bf16-rounded weights/inputs).  Tolerance: 3e-2 relative Frobenius error per gradient tensor."""
+    lib = abi.load_library()
+    n, O = 640, 18
+    torch.manual_seed(7)
+    dev = "cuda"
+    q = lambda t: t.bfloat16().float()  # noqa: E731
+    m = ActorCritic(O, 2, (256, 128, 64), rnn=RNN).to(dev)
+    with torch.no_grad():
+        m.layer_norm.weight.uniform_(0.5, 1.5); m.layer_norm.bias.uniform_(-0.2, 0.2)
+        m.mu.weight.mul_(3.0); m.value.weight.mul_(3.0); m.sigma.uniform_(-0.3, 0.1)
+    r = m.rnn.rnn
+    lpacked = torch.zeros(abi.LSTM_PACKED_BYTES, dtype=torch.uint8, device=dev)
+    lp = [r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, m.layer_norm.weight, m.layer_norm.bias, m.mu.weight,
+          m.mu.bias, m.value.weight, m.value.bias]
+    assert lib.vine_lstm_pack(*[p(t.detach().contiguous()) for t in lp], O, p(lpacked), None) == 0
+    tiles = (n + 127) // 128
+    # inputs of the step
+    u_real = q(torch.randn(n, 64 + O, device=dev))
+    u_full = torch.zeros(n, 128, device=dev); u_full[:, :64 + O] = u_real; u_full[:, 95] = 1.0
+    h_prev = q(torch.randn(n, 256, device=dev) * 0.5)
+    c_prev = torch.randn(n, 256, device=dev) * 0.5
+    nd = (torch.rand(n, device=dev) > 0.3).float()
+    scal = torch.randn(n, 8, device=dev); scal[:, 4] = scal[:, 4] * 0.3 + 2.5
+    logstd_old = torch.tensor([-0.1, 0.05], device=dev)
+    hyp = dict(e_clip=0.2, critic_coef=2.0, entropy_coef=0.0, bounds_loss_coef=1e-4)
+    # ---- kernels ----
+    U, HM = to_tiles(u_full).view(tiles, -1).contiguous(), to_tiles(h_prev * nd[:, None]).contiguous()
+    HH, ACT = torch.zeros_like(HM), torch.zeros(tiles, 16, 128 * 64, dtype=torch.bfloat16, device=dev)
+    c_new = torch.zeros(n, 256, device=dev)
+    st = abi.VineLstmStep(params=lpacked.data_ptr(), u=U.data_ptr(), hm=HM.data_ptr(), c_prev=c_prev.data_ptr(), not_done=nd.data_ptr(),
+                          c=c_new.data_ptr(), hh=HH.data_ptr(), act=ACT.data_ptr(), n=n)
+    assert lib.vine_lstm_step(C.byref(st), None) == 0
+    DH, grads, dbg = torch.zeros_like(HH), torch.zeros(abi.LSTM_HEAD_GRAD_FLOATS, device=dev), torch.zeros(n, 4, device=dev)
+    ht = abi.VineLstmHeadTrain(params=lpacked.data_ptr(), hh=HH.data_ptr(), scalars=scal.data_ptr(), logstd=m.sigma.data_ptr(),
+                               logstd_old=logstd_old.data_ptr(), dh=DH.data_ptr(), grads=grads.data_ptr(), debug_out=dbg.data_ptr(),
+                               n=n, inv_B=1.0 / n, **hyp)
+    assert lib.vine_lstm_head_train(C.byref(ht), None) == 0
+    DG, dc_prev_k = torch.zeros_like(ACT), torch.zeros(n, 256, device=dev)
+    cb = abi.VineLstmCellBwd(act=ACT.data_ptr(), c_prev=c_prev.data_ptr(), c=c_new.data_ptr(), not_done=nd.data_ptr(), dh=DH.data_ptr(),
+                             dg=DG.data_ptr(), dc_prev=dc_prev_k.data_ptr(), n=n)
+    assert lib.vine_lstm_cell_bwd_tiles(C.byref(cb), None) == 0
+    dh3_k, DHREC = torch.zeros(n, 64, device=dev), torch.zeros_like(HH)
+    bg = abi.VineLstmBwdGemm(params=lpacked.data_ptr(), dg=DG.data_ptr(), not_done=nd.data_ptr(), dh3=dh3_k.data_ptr(),
+                             dh_rec=DHREC.data_ptr(), n=n)
+    assert lib.vine_lstm_bwd_gemm(C.byref(bg), None) == 0
+    torch.cuda.synchronize()
+    # ---- torch reference ----
+    u_t = u_real.clone().requires_grad_(True)
+    hp_t = h_prev.clone().requires_grad_(True)
+    cp_t = c_prev.clone().requires_grad_(True)
+    wih, whh = q(r.weight_ih_l0.detach()), q(r.weight_hh_l0.detach())
+    gates = u_t @ wih.t() + (hp_t * nd[:, None]) @ whh.t() + (r.bias_ih_l0 + r.bias_hh_l0).detach()
+    gates.retain_grad()
+    i, f, g, o = gates.chunk(4, -1)
+    c = torch.sigmoid(f) * (cp_t * nd[:, None]) + torch.sigmoid(i) * torch.tanh(g)
+    h = torch.sigmoid(o) * torch.tanh(c)
+    hq = h + (q(h) - h).detach()                     # the kernels store h in bf16 before LayerNorm
+    lng, lnb = m.layer_norm.weight.detach().clone().requires_grad_(True), m.layer_norm.bias.detach().clone().requires_grad_(True)
+    wmu, bmu = m.mu.weight.detach().clone().requires_grad_(True), m.mu.bias.detach().clone().requires_grad_(True)
+    wv, bv = m.value.weight.detach().clone().requires_grad_(True), m.value.bias.detach().clone().requires_grad_(True)
+    logstd = m.sigma.detach().clone().requires_grad_(True)
+    y = torch.nn.functional.layer_norm(hq, (256,), lng, lnb, 1e-5)
+    mu, v = y @ wmu.t() + bmu, (y @ wv.t() + bv).squeeze(-1)
+    act, muo, nlpo, vo, ret, adv = scal[:, :2], scal[:, 2:4], scal[:, 4], scal[:, 5], scal[:, 6], scal[:, 7]
+    sigma = torch.exp(logstd)
+    nlp = 0.5 * (((act - mu) / sigma) ** 2).sum(-1) + math.log(2 * math.pi) + logstd.sum()
+    ratio = torch.exp(nlpo - nlp)
+    a_loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 0.8, 1.2)).mean()
+    v_clip = vo + (v - vo).clamp(-0.2, 0.2)
+    c_loss = torch.max((v - ret) ** 2, (v_clip - ret) ** 2).mean()
+    b_loss = (torch.clamp_min(mu - 1.1, 0) ** 2 + torch.clamp_max(mu + 1.1, 0) ** 2).sum(-1).mean()
+    loss = a_loss + 0.5 * c_loss * 2.0 + b_loss * 1e-4
+    loss.backward()
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-12))  # noqa: E731
+    assert float((dbg[:, :2] - mu.detach()).abs().max()) < 3e-2 and float((dbg[:, 2] - v.detach()).abs().max()) < 3e-2
+    errs = {
+        "ln_g": rel(grads[0:256], lng.grad), "ln_b": rel(grads[256:512], lnb.grad),
+        "w_mu": rel(grads[512:1024].view(2, 256), wmu.grad), "w_v": rel(grads[1024:1280], wv.grad[0]),
+        "b_mu": rel(grads[1280:1282], bmu.grad), "b_v": rel(grads[1282:1283], bv.grad),
+        "logstd": rel(grads[1284:1286], logstd.grad),
+        "dc_prev": rel(dc_prev_k, cp_t.grad),
+        "dG": rel(from_tiles(DG, n, width=64), gates.grad[:, _packed_gate_perm().to(dev)]),
+        "dh3": rel(dh3_k, u_t.grad[:, :64]),
+        "dh_prev": rel(from_tiles(DHREC, n), hp_t.grad),
+    }
+    print({k: f"{e:.2e}" for k, e in errs.items()})
+    assert abs(float(grads[1286]) - float(a_loss)) < 2e-2 * abs(float(a_loss)) + 1e-4 and abs(float(grads[1287]) - float(c_loss)) < 2e-2 * float(c_loss)
+    assert max(errs.values()) < 3e-2, errs

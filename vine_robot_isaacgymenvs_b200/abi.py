@@ -137,7 +137,7 @@ EXPORTED_SYMBOLS = [
     "vine_mlp_pack", "vine_mlp_forward",
     "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
     "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
-    "vine_lstm_cell_fwd", "vine_lstm_cell_bwd", "vine_lstm_pack", "vine_lstm_step", "vine_lstm_mask", "vine_lstm_head",
+    "vine_lstm_cell_fwd", "vine_lstm_cell_bwd", "vine_lstm_pack", "vine_lstm_step", "vine_lstm_mask", "vine_lstm_head", "vine_lstm_head_train", "vine_lstm_cell_bwd_tiles", "vine_lstm_bwd_gemm",
 ]
 METRIC_SUMS, METRIC_MAXES = 45, 30
 METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limit_hit", "abs_tip_y", "tip_z", "tip_velocities",
@@ -145,6 +145,7 @@ METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limi
                   "tip_target_velocity_difference", "progress_buf", "contact_forces", "nonzero_contact_force"]
 MLP_PACKED_BYTES = 102208
 LSTM_PACKED_BYTES = 795664
+LSTM_HEAD_GRAD_FLOATS = 1296
 LSTM_TILE_BYTES = 32768          # one [128 x 128] bf16 activation tile
 PPO_WS_FLOATS = 49664
 PPO_STATE_FLOATS = 16
@@ -167,6 +168,20 @@ class VineLstmHead(C.Structure):
     _fields_ = ([(n, C.c_void_p) for n in ("params", "hh", "value_stats", "mu", "value", "logstd", "rng_counter", "actions",
                                            "neglogp", "env_actions")]
                 + [("n", C.c_int64), ("seed", C.c_uint64), ("global_env_offset", C.c_int64)])
+
+
+class VineLstmHeadTrain(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("params", "hh", "scalars", "logstd", "logstd_old", "dh", "grads", "debug_out")]
+                + [("n", C.c_int64)]
+                + [(n, C.c_float) for n in ("e_clip", "critic_coef", "entropy_coef", "bounds_loss_coef", "inv_B", "reserved_f")])
+
+
+class VineLstmCellBwd(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("act", "c_prev", "c", "not_done", "dh", "dh_rec", "dc_next", "dg", "dc_prev")] + [("n", C.c_int64)]
+
+
+class VineLstmBwdGemm(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("params", "dg", "not_done", "dh3", "dh_rec")] + [("n", C.c_int64)]
 
 
 class VineRolloutPost(C.Structure):
@@ -238,6 +253,9 @@ def _declare(lib):
     lib.vine_lstm_step.argtypes = [C.POINTER(VineLstmStep), vp]
     lib.vine_lstm_mask.argtypes = [vp, vp, C.c_int64, vp, vp]
     lib.vine_lstm_head.argtypes = [C.POINTER(VineLstmHead), vp]
+    lib.vine_lstm_head_train.argtypes = [C.POINTER(VineLstmHeadTrain), vp]
+    lib.vine_lstm_cell_bwd_tiles.argtypes = [C.POINTER(VineLstmCellBwd), vp]
+    lib.vine_lstm_bwd_gemm.argtypes = [C.POINTER(VineLstmBwdGemm), vp]
     lib.vine_ppo_num_params.argtypes = [C.c_int]
     lib.vine_ppo_max_ctas.argtypes = []
     lib.vine_ppo_minibatch.argtypes = [C.POINTER(VinePpoMinibatch), vp]

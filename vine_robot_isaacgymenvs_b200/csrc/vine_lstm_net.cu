@@ -277,6 +277,305 @@ __global__ void __launch_bounds__(256) vine_lstm_head_kernel(const VineLstmHead 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Training: LayerNorm + heads forward, the PPO losses (same formulas as vine_ppo_minibatch_kernel), and their backward
+// down to dh (one warp per row).  Parameter gradients accumulate in registers over the warp's rows, are combined per
+// block in shared memory and added to `grads` (f32, zeroed by the caller) with one atomic per slot and block.
+constexpr int HG_LNG = 0, HG_LNB = HID, HG_WH = 2 * HID, HG_BH = 5 * HID, HG_LS = 5 * HID + 4, HG_STATS = 5 * HID + 6;
+constexpr int HG_FLOATS = 5 * HID + 16;
+static_assert(HG_FLOATS == VINE_LSTM_HEAD_GRAD_FLOATS, "header constant out of date");
+
+__global__ void __launch_bounds__(256) vine_lstm_head_train_kernel(const VineLstmHeadTrain a) {
+  __shared__ float red[HG_FLOATS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const uint8_t* P = reinterpret_cast<const uint8_t*>(a.params);
+  const float* lng = reinterpret_cast<const float*>(P + LP_LNG) + 8 * lane;
+  const float* lnb = reinterpret_cast<const float*>(P + LP_LNB) + 8 * lane;
+  const float* wh = reinterpret_cast<const float*>(P + LP_WH) + 8 * lane;
+  const float* bh = reinterpret_cast<const float*>(P + LP_BH);
+  float g[8], b[8], w0[8], w1[8], w2[8];
+  float ag[8], ab[8], aw0[8], aw1[8], aw2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    g[k] = lng[k], b[k] = lnb[k], w0[k] = wh[k], w1[k] = wh[HID + k], w2[k] = wh[2 * HID + k];
+    ag[k] = ab[k] = aw0[k] = aw1[k] = aw2[k] = 0.f;
+  }
+  float sc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // lane 0: dbh[3], dlogstd[2], a_loss, c_loss, kl, b_loss
+  const float ls0 = a.logstd[0], ls1 = a.logstd[1], lso0 = a.logstd_old[0], lso1 = a.logstd_old[1];
+  const float sig0 = __expf(ls0), sig1 = __expf(ls1), sigo0 = __expf(lso0), sigo1 = __expf(lso1);
+  for (int64_t s = warp0; s < a.n; s += nwarps) {
+    const int64_t tile = s / TILE;
+    const int row = (int)(s % TILE), unit = 8 * lane;
+    const size_t off = ((size_t)tile * 2 + unit / UK) * TILE_BYTES + tile_offset(row, unit % UK, UK);
+    const uint4 hv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.hh) + off);
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+    float h[8], yh[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(hw[k]);
+      h[2 * k] = f.x, h[2 * k + 1] = f.y;
+    }
+    float sm = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm += h[k];
+    const float mean = wsum(sm) * (1.f / HID);
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sq += (h[k] - mean) * (h[k] - mean);
+    const float rstd = rsqrtf(wsum(sq) * (1.f / HID) + 1e-5f);
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      yh[k] = (h[k] - mean) * rstd;
+      const float y = fmaf(yh[k], g[k], b[k]);
+      d0 = fmaf(y, w0[k], d0), d1 = fmaf(y, w1[k], d1), d2 = fmaf(y, w2[k], d2);
+    }
+    const float mu0 = wsum(d0) + bh[0], mu1 = wsum(d1) + bh[1], v = wsum(d2) + bh[2];
+    // ---- PPO losses and their gradient with respect to (mu0, mu1, v); every lane computes the same numbers ----
+    const float* q = a.scalars + 8 * s;
+    const float4 q0 = *reinterpret_cast<const float4*>(q), q1 = *reinterpret_cast<const float4*>(q + 4);
+    const float act0 = q0.x, act1 = q0.y, muo0 = q0.z, muo1 = q0.w, nlpo = q1.x, vo = q1.y, ret = q1.z, adv = q1.w;
+    const float e0 = (act0 - mu0) / sig0, e1 = (act1 - mu1) / sig1;
+    const float nlp = 0.5f * (e0 * e0 + e1 * e1) + 1.8378770664093453f + ls0 + ls1;
+    const float ratio = __expf(nlpo - nlp);
+    const float lo = 1.f - a.e_clip, hi = 1.f + a.e_clip;
+    const float t1 = -adv * ratio, t2 = -adv * fminf(fmaxf(ratio, lo), hi);
+    const bool inside = ratio >= lo && ratio <= hi;
+    const float g_nlp = ((inside || t1 > t2) ? -adv : 0.f) * (-ratio);
+    float dmu0 = g_nlp * (-e0 / sig0), dmu1 = g_nlp * (-e1 / sig1);
+    const float dls0 = g_nlp * (1.f - e0 * e0) - a.entropy_coef, dls1 = g_nlp * (1.f - e1 * e1) - a.entropy_coef;
+    const float dvo = v - vo, vclip = vo + fminf(fmaxf(dvo, -a.e_clip), a.e_clip);
+    const float r1 = v - ret, r2 = vclip - ret, c1 = r1 * r1, c2 = r2 * r2;
+    const float pass2 = (fabsf(dvo) <= a.e_clip) ? 1.f : 0.f;
+    const float dvc = c1 > c2 ? 2.f * r1 : (c2 > c1 ? 2.f * r2 * pass2 : r1 + r2 * pass2);
+    float dv = 0.5f * a.critic_coef * dvc;
+    const float bh0 = fmaxf(mu0 - 1.1f, 0.f), bl0 = fminf(mu0 + 1.1f, 0.f), bh1 = fmaxf(mu1 - 1.1f, 0.f), bl1 = fminf(mu1 + 1.1f, 0.f);
+    dmu0 += a.bounds_loss_coef * 2.f * (bh0 + bl0);
+    dmu1 += a.bounds_loss_coef * 2.f * (bh1 + bl1);
+    const float m0 = mu0 - muo0, m1 = mu1 - muo1;
+    const float kl = __logf(sig0 / sigo0 + 1e-5f) + (sigo0 * sigo0 + m0 * m0) / (2.f * (sig0 * sig0 + 1e-5f)) - 0.5f +
+                     __logf(sig1 / sigo1 + 1e-5f) + (sigo1 * sigo1 + m1 * m1) / (2.f * (sig1 * sig1 + 1e-5f)) - 0.5f;
+    dmu0 *= a.inv_B, dmu1 *= a.inv_B, dv *= a.inv_B;
+    if (lane == 0) {
+      sc[0] += dmu0, sc[1] += dmu1, sc[2] += dv;
+      sc[3] += dls0 * a.inv_B, sc[4] += dls1 * a.inv_B;
+      sc[5] += fmaxf(t1, t2) * a.inv_B, sc[6] += fmaxf(c1, c2) * a.inv_B, sc[7] += kl * a.inv_B;
+      sc[8] += (bh0 * bh0 + bl0 * bl0 + bh1 * bh1 + bl1 * bl1) * a.inv_B;
+      if (a.debug_out) {
+        float* d = a.debug_out + 4 * s;
+        d[0] = mu0, d[1] = mu1, d[2] = v, d[3] = nlp;
+      }
+    }
+    // ---- backward: heads -> LayerNorm -> dh ----
+    float dyh[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float dy = dmu0 * w0[k] + dmu1 * w1[k] + dv * w2[k];
+      const float y = fmaf(yh[k], g[k], b[k]);
+      ag[k] = fmaf(dy, yh[k], ag[k]);
+      ab[k] += dy;
+      aw0[k] = fmaf(dmu0, y, aw0[k]), aw1[k] = fmaf(dmu1, y, aw1[k]), aw2[k] = fmaf(dv, y, aw2[k]);
+      dyh[k] = dy * g[k];
+      s1 += dyh[k], s2 = fmaf(dyh[k], yh[k], s2);
+    }
+    const float mean1 = wsum(s1) * (1.f / HID), mean2 = wsum(s2) * (1.f / HID);
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      o[k] = pack_bf16(rstd * (dyh[2 * k] - mean1 - yh[2 * k] * mean2), rstd * (dyh[2 * k + 1] - mean1 - yh[2 * k + 1] * mean2));
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.dh) + off) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  // ---- combine the 8 warps of the block, then one atomic per slot ----
+  for (int i = threadIdx.x; i < HG_FLOATS; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        red[HG_LNG + 8 * lane + k] += ag[k];
+        red[HG_LNB + 8 * lane + k] += ab[k];
+        red[HG_WH + 8 * lane + k] += aw0[k];
+        red[HG_WH + HID + 8 * lane + k] += aw1[k];
+        red[HG_WH + 2 * HID + 8 * lane + k] += aw2[k];
+      }
+      if (lane == 0) {
+        red[HG_BH] += sc[0], red[HG_BH + 1] += sc[1], red[HG_BH + 2] += sc[2];
+        red[HG_LS] += sc[3], red[HG_LS + 1] += sc[4];
+        red[HG_STATS] += sc[5], red[HG_STATS + 1] += sc[6], red[HG_STATS + 2] += sc[7], red[HG_STATS + 3] += sc[8];
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < HG_FLOATS; i += blockDim.x)
+    if (red[i] != 0.f) atomicAdd(a.grads + i, red[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the cell (pointwise) on the tile layouts: block = (tile, group of 8 hidden units), thread = sequence row.
+//   dh = dh_out + dh_rec ;  dc = dc_next + dh o (1 - tanh^2 c) ;  dG = (dc g i(1-i), dc c_in f(1-f), dc i (1-g^2), dh tanh(c) o(1-o))
+//   dc_prev = dc f nd          (c_in = nd c_prev; dh_rec arrives already masked from vine_lstm_bwd_gemm)
+__global__ void __launch_bounds__(TILE) vine_lstm_cell_bwd_tiles_kernel(const VineLstmCellBwd a) {
+  const int tile = blockIdx.x, ug = blockIdx.y, row = threadIdx.x;
+  const int64_t s = (int64_t)tile * TILE + row;
+  if (s >= a.n) return;
+  const int piece = ug >> 1, sub = ug & 1, unit0 = 8 * ug;
+  const uint8_t* at = reinterpret_cast<const uint8_t*>(a.act) + ((size_t)tile * NPIECE + piece) * ACT_BYTES;
+  uint8_t* dg = reinterpret_cast<uint8_t*>(a.dg) + ((size_t)tile * NPIECE + piece) * ACT_BYTES;
+  float gi[8], gf[8], gg[8], go[8];
+  auto ld8 = [&](const uint8_t* p, float (&o)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(w[k]);
+      o[2 * k] = f.x, o[2 * k + 1] = f.y;
+    }
+  };
+  ld8(at + tile_offset(row, 8 * sub, PIECE_ROWS), gi);
+  ld8(at + tile_offset(row, 16 + 8 * sub, PIECE_ROWS), gf);
+  ld8(at + tile_offset(row, 32 + 8 * sub, PIECE_ROWS), gg);
+  ld8(at + tile_offset(row, 48 + 8 * sub, PIECE_ROWS), go);
+  const size_t hoff = ((size_t)tile * 2 + unit0 / UK) * TILE_BYTES + tile_offset(row, unit0 % UK, UK);
+  float dh[8], dr[8];
+  ld8(reinterpret_cast<const uint8_t*>(a.dh) + hoff, dh);
+  if (a.dh_rec) {
+    ld8(reinterpret_cast<const uint8_t*>(a.dh_rec) + hoff, dr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dh[k] += dr[k];
+  }
+  const float m = a.not_done ? a.not_done[s] : 1.f;
+  float cp[8], cc[8], dc[8];
+  auto ldf8 = [&](const float* p, float (&o)[8]) {
+    const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
+    o[0] = v0.x, o[1] = v0.y, o[2] = v0.z, o[3] = v0.w, o[4] = v1.x, o[5] = v1.y, o[6] = v1.z, o[7] = v1.w;
+  };
+  ldf8(a.c_prev + s * HID + unit0, cp);
+  ldf8(a.c + s * HID + unit0, cc);
+  if (a.dc_next) ldf8(a.dc_next + s * HID + unit0, dc);
+  else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dc[k] = 0.f;
+  }
+  float di[8], df[8], dgg[8], dob[8], dcp[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float t = tanh_(cc[k]);
+    const float d = fmaf(dh[k] * go[k], 1.f - t * t, dc[k]);
+    di[k] = d * gg[k] * gi[k] * (1.f - gi[k]);
+    df[k] = d * cp[k] * m * gf[k] * (1.f - gf[k]);
+    dgg[k] = d * gi[k] * (1.f - gg[k] * gg[k]);
+    dob[k] = dh[k] * t * go[k] * (1.f - go[k]);
+    dcp[k] = d * gf[k] * m;
+  }
+  auto st8 = [&](uint8_t* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  };
+  st8(dg + tile_offset(row, 8 * sub, PIECE_ROWS), di);
+  st8(dg + tile_offset(row, 16 + 8 * sub, PIECE_ROWS), df);
+  st8(dg + tile_offset(row, 32 + 8 * sub, PIECE_ROWS), dgg);
+  st8(dg + tile_offset(row, 48 + 8 * sub, PIECE_ROWS), dob);
+  float* o = a.dc_prev + s * HID + unit0;
+  *reinterpret_cast<float4*>(o) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+  *reinterpret_cast<float4*>(o + 4) = make_float4(dcp[4], dcp[5], dcp[6], dcp[7]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward data GEMM of one time step for a 128-sequence tile:  d[U(:, 0:64) | HM] = dG [128 x 1024] W  (reduction over the
+// 1024 gate rows, streamed as 16 pieces of 64 through a 3-stage ring of bulk copies; W pieces are read as MN-major
+// operands, i.e. the forward weights serve unchanged).  Outputs: dh3 (f32 [n, 64], the gradient of the MLP output) and the
+// recurrent gradient for the previous step, masked with this step's not_done, as bf16 tiles.
+constexpr int BG_STAGES = 3, BG_STAGE_BYTES = 4 * PIECE_BYTES;
+constexpr int BG_BAR = BG_STAGES * BG_STAGE_BYTES;
+constexpr int BG_SMEM = BG_BAR + 128;
+constexpr uint32_t BG_TM_DU = 0, BG_TM_DH = 64;
+
+__global__ void __launch_bounds__(THREADS, 1) vine_lstm_bwd_gemm_kernel(const VineLstmBwdGemm a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const int tile = blockIdx.x;
+  const uint32_t bar0 = smem_u32(smem + BG_BAR);          // full[3] | done[3] | final
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BG_BAR + 64);
+  const uint8_t* P = reinterpret_cast<const uint8_t*>(a.params);
+  const uint8_t* DG = reinterpret_cast<const uint8_t*>(a.dg) + (size_t)tile * NPIECE * ACT_BYTES;
+  auto full = [&](int st) { return bar0 + 8u * st; };
+  auto done = [&](int st) { return bar0 + 24u + 8u * st; };
+  const uint32_t fin = bar0 + 48u;
+  auto load = [&](int p, int st) {
+    const uint32_t dst = smem_u32(smem + st * BG_STAGE_BYTES);
+    mbar_expect_tx(full(st), BG_STAGE_BYTES);
+    bulk_g2s(dst, DG + (size_t)p * ACT_BYTES, ACT_BYTES, full(st));
+    bulk_g2s(dst + PIECE_BYTES, P + LP_WIH + (size_t)p * PIECE_BYTES, PIECE_BYTES, full(st));
+    bulk_g2s(dst + 2 * PIECE_BYTES, P + LP_WHH + (size_t)p * PIECE_BYTES, PIECE_BYTES, full(st));
+    bulk_g2s(dst + 3 * PIECE_BYTES, P + LP_WHH + (size_t)(NPIECE + p) * PIECE_BYTES, PIECE_BYTES, full(st));
+  };
+  if (tid == 0) {
+    for (int i = 0; i < 7; ++i) mbar_init(bar0 + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int p = 0; p < BG_STAGES; ++p) load(p, p);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  if (tid == 0) {
+    for (int p = 0; p < NPIECE; ++p) {
+      const int st = p % BG_STAGES;
+      const uint32_t ph = (uint32_t)((p / BG_STAGES) & 1);
+      mbar_wait(full(st), ph);
+      fence_after_sync();
+      const uint32_t base = smem_u32(smem + st * BG_STAGE_BYTES);
+      const Operand A = k_major(base, PIECE_ROWS);
+      mma_sequence(tmem + BG_TM_DU, A, mn_major(base + PIECE_BYTES, UK), instr_desc(64, false, true), PIECE_ROWS / 16, p > 0);
+      mma_sequence(tmem + BG_TM_DH, A, mn_major(base + 2 * PIECE_BYTES, UK), instr_desc(128, false, true), PIECE_ROWS / 16, p > 0);
+      mma_sequence(tmem + BG_TM_DH + 128, A, mn_major(base + 3 * PIECE_BYTES, UK), instr_desc(128, false, true), PIECE_ROWS / 16, p > 0);
+      mma_commit(done(st));
+      if (p + BG_STAGES < NPIECE) {
+        mbar_wait(done(st), ph);
+        load(p + BG_STAGES, st);
+      }
+    }
+    mma_commit(fin);
+  }
+  mbar_wait(fin, 0);
+  fence_after_sync();
+  const int64_t s = (int64_t)tile * TILE + row;
+  const float m = (s < a.n && a.not_done) ? a.not_done[s] : 1.f;
+  {
+    uint32_t r[32];
+    tmem_ld32(lane_base + BG_TM_DU + half * 32, r);
+    if (s < a.n) {
+      float4* dst = reinterpret_cast<float4*>(a.dh3 + s * H3 + half * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+    }
+  }
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {   // this thread: hidden units 128*half + c0 .. +31 of its row
+    uint32_t r[32];
+    tmem_ld32(lane_base + BG_TM_DH + half * 128 + c0, r);
+    if (a.dh_rec && s < a.n) {
+      uint8_t* dst = reinterpret_cast<uint8_t*>(a.dh_rec) + ((size_t)tile * 2 + half) * TILE_BYTES;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(dst + tile_offset(row, c0 + 8 * q, UK)) =
+            make_uint4(pack_bf16(__uint_as_float(r[8 * q]) * m, __uint_as_float(r[8 * q + 1]) * m),
+                       pack_bf16(__uint_as_float(r[8 * q + 2]) * m, __uint_as_float(r[8 * q + 3]) * m),
+                       pack_bf16(__uint_as_float(r[8 * q + 4]) * m, __uint_as_float(r[8 * q + 5]) * m),
+                       pack_bf16(__uint_as_float(r[8 * q + 6]) * m, __uint_as_float(r[8 * q + 7]) * m));
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 }  // namespace
 
 extern "C" {
@@ -315,6 +614,36 @@ int vine_lstm_mask(const void* hh, const float* not_done, int64_t n, void* hm, v
   if (!hh || !not_done || !hm || n <= 0) return VINE_ERR_INVALID_ARG;
   const int64_t chunks = ((n + TILE - 1) / TILE) * 2 * (TILE_BYTES / 16);
   vine_lstm_mask_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)hh, not_done, n, (uint8_t*)hm);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+int vine_lstm_cell_bwd_tiles(const VineLstmCellBwd* a, void* stream) {
+  if (!a || !a->act || !a->c_prev || !a->c || !a->dh || !a->dg || !a->dc_prev || a->n <= 0) return VINE_ERR_INVALID_ARG;
+  const dim3 grid((unsigned)((a->n + TILE - 1) / TILE), HID / 8);
+  vine_lstm_cell_bwd_tiles_kernel<<<grid, TILE, 0, (cudaStream_t)stream>>>(*a);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+int vine_lstm_bwd_gemm(const VineLstmBwdGemm* a, void* stream) {
+  if (!a || !a->params || !a->dg || !a->dh3 || a->n <= 0) return VINE_ERR_INVALID_ARG;
+  static int configured = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return VINE_ERR_CUDA;
+  if (configured != dev) {
+    if (cudaFuncSetAttribute(vine_lstm_bwd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMEM) != cudaSuccess)
+      return VINE_ERR_CUDA;
+    configured = dev;
+  }
+  vine_lstm_bwd_gemm_kernel<<<(unsigned)((a->n + TILE - 1) / TILE), THREADS, BG_SMEM, (cudaStream_t)stream>>>(*a);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+int vine_lstm_head_train(const VineLstmHeadTrain* a, void* stream) {
+  if (!a || !a->params || !a->hh || !a->scalars || !a->logstd || !a->logstd_old || !a->dh || !a->grads || a->n <= 0)
+    return VINE_ERR_INVALID_ARG;
+  int64_t blocks = (a->n + 7) / 8;
+  if (blocks > 296) blocks = 296;
+  vine_lstm_head_train_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
