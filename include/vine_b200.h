@@ -565,6 +565,32 @@ int vine_lstm_cell_bwd_tiles(const VineLstmCellBwd* args, void* stream);
 int vine_lstm_bwd_gemm(const VineLstmBwdGemm* args, void* stream);
 
 /*
+ * Weight gradients and optimiser of the recurrent half.  Flat f32 parameter vector (torch layouts, this order):
+ *   W_ih[1024, 64+O] W_hh[1024, 256] b_ih[1024] b_hh[1024] ln_gamma[256] ln_beta[256] W_mu[2,256] b_mu[2] W_v[1,256]
+ *   b_v[1] logstd[2]                                   (vine_lstm_num_params(O) floats)
+ *   vine_lstm_wgrad : dW^T = in^T dG over all (step, sequence) rows of the minibatch (tcgen05, both operands MN-major,
+ *       rows streamed through a 2-stage bulk-TMA ring); grid = 12 output blocks x `splits` K ranges; partials go to
+ *       workspace f32 [splits][12][128][256].  ntiles = number of 128-row tiles of u / hm / dg (all steps).
+ *   vine_lstm_reduce : flat[p] = gradient of parameter p (sum of the partials; b_ih/b_hh from the constant-1 column
+ *       of u; LayerNorm / heads / logstd from the head gradient buffer); flat[P..P+3] = a_loss, c_loss, kl, b_loss.
+ *   vine_lstm_adam : torch.optim.Adam on the flat vector + in-place update of the packed block + the loss / KL
+ *       bookkeeping in `state` (same layout and meaning as vine_ppo_adam, which then runs with bookkeeping = 0).
+ */
+typedef struct VineLstmWgrad {
+  const void* u;                 /* [ntiles][128 x 128] bf16 */
+  const void* hm;                /* [ntiles][2][128 x 128] bf16 */
+  const void* dg;                /* [ntiles][16][128 x 64] bf16 */
+  float* workspace;              /* [splits][12][128][256] f32 */
+  int64_t ntiles;
+  int32_t splits, reserved;
+} VineLstmWgrad;
+int vine_lstm_num_params(int num_obs);
+int vine_lstm_wgrad(const VineLstmWgrad* args, void* stream);
+int vine_lstm_reduce(const float* workspace, int splits, const float* head_grads, int num_obs, float* flat, void* stream);
+int vine_lstm_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq, void* packed,
+                   float* state, int num_obs, float beta1, float beta2, float eps, void* stream);
+
+/*
  * Pointwise half of the LSTM layer of the reference's network (Vine5LinkMovingBasePPO.yaml:32-38; rl_games
  * LSTMWithDones, torch gate order i,f,g,o), one fused launch per time step and direction.  `gates` bf16 [S, 4H] are
  * the pre-activations (input projection + recurrent GEMM + biases); not_done [S] multiplies the incoming state
@@ -619,6 +645,9 @@ typedef struct VinePpoMinibatch {
   float* debug_out;              /* NULL or [T*env_count, 4]: mu0, mu1, normalised value, neglogp per sample */
   int32_t horizon, num_envs, env_begin, env_count, num_obs, workspace_ctas, adaptive_lr, reserved;
   float e_clip, critic_coef, entropy_coef, bounds_loss_coef, kl_threshold, lr_min, lr_max, reserved_f;
+  const float* dh3_ext;          /* NULL, or f32 [T*env_count, 64]: d(loss)/d(MLP output) supplied by the LSTM backward
+                                    (vine_lstm_bwd_gemm); the heads and losses are skipped and the loss pointers may be
+                                    NULL -- the kernel recomputes the MLP forward and back-propagates from there */
 } VinePpoMinibatch;
 
 int vine_ppo_num_params(int num_obs);
@@ -628,8 +657,10 @@ int vine_ppo_minibatch(const VinePpoMinibatch* batch, void* stream);
 /* flat[p] = sum of the partials in parameter order, flat[P..P+3] = a_loss, c_loss, kl, b_loss (means) */
 int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* flat, void* stream);
 /* Adam step with g = flat * grad_scale (1/world after an all-reduce); updates params, moments, packed, state */
+/* bookkeeping != 0: also record the loss statistics / pending KL in `state` (0 when vine_lstm_adam does it) */
 int vine_ppo_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq,
-                  void* packed, float* state, int num_obs, float beta1, float beta2, float eps, void* stream);
+                  void* packed, float* state, int num_obs, float beta1, float beta2, float eps, int bookkeeping,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -213,3 +213,79 @@ def test_native_lstm_step_backward_chain_matches_autograd():
     print({k: f"{e:.2e}" for k, e in errs.items()})
     assert abs(float(grads[1286]) - float(a_loss)) < 2e-2 * abs(float(a_loss)) + 1e-4 and abs(float(grads[1287]) - float(c_loss)) < 2e-2 * float(c_loss)
     assert max(errs.values()) < 3e-2, errs
+
+
+def test_native_lstm_minibatch_gradients_match_autograd_end_to_end():
+    """The whole kernel-only minibatch (MLP forward -> 4 LSTM steps with done masks -> LayerNorm/heads/PPO loss -> BPTT -> MLP
+    backward -> weight gradients) vs torch autograd of ppo.ActorCritic on the same data.  Tolerance 4e-2 relative Frobenius
+    error per parameter tensor (bf16 operands through a 4-step recurrence)."""
+    from vine_robot_isaacgymenvs_b200.ppo.lstm_native import NativeLstmPath
+    lib = abi.load_library()
+    L, S, O, dev = 4, 512, 18, "cuda"
+    torch.manual_seed(11)
+    m = ActorCritic(O, 2, (256, 128, 64), rnn=RNN).to(dev)
+    m.fused_cell = False
+    with torch.no_grad():
+        m.layer_norm.weight.uniform_(0.5, 1.5); m.layer_norm.bias.uniform_(-0.2, 0.2)
+        m.mu.weight.mul_(3.0); m.value.weight.mul_(3.0); m.sigma.uniform_(-0.3, 0.1)
+        for prm in m.parameters():     # the kernels see bf16 weights: compare against the same rounded weights
+            if prm.dim() == 2 and prm.shape[0] > 3:
+                prm.copy_(prm.bfloat16().float())
+    z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
+    packed = torch.zeros(abi.MLP_PACKED_BYTES, dtype=torch.uint8, device=dev)
+    mlp = [m.actor_mlp[0].weight, m.actor_mlp[0].bias, m.actor_mlp[2].weight, m.actor_mlp[2].bias, m.actor_mlp[4].weight,
+           m.actor_mlp[4].bias, z(2, 64), z(2), z(1, 64), z(1)]
+    assert lib.vine_mlp_pack(*[p(t.detach().contiguous()) for t in mlp], O, p(packed), None) == 0
+    lpacked = torch.zeros(abi.LSTM_PACKED_BYTES, dtype=torch.uint8, device=dev)
+    r = m.rnn.rnn
+    lp = [r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, m.layer_norm.weight, m.layer_norm.bias, m.mu.weight,
+          m.mu.bias, m.value.weight, m.value.bias]
+    assert lib.vine_lstm_pack(*[p(t.detach().contiguous()) for t in lp], O, p(lpacked), None) == 0
+    hyp = dict(e_clip=0.2, critic_coef=2.0, entropy_coef=0.0, bounds_loss_coef=1e-4)
+    path = NativeLstmPath(O, L, S, dev, hyp)
+    obs = torch.randn(L, S, O, device=dev) * 2
+    mean, inv_std = torch.randn(O, device=dev) * 0.3, 1.0 / (0.5 + torch.rand(O, device=dev))
+    scal = torch.randn(L, S, 8, device=dev); scal[..., 4] = scal[..., 4] * 0.3 + 2.5
+    nd = (torch.rand(L, S, device=dev) > 0.15).float()
+    h0 = (torch.randn(S, 256, device=dev) * 0.5).bfloat16().float()
+    c0 = torch.randn(S, 256, device=dev) * 0.5
+    logstd_old = torch.tensor([-0.1, 0.05], device=dev)
+    vstats, state = torch.tensor([0.0, 1.0], device=dev), torch.zeros(16, device=dev)
+    path.HM[0].copy_(to_tiles(h0 * nd[0][:, None]))
+    path.C0.copy_(c0)
+    dbg = torch.zeros(L * S, 4, device=dev)
+    path.gradients(packed, lpacked, obs, scal, nd, mean, inv_std, vstats, m.sigma.detach(), logstd_old, state, debug_out=dbg)
+    torch.cuda.synchronize()
+    # ---- torch autograd on the same minibatch ----
+    x = torch.clamp((obs - mean) * inv_std, -5, 5)
+    mu, logstd, v, _ = m(x, (h0, c0), nd)
+    mu, v = mu.float(), v.float().squeeze(-1)
+    sc = scal.reshape(L * S, 8)
+    act, muo, nlpo, vo, ret, adv = sc[:, :2], sc[:, 2:4], sc[:, 4], sc[:, 5], sc[:, 6], sc[:, 7]
+    sigma = torch.exp(m.sigma)
+    nlp = 0.5 * (((act - mu) / sigma) ** 2).sum(-1) + math.log(2 * math.pi) + m.sigma.sum()
+    ratio = torch.exp(nlpo - nlp)
+    a_loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 0.8, 1.2)).mean()
+    v_clip = vo + (v - vo).clamp(-0.2, 0.2)
+    c_loss = torch.max((v - ret) ** 2, (v_clip - ret) ** 2).mean()
+    b_loss = (torch.clamp_min(mu - 1.1, 0) ** 2 + torch.clamp_max(mu + 1.1, 0) ** 2).sum(-1).mean()
+    (a_loss + 0.5 * c_loss * 2.0 + b_loss * 1e-4).backward()
+    assert float((dbg[:, :2] - mu.detach()).abs().mean()) < 2e-2 and float((dbg[:, 2] - v.detach()).abs().mean()) < 2e-2
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-12))  # noqa: E731
+    gl, o = path.flat_g_lstm, 0
+    errs = {}
+    for name, prm in (("W_ih", r.weight_ih_l0), ("W_hh", r.weight_hh_l0), ("b_ih", r.bias_ih_l0), ("b_hh", r.bias_hh_l0),
+                      ("ln_g", m.layer_norm.weight), ("ln_b", m.layer_norm.bias), ("W_mu", m.mu.weight), ("b_mu", m.mu.bias),
+                      ("W_v", m.value.weight), ("b_v", m.value.bias), ("logstd", m.sigma)):
+        errs[name] = rel(gl[o:o + prm.numel()].view_as(prm), prm.grad)
+        o += prm.numel()
+    assert o == path.P_lstm
+    gm, o = path.flat_g_mlp, 0
+    for name, prm in (("W1", m.actor_mlp[0].weight), ("b1", m.actor_mlp[0].bias), ("W2", m.actor_mlp[2].weight),
+                      ("b2", m.actor_mlp[2].bias), ("W3", m.actor_mlp[4].weight), ("b3", m.actor_mlp[4].bias)):
+        errs[name] = rel(gm[o:o + prm.numel()].view_as(prm), prm.grad)
+        o += prm.numel()
+    print({k: f"{e:.2e}" for k, e in errs.items()})
+    assert abs(float(gl[path.P_lstm]) - float(a_loss)) < 3e-2 * abs(float(a_loss)) + 1e-4
+    assert abs(float(gl[path.P_lstm + 1]) - float(c_loss)) < 3e-2 * float(c_loss)
+    assert max(errs.values()) < 4e-2, errs

@@ -141,7 +141,7 @@ def test_adam_kernel_matches_torch_adam_and_repacks_the_weights():
             state[1] += 1.0
         ref.grad = out[:P].clone()
         opt.step()
-        assert lib.vine_ppo_adam(p(out), 1.0, p(flat), p(m), p(v), p(packed), p(state), O, 0.9, 0.999, 1e-8, None) == 0
+        assert lib.vine_ppo_adam(p(out), 1.0, p(flat), p(m), p(v), p(packed), p(state), O, 0.9, 0.999, 1e-8, 1, None) == 0
         torch.cuda.synchronize()
         assert float((flat - ref.detach()).abs().max()) < 1e-6
     assert float(state[3]) == 1.0 and abs(float(state[2]) - float(out[P + 2])) < 1e-7 and float(state[8]) == 3.0

@@ -138,6 +138,7 @@ EXPORTED_SYMBOLS = [
     "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
     "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
     "vine_lstm_cell_fwd", "vine_lstm_cell_bwd", "vine_lstm_pack", "vine_lstm_step", "vine_lstm_mask", "vine_lstm_head", "vine_lstm_head_train", "vine_lstm_cell_bwd_tiles", "vine_lstm_bwd_gemm",
+    "vine_lstm_num_params", "vine_lstm_wgrad", "vine_lstm_reduce", "vine_lstm_adam",
 ]
 METRIC_SUMS, METRIC_MAXES = 45, 30
 METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limit_hit", "abs_tip_y", "tip_z", "tip_velocities",
@@ -146,6 +147,7 @@ METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limi
 MLP_PACKED_BYTES = 102208
 LSTM_PACKED_BYTES = 795664
 LSTM_HEAD_GRAD_FLOATS = 1296
+LSTM_WGRAD_BLOCK_FLOATS = 12 * 128 * 256      # per K split
 LSTM_TILE_BYTES = 32768          # one [128 x 128] bf16 activation tile
 PPO_WS_FLOATS = 49664
 PPO_STATE_FLOATS = 16
@@ -184,6 +186,10 @@ class VineLstmBwdGemm(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("params", "dg", "not_done", "dh3", "dh_rec")] + [("n", C.c_int64)]
 
 
+class VineLstmWgrad(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("u", "hm", "dg", "workspace")] + [("ntiles", C.c_int64), ("splits", C.c_int32), ("reserved", C.c_int32)]
+
+
 class VineRolloutPost(C.Structure):
     _fields_ = ([(n, C.c_void_p) for n in (
         "rewards", "resets", "timeouts", "values", "shaped_rewards", "dones_next", "ep_return", "ep_length", "ep_stats",
@@ -207,7 +213,8 @@ class VinePpoMinibatch(C.Structure):
         + [(n, C.c_int32) for n in ("horizon", "num_envs", "env_begin", "env_count", "num_obs", "workspace_ctas",
                                     "adaptive_lr", "reserved")]
         + [(n, C.c_float) for n in ("e_clip", "critic_coef", "entropy_coef", "bounds_loss_coef", "kl_threshold",
-                                    "lr_min", "lr_max", "reserved_f")])
+                                    "lr_min", "lr_max", "reserved_f")]
+        + [("dh3_ext", C.c_void_p)])
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libvine_b200.so")
@@ -256,11 +263,15 @@ def _declare(lib):
     lib.vine_lstm_head_train.argtypes = [C.POINTER(VineLstmHeadTrain), vp]
     lib.vine_lstm_cell_bwd_tiles.argtypes = [C.POINTER(VineLstmCellBwd), vp]
     lib.vine_lstm_bwd_gemm.argtypes = [C.POINTER(VineLstmBwdGemm), vp]
+    lib.vine_lstm_num_params.argtypes = [C.c_int]
+    lib.vine_lstm_wgrad.argtypes = [C.POINTER(VineLstmWgrad), vp]
+    lib.vine_lstm_reduce.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
+    lib.vine_lstm_adam.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, vp]
     lib.vine_ppo_num_params.argtypes = [C.c_int]
     lib.vine_ppo_max_ctas.argtypes = []
     lib.vine_ppo_minibatch.argtypes = [C.POINTER(VinePpoMinibatch), vp]
     lib.vine_ppo_reduce.argtypes = [vp, C.c_int, C.c_int, vp, vp]
-    lib.vine_ppo_adam.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, vp]
+    lib.vine_ppo_adam.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("vine_destroy", "vine_last_error"):

@@ -576,6 +576,186 @@ __global__ void __launch_bounds__(THREADS, 1) vine_lstm_bwd_gemm_kernel(const Vi
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradients of the LSTM:  dW^T[f][R] = sum over all (step, sequence) rows of  in[row][f] * dG[row][R]
+// with in = U (f = U column; column 95 == 1 carries the bias gradient) or HM half (f = hidden unit).  Both operands are the
+// activation tiles read as MN-major operands (reduction over the tile's 128 rows).  CTA = (output block, K split):
+// output block = (input part: U | HM0 | HM1) x (quarter of the gate rows = 4 pieces = 256 columns) -> [128 x 256] f32 in
+// TMEM; the K range (row tiles) streams through a 2-stage ring of bulk copies.  Partials go to a workspace
+// [split][12][128][256] that vine_lstm_reduce sums.
+constexpr int WG_STAGES = 2, WG_STAGE_BYTES = TILE_BYTES + 4 * ACT_BYTES;   // 96 KB
+constexpr int WG_BAR = WG_STAGES * WG_STAGE_BYTES;
+constexpr int WG_SMEM = WG_BAR + 128;
+constexpr int WG_BLOCKS = 12, WG_BLOCK_FLOATS = TILE * 256;
+
+__global__ void __launch_bounds__(THREADS, 1) vine_lstm_wgrad_kernel(const VineLstmWgrad a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const int blk = blockIdx.x, sp = blockIdx.y, part = blk >> 2, nq = blk & 3;
+  const int64_t per = (a.ntiles + gridDim.y - 1) / gridDim.y;
+  const int64_t k0 = (int64_t)sp * per, k1 = (k0 + per < a.ntiles) ? k0 + per : a.ntiles;
+  const uint32_t bar0 = smem_u32(smem + WG_BAR);          // full[2] | done[2] | final
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + WG_BAR + 64);
+  auto full = [&](int st) { return bar0 + 8u * st; };
+  auto done = [&](int st) { return bar0 + 16u + 8u * st; };
+  const uint32_t fin = bar0 + 32u;
+  auto load = [&](int64_t k, int st) {
+    const uint32_t dst = smem_u32(smem + st * WG_STAGE_BYTES);
+    const uint8_t* A = part == 0 ? reinterpret_cast<const uint8_t*>(a.u) + (size_t)k * TILE_BYTES
+                                 : reinterpret_cast<const uint8_t*>(a.hm) + ((size_t)k * 2 + (part - 1)) * TILE_BYTES;
+    mbar_expect_tx(full(st), WG_STAGE_BYTES);
+    bulk_g2s(dst, A, TILE_BYTES, full(st));
+    bulk_g2s(dst + TILE_BYTES, reinterpret_cast<const uint8_t*>(a.dg) + ((size_t)k * NPIECE + 4 * nq) * ACT_BYTES, 4 * ACT_BYTES, full(st));
+  };
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(bar0 + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < WG_STAGES; ++i)
+      if (k0 + i < k1) load(k0 + i, i);
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  if (tid == 0) {
+    for (int64_t k = k0; k < k1; ++k) {
+      const int it = (int)(k - k0), st = it % WG_STAGES;
+      const uint32_t ph = (uint32_t)((it / WG_STAGES) & 1);
+      mbar_wait(full(st), ph);
+      fence_after_sync();
+      const uint32_t base = smem_u32(smem + st * WG_STAGE_BYTES);
+      const Operand A = mn_major(base, UK);
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j)
+        mma_sequence(tmem + 64 * j, A, mn_major(base + TILE_BYTES + j * ACT_BYTES, PIECE_ROWS), instr_desc(64, true, true), TILE / 16, it > 0);
+      mma_commit(done(st));
+      if (k + WG_STAGES < k1) {
+        mbar_wait(done(st), ph);
+        load(k + WG_STAGES, st);
+      }
+    }
+    mma_commit(fin);
+  }
+  mbar_wait(fin, 0);
+  fence_after_sync();
+  float* out = a.workspace + ((size_t)sp * WG_BLOCKS + blk) * WG_BLOCK_FLOATS + (size_t)row * 256 + half * 128;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t r[32];
+    if (k1 > k0) tmem_ld32(lane_base + half * 128 + c0, r);
+    else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = 0u;
+    }
+    float4* dst = reinterpret_cast<float4*>(out + c0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Flat f32 parameter vector of the recurrent half (torch layouts, this order):
+//   W_ih[1024, 64+O]  W_hh[1024, 256]  b_ih[1024]  b_hh[1024]  ln_gamma[256]  ln_beta[256]  W_mu[2,256]  b_mu[2]  W_v[1,256]
+//   b_v[1]  logstd[2]
+__host__ __device__ inline int lstm_num_params(int O) { return GATES * (H3 + O) + GATES * HID + 2 * GATES + 2 * HID + 2 * HID + 2 + HID + 1 + 2; }
+__host__ __device__ inline int packed_gate_row(int torch_row) {
+  const int g_ = torch_row / HID, unit = torch_row % HID;
+  return (unit / 16) * PIECE_ROWS + g_ * 16 + (unit % 16);
+}
+
+struct LstmSeg { int wih, whh, bih, bhh, lng, lnb, wmu, bmu, wv, bv, ls, end; };
+__host__ __device__ inline LstmSeg lstm_segments(int O) {
+  LstmSeg s;
+  s.wih = 0; s.whh = s.wih + GATES * (H3 + O); s.bih = s.whh + GATES * HID; s.bhh = s.bih + GATES; s.lng = s.bhh + GATES;
+  s.lnb = s.lng + HID; s.wmu = s.lnb + HID; s.bmu = s.wmu + 2 * HID; s.wv = s.bmu + 2; s.bv = s.wv + HID; s.ls = s.bv + 1; s.end = s.ls + 2;
+  return s;
+}
+
+// gradient of flat parameter p: sum over the weight-gradient partials, or a slot of the head gradient buffer
+__device__ inline float lstm_grad(int p, int O, const float* __restrict__ ws, int splits, const float* __restrict__ hg) {
+  const LstmSeg sg = lstm_segments(O);
+  int part, f, R;
+  if (p < sg.whh) { const int tr = p / (H3 + O); part = 0; f = p % (H3 + O); R = packed_gate_row(tr); }
+  else if (p < sg.bih) { const int q = p - sg.whh, tr = q / HID, c = q % HID; part = 1 + c / UK; f = c % UK; R = packed_gate_row(tr); }
+  else if (p < sg.lng) { const int tr = (p - sg.bih) % GATES; part = 0; f = UK - 33; R = packed_gate_row(tr); }   // U column 95 == 1
+  else if (p < sg.lnb) return hg[HG_LNG + (p - sg.lng)];
+  else if (p < sg.wmu) return hg[HG_LNB + (p - sg.lnb)];
+  else if (p < sg.bmu) return hg[HG_WH + (p - sg.wmu)];
+  else if (p < sg.wv) return hg[HG_BH + (p - sg.bmu)];
+  else if (p < sg.bv) return hg[HG_WH + 2 * HID + (p - sg.wv)];
+  else if (p < sg.ls) return hg[HG_BH + 2];
+  else return hg[HG_LS + (p - sg.ls)];
+  const size_t off = (size_t)(part * 4 + R / 256) * WG_BLOCK_FLOATS + (size_t)f * 256 + (R % 256);
+  float acc = 0.f;
+  for (int k = 0; k < splits; ++k) acc += ws[(size_t)k * WG_BLOCKS * WG_BLOCK_FLOATS + off];
+  return acc;
+}
+
+__global__ void vine_lstm_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ hg, int O, float* __restrict__ flat) {
+  const int PL = lstm_num_params(O);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < PL) flat[p] = lstm_grad(p, O, ws, splits, hg);
+  else if (p < PL + 4) flat[p] = hg[HG_STATS + (p - PL)];
+}
+
+__global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scale, float* __restrict__ params, float* __restrict__ m,
+                                      float* __restrict__ v, uint8_t* __restrict__ packed, float* __restrict__ state, int O, float beta1,
+                                      float beta2, float eps) {
+  const int PL = lstm_num_params(O);
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= PL) {
+    if (p == PL) {   // loss statistics + the KL that drives the adaptive learning rate (state layout: vine_ppo_adam)
+      for (int j = 0; j < 4; ++j) state[4 + j] += flat[PL + j] * scale;
+      state[8] += 1.f;
+      state[2] = flat[PL + 2] * scale;
+      state[3] = 1.f;
+    }
+    return;
+  }
+  const float lr = state[0], step = state[1];
+  const float g = flat[p] * scale;
+  const float mn = beta1 * m[p] + (1.f - beta1) * g;
+  const float vn = beta2 * v[p] + (1.f - beta2) * g * g;
+  m[p] = mn;
+  v[p] = vn;
+  const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
+  const float w_old = params[p];
+  const float w = w_old - (lr / bc1) * mn / (sqrtf(vn) / sqrtf(bc2) + eps);
+  params[p] = w;
+  const LstmSeg sg = lstm_segments(O);
+  if (p < sg.whh) {
+    const int tr = p / (H3 + O), c = p % (H3 + O), R = packed_gate_row(tr);
+    *reinterpret_cast<__nv_bfloat16*>(packed + LP_WIH + (R / PIECE_ROWS) * PIECE_BYTES + tile_offset(R % PIECE_ROWS, c, UK)) = __float2bfloat16_rn(w);
+  } else if (p < sg.bih) {
+    const int q = p - sg.whh, tr = q / HID, c = q % HID, R = packed_gate_row(tr);
+    *reinterpret_cast<__nv_bfloat16*>(packed + LP_WHH + ((c / UK) * NPIECE + R / PIECE_ROWS) * PIECE_BYTES + tile_offset(R % PIECE_ROWS, c % UK, UK)) =
+        __float2bfloat16_rn(w);
+  } else if (p < sg.lng) {
+    // the kernels use b_ih + b_hh: each of the two parameters adds its own update to the packed sum
+    const int tr = (p - sg.bih) % GATES;
+    atomicAdd(reinterpret_cast<float*>(packed + LP_BIAS) + packed_gate_row(tr), w - w_old);
+  }
+  if (p >= sg.lng) {
+    float* f32 = nullptr;
+    if (p < sg.lnb) f32 = reinterpret_cast<float*>(packed + LP_LNG) + (p - sg.lng);
+    else if (p < sg.wmu) f32 = reinterpret_cast<float*>(packed + LP_LNB) + (p - sg.lnb);
+    else if (p < sg.bmu) f32 = reinterpret_cast<float*>(packed + LP_WH) + (p - sg.wmu);
+    else if (p < sg.wv) f32 = reinterpret_cast<float*>(packed + LP_BH) + (p - sg.bmu);
+    else if (p < sg.bv) f32 = reinterpret_cast<float*>(packed + LP_WH) + 2 * HID + (p - sg.wv);
+    else if (p < sg.ls) f32 = reinterpret_cast<float*>(packed + LP_BH) + 2;
+    if (f32) *f32 = w;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -635,6 +815,39 @@ int vine_lstm_bwd_gemm(const VineLstmBwdGemm* a, void* stream) {
     configured = dev;
   }
   vine_lstm_bwd_gemm_kernel<<<(unsigned)((a->n + TILE - 1) / TILE), THREADS, BG_SMEM, (cudaStream_t)stream>>>(*a);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+int vine_lstm_num_params(int num_obs) { return (num_obs < 1 || num_obs >= K1) ? VINE_ERR_INVALID_ARG : lstm_num_params(num_obs); }
+
+int vine_lstm_wgrad(const VineLstmWgrad* a, void* stream) {
+  if (!a || !a->u || !a->hm || !a->dg || !a->workspace || a->ntiles <= 0 || a->splits < 1 || a->splits > a->ntiles)
+    return VINE_ERR_INVALID_ARG;
+  static int configured = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return VINE_ERR_CUDA;
+  if (configured != dev) {
+    if (cudaFuncSetAttribute(vine_lstm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) != cudaSuccess)
+      return VINE_ERR_CUDA;
+    configured = dev;
+  }
+  vine_lstm_wgrad_kernel<<<dim3(WG_BLOCKS, (unsigned)a->splits), THREADS, WG_SMEM, (cudaStream_t)stream>>>(*a);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+int vine_lstm_reduce(const float* workspace, int splits, const float* head_grads, int num_obs, float* flat, void* stream) {
+  if (!workspace || !head_grads || !flat || splits < 1 || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
+  const int n = lstm_num_params(num_obs) + 4;
+  vine_lstm_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, splits, head_grads, num_obs, flat);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+int vine_lstm_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq, void* packed, float* state,
+                   int num_obs, float beta1, float beta2, float eps, void* stream) {
+  if (!flat || !params || !exp_avg || !exp_avg_sq || !packed || !state || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
+  const int n = lstm_num_params(num_obs) + 1;
+  vine_lstm_adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(flat, grad_scale, params, exp_avg, exp_avg_sq, (uint8_t*)packed,
+                                                                         state, num_obs, beta1, beta2, eps);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 

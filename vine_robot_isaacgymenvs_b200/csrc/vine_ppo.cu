@@ -54,6 +54,7 @@ struct MbArgs {
   const uint8_t* packed;
   const float *obs, *act, *mu_old, *nlp_old, *val_old, *ret, *adv, *obs_mean, *obs_inv_std, *logstd, *logstd_old;
   float *ws, *state, *debug;
+  const float* dh3_ext;   // recurrent network: d(loss)/d(h3) comes from the LSTM backward instead of the MLP heads
   int T, N, e0, E, O;
   float e_clip, critic_coef, entropy_coef, bounds_coef, inv_B, kl_threshold, lr_min, lr_max;
   int adaptive;
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
     const int64_t grow = valid ? (s / a.E) * (int64_t)a.N + a.e0 + (s % a.E) : 0;   // row in the [T, N] rollout buffers
     // rollout scalars of this sample (half 0 threads own the loss of their row)
     float act0 = 0.f, act1 = 0.f, muo0 = 0.f, muo1 = 0.f, nlpo = 0.f, vo = 0.f, ret = 0.f, adv = 0.f;
-    if (half == 0 && valid) {
+    if (half == 0 && valid && !a.dh3_ext) {
       const float2 av = *reinterpret_cast<const float2*>(a.act + 2 * grow);
       const float2 mv = *reinterpret_cast<const float2*>(a.mu_old + 2 * grow);
       act0 = av.x, act1 = av.y, muo0 = mv.x, muo1 = mv.y;
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
     fwd_epilogue<H2>(lane_base + TM_DATA + half * 64, 64, half * 64, biases + H1, a2_t, row);
     mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA2, H2), k_major(sW3, H2), instr_desc(H3, false, false), H2 / 16, false); }, nothing);
     fwd_epilogue<H3>(lane_base + TM_DATA + half * 32, 32, half * 32, biases + H1 + H2, a3_t, row);
+    if (!a.dh3_ext) {
     mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA3, H3), k_major(sW4, H3), instr_desc(NH, false, false), H3 / 16, false); }, nothing);
     // =============================== loss ===============================
     if (half == 0) {
@@ -253,6 +255,23 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
                __syncthreads();   // h3 is overwritten in place next
              });
     bwd_epilogue<H3>(lane_base + TM_DATA + half * 32, 32, half * 32, a3_t, row);   // dz3 over h3
+    } else {
+      // dz3 = dh3 (from the LSTM backward, f32 [B, 64]) * ELU'(h3), written over h3 in place
+      __syncthreads();   // every thread is past its h3 stores / the layer-3 accumulator reads
+      uint32_t r[32];
+      if (valid) {
+        const float4* src = reinterpret_cast<const float4*>(a.dh3_ext + s * H3 + half * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = src[i];
+          r[4 * i] = __float_as_uint(v.x), r[4 * i + 1] = __float_as_uint(v.y), r[4 * i + 2] = __float_as_uint(v.z), r[4 * i + 3] = __float_as_uint(v.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      bwd_chunk<H3>(r, half * 32, a3_t, row);
+    }
     // layer 3: dW3^T += h2^T dz3 (persistent), dh2 = dz3 W3; meanwhile db3 = column sums of dz3
     mma_step(
         [&] {
@@ -407,11 +426,11 @@ __global__ void __launch_bounds__(RED_SLOTS* RED_SPLIT) vine_ppo_reduce_kernel(c
 // torch.optim.Adam (no weight decay, no amsgrad) on the flat parameter vector + re-pack for the tensor cores
 __global__ void vine_ppo_adam_kernel(const float* __restrict__ flat, float scale, float* __restrict__ params, float* __restrict__ m,
                                      float* __restrict__ v, uint8_t* __restrict__ packed, float* __restrict__ state, int O,
-                                     float beta1, float beta2, float eps) {
+                                     float beta1, float beta2, float eps, int bookkeeping) {
   const int P = num_params(O);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) {
-    if (p == P) {   // bookkeeping by exactly one thread
+    if (p == P && bookkeeping) {   // bookkeeping by exactly one thread
       for (int j = 0; j < 4; ++j) state[ST_SUMS + j] += flat[P + j] * scale;
       state[ST_COUNT] += 1.f;
       state[ST_KL] = flat[P + 2] * scale;
@@ -451,8 +470,9 @@ int vine_ppo_max_ctas(void) {
 }
 
 int vine_ppo_minibatch(const VinePpoMinibatch* b, void* stream) {
-  if (!b || !b->packed || !b->obs || !b->actions || !b->mu_old || !b->neglogp_old || !b->values_old || !b->returns ||
-      !b->advantages || !b->obs_mean || !b->obs_inv_std || !b->logstd || !b->logstd_old || !b->workspace || !b->state)
+  if (!b || !b->packed || !b->obs || !b->obs_mean || !b->obs_inv_std || !b->logstd || !b->logstd_old || !b->workspace || !b->state)
+    return VINE_ERR_INVALID_ARG;
+  if (!b->dh3_ext && (!b->actions || !b->mu_old || !b->neglogp_old || !b->values_old || !b->returns || !b->advantages))
     return VINE_ERR_INVALID_ARG;
   if (b->horizon < 1 || b->num_envs < 1 || b->env_count < 1 || b->env_begin < 0 || b->env_begin + b->env_count > b->num_envs ||
       b->num_obs < 1 || b->num_obs >= K1 || (((uintptr_t)b->packed) & 15u) || (((uintptr_t)b->workspace) & 15u))
@@ -475,6 +495,7 @@ int vine_ppo_minibatch(const VinePpoMinibatch* b, void* stream) {
   a.obs = b->obs, a.act = b->actions, a.mu_old = b->mu_old, a.nlp_old = b->neglogp_old, a.val_old = b->values_old;
   a.ret = b->returns, a.adv = b->advantages, a.obs_mean = b->obs_mean, a.obs_inv_std = b->obs_inv_std;
   a.logstd = b->logstd, a.logstd_old = b->logstd_old, a.ws = b->workspace, a.state = b->state, a.debug = b->debug_out;
+  a.dh3_ext = b->dh3_ext;
   a.T = b->horizon, a.N = b->num_envs, a.e0 = b->env_begin, a.E = b->env_count, a.O = b->num_obs;
   a.e_clip = b->e_clip, a.critic_coef = b->critic_coef, a.entropy_coef = b->entropy_coef, a.bounds_coef = b->bounds_loss_coef;
   a.inv_B = 1.0f / (float)B, a.kl_threshold = b->kl_threshold, a.lr_min = b->lr_min, a.lr_max = b->lr_max, a.adaptive = b->adaptive_lr;
@@ -492,11 +513,12 @@ int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* 
 }
 
 int vine_ppo_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq, void* packed,
-                  float* state, int num_obs, float beta1, float beta2, float eps, void* stream) {
+                  float* state, int num_obs, float beta1, float beta2, float eps, int bookkeeping, void* stream) {
   if (!flat || !params || !exp_avg || !exp_avg_sq || !packed || !state || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
   const int n = num_params(num_obs) + 1;
   vine_ppo_adam_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(flat, grad_scale, params, exp_avg, exp_avg_sq,
-                                                                         (uint8_t*)packed, state, num_obs, beta1, beta2, eps);
+                                                                         (uint8_t*)packed, state, num_obs, beta1, beta2, eps,
+                                                                         bookkeeping);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 

@@ -515,7 +515,7 @@ class PPOAgent:
                 if self.world > 1:   # ONE collective per minibatch: gradients + loss statistics (incl. the KL)
                     torch.distributed.all_reduce(self._flat_grads)
                 assert lib.vine_ppo_adam(p(self._flat_grads), 1.0 / self.world, p(self.flat), p(self.adam_m), p(self.adam_v),
-                                         p(self._packed), p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, stream) == 0
+                                         p(self._packed), p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, 1, stream) == 0
 
     def capture_graphs(self, warmup=3):
         """Warm up eagerly on a side stream, then capture the rollout and the update as two graphs."""
