@@ -20,13 +20,14 @@ def make_agent(extra, graphs, n=512, **kw):
 MLP = ["train.params.network.rnn=null"]
 
 
-@pytest.mark.parametrize("variant", ["lstm", "mlp_fused", "mlp_torch"])
+@pytest.mark.parametrize("variant", ["lstm_native", "lstm_torch", "mlp_fused", "mlp_torch"])
 @pytest.mark.parametrize("graphs", [False, True], ids=["eager", "graphs"])
 def test_ppo_iterations_are_finite_and_learn_something(variant, graphs):
-    rnn = variant == "lstm"
-    agent = make_agent([] if rnn else MLP, graphs, use_fused_update=variant == "mlp_fused")
+    rnn = variant.startswith("lstm")
+    native = variant in ("lstm_native", "mlp_fused")
+    agent = make_agent([] if rnn else MLP, graphs, use_fused_update=native)
     assert agent.has_rnn == rnn and agent.seq_len == (4 if rnn else 1)
-    assert agent.fused_update == (variant == "mlp_fused") and agent.fused == (not rnn)
+    assert agent.fused_update == native and agent.fused == (not rnn) and agent.native_lstm == (variant == "lstm_native")
     before = [p.detach().clone() for p in agent.model.parameters()]
     for _ in range(6):
         agent.train_epoch()
@@ -60,6 +61,39 @@ def test_fused_update_moves_the_parameters_like_the_torch_update():
     for k in ("a_loss", "c_loss", "kl"):
         assert abs(sa[k] - sb[k]) <= 3e-2 * abs(sb[k]) + 1e-4, (k, sa[k], sb[k])
     assert torch.allclose(a.obs_rms.running_mean, b.obs_rms.running_mean, atol=1e-6)
+
+
+def test_native_lstm_update_moves_the_parameters_like_the_torch_update():
+    """Reference network, same rollout, one minibatch, one Adam step: kernels-only path vs torch autograd + torch Adam."""
+    one = ["train.params.config.mini_epochs=1", "train.params.config.minibatch_size=8192"]
+    a = make_agent(one, False, use_fused_update=True)
+    b = make_agent(one, False, use_fused_update=False)
+    assert a.native_lstm and not b.native_lstm
+    b.load_state_dict(a.state_dict())
+    start = torch.cat([a.flat[:a.flat.numel() - 197].clone(), a.flat_l.clone()])     # MLP half without the dummy heads
+    a._rollout()
+    for name in ("b_obs", "b_act", "b_mu", "b_nlp", "b_val", "b_ret", "b_adv", "b_done"):
+        getattr(b, name).copy_(getattr(a, name))
+    from vine_robot_isaacgymenvs_b200.ppo.tiles import from_tiles
+    for ck in range(a.T // a.seq_len):                                               # LSTM state at the chunk starts
+        b.b_h[ck].copy_(from_tiles(a._HH_saved[ck], a.n))
+        b.b_c[ck].copy_(a._C_saved[ck])
+    a._update_any()
+    b._update_any()
+    torch.cuda.synchronize()
+    mb = [b.model.actor_mlp[0].weight, b.model.actor_mlp[0].bias, b.model.actor_mlp[2].weight, b.model.actor_mlp[2].bias,
+          b.model.actor_mlp[4].weight, b.model.actor_mlp[4].bias]
+    rb = b.model.rnn.rnn
+    lb = [rb.weight_ih_l0, rb.weight_hh_l0, rb.bias_ih_l0, rb.bias_hh_l0, b.model.layer_norm.weight, b.model.layer_norm.bias,
+          b.model.mu.weight, b.model.mu.bias, b.model.value.weight, b.model.value.bias, b.model.sigma]
+    after_b = torch.cat([p.detach().reshape(-1) for p in mb + lb])
+    after_a = torch.cat([a.flat[:a.flat.numel() - 197], a.flat_l])
+    da, db = after_a - start, after_b - start
+    cos = float((da * db).sum() / (da.norm() * db.norm()))
+    assert cos > 0.9, cos                                      # first Adam step = lr * sign(g): agreement of gradient signs
+    sa, sb = a.pop_stats(), b.pop_stats()
+    for k in ("a_loss", "c_loss", "kl"):
+        assert abs(sa[k] - sb[k]) <= 5e-2 * abs(sb[k]) + 2e-4, (k, sa[k], sb[k])
 
 
 def test_checkpoint_roundtrip_uses_rl_games_layout(tmp_path):

@@ -195,9 +195,18 @@ class PPOAgent:
         self.fused = (bool(use_fused_policy) and not self.has_rnn and list(units) == [256, 128, 64] and self.A == 2
                       and self.O <= 31 and self.normalize_input and self.normalize_value)
         self.fused_update = self.fused and bool(use_fused_update) and not self.truncate_grads
+        # the reference network (MLP -> LSTM 256 -> LayerNorm -> heads) on hand-written kernels as well (ppo/lstm_native.py)
+        rnn_cfg = net.get("rnn") or {}
+        self.native_lstm = (self.has_rnn and bool(use_fused_update) and bool(use_fused_policy) and not self.truncate_grads
+                            and list(units) == [256, 128, 64] and self.A == 2 and self.O <= 30 and self.normalize_input
+                            and self.normalize_value and int(rnn_cfg.get("units", 0)) == 256 and bool(rnn_cfg.get("concat_input"))
+                            and bool(rnn_cfg.get("layer_norm")) and self.n % 128 == 0 and self.mb_envs % 128 == 0)
+        self.fused_update = self.fused_update or self.native_lstm
         # CUDA graphs: single GPU always; multi-GPU only for the kernel-only path (its NCCL all-reduces are captured too)
         self.use_graphs = self._want_graphs and (self.world == 1 or (self.fused_update and bool(c.get("graph_nccl", True))))
-        if self.fused_update:
+        if self.native_lstm:
+            self._init_native_lstm(float(c["learning_rate"]))
+        elif self.fused_update:
             self._init_fused_update(float(c["learning_rate"]))
         else:
             self.lr_t = torch.tensor(float(c["learning_rate"]), device=dev)   # device-side: no sync in the schedule
@@ -224,8 +233,10 @@ class PPOAgent:
         self.loss_stats = torch.zeros(4, device=dev, dtype=torch.float64)
         self.ep_ret, self.ep_len = f(n), f(n)
         self._g_rollout = self._g_update = None
-        if self.fused:   # fused tcgen05/TMEM policy forward for the rollout (vine_mlp_forward)
+        if self.fused or self.native_lstm:   # tcgen05/TMEM policy forward for the rollout
             self._packed = torch.zeros(abi.MLP_PACKED_BYTES, dtype=torch.uint8, device=dev)
+            if self.native_lstm:
+                self._lpacked = torch.zeros(abi.LSTM_PACKED_BYTES, dtype=torch.uint8, device=dev)
             self._obs_mean_f, self._obs_inv_std_f = f(self.O), f(self.O)
             self._val_stats = f(2)
             self._mu_buf, self._val_buf = f(n, self.A), f(n)
@@ -263,6 +274,164 @@ class PPOAgent:
         self._moments = torch.zeros(2 * self.O + 4, dtype=torch.float64, device=dev)
         self._adv_stats = torch.zeros(2, device=dev)
 
+    # ------------------------------------------------------------------ reference network on kernels only
+    def _lstm_param_order(self):
+        """Flat parameter order of the recurrent half (include/vine_b200.h, vine_lstm_*)."""
+        m, r = self.model, self.model.rnn.rnn
+        return [r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, m.layer_norm.weight, m.layer_norm.bias,
+                m.mu.weight, m.mu.bias, m.value.weight, m.value.bias, m.sigma]
+
+    @torch.no_grad()
+    def _init_native_lstm(self, lr):
+        from .lstm_native import NativeLstmPath
+        dev, lib, m = self.device, self._lib, self.model
+        z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
+        # MLP half: the flat layout of vine_ppo_* with the (unused) 64-wide heads kept as zeros
+        mlp = [m.actor_mlp[0].weight, m.actor_mlp[0].bias, m.actor_mlp[2].weight, m.actor_mlp[2].bias, m.actor_mlp[4].weight,
+               m.actor_mlp[4].bias]
+        self._mlp_dummy = [z(2, 64), z(2), z(1, 64), z(1), z(2)]
+        self.flat = torch.cat([p.detach().reshape(-1) for p in mlp + self._mlp_dummy]).contiguous()
+        assert self.flat.numel() == lib.vine_ppo_num_params(self.O)
+        o = 0
+        for p in mlp + self._mlp_dummy:
+            p.data = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        order = self._lstm_param_order()
+        self.flat_l = torch.cat([p.detach().reshape(-1) for p in order]).contiguous()
+        assert self.flat_l.numel() == lib.vine_lstm_num_params(self.O)
+        o = 0
+        for p in order:
+            p.data = self.flat_l[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.adam_m, self.adam_v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.adam_ml, self.adam_vl = torch.zeros_like(self.flat_l), torch.zeros_like(self.flat_l)
+        self.ppo_state = torch.zeros(abi.PPO_STATE_FLOATS, device=dev)
+        self.ppo_state[0] = lr
+        self.lr_t = self.ppo_state[0]
+        self._logstd_old = z(2)
+        zz = lambda: z(self.T, self.n)  # noqa: E731
+        self._val_old_n, self._ret_n, self._adv_n = zz(), zz(), zz()
+        self._mb_structs = self._roll_structs = None
+        self._rng_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._moments = torch.zeros(2 * self.O + 4, dtype=torch.float64, device=dev)
+        self._adv_stats = z(2)
+        L, chunks, tiles_n = self.seq_len, self.T // self.seq_len, self.n // 128
+        hyper = dict(e_clip=self.e_clip, critic_coef=self.critic_coef, entropy_coef=self.entropy_coef,
+                     bounds_loss_coef=self.bounds_coef, adaptive_lr=int(self.adaptive), kl_threshold=self.kl_threshold)
+        self._path = NativeLstmPath(self.O, L, chunks * self.mb_envs, dev, hyper)
+        from .lstm_native import TB
+        bf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)  # noqa: E731
+        self._r_U, self._r_HM = bf(tiles_n, TB), bf(tiles_n, 2, TB)
+        self._r_HH = [bf(tiles_n, 2, TB), bf(tiles_n, 2, TB)]          # current / next hidden state tiles
+        self._r_C = [z(self.n, 256), z(self.n, 256)]
+        self._r_cur = 0
+        self._HH_saved, self._C_saved = bf(chunks, tiles_n, 2, TB), z(chunks, self.n, 256)
+        self._nd_ext = torch.zeros(self.T + 1, self.n, device=dev)       # 1 - dones before step t
+        self._ones_n = torch.ones(self.n, device=dev)
+        self._scal = z(self.T, self.n, 8)
+        self._mb_obs, self._mb_scal = z(L, chunks * self.mb_envs, self.O), z(L, chunks * self.mb_envs, 8)
+        self._mb_nd = z(L, chunks * self.mb_envs)
+
+    @torch.no_grad()
+    def _rollout_native_lstm(self):
+        """Rollout of the recurrent policy on kernels only: per step vine_policy_act (MLP -> U tiles, obs copy), vine_lstm_mask,
+        vine_lstm_step, vine_lstm_head (LayerNorm, heads, sampling, buffer writes), the fused env step, vine_rollout_post."""
+        env, lib, T, n, L = self.env, self._lib, self.T, self.n, self.seq_len
+        ptr = lambda x: x.data_ptr()  # noqa: E731
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        common = dict(packed=ptr(self._packed), obs=ptr(env._obs_clamped), obs_mean=ptr(self._obs_mean_f),
+                      obs_inv_std=ptr(self._obs_inv_std_f), value_stats=ptr(self._val_stats), n=n, num_obs=self.O)
+        seed, goff = int(env._seed) ^ 0x5DEECE66D, int(env._global_env_offset)
+        self._done_ext[0].copy_(self._done_ext[T])
+        for t in range(T + 1):
+            cur, nxt = self._r_cur, self._r_cur ^ 1
+            last = t == T
+            torch.sub(self._ones_n, self._done_ext[t], out=self._nd_ext[t])
+            if not last and t % L == 0:   # LSTM state at the start of every seq_len chunk (truncated BPTT restarts here)
+                self._HH_saved[t // L].copy_(self._r_HH[cur])
+                self._C_saved[t // L].copy_(self._r_C[cur])
+            act = abi.VinePolicyAct(u_out=ptr(self._r_U), obs_copy=None if last else ptr(self.b_obs[t]), **common)
+            assert lib.vine_policy_act(C.byref(act), stream) == 0
+            assert lib.vine_lstm_mask(C.c_void_p(ptr(self._r_HH[cur])), C.c_void_p(ptr(self._nd_ext[t])), n,
+                                      C.c_void_p(ptr(self._r_HM)), stream) == 0
+            st = abi.VineLstmStep(params=ptr(self._lpacked), u=ptr(self._r_U), hm=ptr(self._r_HM), c_prev=ptr(self._r_C[cur]),
+                                  not_done=ptr(self._nd_ext[t]), c=ptr(self._r_C[nxt]), hh=ptr(self._r_HH[nxt]), n=n)
+            assert lib.vine_lstm_step(C.byref(st), stream) == 0
+            if last:   # bootstrap value of the final observation: the persistent state is NOT advanced
+                hd = abi.VineLstmHead(params=ptr(self._lpacked), hh=ptr(self._r_HH[nxt]), value_stats=ptr(self._val_stats),
+                                      value=ptr(self.last_value), n=n)
+                assert lib.vine_lstm_head(C.byref(hd), stream) == 0
+                break
+            hd = abi.VineLstmHead(params=ptr(self._lpacked), hh=ptr(self._r_HH[nxt]), value_stats=ptr(self._val_stats),
+                                  mu=ptr(self.b_mu[t]), value=ptr(self.b_val[t]), logstd=ptr(self.model.sigma),
+                                  rng_counter=ptr(self._rng_counter), actions=ptr(self.b_act[t]), neglogp=ptr(self.b_nlp[t]),
+                                  env_actions=ptr(env.actions), n=n, seed=seed, global_env_offset=goff)
+            assert lib.vine_lstm_head(C.byref(hd), stream) == 0
+            self._r_cur = nxt
+            env.step_device()
+            post = abi.VineRolloutPost(rewards=ptr(env.rew_buf), resets=ptr(env.reset_buf), timeouts=ptr(env.timeout_buf),
+                                       values=ptr(self.b_val[t]), shaped_rewards=ptr(self.b_rew[t]), dones_next=ptr(self._done_ext[t + 1]),
+                                       ep_return=ptr(self.ep_ret), ep_length=ptr(self.ep_len), ep_stats=ptr(self.ep_stats),
+                                       rng_counter=ptr(self._rng_counter), n=n, reward_scale=self.reward_scale, gamma=self.gamma,
+                                       value_bootstrap=int(self.value_bootstrap), success_reward_threshold=500.0)
+            assert lib.vine_rollout_post(C.byref(post), stream) == 0
+        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        rc = lib.vine_gae(p(self.b_rew), p(self.b_val), p(self.b_done), p(self.last_value), p(self.dones),
+                          T, n, self.gamma, self.tau, p(self.b_adv), p(self.b_ret), stream)
+        assert rc == 0
+
+    @torch.no_grad()
+    def _update_native_lstm(self):
+        """Update of the recurrent policy on kernels only (ppo/lstm_native.py lists the launches of one minibatch)."""
+        T, n, L, E, lib = self.T, self.n, self.seq_len, self.mb_envs, self._lib
+        chunks = T // L
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ptr = lambda x: x.data_ptr()  # noqa: E731
+        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        if self._mb_structs is None:
+            self._prologue = abi.VinePpoPrologue(
+                obs=ptr(self.b_obs), values=ptr(self.b_val), returns=ptr(self.b_ret), moments=ptr(self._moments),
+                obs_mean=ptr(self.obs_rms.running_mean), obs_var=ptr(self.obs_rms.running_var),
+                obs_count=ptr(self.obs_rms.count), val_mean=ptr(self.val_rms.running_mean),
+                val_var=ptr(self.val_rms.running_var), val_count=ptr(self.val_rms.count),
+                obs_mean_f=ptr(self._obs_mean_f), obs_inv_std_f=ptr(self._obs_inv_std_f), value_stats=ptr(self._val_stats),
+                adv_stats=ptr(self._adv_stats), values_n=ptr(self._val_old_n), returns_n=ptr(self._ret_n),
+                advantages_n=ptr(self._adv_n), count=T * n, num_obs=self.O, world=self.world,
+                normalize_advantage=int(self.normalize_advantage))
+            self._mb_structs = True
+        assert lib.vine_ppo_moments(C.byref(self._prologue), stream) == 0
+        if self.world > 1:
+            torch.distributed.all_reduce(self._moments)
+        assert lib.vine_ppo_finalize(C.byref(self._prologue), stream) == 0
+        self._logstd_old.copy_(self.model.sigma)
+        # per-row scalars of the loss, once per iteration: action(2), mu_old(2), neglogp_old, value_old, return, advantage
+        torch.cat([self.b_act, self.b_mu, self.b_nlp.unsqueeze(-1), self._val_old_n.unsqueeze(-1), self._ret_n.unsqueeze(-1),
+                   self._adv_n.unsqueeze(-1)], dim=-1, out=self._scal)
+        path = self._path
+        mbv = lambda dst, src, e0: dst.view(L, chunks, E, *dst.shape[2:]).copy_(  # noqa: E731
+            src.view(chunks, L, n, *src.shape[2:])[:, :, e0:e0 + E].transpose(0, 1))
+        for _ in range(self.mini_epochs):
+            for e0 in range(0, n, E):
+                # rows of the minibatch ordered [step in chunk][chunk, env]: one strided copy per tensor
+                mbv(self._mb_obs, self.b_obs, e0)
+                mbv(self._mb_scal, self._scal, e0)
+                mbv(self._mb_nd, self._nd_ext[:T], e0)
+                for ck in range(chunks):   # initial LSTM state of every sequence: saved tiles -> masked recurrent input, cell state
+                    assert lib.vine_lstm_mask(C.c_void_p(ptr(self._HH_saved[ck]) + (e0 // 128) * 2 * abi.LSTM_TILE_BYTES),
+                                              C.c_void_p(ptr(self._nd_ext[ck * L]) + e0 * 4), E,
+                                              C.c_void_p(ptr(path.HM[0]) + ck * (E // 128) * 2 * abi.LSTM_TILE_BYTES), stream) == 0
+                    path.C0[ck * E:(ck + 1) * E].copy_(self._C_saved[ck, e0:e0 + E])
+                path.gradients(self._packed, self._lpacked, self._mb_obs, self._mb_scal, self._mb_nd, self._obs_mean_f,
+                               self._obs_inv_std_f, self._val_stats, self.model.sigma, self._logstd_old, self.ppo_state)
+                if self.world > 1:   # gradients + loss statistics (incl. the KL) of both halves
+                    torch.distributed.all_reduce(path.flat_g_mlp)
+                    torch.distributed.all_reduce(path.flat_g_lstm)
+                sc = 1.0 / self.world
+                assert lib.vine_ppo_adam(p(path.flat_g_mlp), sc, p(self.flat), p(self.adam_m), p(self.adam_v), p(self._packed),
+                                         p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, 0, stream) == 0
+                assert lib.vine_lstm_adam(p(path.flat_g_lstm), sc, p(self.flat_l), p(self.adam_ml), p(self.adam_vl), p(self._lpacked),
+                                          p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, stream) == 0
+
     @torch.no_grad()
     def _refresh_fused(self, pack=False):
         """Refresh the normalisation statistics the kernels read; ``pack``: also re-pack the weights (bf16, tensor-core
@@ -273,9 +442,16 @@ class PPOAgent:
                                            torch.sqrt(self.val_rms.running_var.float() + self.val_rms.eps)]))
         if pack:
             p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
-            args = [p(t) for t in self._param_order()[:10]]
-            rc = self._lib.vine_mlp_pack(*args, self.O, p(self._packed), C.c_void_p(torch.cuda.current_stream().cuda_stream))
-            assert rc == 0
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if self.native_lstm:
+                m = self.model
+                mlp = [m.actor_mlp[0].weight, m.actor_mlp[0].bias, m.actor_mlp[2].weight, m.actor_mlp[2].bias,
+                       m.actor_mlp[4].weight, m.actor_mlp[4].bias] + self._mlp_dummy[:4]
+                assert self._lib.vine_mlp_pack(*[p(t) for t in mlp], self.O, p(self._packed), st) == 0
+                assert self._lib.vine_lstm_pack(*[p(t) for t in self._lstm_param_order()[:10]], self.O, p(self._lpacked), st) == 0
+            else:
+                args = [p(t) for t in self._param_order()[:10]]
+                assert self._lib.vine_mlp_pack(*args, self.O, p(self._packed), st) == 0
 
     @property
     def lr(self):
@@ -338,6 +514,8 @@ class PPOAgent:
 
     @torch.no_grad()
     def _rollout(self):
+        if self.native_lstm:
+            return self._rollout_native_lstm()
         if self.fused_update:
             return self._rollout_fused()
         env = self.env
@@ -469,7 +647,7 @@ class PPOAgent:
                     self._update_lr(kl)
                     self.loss_stats += torch.stack([a_loss.detach(), c_loss.detach(), kl,
                                                     torch.ones((), device=kl.device)]).double()
-        if self.fused:
+        if self.fused or self.native_lstm:
             self._refresh_fused(pack=True)
 
     @torch.no_grad()
@@ -547,7 +725,9 @@ class PPOAgent:
         self.epoch += 1
 
     def _update_any(self):
-        if self.fused_update:
+        if self.native_lstm:
+            self._update_native_lstm()
+        elif self.fused_update:
             self._update_fused()
         else:
             self._update()
@@ -595,8 +775,10 @@ class PPOAgent:
 
     def _optimizer_state(self):
         if self.fused_update:
-            return {"fused_adam": {"exp_avg": self.adam_m.clone(), "exp_avg_sq": self.adam_v.clone(),
-                                   "step": float(self.ppo_state[1])}}
+            sd = {"exp_avg": self.adam_m.clone(), "exp_avg_sq": self.adam_v.clone(), "step": float(self.ppo_state[1])}
+            if self.native_lstm:
+                sd.update({"exp_avg_lstm": self.adam_ml.clone(), "exp_avg_sq_lstm": self.adam_vl.clone()})
+            return {"fused_adam": sd}
         return self.opt.state_dict()
 
     def state_dict(self):
@@ -622,9 +804,12 @@ class PPOAgent:
             self.adam_m.copy_(opt["fused_adam"]["exp_avg"])
             self.adam_v.copy_(opt["fused_adam"]["exp_avg_sq"])
             self.ppo_state[1] = float(opt["fused_adam"]["step"])
+            if self.native_lstm and "exp_avg_lstm" in opt["fused_adam"]:
+                self.adam_ml.copy_(opt["fused_adam"]["exp_avg_lstm"])
+                self.adam_vl.copy_(opt["fused_adam"]["exp_avg_sq_lstm"])
         elif opt and not self.fused_update and "fused_adam" not in opt:
             self.opt.load_state_dict(opt)
         self.epoch, self.frames = sd.get("epoch", 0), sd.get("frame", 0)
         self.lr_t.fill_(float(sd.get("last_lr", self.lr)))
-        if self.fused:
+        if self.fused or self.native_lstm:
             self._refresh_fused(pack=True)
