@@ -318,9 +318,11 @@ def run_ours(args, rank, world, local_rank):
                                   if not agent.has_rnn else None),
                 "network": "mlp[256,128,64]+lstm256+ln" if agent.has_rnn else "mlp[256,128,64]",
                 "cuda_graphs": agent.use_graphs,
-                "update": "vine_ppo_minibatch/reduce/adam (tcgen05, hand-written)" if agent.fused_update
-                          else "torch autograd + cuBLAS/cuDNN + torch Adam",
-                "policy_forward": "vine_mlp_forward (tcgen05)" if agent.fused else "torch",
+                "update": ("vine_lstm_* + vine_ppo_minibatch (tcgen05, hand-written; ppo/lstm_native.py)" if agent.native_lstm else
+                           "vine_ppo_minibatch/reduce/adam (tcgen05, hand-written)" if agent.fused_update
+                           else "torch autograd + cuBLAS/cuDNN + torch Adam"),
+                "policy_forward": ("vine_policy_act + vine_lstm_step/head (tcgen05)" if agent.native_lstm else
+                                   "vine_policy_act (tcgen05)" if agent.fused else "torch"),
                 "collectives": "none" if world == 1 else "NCCL all-reduce: grads+KL per minibatch, running stats per iteration"}
 
     ppo = None
@@ -330,10 +332,13 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.empty_cache()
         ppo = {"config": "BASELINE configs[1]: FSTR num_envs=4096 rollout+PPO",
                "reference_network": measure_ppo(4096, args.ppo_iters, 5, []),
+               "reference_network_torch_update": measure_ppo(4096, max(3, args.ppo_iters // 2), 3, [], fused_update=False),
                "mlp_only": measure_ppo(4096, args.ppo_iters, 5, ["train.params.network.rnn=null"]),
                "mlp_only_torch_update": measure_ppo(4096, args.ppo_iters, 5, ["train.params.network.rnn=null"],
                                                     fused_update=False)}
         if not args.no_sweep:
+            ppo["reference_network_65536_envs"] = measure_ppo(65536, max(3, args.ppo_iters // 4), 3,
+                                                              ["train.params.config.minibatch_size=131072"])
             ppo["mlp_only_65536_envs"] = measure_ppo(65536, max(3, args.ppo_iters // 4), 3,
                                                      ["train.params.network.rnn=null",
                                                       "train.params.config.minibatch_size=131072"])
