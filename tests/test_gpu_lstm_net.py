@@ -157,11 +157,14 @@ def test_native_lstm_step_backward_chain_matches_autograd():
     st = abi.VineLstmStep(params=lpacked.data_ptr(), u=U.data_ptr(), hm=HM.data_ptr(), c_prev=c_prev.data_ptr(), not_done=nd.data_ptr(),
                           c=c_new.data_ptr(), hh=HH.data_ptr(), act=ACT.data_ptr(), n=n)
     assert lib.vine_lstm_step(C.byref(st), None) == 0
-    DH, grads, dbg = torch.zeros_like(HH), torch.zeros(abi.LSTM_HEAD_GRAD_FLOATS, device=dev), torch.zeros(n, 4, device=dev)
+    DH, gparts, dbg = torch.zeros_like(HH), torch.zeros(abi.LSTM_HEAD_GRAD_PARTS, abi.LSTM_HEAD_GRAD_FLOATS, device=dev), torch.zeros(n, 4, device=dev)
     ht = abi.VineLstmHeadTrain(params=lpacked.data_ptr(), hh=HH.data_ptr(), scalars=scal.data_ptr(), logstd=m.sigma.data_ptr(),
-                               logstd_old=logstd_old.data_ptr(), dh=DH.data_ptr(), grads=grads.data_ptr(), debug_out=dbg.data_ptr(),
+                               logstd_old=logstd_old.data_ptr(), dh=DH.data_ptr(), grads=gparts.data_ptr(), debug_out=dbg.data_ptr(),
                                n=n, inv_B=1.0 / n, **hyp)
-    assert lib.vine_lstm_head_train(C.byref(ht), None) == 0
+    nparts = lib.vine_lstm_head_train(C.byref(ht), None)
+    assert 0 < nparts <= abi.LSTM_HEAD_GRAD_PARTS
+    torch.cuda.synchronize()
+    grads = gparts[:nparts].sum(0)
     DG, dc_prev_k = torch.zeros_like(ACT), torch.zeros(n, 256, device=dev)
     cb = abi.VineLstmCellBwd(act=ACT.data_ptr(), c_prev=c_prev.data_ptr(), c=c_new.data_ptr(), not_done=nd.data_ptr(), dh=DH.data_ptr(),
                              dg=DG.data_ptr(), dc_prev=dc_prev_k.data_ptr(), n=n)

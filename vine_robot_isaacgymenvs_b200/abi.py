@@ -147,6 +147,7 @@ METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limi
 MLP_PACKED_BYTES = 102208
 LSTM_PACKED_BYTES = 795664
 LSTM_HEAD_GRAD_FLOATS = 1296
+LSTM_HEAD_GRAD_PARTS = 296
 LSTM_WGRAD_BLOCK_FLOATS = 12 * 128 * 256      # per K split
 LSTM_TILE_BYTES = 32768          # one [128 x 128] bf16 activation tile
 PPO_WS_FLOATS = 49664
@@ -265,7 +266,7 @@ def _declare(lib):
     lib.vine_lstm_bwd_gemm.argtypes = [C.POINTER(VineLstmBwdGemm), vp]
     lib.vine_lstm_num_params.argtypes = [C.c_int]
     lib.vine_lstm_wgrad.argtypes = [C.POINTER(VineLstmWgrad), vp]
-    lib.vine_lstm_reduce.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
+    lib.vine_lstm_reduce.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
     lib.vine_lstm_adam.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, vp]
     lib.vine_ppo_num_params.argtypes = [C.c_int]
     lib.vine_ppo_max_ctas.argtypes = []

@@ -13,8 +13,9 @@
 // columns = U's columns), W_hh as [2 halves][16 pieces][64 x 128], then f32: bias (same row order), LayerNorm gamma/beta,
 // head weights [3][256] (mu0, mu1, v) and head biases.
 //
-// vine_lstm_step  : one LSTM time step for every 128-sequence tile; CTA = (tile, slice of 128 gate rows = 32 hidden units):
-//                   6 bulk copies (192 KB) -> 22 tcgen05.mma (M128 N128 K16) into TMEM -> cell epilogue per row.
+// vine_lstm_step  : one LSTM time step for every 128-sequence tile; CTA = (tile, half of the hidden units): resident A tile,
+//                   weight pieces streamed through a bulk-TMA ring, tcgen05.mma into ping-pong TMEM accumulators, cell
+//                   epilogue per row overlapped with the next piece (warp-specialised).
 // vine_lstm_head  : LayerNorm + heads per row (one warp per row) + Gaussian sampling / neglogp (rollout).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -81,35 +82,35 @@ __global__ void vine_lstm_pack_kernel(const float* __restrict__ w_ih, const floa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoid_(float x) { return 1.f / (1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_(float x) {
-  const float e = __expf(-2.f * fabsf(x));
-  const float t = (1.f - e) / (1.f + e);
-  return x < 0.f ? -t : t;
-}
+__device__ __forceinline__ float sigmoid_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }   // +-1 at +-inf
 
-constexpr int SO_U = 0, SO_HM = TILE_BYTES, SO_WIH = 3 * TILE_BYTES, SO_WHH = 4 * TILE_BYTES, SO_BIAS = 6 * TILE_BYTES;
-constexpr int SO_BAR = SO_BIAS + 512;
-constexpr int STEP_SMEM = SO_BAR + 64;
+// CTA = (tile of 128 sequences, half of the hidden units).  A = [U | HM] (96 KB) stays resident; the CTA's 8 weight pieces
+// (16 hidden units x 4 gates each, 48 KB: W_ih piece + the two W_hh half pieces) stream through a 2-stage ring of bulk copies;
+// the gate accumulators ping-pong between two TMEM buffers, so the tensor core works on piece p+1 and the copy engine on
+// piece p+2 while the 8 epilogue warps run the cell update of piece p.  Warp 8 (one lane) is producer + MMA issuer.
+constexpr int SO_U = 0, SO_HM = TILE_BYTES, SO_RING = 3 * TILE_BYTES, RING_STAGE = 3 * PIECE_BYTES, SO_BIAS = SO_RING + 2 * RING_STAGE;
+constexpr int SO_BAR = SO_BIAS + 2048;
+constexpr int STEP_SMEM = SO_BAR + 128;
+constexpr int STEP_THREADS = THREADS + 32, PIECES_PER_CTA = NPIECE / 2;
 
-__global__ void __launch_bounds__(THREADS, 1) vine_lstm_step_kernel(const VineLstmStep a) {
+__global__ void __launch_bounds__(STEP_THREADS, 1) vine_lstm_step_kernel(const VineLstmStep a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
-  const int tile = blockIdx.x, slice = blockIdx.y;
-  const uint32_t bar_ld = smem_u32(smem + SO_BAR), bar_mma = bar_ld + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SO_BAR + 16);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x, hf = blockIdx.y;
+  const uint32_t bar0 = smem_u32(smem + SO_BAR);
+  const uint32_t bar_a = bar0;                                       // A + bias landed
+  auto full = [&](int st) { return bar0 + 8u + 8u * st; };           // ring stage filled
+  auto done = [&](int st) { return bar0 + 24u + 8u * st; };          // ring stage consumed by the tensor core
+  auto acc_full = [&](int b) { return bar0 + 40u + 8u * b; };        // accumulator buffer complete
+  auto acc_empty = [&](int b) { return bar0 + 56u + 8u * b; };       // accumulator buffer drained by the epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SO_BAR + 96);
   const uint8_t* P = reinterpret_cast<const uint8_t*>(a.params);
+  const int piece0 = hf * PIECES_PER_CTA;
   if (tid == 0) {
-    mbar_init(bar_ld, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(bar_a, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(full(i), 1); mbar_init(done(i), 1); mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar_ld, 6 * TILE_BYTES + 512);
-    bulk_g2s(smem_u32(smem + SO_U), reinterpret_cast<const uint8_t*>(a.u) + (size_t)tile * TILE_BYTES, TILE_BYTES, bar_ld);
-    bulk_g2s(smem_u32(smem + SO_HM), reinterpret_cast<const uint8_t*>(a.hm) + (size_t)tile * 2 * TILE_BYTES, 2 * TILE_BYTES, bar_ld);
-    bulk_g2s(smem_u32(smem + SO_WIH), P + LP_WIH + (size_t)slice * 2 * PIECE_BYTES, 2 * PIECE_BYTES, bar_ld);
-    bulk_g2s(smem_u32(smem + SO_WHH), P + LP_WHH + (size_t)(slice * 2) * PIECE_BYTES, 2 * PIECE_BYTES, bar_ld);
-    bulk_g2s(smem_u32(smem + SO_WHH + TILE_BYTES), P + LP_WHH + (size_t)(NPIECE + slice * 2) * PIECE_BYTES, 2 * PIECE_BYTES, bar_ld);
-    bulk_g2s(smem_u32(smem + SO_BIAS), P + LP_BIAS + (size_t)slice * 512, 512, bar_ld);
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -119,68 +120,115 @@ __global__ void __launch_bounds__(THREADS, 1) vine_lstm_step_kernel(const VineLs
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  if (tid == 0) {
-    mbar_wait(bar_ld, 0);
-    fence_after_sync();
-    const uint32_t idesc = instr_desc(128, false, false);
-    mma_sequence(tmem, k_major(smem_u32(smem + SO_U), UK), k_major(smem_u32(smem + SO_WIH), UK), idesc, 96 / 16, false);
-    mma_sequence(tmem, k_major(smem_u32(smem + SO_HM), UK), k_major(smem_u32(smem + SO_WHH), UK), idesc, UK / 16, true);
-    mma_sequence(tmem, k_major(smem_u32(smem + SO_HM + TILE_BYTES), UK), k_major(smem_u32(smem + SO_WHH + TILE_BYTES), UK), idesc,
-                 UK / 16, true);
-    mma_commit(bar_mma);
-  }
-  mbar_wait(bar_ld, 0);    // the bias slice is read below by every thread
-  mbar_wait(bar_mma, 0);
-  fence_after_sync();
-  // ---- cell epilogue: this thread = one sequence x 16 hidden units (piece = 2*slice + half) ----
-  const int64_t s = (int64_t)tile * TILE + row;
-  const int piece = 2 * slice + half, unit0 = 16 * piece;
-  uint32_t gi[16], gf[16], gg[16], go[16];
-  tmem_ld16(lane_base + half * 64, gi);
-  tmem_ld16(lane_base + half * 64 + 16, gf);
-  tmem_ld16(lane_base + half * 64 + 32, gg);
-  tmem_ld16(lane_base + half * 64 + 48, go);
-  if (s < a.n) {
-    const float* sb = reinterpret_cast<const float*>(smem + SO_BIAS) + half * 64;
-    const float m = a.not_done ? a.not_done[s] : 1.f;
-    const float mn = a.not_done_next ? a.not_done_next[s] : 1.f;
-    float cp[16], cn[16], hn[16], act[64];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(a.c_prev + s * HID + unit0 + 4 * q);
-      cp[4 * q] = v.x, cp[4 * q + 1] = v.y, cp[4 * q + 2] = v.z, cp[4 * q + 3] = v.w;
+
+  if (warp == 8) {
+    if ((tid & 31) == 0) {
+      auto load_b = [&](int p, int st) {
+        const uint32_t dst = smem_u32(smem + SO_RING + st * RING_STAGE);
+        mbar_expect_tx(full(st), RING_STAGE);
+        bulk_g2s(dst, P + LP_WIH + (size_t)(piece0 + p) * PIECE_BYTES, PIECE_BYTES, full(st));
+        bulk_g2s(dst + PIECE_BYTES, P + LP_WHH + (size_t)(piece0 + p) * PIECE_BYTES, PIECE_BYTES, full(st));
+        bulk_g2s(dst + 2 * PIECE_BYTES, P + LP_WHH + (size_t)(NPIECE + piece0 + p) * PIECE_BYTES, PIECE_BYTES, full(st));
+      };
+      mbar_expect_tx(bar_a, 3 * TILE_BYTES + 2048);
+      bulk_g2s(smem_u32(smem + SO_U), reinterpret_cast<const uint8_t*>(a.u) + (size_t)tile * TILE_BYTES, TILE_BYTES, bar_a);
+      bulk_g2s(smem_u32(smem + SO_HM), reinterpret_cast<const uint8_t*>(a.hm) + (size_t)tile * 2 * TILE_BYTES, 2 * TILE_BYTES, bar_a);
+      bulk_g2s(smem_u32(smem + SO_BIAS), P + LP_BIAS + (size_t)piece0 * PIECE_ROWS * 4, 2048, bar_a);
+      load_b(0, 0);
+      load_b(1, 1);
+      mbar_wait(bar_a, 0);
+      const uint32_t idesc = instr_desc(PIECE_ROWS, false, false);
+      const Operand aU = k_major(smem_u32(smem + SO_U), UK), aH0 = k_major(smem_u32(smem + SO_HM), UK),
+                    aH1 = k_major(smem_u32(smem + SO_HM + TILE_BYTES), UK);
+      for (int p = 0; p < PIECES_PER_CTA; ++p) {
+        const int st = p & 1;
+        const uint32_t ph = (uint32_t)((p >> 1) & 1);
+        mbar_wait(full(st), ph);
+        if (p >= 2) mbar_wait(acc_empty(st), ph ^ 1u);     // completion #(p/2 - 1) of this buffer's drain
+        fence_after_sync();
+        const uint32_t base = smem_u32(smem + SO_RING + st * RING_STAGE), acc = tmem + 64u * st;
+        mma_sequence(acc, aU, k_major(base, UK), idesc, 96 / 16, false);
+        mma_sequence(acc, aH0, k_major(base + PIECE_BYTES, UK), idesc, UK / 16, true);
+        mma_sequence(acc, aH1, k_major(base + 2 * PIECE_BYTES, UK), idesc, UK / 16, true);
+        mma_commit(acc_full(st));
+        mma_commit(done(st));
+        if (p + 2 < PIECES_PER_CTA) {
+          mbar_wait(done(st), ph);
+          load_b(p + 2, st);
+        }
+      }
     }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float i_ = sigmoid_(__uint_as_float(gi[k]) + sb[k]), f_ = sigmoid_(__uint_as_float(gf[k]) + sb[16 + k]);
-      const float g_ = tanh_(__uint_as_float(gg[k]) + sb[32 + k]), o_ = sigmoid_(__uint_as_float(go[k]) + sb[48 + k]);
-      cn[k] = fmaf(f_, cp[k] * m, i_ * g_);
-      hn[k] = o_ * tanh_(cn[k]);
-      act[k] = i_, act[16 + k] = f_, act[32 + k] = g_, act[48 + k] = o_;
+  } else {
+    // ---- epilogue warps: thread = (sequence row, 8 of the piece's 16 hidden units) ----
+    const int row = tid & 127, sub = tid >> 7;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int64_t s = (int64_t)tile * TILE + row;
+    const bool valid = s < a.n;
+    const float m = (valid && a.not_done) ? a.not_done[s] : 1.f;
+    const float mn = (valid && a.not_done_next) ? a.not_done_next[s] : 1.f;
+    mbar_wait(bar_a, 0);   // bias slice
+    uint8_t* hh_t = reinterpret_cast<uint8_t*>(a.hh) + ((size_t)tile * 2 + hf) * TILE_BYTES;
+    uint8_t* hm_t = a.hm_next ? reinterpret_cast<uint8_t*>(a.hm_next) + ((size_t)tile * 2 + hf) * TILE_BYTES : nullptr;
+    // cell state of the next piece is fetched while the current one is processed (the load latency is otherwise exposed)
+    float4 cq0 = make_float4(0.f, 0.f, 0.f, 0.f), cq1 = cq0;
+    if (valid) {
+      cq0 = *reinterpret_cast<const float4*>(a.c_prev + s * HID + 16 * piece0 + 8 * sub);
+      cq1 = *reinterpret_cast<const float4*>(a.c_prev + s * HID + 16 * piece0 + 8 * sub + 4);
     }
+#pragma unroll 1
+    for (int p = 0; p < PIECES_PER_CTA; ++p) {
+      const int b = p & 1;
+      const float4 c0 = cq0, c1 = cq1;
+      if (valid && p + 1 < PIECES_PER_CTA) {
+        cq0 = *reinterpret_cast<const float4*>(a.c_prev + s * HID + 16 * (piece0 + p + 1) + 8 * sub);
+        cq1 = *reinterpret_cast<const float4*>(a.c_prev + s * HID + 16 * (piece0 + p + 1) + 8 * sub + 4);
+      }
+      mbar_wait(acc_full(b), (uint32_t)((p >> 1) & 1));
+      fence_after_sync();
+      uint32_t gi[8], gf[8], gg[8], go[8];
+      const uint32_t t0 = lane_base + 64u * b + 8u * sub;
+      tmem_ld8_async(t0, gi);
+      tmem_ld8_async(t0 + 16, gf);
+      tmem_ld8_async(t0 + 32, gg);
+      tmem_ld8_async(t0 + 48, go);
+      tmem_wait8(gi, gf, gg, go);
+      fence_before_sync();
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(acc_empty(b));   // this warp's lanes hold their accumulator values in registers
+      if (!valid) continue;
+      const int piece = piece0 + p, unit0 = 16 * piece + 8 * sub;
+      const float* sb = reinterpret_cast<const float*>(smem + SO_BIAS) + p * PIECE_ROWS + 8 * sub;
+      const float cp[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      float cn[8], hn[8], ai[8], af[8], ag[8], ao[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<float4*>(a.c + s * HID + unit0 + 4 * q) = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
-    const size_t hoff = ((size_t)tile * 2 + unit0 / UK) * TILE_BYTES;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int off = tile_offset(row, unit0 % UK + 8 * q, UK);
-      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.hh) + hoff + off) =
-          make_uint4(pack_bf16(hn[8 * q], hn[8 * q + 1]), pack_bf16(hn[8 * q + 2], hn[8 * q + 3]),
-                     pack_bf16(hn[8 * q + 4], hn[8 * q + 5]), pack_bf16(hn[8 * q + 6], hn[8 * q + 7]));
-      if (a.hm_next)
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.hm_next) + hoff + off) =
-            make_uint4(pack_bf16(hn[8 * q] * mn, hn[8 * q + 1] * mn), pack_bf16(hn[8 * q + 2] * mn, hn[8 * q + 3] * mn),
-                       pack_bf16(hn[8 * q + 4] * mn, hn[8 * q + 5] * mn), pack_bf16(hn[8 * q + 6] * mn, hn[8 * q + 7] * mn));
-    }
-    if (a.act) {
-      uint8_t* at = reinterpret_cast<uint8_t*>(a.act) + ((size_t)tile * NPIECE + piece) * ACT_BYTES;
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<uint4*>(at + tile_offset(row, 8 * q, PIECE_ROWS)) =
-            make_uint4(pack_bf16(act[8 * q], act[8 * q + 1]), pack_bf16(act[8 * q + 2], act[8 * q + 3]),
-                       pack_bf16(act[8 * q + 4], act[8 * q + 5]), pack_bf16(act[8 * q + 6], act[8 * q + 7]));
+      for (int k = 0; k < 8; ++k) {
+        ai[k] = sigmoid_(__uint_as_float(gi[k]) + sb[k]);
+        af[k] = sigmoid_(__uint_as_float(gf[k]) + sb[16 + k]);
+        ag[k] = tanh_(__uint_as_float(gg[k]) + sb[32 + k]);
+        ao[k] = sigmoid_(__uint_as_float(go[k]) + sb[48 + k]);
+        cn[k] = fmaf(af[k], cp[k] * m, ai[k] * ag[k]);
+        hn[k] = ao[k] * tanh_(cn[k]);
+      }
+      float* co = a.c + s * HID + unit0;
+      *reinterpret_cast<float4*>(co) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      *reinterpret_cast<float4*>(co + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+      const int off = tile_offset(row, unit0 % UK, UK);
+      *reinterpret_cast<uint4*>(hh_t + off) =
+          make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]), pack_bf16(hn[6], hn[7]));
+      if (hm_t)
+        *reinterpret_cast<uint4*>(hm_t + off) = make_uint4(pack_bf16(hn[0] * mn, hn[1] * mn), pack_bf16(hn[2] * mn, hn[3] * mn),
+                                                           pack_bf16(hn[4] * mn, hn[5] * mn), pack_bf16(hn[6] * mn, hn[7] * mn));
+      if (a.act) {
+        uint8_t* at = reinterpret_cast<uint8_t*>(a.act) + ((size_t)tile * NPIECE + piece) * ACT_BYTES;
+        auto st8 = [&](int col, const float (&v)[8]) {
+          *reinterpret_cast<uint4*>(at + tile_offset(row, col, PIECE_ROWS)) =
+              make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        };
+        st8(8 * sub, ai);
+        st8(16 + 8 * sub, af);
+        st8(32 + 8 * sub, ag);
+        st8(48 + 8 * sub, ao);
+      }
     }
   }
   fence_before_sync();
@@ -280,7 +328,7 @@ __global__ void __launch_bounds__(256) vine_lstm_head_kernel(const VineLstmHead 
 // ---------------------------------------------------------------------------------------------------------------
 // Training: LayerNorm + heads forward, the PPO losses (same formulas as vine_ppo_minibatch_kernel), and their backward
 // down to dh (one warp per row).  Parameter gradients accumulate in registers over the warp's rows, are combined per
-// block in shared memory and added to `grads` (f32, zeroed by the caller) with one atomic per slot and block.
+// block in shared memory and written as one partial per block (`grads` [blocks][HG_FLOATS]; vine_lstm_reduce sums them).
 constexpr int HG_LNG = 0, HG_LNB = HID, HG_WH = 2 * HID, HG_BH = 5 * HID, HG_LS = 5 * HID + 4, HG_STATS = 5 * HID + 6;
 constexpr int HG_FLOATS = 5 * HID + 16;
 static_assert(HG_FLOATS == VINE_LSTM_HEAD_GRAD_FLOATS, "header constant out of date");
@@ -407,8 +455,7 @@ __global__ void __launch_bounds__(256) vine_lstm_head_train_kernel(const VineLst
     }
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < HG_FLOATS; i += blockDim.x)
-    if (red[i] != 0.f) atomicAdd(a.grads + i, red[i]);
+  for (int i = threadIdx.x; i < HG_FLOATS; i += blockDim.x) a.grads[(size_t)blockIdx.x * HG_FLOATS + i] = red[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -681,30 +728,38 @@ __host__ __device__ inline LstmSeg lstm_segments(int O) {
 }
 
 // gradient of flat parameter p: sum over the weight-gradient partials, or a slot of the head gradient buffer
-__device__ inline float lstm_grad(int p, int O, const float* __restrict__ ws, int splits, const float* __restrict__ hg) {
+__device__ inline float head_sum(const float* __restrict__ hg, int parts, int slot) {
+  float acc = 0.f;
+  for (int k = 0; k < parts; ++k) acc += hg[(size_t)k * HG_FLOATS + slot];
+  return acc;
+}
+
+__device__ inline float lstm_grad(int p, int O, const float* __restrict__ ws, int splits, const float* __restrict__ hgp, int hparts) {
   const LstmSeg sg = lstm_segments(O);
   int part, f, R;
+  auto hg = [&](int slot) { return head_sum(hgp, hparts, slot); };
   if (p < sg.whh) { const int tr = p / (H3 + O); part = 0; f = p % (H3 + O); R = packed_gate_row(tr); }
   else if (p < sg.bih) { const int q = p - sg.whh, tr = q / HID, c = q % HID; part = 1 + c / UK; f = c % UK; R = packed_gate_row(tr); }
   else if (p < sg.lng) { const int tr = (p - sg.bih) % GATES; part = 0; f = UK - 33; R = packed_gate_row(tr); }   // U column 95 == 1
-  else if (p < sg.lnb) return hg[HG_LNG + (p - sg.lng)];
-  else if (p < sg.wmu) return hg[HG_LNB + (p - sg.lnb)];
-  else if (p < sg.bmu) return hg[HG_WH + (p - sg.wmu)];
-  else if (p < sg.wv) return hg[HG_BH + (p - sg.bmu)];
-  else if (p < sg.bv) return hg[HG_WH + 2 * HID + (p - sg.wv)];
-  else if (p < sg.ls) return hg[HG_BH + 2];
-  else return hg[HG_LS + (p - sg.ls)];
+  else if (p < sg.lnb) return hg(HG_LNG + (p - sg.lng));
+  else if (p < sg.wmu) return hg(HG_LNB + (p - sg.lnb));
+  else if (p < sg.bmu) return hg(HG_WH + (p - sg.wmu));
+  else if (p < sg.wv) return hg(HG_BH + (p - sg.bmu));
+  else if (p < sg.bv) return hg(HG_WH + 2 * HID + (p - sg.wv));
+  else if (p < sg.ls) return hg(HG_BH + 2);
+  else return hg(HG_LS + (p - sg.ls));
   const size_t off = (size_t)(part * 4 + R / 256) * WG_BLOCK_FLOATS + (size_t)f * 256 + (R % 256);
   float acc = 0.f;
   for (int k = 0; k < splits; ++k) acc += ws[(size_t)k * WG_BLOCKS * WG_BLOCK_FLOATS + off];
   return acc;
 }
 
-__global__ void vine_lstm_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ hg, int O, float* __restrict__ flat) {
+__global__ void vine_lstm_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ hg, int hparts, int O,
+                                        float* __restrict__ flat) {
   const int PL = lstm_num_params(O);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < PL) flat[p] = lstm_grad(p, O, ws, splits, hg);
-  else if (p < PL + 4) flat[p] = hg[HG_STATS + (p - PL)];
+  if (p < PL) flat[p] = lstm_grad(p, O, ws, splits, hg, hparts);
+  else if (p < PL + 4) flat[p] = head_sum(hg, hparts, HG_STATS + (p - PL));
 }
 
 __global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scale, float* __restrict__ params, float* __restrict__ m,
@@ -785,8 +840,8 @@ int vine_lstm_step(const VineLstmStep* a, void* stream) {
       return VINE_ERR_CUDA;
     configured = dev;
   }
-  const dim3 grid((unsigned)((a->n + TILE - 1) / TILE), 8);
-  vine_lstm_step_kernel<<<grid, THREADS, STEP_SMEM, (cudaStream_t)stream>>>(*a);
+  const dim3 grid((unsigned)((a->n + TILE - 1) / TILE), 2);
+  vine_lstm_step_kernel<<<grid, STEP_THREADS, STEP_SMEM, (cudaStream_t)stream>>>(*a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -835,10 +890,10 @@ int vine_lstm_wgrad(const VineLstmWgrad* a, void* stream) {
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
-int vine_lstm_reduce(const float* workspace, int splits, const float* head_grads, int num_obs, float* flat, void* stream) {
-  if (!workspace || !head_grads || !flat || splits < 1 || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
+int vine_lstm_reduce(const float* workspace, int splits, const float* head_grads, int head_parts, int num_obs, float* flat, void* stream) {
+  if (!workspace || !head_grads || !flat || splits < 1 || head_parts < 1 || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
   const int n = lstm_num_params(num_obs) + 4;
-  vine_lstm_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, splits, head_grads, num_obs, flat);
+  vine_lstm_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, splits, head_grads, head_parts, num_obs, flat);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -855,9 +910,9 @@ int vine_lstm_head_train(const VineLstmHeadTrain* a, void* stream) {
   if (!a || !a->params || !a->hh || !a->scalars || !a->logstd || !a->logstd_old || !a->dh || !a->grads || a->n <= 0)
     return VINE_ERR_INVALID_ARG;
   int64_t blocks = (a->n + 7) / 8;
-  if (blocks > 296) blocks = 296;
+  if (blocks > VINE_LSTM_HEAD_GRAD_PARTS) blocks = VINE_LSTM_HEAD_GRAD_PARTS;
   vine_lstm_head_train_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
-  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+  return cudaGetLastError() == cudaSuccess ? (int)blocks : VINE_ERR_CUDA;   // number of gradient partials written
 }
 
 int vine_lstm_head(const VineLstmHead* a, void* stream) {

@@ -35,7 +35,7 @@ class NativeLstmPath:
         self.Cs, self.C0 = f32(L, S, 256), f32(S, 256)
         self.DC = [f32(S, 256), f32(S, 256)]
         self.DH3 = f32(L, S, 64)
-        self.head_grads = f32(abi.LSTM_HEAD_GRAD_FLOATS)
+        self.head_grads = f32(abi.LSTM_HEAD_GRAD_PARTS, abi.LSTM_HEAD_GRAD_FLOATS)
         self.splits = min(wgrad_splits, L * tl)
         self.wg_ws = f32(self.splits, abi.LSTM_WGRAD_BLOCK_FLOATS)
         self.mlp_ctas = self.lib.vine_ppo_max_ctas()
@@ -62,14 +62,14 @@ class NativeLstmPath:
                                  not_done_next=None if last else _ptr(not_done[t + 1]), c=_ptr(self.Cs[t]), hh=_ptr(self.HH[t]),
                                  hm_next=None if last else _ptr(self.HM[t + 1]), act=_ptr(self.ACT[t]), n=S)
             assert lib.vine_lstm_step(C.byref(a), st) == 0
-        self.head_grads.zero_()
         h = self.hyper
         ht = abi.VineLstmHeadTrain(params=_ptr(packed_lstm), hh=_ptr(self.HH), scalars=_ptr(scalars), logstd=_ptr(logstd),
                                    logstd_old=_ptr(logstd_old), dh=_ptr(self.DH), grads=_ptr(self.head_grads),
                                    debug_out=_ptr(debug_out) if debug_out is not None else None, n=n, inv_B=1.0 / n,
                                    e_clip=h["e_clip"], critic_coef=h["critic_coef"], entropy_coef=h["entropy_coef"],
                                    bounds_loss_coef=h["bounds_loss_coef"])
-        assert lib.vine_lstm_head_train(C.byref(ht), st) == 0
+        hparts = lib.vine_lstm_head_train(C.byref(ht), st)
+        assert hparts > 0, hparts
         for t in range(L - 1, -1, -1):
             last = t == L - 1
             cb = abi.VineLstmCellBwd(act=_ptr(self.ACT[t]), c_prev=_ptr(self.Cs[t - 1] if t else self.C0), c=_ptr(self.Cs[t]),
@@ -92,5 +92,5 @@ class NativeLstmPath:
         wg = abi.VineLstmWgrad(u=_ptr(self.U), hm=_ptr(self.HM), dg=_ptr(self.DG), workspace=_ptr(self.wg_ws), ntiles=L * tl,
                                splits=self.splits)
         assert lib.vine_lstm_wgrad(C.byref(wg), st) == 0
-        assert lib.vine_lstm_reduce(C.c_void_p(_ptr(self.wg_ws)), self.splits, C.c_void_p(_ptr(self.head_grads)), self.O,
+        assert lib.vine_lstm_reduce(C.c_void_p(_ptr(self.wg_ws)), self.splits, C.c_void_p(_ptr(self.head_grads)), hparts, self.O,
                                     C.c_void_p(_ptr(self.flat_g_lstm)), st) == 0
