@@ -514,13 +514,13 @@ int vine_lstm_head(const VineLstmHead* args, void* stream);
  * Training counterpart of vine_lstm_head over all rows of a minibatch (rows = [step][sequence]): LayerNorm + heads,
  * the PPO losses of vine_ppo_minibatch (same formulas), and the backward down to dh (bf16 tiles like hh).
  * scalars f32 [n, 8] per row: action0, action1, mu_old0, mu_old1, neglogp_old, value_old (normalised), return
- * (normalised), advantage (normalised).  grads f32 [VINE_LSTM_HEAD_GRAD_PARTS][VINE_LSTM_HEAD_GRAD_FLOATS] receives one
+ * (normalised), advantage (normalised).  grads f32 [VINE_LSTM_HEAD_GRAD_PARTS + 1][VINE_LSTM_HEAD_GRAD_FLOATS] receives one
  * partial per thread block (the call returns how many; vine_lstm_reduce sums them): d(LayerNorm gamma)[256],
  * d(beta)[256], d(W_mu0, W_mu1, W_v)[3][256], d(b)[3] (+1 pad), d(logstd)[2], loss statistics a_loss, c_loss, kl,
  * b_loss (means), padding.
  */
 #define VINE_LSTM_HEAD_GRAD_FLOATS 1296
-#define VINE_LSTM_HEAD_GRAD_PARTS 296   /* max per-block gradient partials one vine_lstm_head_train call writes */
+#define VINE_LSTM_HEAD_GRAD_PARTS 1184  /* max per-block gradient partials one vine_lstm_head_train call writes */
 typedef struct VineLstmHeadTrain {
   const void* params;
   const void* hh;                /* [tiles][2][128 x 128] bf16 */
@@ -588,8 +588,8 @@ typedef struct VineLstmWgrad {
 } VineLstmWgrad;
 int vine_lstm_num_params(int num_obs);
 int vine_lstm_wgrad(const VineLstmWgrad* args, void* stream);
-int vine_lstm_reduce(const float* workspace, int splits, const float* head_grads, int head_parts, int num_obs, float* flat,
-                     void* stream);
+int vine_lstm_reduce(const float* workspace, int splits, float* head_grads, int head_parts, int num_obs, float* flat,
+                     void* stream);   /* head_grads: the partials of vine_lstm_head_train; its last row is scratch for their sum */
 int vine_lstm_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq, void* packed,
                    float* state, int num_obs, float beta1, float beta2, float eps, void* stream);
 

@@ -147,7 +147,7 @@ METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limi
 MLP_PACKED_BYTES = 102208
 LSTM_PACKED_BYTES = 795664
 LSTM_HEAD_GRAD_FLOATS = 1296
-LSTM_HEAD_GRAD_PARTS = 296
+LSTM_HEAD_GRAD_PARTS = 1184
 LSTM_WGRAD_BLOCK_FLOATS = 12 * 128 * 256      # per K split
 LSTM_TILE_BYTES = 32768          # one [128 x 128] bf16 activation tile
 PPO_WS_FLOATS = 49664

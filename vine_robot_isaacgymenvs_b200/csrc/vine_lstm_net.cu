@@ -333,7 +333,7 @@ constexpr int HG_LNG = 0, HG_LNB = HID, HG_WH = 2 * HID, HG_BH = 5 * HID, HG_LS 
 constexpr int HG_FLOATS = 5 * HID + 16;
 static_assert(HG_FLOATS == VINE_LSTM_HEAD_GRAD_FLOATS, "header constant out of date");
 
-__global__ void __launch_bounds__(256) vine_lstm_head_train_kernel(const VineLstmHeadTrain a) {
+__global__ void __launch_bounds__(256, 2) vine_lstm_head_train_kernel(const VineLstmHeadTrain a) {
   __shared__ float red[HG_FLOATS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -540,7 +540,7 @@ constexpr uint32_t BG_TM_DU = 0, BG_TM_DH = 64;
 __global__ void __launch_bounds__(THREADS, 1) vine_lstm_bwd_gemm_kernel(const VineLstmBwdGemm a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.x, part = blockIdx.y;          // part 0: d U(:, 0:64) and d HM half 0;  part 1: d HM half 1
   const uint32_t bar0 = smem_u32(smem + BG_BAR);          // full[3] | done[3] | final
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BG_BAR + 64);
   const uint8_t* P = reinterpret_cast<const uint8_t*>(a.params);
@@ -550,11 +550,14 @@ __global__ void __launch_bounds__(THREADS, 1) vine_lstm_bwd_gemm_kernel(const Vi
   const uint32_t fin = bar0 + 48u;
   auto load = [&](int p, int st) {
     const uint32_t dst = smem_u32(smem + st * BG_STAGE_BYTES);
-    mbar_expect_tx(full(st), BG_STAGE_BYTES);
+    mbar_expect_tx(full(st), part == 0 ? 3 * PIECE_BYTES : 2 * PIECE_BYTES);
     bulk_g2s(dst, DG + (size_t)p * ACT_BYTES, ACT_BYTES, full(st));
-    bulk_g2s(dst + PIECE_BYTES, P + LP_WIH + (size_t)p * PIECE_BYTES, PIECE_BYTES, full(st));
-    bulk_g2s(dst + 2 * PIECE_BYTES, P + LP_WHH + (size_t)p * PIECE_BYTES, PIECE_BYTES, full(st));
-    bulk_g2s(dst + 3 * PIECE_BYTES, P + LP_WHH + (size_t)(NPIECE + p) * PIECE_BYTES, PIECE_BYTES, full(st));
+    if (part == 0) {
+      bulk_g2s(dst + PIECE_BYTES, P + LP_WIH + (size_t)p * PIECE_BYTES, PIECE_BYTES, full(st));
+      bulk_g2s(dst + 2 * PIECE_BYTES, P + LP_WHH + (size_t)p * PIECE_BYTES, PIECE_BYTES, full(st));
+    } else {
+      bulk_g2s(dst + 3 * PIECE_BYTES, P + LP_WHH + (size_t)(NPIECE + p) * PIECE_BYTES, PIECE_BYTES, full(st));
+    }
   };
   if (tid == 0) {
     for (int i = 0; i < 7; ++i) mbar_init(bar0 + 8u * i, 1);
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_lstm_bwd_gemm_kernel(const Vi
     for (int p = 0; p < BG_STAGES; ++p) load(p, p);
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   fence_before_sync();
@@ -578,9 +581,12 @@ __global__ void __launch_bounds__(THREADS, 1) vine_lstm_bwd_gemm_kernel(const Vi
       fence_after_sync();
       const uint32_t base = smem_u32(smem + st * BG_STAGE_BYTES);
       const Operand A = k_major(base, PIECE_ROWS);
-      mma_sequence(tmem + BG_TM_DU, A, mn_major(base + PIECE_BYTES, UK), instr_desc(64, false, true), PIECE_ROWS / 16, p > 0);
-      mma_sequence(tmem + BG_TM_DH, A, mn_major(base + 2 * PIECE_BYTES, UK), instr_desc(128, false, true), PIECE_ROWS / 16, p > 0);
-      mma_sequence(tmem + BG_TM_DH + 128, A, mn_major(base + 3 * PIECE_BYTES, UK), instr_desc(128, false, true), PIECE_ROWS / 16, p > 0);
+      if (part == 0) {
+        mma_sequence(tmem + BG_TM_DU, A, mn_major(base + PIECE_BYTES, UK), instr_desc(64, false, true), PIECE_ROWS / 16, p > 0);
+        mma_sequence(tmem + BG_TM_DH, A, mn_major(base + 2 * PIECE_BYTES, UK), instr_desc(128, false, true), PIECE_ROWS / 16, p > 0);
+      } else {
+        mma_sequence(tmem + BG_TM_DH, A, mn_major(base + 3 * PIECE_BYTES, UK), instr_desc(128, false, true), PIECE_ROWS / 16, p > 0);
+      }
       mma_commit(done(st));
       if (p + BG_STAGES < NPIECE) {
         mbar_wait(done(st), ph);
@@ -593,7 +599,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_lstm_bwd_gemm_kernel(const Vi
   fence_after_sync();
   const int64_t s = (int64_t)tile * TILE + row;
   const float m = (s < a.n && a.not_done) ? a.not_done[s] : 1.f;
-  {
+  if (part == 0) {
     uint32_t r[32];
     tmem_ld32(lane_base + BG_TM_DU + half * 32, r);
     if (s < a.n) {
@@ -604,11 +610,11 @@ __global__ void __launch_bounds__(THREADS, 1) vine_lstm_bwd_gemm_kernel(const Vi
     }
   }
 #pragma unroll 1
-  for (int c0 = 0; c0 < 128; c0 += 32) {   // this thread: hidden units 128*half + c0 .. +31 of its row
+  for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {   // this thread: hidden units 128*part + c0 .. +31 of its row
     uint32_t r[32];
-    tmem_ld32(lane_base + BG_TM_DH + half * 128 + c0, r);
+    tmem_ld32(lane_base + BG_TM_DH + c0, r);
     if (a.dh_rec && s < a.n) {
-      uint8_t* dst = reinterpret_cast<uint8_t*>(a.dh_rec) + ((size_t)tile * 2 + half) * TILE_BYTES;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(a.dh_rec) + ((size_t)tile * 2 + part) * TILE_BYTES;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         *reinterpret_cast<uint4*>(dst + tile_offset(row, c0 + 8 * q, UK)) =
@@ -620,7 +626,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_lstm_bwd_gemm_kernel(const Vi
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -754,6 +760,21 @@ __device__ inline float lstm_grad(int p, int O, const float* __restrict__ ws, in
   return acc;
 }
 
+// sum of the head kernel's per-block partials: block = 4 slots, thread = every 128th partial
+__global__ void __launch_bounds__(128) vine_lstm_head_sum_kernel(const float* __restrict__ hg, int parts, float* __restrict__ out) {
+  __shared__ float red[4][4];
+  const int slot0 = blockIdx.x * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = threadIdx.x; k < parts; k += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(hg + (size_t)k * HG_FLOATS + slot0);
+    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  }
+  acc.x = wsum(acc.x), acc.y = wsum(acc.y), acc.z = wsum(acc.z), acc.w = wsum(acc.w);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][0] = acc.x, red[threadIdx.x >> 5][1] = acc.y, red[threadIdx.x >> 5][2] = acc.z, red[threadIdx.x >> 5][3] = acc.w;
+  __syncthreads();
+  if (threadIdx.x < 4) out[slot0 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+}
+
 __global__ void vine_lstm_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ hg, int hparts, int O,
                                         float* __restrict__ flat) {
   const int PL = lstm_num_params(O);
@@ -869,7 +890,7 @@ int vine_lstm_bwd_gemm(const VineLstmBwdGemm* a, void* stream) {
       return VINE_ERR_CUDA;
     configured = dev;
   }
-  vine_lstm_bwd_gemm_kernel<<<(unsigned)((a->n + TILE - 1) / TILE), THREADS, BG_SMEM, (cudaStream_t)stream>>>(*a);
+  vine_lstm_bwd_gemm_kernel<<<dim3((unsigned)((a->n + TILE - 1) / TILE), 2), THREADS, BG_SMEM, (cudaStream_t)stream>>>(*a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -890,10 +911,15 @@ int vine_lstm_wgrad(const VineLstmWgrad* a, void* stream) {
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
-int vine_lstm_reduce(const float* workspace, int splits, const float* head_grads, int head_parts, int num_obs, float* flat, void* stream) {
-  if (!workspace || !head_grads || !flat || splits < 1 || head_parts < 1 || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
+int vine_lstm_reduce(const float* workspace, int splits, float* head_grads, int head_parts, int num_obs, float* flat, void* stream) {
+  if (!workspace || !head_grads || !flat || splits < 1 || head_parts < 1 || head_parts > VINE_LSTM_HEAD_GRAD_PARTS || num_obs < 1 ||
+      num_obs >= K1)
+    return VINE_ERR_INVALID_ARG;
   const int n = lstm_num_params(num_obs) + 4;
-  vine_lstm_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, splits, head_grads, head_parts, num_obs, flat);
+  // the per-block partials of the head kernel are summed in parallel into the extra row [VINE_LSTM_HEAD_GRAD_PARTS]
+  float* hsum = head_grads + (size_t)VINE_LSTM_HEAD_GRAD_PARTS * HG_FLOATS;
+  vine_lstm_head_sum_kernel<<<HG_FLOATS / 4, 128, 0, (cudaStream_t)stream>>>(head_grads, head_parts, hsum);
+  vine_lstm_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, splits, hsum, 1, num_obs, flat);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -910,7 +936,7 @@ int vine_lstm_head_train(const VineLstmHeadTrain* a, void* stream) {
   if (!a || !a->params || !a->hh || !a->scalars || !a->logstd || !a->logstd_old || !a->dh || !a->grads || a->n <= 0)
     return VINE_ERR_INVALID_ARG;
   int64_t blocks = (a->n + 7) / 8;
-  if (blocks > VINE_LSTM_HEAD_GRAD_PARTS) blocks = VINE_LSTM_HEAD_GRAD_PARTS;
+  if (blocks > 296) blocks = 296;   // 2 resident blocks per SM (128 registers per thread), one wave; <= VINE_LSTM_HEAD_GRAD_PARTS
   vine_lstm_head_train_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
   return cudaGetLastError() == cudaSuccess ? (int)blocks : VINE_ERR_CUDA;   // number of gradient partials written
 }

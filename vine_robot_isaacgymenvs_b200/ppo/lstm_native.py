@@ -35,7 +35,7 @@ class NativeLstmPath:
         self.Cs, self.C0 = f32(L, S, 256), f32(S, 256)
         self.DC = [f32(S, 256), f32(S, 256)]
         self.DH3 = f32(L, S, 64)
-        self.head_grads = f32(abi.LSTM_HEAD_GRAD_PARTS, abi.LSTM_HEAD_GRAD_FLOATS)
+        self.head_grads = f32(abi.LSTM_HEAD_GRAD_PARTS + 1, abi.LSTM_HEAD_GRAD_FLOATS)   # + 1 row: their sum
         self.splits = min(wgrad_splits, L * tl)
         self.wg_ws = f32(self.splits, abi.LSTM_WGRAD_BLOCK_FLOATS)
         self.mlp_ctas = self.lib.vine_ppo_max_ctas()
