@@ -416,7 +416,9 @@ def run_ours(args, rank, world, local_rank):
                 "api": f"env.step_host(pinned host buffers, chunks={args.e2e_chunks}): H2D, step and D2H of different "
                        "env chunks overlap on separate streams; returns after all results are on the host",
                 "unpipelined_value": e2e_simple},
-        "clocks": clocks, "gpu_launches": args.steps, "sweep": sweep, "ppo": ppo,
+        "clocks": clocks, "gpu_launches": args.steps, "sweep": sweep,
+        # second half of BASELINE.json's metric: PPO frames/s at configs[1] with the reference's own network
+        "ppo_frames_per_s": (ppo or {}).get("reference_network", {}).get("value"), "ppo": ppo,
     }
     print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
