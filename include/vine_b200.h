@@ -578,6 +578,27 @@ int vine_lstm_bwd_gemm(const VineLstmBwdGemm* args, void* stream);
  *   vine_lstm_adam : torch.optim.Adam on the flat vector + in-place update of the packed block + the loss / KL
  *       bookkeeping in `state` (same layout and meaning as vine_ppo_adam, which then runs with bookkeeping = 0).
  */
+/*
+ * Minibatch assembly of the recurrent update in one launch: envs [env_begin, env_begin+env_count) x all horizon steps of
+ * the [T, N] rollout buffers -> rows ordered [step in chunk][chunk, env] (T = chunks * seq_len; sequences = chunks *
+ * env_count), plus the initial cell state and the masked initial hidden-state tiles of every sequence from the snapshots the
+ * rollout took at the chunk starts.  num_envs, env_begin and env_count must be multiples of 128.
+ */
+typedef struct VineLstmGather {
+  const float* obs;              /* [T, N, O] */
+  const float* scalars;          /* [T, N, 8] */
+  const float* not_done;         /* [T, N] */
+  const float* c_saved;          /* [chunks, N, 256] */
+  const void* hh_saved;          /* [chunks][N/128][2][128 x 128] bf16 */
+  float* mb_obs;                 /* [L, S, O] out */
+  float* mb_scalars;             /* [L, S, 8] out */
+  float* mb_not_done;            /* [L, S] out */
+  float* c0;                     /* [S, 256] out */
+  void* hm0;                     /* [S/128][2][128 x 128] bf16 out: not_done[first step] * h */
+  int32_t seq_len, chunks, num_envs, env_begin, env_count, num_obs;
+} VineLstmGather;
+int vine_lstm_gather(const VineLstmGather* args, void* stream);
+
 typedef struct VineLstmWgrad {
   const void* u;                 /* [ntiles][128 x 128] bf16 */
   const void* hm;                /* [ntiles][2][128 x 128] bf16 */

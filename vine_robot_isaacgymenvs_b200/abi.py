@@ -138,7 +138,7 @@ EXPORTED_SYMBOLS = [
     "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
     "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
     "vine_lstm_cell_fwd", "vine_lstm_cell_bwd", "vine_lstm_pack", "vine_lstm_step", "vine_lstm_mask", "vine_lstm_head", "vine_lstm_head_train", "vine_lstm_cell_bwd_tiles", "vine_lstm_bwd_gemm",
-    "vine_lstm_num_params", "vine_lstm_wgrad", "vine_lstm_reduce", "vine_lstm_adam",
+    "vine_lstm_gather", "vine_lstm_num_params", "vine_lstm_wgrad", "vine_lstm_reduce", "vine_lstm_adam",
 ]
 METRIC_SUMS, METRIC_MAXES = 45, 30
 METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limit_hit", "abs_tip_y", "tip_z", "tip_velocities",
@@ -185,6 +185,12 @@ class VineLstmCellBwd(C.Structure):
 
 class VineLstmBwdGemm(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("params", "dg", "not_done", "dh3", "dh_rec")] + [("n", C.c_int64)]
+
+
+class VineLstmGather(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("obs", "scalars", "not_done", "c_saved", "hh_saved", "mb_obs", "mb_scalars", "mb_not_done",
+                                           "c0", "hm0")]
+                + [(n, C.c_int32) for n in ("seq_len", "chunks", "num_envs", "env_begin", "env_count", "num_obs")])
 
 
 class VineLstmWgrad(C.Structure):
@@ -264,6 +270,7 @@ def _declare(lib):
     lib.vine_lstm_head_train.argtypes = [C.POINTER(VineLstmHeadTrain), vp]
     lib.vine_lstm_cell_bwd_tiles.argtypes = [C.POINTER(VineLstmCellBwd), vp]
     lib.vine_lstm_bwd_gemm.argtypes = [C.POINTER(VineLstmBwdGemm), vp]
+    lib.vine_lstm_gather.argtypes = [C.POINTER(VineLstmGather), vp]
     lib.vine_lstm_num_params.argtypes = [C.c_int]
     lib.vine_lstm_wgrad.argtypes = [C.POINTER(VineLstmWgrad), vp]
     lib.vine_lstm_reduce.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]

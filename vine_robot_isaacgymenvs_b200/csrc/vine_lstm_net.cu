@@ -92,12 +92,13 @@ __device__ __forceinline__ float tanh_(float x) { return 1.f - __fdividef(2.f, 1
 constexpr int SO_U = 0, SO_HM = TILE_BYTES, SO_RING = 3 * TILE_BYTES, RING_STAGE = 3 * PIECE_BYTES, SO_BIAS = SO_RING + 2 * RING_STAGE;
 constexpr int SO_BAR = SO_BIAS + 2048;
 constexpr int STEP_SMEM = SO_BAR + 128;
-constexpr int STEP_THREADS = THREADS + 32, PIECES_PER_CTA = NPIECE / 2;
+constexpr int STEP_THREADS = THREADS + 32;
 
 __global__ void __launch_bounds__(STEP_THREADS, 1) vine_lstm_step_kernel(const VineLstmStep a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tile = blockIdx.x, hf = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int PIECES_PER_CTA = NPIECE / (int)gridDim.y;                // gridDim.y = 2 (8 pieces) or 4 (4 pieces: small batches)
   const uint32_t bar0 = smem_u32(smem + SO_BAR);
   const uint32_t bar_a = bar0;                                       // A + bias landed
   auto full = [&](int st) { return bar0 + 8u + 8u * st; };           // ring stage filled
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) vine_lstm_step_kernel(const V
   auto acc_empty = [&](int b) { return bar0 + 56u + 8u * b; };       // accumulator buffer drained by the epilogue warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SO_BAR + 96);
   const uint8_t* P = reinterpret_cast<const uint8_t*>(a.params);
-  const int piece0 = hf * PIECES_PER_CTA;
+  const int piece0 = (int)blockIdx.y * PIECES_PER_CTA, hf = piece0 / (NPIECE / 2);
   if (tid == 0) {
     mbar_init(bar_a, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(full(i), 1); mbar_init(done(i), 1); mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 8); }
@@ -130,10 +131,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) vine_lstm_step_kernel(const V
         bulk_g2s(dst + PIECE_BYTES, P + LP_WHH + (size_t)(piece0 + p) * PIECE_BYTES, PIECE_BYTES, full(st));
         bulk_g2s(dst + 2 * PIECE_BYTES, P + LP_WHH + (size_t)(NPIECE + piece0 + p) * PIECE_BYTES, PIECE_BYTES, full(st));
       };
-      mbar_expect_tx(bar_a, 3 * TILE_BYTES + 2048);
+      mbar_expect_tx(bar_a, 3 * TILE_BYTES + PIECES_PER_CTA * 256);
       bulk_g2s(smem_u32(smem + SO_U), reinterpret_cast<const uint8_t*>(a.u) + (size_t)tile * TILE_BYTES, TILE_BYTES, bar_a);
       bulk_g2s(smem_u32(smem + SO_HM), reinterpret_cast<const uint8_t*>(a.hm) + (size_t)tile * 2 * TILE_BYTES, 2 * TILE_BYTES, bar_a);
-      bulk_g2s(smem_u32(smem + SO_BIAS), P + LP_BIAS + (size_t)piece0 * PIECE_ROWS * 4, 2048, bar_a);
+      bulk_g2s(smem_u32(smem + SO_BIAS), P + LP_BIAS + (size_t)piece0 * PIECE_ROWS * 4, PIECES_PER_CTA * 256, bar_a);
       load_b(0, 0);
       load_b(1, 1);
       mbar_wait(bar_a, 0);
@@ -832,6 +833,52 @@ __global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scal
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Minibatch assembly for the recurrent update in ONE launch: rows ordered [step in chunk][chunk, env] gathered from the
+// [T, N] rollout buffers (observations, loss scalars, not_done), the initial cell state and the masked initial hidden-state
+// tiles of every sequence (saved at the chunk starts of the rollout).
+__global__ void __launch_bounds__(256) vine_lstm_gather_kernel(const VineLstmGather a) {
+  const int64_t S = (int64_t)a.chunks * a.env_count;
+  const int64_t rows = (int64_t)a.seq_len * S;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = a.num_obs + 8 + 1;
+  if (i < rows * W) {                       // one element of (obs | scalars | not_done) per thread
+    const int64_t r = i / W;
+    const int c = (int)(i % W);
+    const int t = (int)(r / S);
+    const int64_t sq = r % S;
+    const int ck = (int)(sq / a.env_count), e = a.env_begin + (int)(sq % a.env_count);
+    const int64_t src = ((int64_t)ck * a.seq_len + t) * a.num_envs + e;
+    if (c < a.num_obs) a.mb_obs[r * a.num_obs + c] = a.obs[src * a.num_obs + c];
+    else if (c < a.num_obs + 8) a.mb_scalars[r * 8 + (c - a.num_obs)] = a.scalars[src * 8 + (c - a.num_obs)];
+    else a.mb_not_done[r] = a.not_done[src];
+  }
+  // initial state: thread -> one 16-byte chunk (8 hidden units) of one sequence
+  const int64_t nchunks = S * (HID / 8);
+  if (i < nchunks) {
+    const int64_t sq = i / (HID / 8);
+    const int ug = (int)(i % (HID / 8)), unit0 = 8 * ug;
+    const int ck = (int)(sq / a.env_count), el = (int)(sq % a.env_count), e = a.env_begin + el;
+    const float m = a.not_done[((int64_t)ck * a.seq_len) * a.num_envs + e];
+    // cell state rows
+    const float4* cs = reinterpret_cast<const float4*>(a.c_saved + ((int64_t)ck * a.num_envs + e) * HID + unit0);
+    float4* cd = reinterpret_cast<float4*>(a.c0 + sq * HID + unit0);
+    cd[0] = cs[0], cd[1] = cs[1];
+    // hidden state: saved tiles [chunk][N/128][2] -> masked tiles [S/128][2]
+    const int64_t st = (int64_t)ck * (a.num_envs / TILE) + e / TILE, dt = sq / TILE;
+    const int half = unit0 / UK, off_s = tile_offset(e % TILE, unit0 % UK, UK), off_d = tile_offset((int)(sq % TILE), unit0 % UK, UK);
+    const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.hh_saved) + (st * 2 + half) * TILE_BYTES + off_s);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(w[k]);
+      o[k] = pack_bf16(f.x * m, f.y * m);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.hm0) + (dt * 2 + half) * TILE_BYTES + off_d) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -861,7 +908,8 @@ int vine_lstm_step(const VineLstmStep* a, void* stream) {
       return VINE_ERR_CUDA;
     configured = dev;
   }
-  const dim3 grid((unsigned)((a->n + TILE - 1) / TILE), 2);
+  const unsigned tiles = (unsigned)((a->n + TILE - 1) / TILE);
+  const dim3 grid(tiles, tiles * 2 <= 74 ? 4 : 2);   // small batches (rollout): 4 CTAs per tile to fill more SMs
   vine_lstm_step_kernel<<<grid, STEP_THREADS, STEP_SMEM, (cudaStream_t)stream>>>(*a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
@@ -891,6 +939,18 @@ int vine_lstm_bwd_gemm(const VineLstmBwdGemm* a, void* stream) {
     configured = dev;
   }
   vine_lstm_bwd_gemm_kernel<<<dim3((unsigned)((a->n + TILE - 1) / TILE), 2), THREADS, BG_SMEM, (cudaStream_t)stream>>>(*a);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+int vine_lstm_gather(const VineLstmGather* a, void* stream) {
+  if (!a || !a->obs || !a->scalars || !a->not_done || !a->c_saved || !a->hh_saved || !a->mb_obs || !a->mb_scalars || !a->mb_not_done ||
+      !a->c0 || !a->hm0 || a->seq_len < 1 || a->chunks < 1 || a->env_count < 1 || a->env_begin < 0 ||
+      a->env_begin + a->env_count > a->num_envs || a->num_envs % TILE || a->env_count % TILE || a->env_begin % TILE || a->num_obs < 1)
+    return VINE_ERR_INVALID_ARG;
+  const int64_t S = (int64_t)a->chunks * a->env_count, rows = (int64_t)a->seq_len * S;
+  int64_t work = rows * (a->num_obs + 9);
+  if (S * (HID / 8) > work) work = S * (HID / 8);
+  vine_lstm_gather_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 

@@ -408,19 +408,15 @@ class PPOAgent:
         torch.cat([self.b_act, self.b_mu, self.b_nlp.unsqueeze(-1), self._val_old_n.unsqueeze(-1), self._ret_n.unsqueeze(-1),
                    self._adv_n.unsqueeze(-1)], dim=-1, out=self._scal)
         path = self._path
-        mbv = lambda dst, src, e0: dst.view(L, chunks, E, *dst.shape[2:]).copy_(  # noqa: E731
-            src.view(chunks, L, n, *src.shape[2:])[:, :, e0:e0 + E].transpose(0, 1))
         for _ in range(self.mini_epochs):
             for e0 in range(0, n, E):
-                # rows of the minibatch ordered [step in chunk][chunk, env]: one strided copy per tensor
-                mbv(self._mb_obs, self.b_obs, e0)
-                mbv(self._mb_scal, self._scal, e0)
-                mbv(self._mb_nd, self._nd_ext[:T], e0)
-                for ck in range(chunks):   # initial LSTM state of every sequence: saved tiles -> masked recurrent input, cell state
-                    assert lib.vine_lstm_mask(C.c_void_p(ptr(self._HH_saved[ck]) + (e0 // 128) * 2 * abi.LSTM_TILE_BYTES),
-                                              C.c_void_p(ptr(self._nd_ext[ck * L]) + e0 * 4), E,
-                                              C.c_void_p(ptr(path.HM[0]) + ck * (E // 128) * 2 * abi.LSTM_TILE_BYTES), stream) == 0
-                    path.C0[ck * E:(ck + 1) * E].copy_(self._C_saved[ck, e0:e0 + E])
+                # rows of the minibatch ordered [step in chunk][chunk, env] + the initial LSTM state of every sequence: one launch
+                ga = abi.VineLstmGather(obs=ptr(self.b_obs), scalars=ptr(self._scal), not_done=ptr(self._nd_ext),
+                                        c_saved=ptr(self._C_saved), hh_saved=ptr(self._HH_saved), mb_obs=ptr(self._mb_obs),
+                                        mb_scalars=ptr(self._mb_scal), mb_not_done=ptr(self._mb_nd), c0=ptr(path.C0),
+                                        hm0=ptr(path.HM[0]), seq_len=L, chunks=chunks, num_envs=n, env_begin=e0, env_count=E,
+                                        num_obs=self.O)
+                assert lib.vine_lstm_gather(C.byref(ga), stream) == 0
                 path.gradients(self._packed, self._lpacked, self._mb_obs, self._mb_scal, self._mb_nd, self._obs_mean_f,
                                self._obs_inv_std_f, self._val_stats, self.model.sigma, self._logstd_old, self.ppo_state)
                 if self.world > 1:   # gradients + loss statistics (incl. the KL) of both halves
