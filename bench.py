@@ -314,8 +314,11 @@ def run_ours(args, rank, world, local_rank):
                 "num_envs_per_gpu": num_envs, "horizon": agent.T, "minibatch": agent.minibatch,
                 "mini_epochs": agent.mini_epochs, "iterations": iters, **parts,
                 # algorithmic tensor work of the update: 3 x forward MACs x 2 per sample per mini-epoch (MLP: 18*256+256*128+128*64+64*3 = 45,760 MAC)
-                "update_tflops": (6 * 45760 * agent.T * num_envs * agent.mini_epochs / (parts["update_ms"] * 1e-3) / 1e12
-                                  if not agent.has_rnn else None),
+                # algorithmic tensor work of the update per sample and mini-epoch = 3 GEMM passes (forward, backward data,
+                # weight gradients) x 2 FLOP x MACs; MLP: 18*256+256*128+128*64+64*3 = 45,760 MAC; reference network:
+                # MLP body 45,568 + LSTM (64+18)*1024 + 256*1024 = 346,112 + heads 768 = 392,448 MAC
+                "update_tflops": 6 * (392448 if agent.has_rnn else 45760) * agent.T * num_envs * agent.mini_epochs
+                                 / (parts["update_ms"] * 1e-3) / 1e12,
                 "network": "mlp[256,128,64]+lstm256+ln" if agent.has_rnn else "mlp[256,128,64]",
                 "cuda_graphs": agent.use_graphs,
                 "update": ("vine_lstm_* + vine_ppo_minibatch (tcgen05, hand-written; ppo/lstm_native.py)" if agent.native_lstm else
