@@ -41,7 +41,9 @@ class NativeLstmPath:
         self.mlp_ctas = self.lib.vine_ppo_max_ctas()
         self.mlp_ws = torch.empty(self.mlp_ctas, abi.PPO_WS_FLOATS, device=device)
         self.P_mlp, self.P_lstm = self.lib.vine_ppo_num_params(num_obs), self.lib.vine_lstm_num_params(num_obs)
-        self.flat_g_mlp, self.flat_g_lstm = f32(self.P_mlp + 4), f32(self.P_lstm + 4)
+        # both gradient vectors (+ 4 loss statistics each) in ONE buffer: one all-reduce per minibatch across ranks
+        self.flat_g = f32(self.P_mlp + 4 + self.P_lstm + 4)
+        self.flat_g_mlp, self.flat_g_lstm = self.flat_g[:self.P_mlp + 4], self.flat_g[self.P_mlp + 4:]
         self.hyper = hyper
         self._stream = lambda: C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 

@@ -419,9 +419,8 @@ class PPOAgent:
                 assert lib.vine_lstm_gather(C.byref(ga), stream) == 0
                 path.gradients(self._packed, self._lpacked, self._mb_obs, self._mb_scal, self._mb_nd, self._obs_mean_f,
                                self._obs_inv_std_f, self._val_stats, self.model.sigma, self._logstd_old, self.ppo_state)
-                if self.world > 1:   # gradients + loss statistics (incl. the KL) of both halves
-                    torch.distributed.all_reduce(path.flat_g_mlp)
-                    torch.distributed.all_reduce(path.flat_g_lstm)
+                if self.world > 1:   # ONE collective per minibatch: gradients + loss statistics (incl. the KL) of both halves
+                    torch.distributed.all_reduce(path.flat_g)
                 sc = 1.0 / self.world
                 assert lib.vine_ppo_adam(p(path.flat_g_mlp), sc, p(self.flat), p(self.adam_m), p(self.adam_v), p(self._packed),
                                          p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, 0, stream) == 0
