@@ -79,9 +79,10 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
 }
 // D[128 x N] (+)= A * B over `ksteps` steps of K=16; issued by ONE thread
 __device__ __forceinline__ void mma_sequence(uint32_t tmem_d, Operand a, Operand b, uint32_t idesc, int ksteps, bool accumulate) {
-  for (int ks = 0; ks < ksteps; ++ks)
-    mma_bf16(tmem_d, smem_desc(a.addr + ks * a.kstep, a.lbo, a.sbo), smem_desc(b.addr + ks * b.kstep, b.lbo, b.sbo), idesc,
-             (accumulate || ks > 0) ? 1u : 0u);
+  // the descriptors of consecutive K steps differ only in the start-address field (16-byte units): one add per operand
+  uint64_t ad = smem_desc(a.addr, a.lbo, a.sbo), bd = smem_desc(b.addr, b.lbo, b.sbo);
+  const uint64_t astep = a.kstep >> 4, bstep = b.kstep >> 4;
+  for (int ks = 0; ks < ksteps; ++ks, ad += astep, bd += bstep) mma_bf16(tmem_d, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
 }
 // mbarrier arrives when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
