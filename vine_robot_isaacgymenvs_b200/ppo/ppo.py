@@ -9,12 +9,20 @@ In-repo analogue of the same math: isaacgymenvs/learning/common_agent.py:257-314
 :319-435 (update), :482-517 (losses).  rl_games itself is not vendored in the reference
 (setup.py:22) and not installed here: PARITY UNPINNED, checked by learning curves only.
 
-The whole iteration is free of host synchronisation (episode statistics, KL and the learning
-rate live on the device), so the rollout (16 x {policy, fused env step} + GAE) and the update
-(mini_epochs x minibatches of forward/backward/Adam) are each captured into ONE CUDA graph
-(``use_graphs=True``, single GPU).  Multi-GPU: one process per GPU, envs sharded; per minibatch ONE
-all-reduce carrying the flattened gradients plus the KL scalar; per epoch one all-reduce of the
-running-statistics moments.
+The whole iteration is free of host synchronisation (episode statistics, KL and the learning rate live on the device), so
+the rollout (16 x {policy, fused env step} + GAE) and the update (mini_epochs x minibatches) are each captured into ONE
+CUDA graph (``use_graphs=True``).  Three execution paths, chosen per network:
+
+  * reference network (MLP -> LSTM 256 -> LayerNorm -> heads, ``train.params.network.rnn``): hand-written kernels only,
+    ``_rollout_native_lstm`` / ``_update_native_lstm`` (launch order: ppo/lstm_native.py; kernels: csrc/vine_lstm_net.cu);
+  * MLP actor-critic (``rnn=null``): hand-written kernels only, ``_rollout_fused`` / ``_update_fused`` (csrc/vine_rollout.cu,
+    csrc/vine_ppo.cu);
+  * ``use_fused_update=False`` (or a network shape the kernels do not cover): torch autograd + cuBLAS + torch Adam, the
+    library baseline the kernel paths are tested against (``_rollout`` / ``_update``).
+
+Multi-GPU: one process per GPU, envs sharded; per minibatch ONE all-reduce carrying the flat gradient vector(s) plus the
+loss statistics (incl. the KL that drives the adaptive learning rate); per iteration one all-reduce of the f64
+running-statistics moments.  On the kernel paths the NCCL calls are captured inside the CUDA graphs.
 """
 import ctypes as C
 import math
@@ -375,6 +383,10 @@ class PPOAgent:
                                        rng_counter=ptr(self._rng_counter), n=n, reward_scale=self.reward_scale, gamma=self.gamma,
                                        value_bootstrap=int(self.value_bootstrap), success_reward_threshold=500.0)
             assert lib.vine_rollout_post(C.byref(post), stream) == 0
+        if self._r_cur != 0:   # odd horizon: keep the persistent state in buffer 0 so a captured graph can be replayed
+            self._r_HH[0].copy_(self._r_HH[1])
+            self._r_C[0].copy_(self._r_C[1])
+            self._r_cur = 0
         p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
         rc = lib.vine_gae(p(self.b_rew), p(self.b_val), p(self.b_done), p(self.last_value), p(self.dones),
                           T, n, self.gamma, self.tau, p(self.b_adv), p(self.b_ret), stream)
