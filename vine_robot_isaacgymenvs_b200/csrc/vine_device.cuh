@@ -214,6 +214,16 @@ VDEV void capsule_rect(const VineParams& p, const Rect& R, float Ay, float Az, f
                        bool test_a, bool closed_end, float jy, float jz, float jvy, float jvz, float w,
                        LinkLoad& L, float& ofy, float& ofz) {
   const float ay = R.ay, az = R.az, ny = -az, nz = ay;
+  {
+    // separating-axis cull in the rectangle's frame (exact: every distance used below is >= the separation along either
+    // rectangle axis, and a contact needs distance < radius + rest)
+    const float laA = (Ay - R.cy) * ay + (Az - R.cz) * az, lnA = (Ay - R.cy) * ny + (Az - R.cz) * nz;
+    const float laB = (By - R.cy) * ay + (Bz - R.cz) * az, lnB = (By - R.cy) * ny + (Bz - R.cz) * nz;
+    const float reach = radius + p.rest;
+    if (fminf(lnA, lnB) >= R.hn + reach || fmaxf(lnA, lnB) <= -(R.hn + reach) || fminf(laA, laB) >= R.ha + reach ||
+        fmaxf(laA, laB) <= -(R.ha + reach))
+      return;
+  }
   // (i) capsule end points against the rectangle's faces
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
