@@ -16,8 +16,11 @@
 
 #define VINE_BLOCK 128
 #ifndef VINE_STEP_MIN_BLOCKS
-#define VINE_STEP_MIN_BLOCKS 1   // occupancy experiments: -DVINE_STEP_MIN_BLOCKS=5 caps the step kernel at 102 registers
+#define VINE_STEP_MIN_BLOCKS 0   // 0 = unspecified: the compiler's own choice (125 registers, 16 warps/SM) is the fastest measured (1 -> 167 registers, -8 %; 4 -> 121, -3 %; 5 -> 96 + spills, -6 %)
 #endif
+#ifndef VINE_STEP_MIN_BLOCKS_CONTACT
+#define VINE_STEP_MIN_BLOCKS_CONTACT 3   // contact variant: 160 registers (no spills) instead of 200 -> 12 warps/SM; measured
+#endif                                   // +14 % (shelf) / +11 % (pipe): hides the per-warp load imbalance of the narrow phase
 #define VINE_DBG_W 20  // u_rail,u_fpam,prev_u_rail,rail_force,tipvel y,z, reward_matrix[13], pad
 
 struct StepArgs {
@@ -80,7 +83,7 @@ __device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64
 // THE fused control step == VecTask.step (VT:319-380)
 // ------------------------------------------------------------------------------------------
 template <bool CONTACT>
-__global__ void __launch_bounds__(VINE_BLOCK, VINE_STEP_MIN_BLOCKS) vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
+__global__ void __launch_bounds__(VINE_BLOCK, CONTACT ? VINE_STEP_MIN_BLOCKS_CONTACT : VINE_STEP_MIN_BLOCKS) vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
   __shared__ float s_obs[VINE_BLOCK * (VINE_MAX_OBS + 1)];
   const int64_t e = a.first + (int64_t)blockIdx.x * VINE_BLOCK + threadIdx.x;
   if (e < a.end) {
