@@ -151,3 +151,24 @@ def test_fused_lstm_cell_kernels_match_the_torch_restatement():
     assert set(g_f) == set(g_r)
     errs = {k: rel(g_f[k], g_r[k]) for k in g_r}
     assert max(errs.values()) < 2e-2, errs
+
+
+def test_train_entry_point_trains_saves_and_plays_back(tmp_path, monkeypatch):
+    """``python -m vine_robot_isaacgymenvs_b200.train`` surface (reference train.py:35-171): a short training run writes
+    runs/<name>/nn/<name>.pth in rl_games' layout, and ``test=True checkpoint=...`` replays the policy without learning."""
+    from vine_robot_isaacgymenvs_b200 import train
+    monkeypatch.chdir(tmp_path)
+    base = vcfg.FSTR_OVERRIDES + ["num_envs=512", "headless=True", "train.params.config.minibatch_size=4096"]
+    hist = train.launch(base + ["max_iterations=4"])
+    assert len(hist) >= 1 and hist[-1]["epoch"] >= 4 and hist[-1]["frames"] > 0
+    ck = tmp_path / "runs" / "Vine5LinkMovingBase" / "nn" / "Vine5LinkMovingBase.pth"
+    assert ck.exists()
+    sd = torch.load(ck, map_location="cpu")
+    assert "a2c_network.rnn.rnn.weight_ih_l0" in sd["model"] and "running_mean_std.running_var" in sd["model"]
+    stats = train.launch(base + ["test=True", f"checkpoint={ck}", "play_steps=64"])
+    assert stats["episodes"] > 0 and 0.0 <= stats["success_rate"] <= 1.0
+    # the deployment-side player restores the same file
+    from vine_robot_isaacgymenvs_b200.player import PolicyPlayer
+    pl = PolicyPlayer(18, device="cuda").restore(str(ck))
+    a = pl.get_action(torch.zeros(18, device="cuda"), is_deterministic=True)
+    assert a.shape == (2,) and bool(torch.isfinite(a).all())

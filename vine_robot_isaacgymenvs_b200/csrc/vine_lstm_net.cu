@@ -82,8 +82,8 @@ __global__ void vine_lstm_pack_kernel(const float* __restrict__ w_ih, const floa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoid_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }   // +-1 at +-inf
+__device__ __forceinline__ float sigmoid_(float x) { return fast_rcp(1.f + fast_exp(-x)); }
+__device__ __forceinline__ float tanh_(float x) { return 1.f - 2.f * fast_rcp(1.f + fast_exp(2.f * x)); }   // +-1 at +-inf
 
 // CTA = (tile of 128 sequences, half of the hidden units).  A = [U | HM] (96 KB) stays resident; the CTA's 8 weight pieces
 // (16 hidden units x 4 gates each, 48 KB: W_ih piece + the two W_hh half pieces) stream through a 2-stage ring of bulk copies;

@@ -26,7 +26,18 @@ constexpr int OFF_A3 = OFF_A2 + TILE * H2 * 2;     // h3 [128 x 64]
 constexpr int OFF_END = OFF_A3 + TILE * H3 * 2;
 static_assert(PACKED_BYTES <= OFF_X, "packed block overlaps the activation tiles");
 
-__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+// exp / reciprocal straight on the SFU (flush-to-zero variants: no denormal fix-up code around MUFU)
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : fast_exp(x) - 1.f; }
 
 // 32 accumulator columns (already in registers) -> bias + ELU -> bf16 -> tile columns [c_out, c_out+32) of row `row`
 template <int KL>
