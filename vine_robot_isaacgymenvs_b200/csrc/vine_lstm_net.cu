@@ -734,33 +734,6 @@ __host__ __device__ inline LstmSeg lstm_segments(int O) {
   return s;
 }
 
-// gradient of flat parameter p: sum over the weight-gradient partials, or a slot of the head gradient buffer
-__device__ inline float head_sum(const float* __restrict__ hg, int parts, int slot) {
-  float acc = 0.f;
-  for (int k = 0; k < parts; ++k) acc += hg[(size_t)k * HG_FLOATS + slot];
-  return acc;
-}
-
-__device__ inline float lstm_grad(int p, int O, const float* __restrict__ ws, int splits, const float* __restrict__ hgp, int hparts) {
-  const LstmSeg sg = lstm_segments(O);
-  int part, f, R;
-  auto hg = [&](int slot) { return head_sum(hgp, hparts, slot); };
-  if (p < sg.whh) { const int tr = p / (H3 + O); part = 0; f = p % (H3 + O); R = packed_gate_row(tr); }
-  else if (p < sg.bih) { const int q = p - sg.whh, tr = q / HID, c = q % HID; part = 1 + c / UK; f = c % UK; R = packed_gate_row(tr); }
-  else if (p < sg.lng) { const int tr = (p - sg.bih) % GATES; part = 0; f = UK - 33; R = packed_gate_row(tr); }   // U column 95 == 1
-  else if (p < sg.lnb) return hg(HG_LNG + (p - sg.lng));
-  else if (p < sg.wmu) return hg(HG_LNB + (p - sg.lnb));
-  else if (p < sg.bmu) return hg(HG_WH + (p - sg.wmu));
-  else if (p < sg.wv) return hg(HG_BH + (p - sg.bmu));
-  else if (p < sg.bv) return hg(HG_WH + 2 * HID + (p - sg.wv));
-  else if (p < sg.ls) return hg(HG_BH + 2);
-  else return hg(HG_LS + (p - sg.ls));
-  const size_t off = (size_t)(part * 4 + R / 256) * WG_BLOCK_FLOATS + (size_t)f * 256 + (R % 256);
-  float acc = 0.f;
-  for (int k = 0; k < splits; ++k) acc += ws[(size_t)k * WG_BLOCKS * WG_BLOCK_FLOATS + off];
-  return acc;
-}
-
 // sum of the head kernel's per-block partials: block = 4 slots, thread = every 128th partial
 __global__ void __launch_bounds__(128) vine_lstm_head_sum_kernel(const float* __restrict__ hg, int parts, float* __restrict__ out) {
   __shared__ float red[4][4];
@@ -776,12 +749,46 @@ __global__ void __launch_bounds__(128) vine_lstm_head_sum_kernel(const float* __
   if (threadIdx.x < 4) out[slot0 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
 }
 
-__global__ void vine_lstm_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ hg, int hparts, int O,
-                                        float* __restrict__ flat) {
-  const int PL = lstm_num_params(O);
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < PL) flat[p] = lstm_grad(p, O, ws, splits, hg, hparts);
-  else if (p < PL + 4) flat[p] = head_sum(hg, hparts, HG_STATS + (p - PL));
+// flat gradient vector from the weight-gradient partials: one thread per workspace slot (coalesced reads over the K splits),
+// scattered write to the slot's parameter; the parameters fed by the head kernel come from the summed head buffer.
+__global__ void __launch_bounds__(256) vine_lstm_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ hsum, int O,
+                                                               float* __restrict__ flat) {
+  const LstmSeg sg = lstm_segments(O);
+  const int PL = sg.end;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int SLOTS = WG_BLOCKS * WG_BLOCK_FLOATS;
+  if (w < SLOTS) {
+    const int blk = w / WG_BLOCK_FLOATS, f = (w % WG_BLOCK_FLOATS) / 256, R = (blk & 3) * 256 + (w & 255), part = blk >> 2;
+    const int tr = torch_gate_row(R);
+    int p = -1, p2 = -1;
+    if (part == 0) {
+      if (f < H3 + O) p = sg.wih + tr * (H3 + O) + f;
+      else if (f == UK - 33) { p = sg.bih + tr; p2 = sg.bhh + tr; }     // U column 95 == 1: d(b_ih) == d(b_hh)
+    } else {
+      p = sg.whh + tr * HID + (part - 1) * UK + f;
+    }
+    if (p >= 0) {
+      float acc0 = 0.f, acc1 = 0.f;
+      int k = 0;
+      for (; k + 1 < splits; k += 2) {
+        acc0 += ws[(size_t)k * SLOTS + w];
+        acc1 += ws[(size_t)(k + 1) * SLOTS + w];
+      }
+      if (k < splits) acc0 += ws[(size_t)k * SLOTS + w];
+      flat[p] = acc0 + acc1;
+      if (p2 >= 0) flat[p2] = acc0 + acc1;
+    }
+  } else {
+    const int q = w - SLOTS;   // LayerNorm, heads, logstd, statistics
+    if (q < HID) flat[sg.lng + q] = hsum[HG_LNG + q];
+    else if (q < 2 * HID) flat[sg.lnb + q - HID] = hsum[HG_LNB + q - HID];
+    else if (q < 4 * HID) flat[sg.wmu + q - 2 * HID] = hsum[HG_WH + q - 2 * HID];
+    else if (q < 5 * HID) flat[sg.wv + q - 4 * HID] = hsum[HG_WH + 2 * HID + q - 4 * HID];
+    else if (q < 5 * HID + 2) flat[sg.bmu + q - 5 * HID] = hsum[HG_BH + q - 5 * HID];
+    else if (q == 5 * HID + 2) flat[sg.bv] = hsum[HG_BH + 2];
+    else if (q < 5 * HID + 5) flat[sg.ls + q - 5 * HID - 3] = hsum[HG_LS + q - 5 * HID - 3];
+    else if (q < 5 * HID + 9) flat[PL + q - 5 * HID - 5] = hsum[HG_STATS + q - 5 * HID - 5];
+  }
 }
 
 __global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scale, float* __restrict__ params, float* __restrict__ m,
@@ -979,7 +986,9 @@ int vine_lstm_reduce(const float* workspace, int splits, float* head_grads, int 
   // the per-block partials of the head kernel are summed in parallel into the extra row [VINE_LSTM_HEAD_GRAD_PARTS]
   float* hsum = head_grads + (size_t)VINE_LSTM_HEAD_GRAD_PARTS * HG_FLOATS;
   vine_lstm_head_sum_kernel<<<HG_FLOATS / 4, 128, 0, (cudaStream_t)stream>>>(head_grads, head_parts, hsum);
-  vine_lstm_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, splits, hsum, 1, num_obs, flat);
+  const int threads = WG_BLOCKS * WG_BLOCK_FLOATS + 5 * HID + 9;
+  (void)n;
+  vine_lstm_reduce_kernel<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, splits, hsum, num_obs, flat);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
