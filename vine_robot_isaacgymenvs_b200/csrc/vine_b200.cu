@@ -19,7 +19,7 @@
 #define VINE_STEP_MIN_BLOCKS 0   // 0 = unspecified: the compiler's own choice (125 registers, 16 warps/SM) is the fastest measured (1 -> 167 registers, -8 %; 4 -> 121, -3 %; 5 -> 96 + spills, -6 %)
 #endif
 #ifndef VINE_STEP_MIN_BLOCKS_CONTACT
-#define VINE_STEP_MIN_BLOCKS_CONTACT 3   // contact variant: 160 registers (no spills) instead of 200 -> 12 warps/SM; measured
+#define VINE_STEP_MIN_BLOCKS_CONTACT 12  // contact variant (1-warp blocks): 160 registers (no spills) instead of 200 -> 12 warps/SM; measured
 #endif                                   // +14 % (shelf) / +11 % (pipe): hides the per-warp load imbalance of the narrow phase
 #define VINE_DBG_W 20  // u_rail,u_fpam,prev_u_rail,rail_force,tipvel y,z, reward_matrix[13], pad
 
@@ -59,14 +59,15 @@ static char g_create_err[256] = "";
 // ------------------------------------------------------------------------------------------
 // coalesced store of a block's observation rows staged in shared memory
 // ------------------------------------------------------------------------------------------
+template <int BLOCK>
 __device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64_t first, int64_t end, float clip,
                                                 float* __restrict__ obs, float* __restrict__ obs_clamped) {
-  const int64_t row0 = first + (int64_t)blockIdx.x * VINE_BLOCK;
-  const int rows = (int)min((int64_t)VINE_BLOCK, end - row0);
+  const int64_t row0 = first + (int64_t)blockIdx.x * BLOCK;
+  const int rows = (int)min((int64_t)BLOCK, end - row0);
   const int count2 = rows * O / 2;  // O is even for every ObservationType
   float2* g = reinterpret_cast<float2*>(obs + row0 * O);
   float2* gc = obs_clamped ? reinterpret_cast<float2*>(obs_clamped + row0 * O) : nullptr;
-  for (int i = threadIdx.x; i < count2; i += VINE_BLOCK) {
+  for (int i = threadIdx.x; i < count2; i += BLOCK) {
     const int e0 = 2 * i, r0 = e0 / O, c0 = e0 - r0 * O;  // c0 even, c0+1 < O
     float2 v;
     v.x = s_obs[r0 * (VINE_MAX_OBS + 1) + c0];
@@ -82,10 +83,18 @@ __device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64
 // ------------------------------------------------------------------------------------------
 // THE fused control step == VecTask.step (VT:319-380)
 // ------------------------------------------------------------------------------------------
+// Block size: 128 for the free-space variant.  The contact variant uses one warp per block: its warps finish at very
+// different times (the narrow phase runs only where something touches), and a block holds its registers until its slowest
+// warp is done -- ncu showed 3.2 warps per issue slot parked at the block barrier with 128-thread blocks.
+#ifndef VINE_BLOCK_CONTACT
+#define VINE_BLOCK_CONTACT 32
+#endif
 template <bool CONTACT>
-__global__ void __launch_bounds__(VINE_BLOCK, CONTACT ? VINE_STEP_MIN_BLOCKS_CONTACT : VINE_STEP_MIN_BLOCKS) vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
-  __shared__ float s_obs[VINE_BLOCK * (VINE_MAX_OBS + 1)];
-  const int64_t e = a.first + (int64_t)blockIdx.x * VINE_BLOCK + threadIdx.x;
+__global__ void __launch_bounds__(CONTACT ? VINE_BLOCK_CONTACT : VINE_BLOCK, CONTACT ? VINE_STEP_MIN_BLOCKS_CONTACT : VINE_STEP_MIN_BLOCKS)
+vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
+  constexpr int BLOCK = CONTACT ? VINE_BLOCK_CONTACT : VINE_BLOCK;
+  __shared__ float s_obs[BLOCK * (VINE_MAX_OBS + 1)];
+  const int64_t e = a.first + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (e < a.end) {
     const float4 s0 = a.S0[e], s1 = a.S1[e], s2 = a.S2[e], s3 = a.S3[e], s4 = a.S4[e], s5 = a.S5[e];
     float q[6] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y};
@@ -251,7 +260,7 @@ __global__ void __launch_bounds__(VINE_BLOCK, CONTACT ? VINE_STEP_MIN_BLOCKS_CON
     }
   }
   __syncthreads();
-  store_obs_block(s_obs, p.O, a.first, a.end, p.clip_obs, a.obs, a.obs_clamped);
+  store_obs_block<BLOCK>(s_obs, p.O, a.first, a.end, p.clip_obs, a.obs, a.obs_clamped);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -726,9 +735,8 @@ int vine_step(VineEnv* env, void* stream) {
   if (!env) return VINE_ERR_INVALID_ARG;
   if (!env->bound) { snprintf(env->err, 256, "vine_step: call vine_bind_io first"); return VINE_ERR_NOT_BOUND; }
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = grid_for(env->a.n, VINE_BLOCK);
-  if (env->p.shelf || env->p.pipe) vine_step_kernel<true><<<grid, VINE_BLOCK, 0, st>>>(env->p, env->a);
-  else vine_step_kernel<false><<<grid, VINE_BLOCK, 0, st>>>(env->p, env->a);
+  if (env->p.shelf || env->p.pipe) vine_step_kernel<true><<<grid_for(env->a.n, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, st>>>(env->p, env->a);
+  else vine_step_kernel<false><<<grid_for(env->a.n, VINE_BLOCK), VINE_BLOCK, 0, st>>>(env->p, env->a);
   CUDA_TRY(env, cudaGetLastError());
   return VINE_OK;
 }
@@ -742,9 +750,8 @@ int vine_step_range(VineEnv* env, int64_t first, int64_t count, void* stream) {
   }
   StepArgs a = env->a;
   a.first = first; a.end = first + count;
-  const unsigned grid = grid_for(count, VINE_BLOCK);
-  if (env->p.shelf || env->p.pipe) vine_step_kernel<true><<<grid, VINE_BLOCK, 0, (cudaStream_t)stream>>>(env->p, a);
-  else vine_step_kernel<false><<<grid, VINE_BLOCK, 0, (cudaStream_t)stream>>>(env->p, a);
+  if (env->p.shelf || env->p.pipe) vine_step_kernel<true><<<grid_for(count, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, (cudaStream_t)stream>>>(env->p, a);
+  else vine_step_kernel<false><<<grid_for(count, VINE_BLOCK), VINE_BLOCK, 0, (cudaStream_t)stream>>>(env->p, a);
   CUDA_TRY(env, cudaGetLastError());
   return VINE_OK;
 }

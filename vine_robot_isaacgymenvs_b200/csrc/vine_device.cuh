@@ -210,6 +210,9 @@ VDEV void contact_point(const VineParams& p, float Py, float Pz, float ny, float
 }
 
 // capsule (core A-B, radius r) of a link whose proximal joint is at (jy,jz) moving with (jvy,jvz), spin w
+// The two inner loops are kept rolled on purpose: with everything unrolled the ten inlined copies (5 links x 2 capsules)
+// made the contact kernel 140 KB of code and the instruction cache its bottleneck (ncu: 3.2 warps per issue slot stalled
+// on "no instruction"); a non-inlined function fixed that but cost latency at small env counts (argument spills).
 VDEV void capsule_rect(const VineParams& p, const Rect& R, float Ay, float Az, float By, float Bz, float radius,
                        bool test_a, bool closed_end, float jy, float jz, float jvy, float jvz, float w,
                        LinkLoad& L, float& ofy, float& ofz) {
@@ -225,7 +228,7 @@ VDEV void capsule_rect(const VineParams& p, const Rect& R, float Ay, float Az, f
       return;
   }
   // (i) capsule end points against the rectangle's faces
-#pragma unroll
+#pragma unroll 1
   for (int e = 0; e < 2; ++e) {
     if (e == 0 && !test_a) continue;
     const float Py = e == 0 ? Ay : By, Pz = e == 0 ? Az : Bz;
@@ -240,7 +243,7 @@ VDEV void capsule_rect(const VineParams& p, const Rect& R, float Ay, float Az, f
   // (ii) rectangle corners against the capsule segment
   const float ey = By - Ay, ez = Bz - Az;
   const float inv_ee = __fdividef(1.f, ey * ey + ez * ez);
-#pragma unroll
+#pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     const float sa = (c & 1) ? 1.f : -1.f, sn = (c & 2) ? 1.f : -1.f;
     const float Vy = R.cy + sa * R.ha * ay + sn * R.hn * ny, Vz = R.cz + sa * R.ha * az + sn * R.hn * nz;
@@ -298,10 +301,13 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, const Dyn& d
         if (fabsf(dy * R.ay + dz * R.az) > R.ha + reach || fabsf(dz * R.ay - dy * R.az) > R.hn + reach) continue;
       }
       float ofy = 0.f, ofz = 0.f;
-      capsule_rect(p, ob.r[r], py[j], pz[j], By, Bz, VINE_LINK_RADIUS, j == 0, last,
-                   py[j], pz[j], vy[j], vz[j], d.v[j + 1], L[j], ofy, ofz);
-      capsule_rect(p, ob.r[r], py[j] + oy, pz[j] + oz, FBy, FBz, VINE_FPAM_RADIUS, true, true,
-                   py[j], pz[j], vy[j], vz[j], d.v[j + 1], L[j], ofy, ofz);
+#pragma unroll 1
+      for (int cap = 0; cap < 2; ++cap) {   // main cylinder, FPAM cylinder: one rolled copy of the narrow phase (code size)
+        const bool fp = cap != 0;
+        capsule_rect(p, ob.r[r], fp ? py[j] + oy : py[j], fp ? pz[j] + oz : pz[j], fp ? FBy : By, fp ? FBz : Bz,
+                     fp ? VINE_FPAM_RADIUS : VINE_LINK_RADIUS, fp || j == 0, fp || last, py[j], pz[j], vy[j], vz[j], d.v[j + 1],
+                     L[j], ofy, ofz);
+      }
       if (r == ob.lip) { lfy += ofy; lfz += ofz; }
     }
   }
