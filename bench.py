@@ -30,6 +30,7 @@ if REPO not in sys.path:
 
 OUT = sys.stdout
 METRIC = "env-steps/s (whole box, device-timed)"
+WORKLOAD = "FSTR (README.md:63 / BASELINE configs[1] knobs) env step, U(-1,1) actions, env-step only"
 UNIT = "env-steps/s"
 # Algorithmic work per env-step of the FSTR workload (derivations: DESIGN.md §6)
 HBM_BYTES_PER_ENV_STEP = 273.0      # O=18, ACTION_DELAY=1
@@ -146,7 +147,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "FSTR (README.md:63) env step, random actions", "sample_envs_per_step": n},
+        "config": {"workload": WORKLOAD, "sample_envs_per_step": n,
+                   "note": "same workload as the CUDA arm; each step is a bounded sample of it on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n} envs x {steps} control steps, oracle f32 dynamics, OpenMP x{cores}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -406,8 +408,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "FSTR (README.md:63 / BASELINE configs[1] knobs) env step, U(-1,1) actions, "
-                               "env-step only", "num_envs_per_gpu": n, "global_envs": n * world,
+        "config": {"workload": WORKLOAD, "num_envs_per_gpu": n, "global_envs": n * world,
                    "obs": cfg["task"]["env"]["OBSERVATION_TYPE"], "substeps_per_step":
                        cfg["task"]["sim"]["substeps"] * cfg["task"]["env"]["controlFrequencyInv"],
                    "parallelism": f"env-sharded x{world}, no collective in the step",
