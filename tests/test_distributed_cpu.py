@@ -39,6 +39,19 @@ def _worker(rank, world, port, q):
     m2 = ((x - mean) ** 2).sum(0)
     c, gm, gm2 = vd.merge_moments(count, mean, m2)
     out["count"], out["mean"], out["var"] = float(c), gm.numpy(), (gm2 / c).numpy()
+    # 0-dim statistics (the value normaliser) keep their shape through the merge, and the RunningMeanStd of the PPO agent
+    # ends up identical on every rank and equal to the single-process statistics of the whole data set
+    from vine_robot_isaacgymenvs_b200.ppo.ppo import RunningMeanStd
+    v = torch.from_numpy(data[start:start + count, 0].copy())
+    c0, m0, s0 = vd.merge_moments(count, v.mean(), ((v - v.mean()) ** 2).sum())
+    out["scalar_shape"] = (tuple(m0.shape), tuple(s0.shape))
+    rms = RunningMeanStd(())
+    rms.update(v)
+    out["rms"] = (float(rms.running_mean), float(rms.running_var), float(rms.count))
+    # the flat gradient vector (+ loss statistics) of the kernel-only PPO paths: one sum all-reduce, scaled by 1/world
+    flat = torch.arange(8, dtype=torch.float32) * (rank + 1)
+    dist.all_reduce(flat)
+    out["flat"] = (flat / world).numpy()
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -64,3 +77,8 @@ def test_collectives_world2_gloo():
         assert o["count"] == 1000
         assert np.allclose(o["mean"], data.mean(0), atol=1e-5)
         assert np.allclose(o["var"], data.var(0), rtol=1e-4)
+        assert o["scalar_shape"] == ((), ())
+        ref = __import__("vine_robot_isaacgymenvs_b200.ppo.ppo", fromlist=["RunningMeanStd"]).RunningMeanStd(())
+        ref.update(torch.from_numpy(data[:, 0].copy()))
+        assert np.allclose(o["rms"], (float(ref.running_mean), float(ref.running_var), float(ref.count)), rtol=1e-5)
+        assert np.allclose(o["flat"], np.arange(8) * 1.5)
