@@ -433,6 +433,7 @@ typedef struct VineRolloutPost {
   float reward_scale, gamma;
   int32_t value_bootstrap;
   float success_reward_threshold;
+  float* not_done_next;          /* NULL or [n] out: 1 - dones_next (the mask of the recurrent state) */
 } VineRolloutPost;
 int vine_rollout_post(const VineRolloutPost* args, void* stream);
 

@@ -202,7 +202,7 @@ class VineRolloutPost(C.Structure):
         "rewards", "resets", "timeouts", "values", "shaped_rewards", "dones_next", "ep_return", "ep_length", "ep_stats",
         "rng_counter")]
         + [("n", C.c_int64), ("reward_scale", C.c_float), ("gamma", C.c_float), ("value_bootstrap", C.c_int32),
-           ("success_reward_threshold", C.c_float)])
+           ("success_reward_threshold", C.c_float), ("not_done_next", C.c_void_p)])
 
 
 class VinePpoPrologue(C.Structure):

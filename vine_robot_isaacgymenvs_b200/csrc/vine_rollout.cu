@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(256) vine_rollout_post_kernel(const VineRollou
     if (a.value_bootstrap && a.timeouts[i]) shaped += a.gamma * a.values[i];   // Vine5LinkMovingBasePPO.yaml:56
     a.shaped_rewards[i] = shaped;
     a.dones_next[i] = d;
+    if (a.not_done_next) a.not_done_next[i] = 1.f - d;
     const float er = a.ep_return[i] + rew, el = a.ep_length[i] + 1.f;
     if (d != 0.f) {   // episode statistics; success == the 1000-point "Position Success" term fired (V5:1507)
       s0 = 1.0, s1 = rew > a.success_reward_threshold ? 1.0 : 0.0, s2 = er, s3 = el;

@@ -351,10 +351,10 @@ class PPOAgent:
                       obs_inv_std=ptr(self._obs_inv_std_f), value_stats=ptr(self._val_stats), n=n, num_obs=self.O)
         seed, goff = int(env._seed) ^ 0x5DEECE66D, int(env._global_env_offset)
         self._done_ext[0].copy_(self._done_ext[T])
+        torch.sub(self._ones_n, self._done_ext[0], out=self._nd_ext[0])   # later rows are written by vine_rollout_post
         for t in range(T + 1):
             cur, nxt = self._r_cur, self._r_cur ^ 1
             last = t == T
-            torch.sub(self._ones_n, self._done_ext[t], out=self._nd_ext[t])
             if not last and t % L == 0:   # LSTM state at the start of every seq_len chunk (truncated BPTT restarts here)
                 self._HH_saved[t // L].copy_(self._r_HH[cur])
                 self._C_saved[t // L].copy_(self._r_C[cur])
@@ -381,7 +381,8 @@ class PPOAgent:
                                        values=ptr(self.b_val[t]), shaped_rewards=ptr(self.b_rew[t]), dones_next=ptr(self._done_ext[t + 1]),
                                        ep_return=ptr(self.ep_ret), ep_length=ptr(self.ep_len), ep_stats=ptr(self.ep_stats),
                                        rng_counter=ptr(self._rng_counter), n=n, reward_scale=self.reward_scale, gamma=self.gamma,
-                                       value_bootstrap=int(self.value_bootstrap), success_reward_threshold=500.0)
+                                       value_bootstrap=int(self.value_bootstrap), success_reward_threshold=500.0,
+                                       not_done_next=ptr(self._nd_ext[t + 1]))
             assert lib.vine_rollout_post(C.byref(post), stream) == 0
         if self._r_cur != 0:   # odd horizon: keep the persistent state in buffer 0 so a captured graph can be replayed
             self._r_HH[0].copy_(self._r_HH[1])
