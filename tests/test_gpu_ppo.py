@@ -172,3 +172,21 @@ def test_train_entry_point_trains_saves_and_plays_back(tmp_path, monkeypatch):
     pl = PolicyPlayer(18, device="cuda").restore(str(ck))
     a = pl.get_action(torch.zeros(18, device="cuda"), is_deterministic=True)
     assert a.shape == (2,) and bool(torch.isfinite(a).all())
+
+
+def test_native_paths_run_on_the_default_task_config():
+    """The reference's default task config (pipe obstacle, POS_AND_FD_VEL_AND_OBJ_INFO = 28 observations) through both
+    kernel-only paths: a few PPO iterations stay finite and move the parameters."""
+    for extra in ([], MLP):
+        cfg = vcfg.compose(["num_envs=512", "headless=True", "train.params.config.minibatch_size=4096",
+                            "task.env.maxEpisodeLength=50"] + extra)
+        agent = PPOAgent(vine.make(cfg=cfg), cfg["train"], seed=3, use_graphs=False)
+        assert agent.O == 28 and agent.fused_update and agent.native_lstm == (not extra)
+        w0 = agent.model.actor_mlp[0].weight.detach().clone()
+        for _ in range(3):
+            agent.train_epoch()
+        torch.cuda.synchronize()
+        st = agent.pop_stats()
+        assert all(x == x and abs(x) < 1e6 for x in (st["a_loss"], st["c_loss"], st["kl"]))
+        assert all(torch.isfinite(p).all() for p in agent.model.parameters())
+        assert not torch.equal(w0, agent.model.actor_mlp[0].weight)
