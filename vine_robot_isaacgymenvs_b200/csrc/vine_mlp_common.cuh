@@ -56,8 +56,39 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], int c_out, co
 }
 
 // accumulator columns [taddr, taddr+ncols) -> tile columns [c_out, c_out+ncols); ncols = 32 or 64 (both TMEM loads in flight)
+// 8 accumulator columns -> bias + ELU -> bf16 -> one 16-byte chunk of the tile
+template <int KL>
+__device__ __forceinline__ void fwd_group8(const uint32_t* r, int c, const float* bias, uint8_t* tile, int row) {
+  const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+  *reinterpret_cast<uint4*>(tile + tile_offset(row, c, KL)) =
+      make_uint4(pack_bf16(elu(__uint_as_float(r[0]) + b0.x), elu(__uint_as_float(r[1]) + b0.y)),
+                 pack_bf16(elu(__uint_as_float(r[2]) + b0.z), elu(__uint_as_float(r[3]) + b0.w)),
+                 pack_bf16(elu(__uint_as_float(r[4]) + b1.x), elu(__uint_as_float(r[5]) + b1.y)),
+                 pack_bf16(elu(__uint_as_float(r[6]) + b1.z), elu(__uint_as_float(r[7]) + b1.w)));
+}
+template <int KL>
+__device__ __forceinline__ void bwd_group8(const uint32_t* r, int c, uint8_t* tile, int row) {
+  uint4* p = reinterpret_cast<uint4*>(tile + tile_offset(row, c, KL));
+  const uint4 hv = *p;
+  const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 h = unpack_bf16(hw[i]);
+    w[i] = pack_bf16(__uint_as_float(r[2 * i]) * (h.x > 0.f ? 1.f : h.x + 1.f), __uint_as_float(r[2 * i + 1]) * (h.y > 0.f ? 1.f : h.y + 1.f));
+  }
+  *p = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <int KL>
 __device__ __forceinline__ void fwd_epilogue(uint32_t taddr, int ncols, int c_out, const float* bias, uint8_t* tile, int row) {
+  if (ncols == 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr, r);
+    fwd_group8<KL>(r, c_out, bias, tile, row);
+    fwd_group8<KL>(r + 8, c_out + 8, bias, tile, row);
+    return;
+  }
   uint32_t r0[32], r1[32];
   tmem_ld32_async(taddr, r0);
   if (ncols > 32) {
@@ -90,6 +121,13 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t (&r)[32], int c_out, ui
 }
 template <int KL>
 __device__ __forceinline__ void bwd_epilogue(uint32_t taddr, int ncols, int c_out, uint8_t* tile, int row) {
+  if (ncols == 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr, r);
+    bwd_group8<KL>(r, c_out, tile, row);
+    bwd_group8<KL>(r + 8, c_out + 8, tile, row);
+    return;
+  }
   uint32_t r0[32], r1[32];
   tmem_ld32_async(taddr, r0);
   if (ncols > 32) {
@@ -143,13 +181,14 @@ __device__ __forceinline__ float bf16_at(const uint8_t* tile, int row, int col, 
 
 // normalised observation row -> bf16 x tile (this thread: 16 of the 32 padded columns of its row); optionally copies
 // the raw observation out (rollout buffer) and plants the constant 1 in column 31 (bias gradient through dW1)
-__device__ __forceinline__ void build_x_tile(uint8_t* x_t, int row, int half, bool valid, const float* __restrict__ obs_row,
+template <int CPT = 16>   // columns per thread: 16 (two threads per row) or 8 (four threads per row)
+__device__ __forceinline__ void build_x_tile(uint8_t* x_t, int row, int part, bool valid, const float* __restrict__ obs_row,
                                              const float* __restrict__ mean, const float* __restrict__ inv_std, int O,
                                              bool ones_column, float* __restrict__ obs_copy_row) {
-  const int k0 = half * 16;
-  float x[16];
+  const int k0 = part * CPT;
+  float x[CPT];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < CPT; ++i) {
     const int k = k0 + i;
     float v = 0.f;
     if (valid && k < O) {
@@ -161,7 +200,7 @@ __device__ __forceinline__ void build_x_tile(uint8_t* x_t, int row, int half, bo
     x[i] = v;
   }
 #pragma unroll
-  for (int g = 0; g < 2; ++g)
+  for (int g = 0; g < CPT / 8; ++g)
     *reinterpret_cast<uint4*>(x_t + tile_offset(row, k0 + g * 8, K1)) =
         make_uint4(pack_bf16(x[g * 8], x[g * 8 + 1]), pack_bf16(x[g * 8 + 2], x[g * 8 + 3]),
                    pack_bf16(x[g * 8 + 4], x[g * 8 + 5]), pack_bf16(x[g * 8 + 6], x[g * 8 + 7]));

@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "vine_mlp_common.cuh"
 
@@ -60,14 +61,18 @@ struct MbArgs {
   int adaptive;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const MbArgs a) {
+// Q = epilogue threads per row (2 or 4): thread (row, part) owns the columns [part * N/Q, (part+1) * N/Q) of every N-wide
+// accumulator; with Q = 4 the SM has 4 warps per sub-partition to hide the TMEM/shared-memory latencies of the epilogues.
+template <int Q>
+__global__ void __launch_bounds__(128 * Q, 1) vine_ppo_minibatch_kernel(const MbArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  constexpr int C128 = 128 / Q, C64 = 64 / Q;
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, part = tid >> 7;
   const uint32_t bar_w = smem_u32(smem + OFF_BAR), bar_mma = bar_w + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
   const float* biases = reinterpret_cast<const float*>(smem + OFF_B);
   float* acc_s = reinterpret_cast<float*>(smem + OFF_ACC);
-  for (int i = tid; i < ACC_FLOATS; i += THREADS) acc_s[i] = 0.f;
+  for (int i = tid; i < ACC_FLOATS; i += 128 * Q) acc_s[i] = 0.f;
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
   auto nothing = [] {};
 
   // persistent per-thread accumulators
-  float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // a_loss, c_loss, kl, b_loss, dlogstd0, dlogstd1 (half 0 threads)
+  float st[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // a_loss, c_loss, kl, b_loss, dlogstd0, dlogstd1 (part 0 threads)
 
   const int64_t B = (int64_t)a.T * a.E;
   const int64_t ntiles = (B + TILE - 1) / TILE;
@@ -139,31 +144,31 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
     const int64_t s = tile * TILE + row;
     const bool valid = s < B;
     const int64_t grow = valid ? (s / a.E) * (int64_t)a.N + a.e0 + (s % a.E) : 0;   // row in the [T, N] rollout buffers
-    // rollout scalars of this sample (half 0 threads own the loss of their row)
+    // rollout scalars of this sample (part 0 threads own the loss of their row)
     float act0 = 0.f, act1 = 0.f, muo0 = 0.f, muo1 = 0.f, nlpo = 0.f, vo = 0.f, ret = 0.f, adv = 0.f;
-    if (half == 0 && valid && !a.dh3_ext) {
+    if (part == 0 && valid && !a.dh3_ext) {
       const float2 av = *reinterpret_cast<const float2*>(a.act + 2 * grow);
       const float2 mv = *reinterpret_cast<const float2*>(a.mu_old + 2 * grow);
       act0 = av.x, act1 = av.y, muo0 = mv.x, muo1 = mv.y;
       nlpo = a.nlp_old[grow], vo = a.val_old[grow], ret = a.ret[grow], adv = a.adv[grow];
     }
     // ---- x tile: normalised observation, bf16, zero padded to K1; column 31 is the constant 1 (bias gradient) ----
-    build_x_tile(x_t, row, half, valid, a.obs + grow * a.O, a.obs_mean, a.obs_inv_std, a.O, true, nullptr);
+    build_x_tile<K1 / Q>(x_t, row, part, valid, a.obs + grow * a.O, a.obs_mean, a.obs_inv_std, a.O, true, nullptr);
     // =============================== forward ===============================
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {   // layer 1 in two halves of 128 output features (working accumulator = 128 columns)
       mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sX, K1), k_major(sW1, K1, h * 128), instr_desc(128, false, false), K1 / 16, false); },
                nothing);
-      fwd_epilogue<H1>(lane_base + TM_DATA + half * 64, 64, h * 128 + half * 64, biases, a1_t, row);
+      fwd_epilogue<H1>(lane_base + TM_DATA + part * C128, C128, h * 128 + part * C128, biases, a1_t, row);
     }
     mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA1, H1), k_major(sW2, H1), instr_desc(H2, false, false), H1 / 16, false); }, nothing);
-    fwd_epilogue<H2>(lane_base + TM_DATA + half * 64, 64, half * 64, biases + H1, a2_t, row);
+    fwd_epilogue<H2>(lane_base + TM_DATA + part * C128, C128, part * C128, biases + H1, a2_t, row);
     mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA2, H2), k_major(sW3, H2), instr_desc(H3, false, false), H2 / 16, false); }, nothing);
-    fwd_epilogue<H3>(lane_base + TM_DATA + half * 32, 32, half * 32, biases + H1 + H2, a3_t, row);
+    fwd_epilogue<H3>(lane_base + TM_DATA + part * C64, C64, part * C64, biases + H1 + H2, a3_t, row);
     if (!a.dh3_ext) {
     mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA3, H3), k_major(sW4, H3), instr_desc(NH, false, false), H3 / 16, false); }, nothing);
     // =============================== loss ===============================
-    if (half == 0) {
+    if (part == 0) {
       uint32_t r[16];
       tmem_ld16(lane_base + TM_DATA, r);
       const float* bh = biases + H1 + H2 + H3;
@@ -212,7 +217,8 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
     // =============================== backward ===============================
     // heads: dh3 = dzh Wh (reduction over the 16 padded head rows); meanwhile dWh = dzh^T h3 and dbh on CUDA cores
     mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sDZH, NH), mn_major(sW4, H3), instr_desc(H3, false, true), NH / 16, false); },
-             [&] {   // warp w owns columns [8w, 8w+8) of h3; lanes = 8 rows x 4 row-group phases (see column_sums)
+             [&] {   // warp w < 8 owns columns [8w, 8w+8) of h3; lanes = 8 rows x 4 row-group phases (see column_sums)
+               if (warp < 8) {
                const int lane = tid & 31, r8 = lane & 7, ph = lane >> 3;
                float acc[3][8];
 #pragma unroll
@@ -252,25 +258,27 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
                    if (lane == 0) acc_s[ACC_BH + j] += t;
                  }
                }
+               }
                __syncthreads();   // h3 is overwritten in place next
              });
-    bwd_epilogue<H3>(lane_base + TM_DATA + half * 32, 32, half * 32, a3_t, row);   // dz3 over h3
+    bwd_epilogue<H3>(lane_base + TM_DATA + part * C64, C64, part * C64, a3_t, row);   // dz3 over h3
     } else {
       // dz3 = dh3 (from the LSTM backward, f32 [B, 64]) * ELU'(h3), written over h3 in place
       __syncthreads();   // every thread is past its h3 stores / the layer-3 accumulator reads
-      uint32_t r[32];
+      uint32_t r[C64];
       if (valid) {
-        const float4* src = reinterpret_cast<const float4*>(a.dh3_ext + s * H3 + half * 32);
+        const float4* src = reinterpret_cast<const float4*>(a.dh3_ext + s * H3 + part * C64);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < C64 / 4; ++i) {
           const float4 v = src[i];
           r[4 * i] = __float_as_uint(v.x), r[4 * i + 1] = __float_as_uint(v.y), r[4 * i + 2] = __float_as_uint(v.z), r[4 * i + 3] = __float_as_uint(v.w);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = 0u;
+        for (int i = 0; i < C64; ++i) r[i] = 0u;
       }
-      bwd_chunk<H3>(r, half * 32, a3_t, row);
+#pragma unroll
+      for (int g = 0; g < C64 / 8; ++g) bwd_group8<H3>(r + 8 * g, part * C64 + 8 * g, a3_t, row);
     }
     // layer 3: dW3^T += h2^T dz3 (persistent), dh2 = dz3 W3; meanwhile db3 = column sums of dz3
     mma_step(
@@ -278,19 +286,19 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
           mma_sequence(tmem + TM_DW3T, mn_major(sA2, H2), mn_major(sA3, H3), instr_desc(H3, true, true), TILE / 16, !first);
           mma_sequence(tmem + TM_DATA, k_major(sA3, H3), mn_major(sW3, H2), instr_desc(H2, false, true), H3 / 16, false);
         },
-        [&] { column_sums<H3>(a3_t, acc_s + ACC_B3, tid); });
-    bwd_epilogue<H2>(lane_base + TM_DATA + half * 64, 64, half * 64, a2_t, row);   // dz2 over h2
+        [&] { if (warp < 8) column_sums<H3>(a3_t, acc_s + ACC_B3, tid); });
+    bwd_epilogue<H2>(lane_base + TM_DATA + part * C128, C128, part * C128, a2_t, row);   // dz2 over h2
     // layer 2: dW2 += dz2^T h1 (persistent), dh1[:, 0:128] = dz2 W2[:, 0:128]; meanwhile db2
     mma_step(
         [&] {
           mma_sequence(tmem + TM_DW2, mn_major(sA2, H2), mn_major(sA1, H1), instr_desc(H1, true, true), TILE / 16, !first);
           mma_sequence(tmem + TM_DATA, k_major(sA2, H2), mn_major(sW2, H1, 0), instr_desc(128, false, true), H2 / 16, false);
         },
-        [&] { column_sums<H2>(a2_t, acc_s + ACC_B2, tid); });
-    bwd_epilogue<H1>(lane_base + TM_DATA + half * 64, 64, half * 64, a1_t, row);           // dz1[:, 0:128] over h1
+        [&] { if (warp < 8) column_sums<H2>(a2_t, acc_s + ACC_B2, tid); });
+    bwd_epilogue<H1>(lane_base + TM_DATA + part * C128, C128, part * C128, a1_t, row);           // dz1[:, 0:128] over h1
     mma_step([&] { mma_sequence(tmem + TM_DATA, k_major(sA2, H2), mn_major(sW2, H1, 128), instr_desc(128, false, true), H2 / 16, false); },
              nothing);
-    bwd_epilogue<H1>(lane_base + TM_DATA + half * 64, 64, 128 + half * 64, a1_t, row);     // dz1[:, 128:256]
+    bwd_epilogue<H1>(lane_base + TM_DATA + part * C128, C128, 128 + part * C128, a1_t, row);     // dz1[:, 128:256]
     // layer 1: dW1 += dz1^T x (two halves of 128 output features; x column 31 == 1 gives db1)
     mma_step(
         [&] {
@@ -305,23 +313,25 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
   {
     uint32_t r[32];
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {   // dW2: lane = output feature, 256 columns, this thread's half
-      tmem_ld32(lane_base + TM_DW2 + half * 128 + c0, r);
-      float4* dst = reinterpret_cast<float4*>(ws + WS_W2 + row * H1 + half * 128 + c0);
+    for (int c0 = 0; c0 < 256 / Q; c0 += 32) {   // dW2: lane = output feature, 256 columns, this thread's share
+      tmem_ld32(lane_base + TM_DW2 + part * (256 / Q) + c0, r);
+      float4* dst = reinterpret_cast<float4*>(ws + WS_W2 + row * H1 + part * (256 / Q) + c0);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
     }
-    tmem_ld32(lane_base + TM_DW1 + half * K1, r);   // dW1: half h holds output features h*128 + lane
-    {
-      float4* dst = reinterpret_cast<float4*>(ws + WS_W1 + (half * 128 + row) * K1);
+    if (part < 2) {   // dW1: accumulator h holds output features h*128 + lane, 32 columns
+      tmem_ld32(lane_base + TM_DW1 + part * K1, r);
+      float4* dst = reinterpret_cast<float4*>(ws + WS_W1 + (part * 128 + row) * K1);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+    } else {          // (warp-uniform: whole warps share `part`)
     }
-    tmem_ld32(lane_base + TM_DW3T + half * 32, r);  // dW3^T: lane = input feature, 64 columns
-    {
-      float4* dst = reinterpret_cast<float4*>(ws + WS_W3T + row * H3 + half * 32);
+    if (Q == 2 || part >= 2) {   // dW3^T: lane = input feature, 64 columns: two threads x 32
+      const int hsel = Q == 2 ? part : part - 2;
+      tmem_ld32(lane_base + TM_DW3T + hsel * 32, r);
+      float4* dst = reinterpret_cast<float4*>(ws + WS_W3T + row * H3 + hsel * 32);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
@@ -334,7 +344,7 @@ __global__ void __launch_bounds__(THREADS, 1) vine_ppo_minibatch_kernel(const Mb
   else if (tid < 3 * H3 + 3) ws[WS_BH + tid - 3 * H3] = acc_s[ACC_BH + tid - 3 * H3];
   // loss statistics + d(logstd): reduce over the 128 sample-owning threads
   float* red = reinterpret_cast<float*>(smem + OFF_RED);
-  if (half == 0) {
+  if (part == 0) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       float v = st[j];
@@ -477,12 +487,15 @@ int vine_ppo_minibatch(const VinePpoMinibatch* b, void* stream) {
   if (b->horizon < 1 || b->num_envs < 1 || b->env_count < 1 || b->env_begin < 0 || b->env_begin + b->env_count > b->num_envs ||
       b->num_obs < 1 || b->num_obs >= K1 || (((uintptr_t)b->packed) & 15u) || (((uintptr_t)b->workspace) & 15u))
     return VINE_ERR_INVALID_ARG;
-  static int configured = -1;
+  static int configured = -1, q4 = 1;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return VINE_ERR_CUDA;
   if (configured != dev) {
-    if (cudaFuncSetAttribute(vine_ppo_minibatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(vine_ppo_minibatch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(vine_ppo_minibatch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
       return VINE_ERR_CUDA;
+    const char* e = getenv("VINE_PPO_EPILOGUE_THREADS");   // A/B switch: 2 or 4 epilogue threads per row (default 4)
+    q4 = !(e && e[0] == '2');
     configured = dev;
   }
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -499,7 +512,8 @@ int vine_ppo_minibatch(const VinePpoMinibatch* b, void* stream) {
   a.T = b->horizon, a.N = b->num_envs, a.e0 = b->env_begin, a.E = b->env_count, a.O = b->num_obs;
   a.e_clip = b->e_clip, a.critic_coef = b->critic_coef, a.entropy_coef = b->entropy_coef, a.bounds_coef = b->bounds_loss_coef;
   a.inv_B = 1.0f / (float)B, a.kl_threshold = b->kl_threshold, a.lr_min = b->lr_min, a.lr_max = b->lr_max, a.adaptive = b->adaptive_lr;
-  vine_ppo_minibatch_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  if (q4) vine_ppo_minibatch_kernel<4><<<grid, 512, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  else vine_ppo_minibatch_kernel<2><<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(a);
   if (cudaGetLastError() != cudaSuccess) return VINE_ERR_CUDA;
   return grid;   // number of gradient partials written (>= 1)
 }
