@@ -687,6 +687,11 @@ int vine_ppo_adam(const float* flat, float grad_scale, float* params, float* exp
                   void* packed, float* state, int num_obs, float beta1, float beta2, float eps, int bookkeeping,
                   void* stream);
 
+/* sizeof of the argument structs of the PPO entry points, in declaration order (VinePolicyAct = 0, VineRolloutPost,
+ * VinePpoPrologue, VinePpoMinibatch, VineLstmStep, VineLstmHead, VineLstmHeadTrain, VineLstmCellBwd, VineLstmBwdGemm,
+ * VineLstmWgrad, VineLstmGather = 10): lets a foreign-function binding verify its mirror of the layouts. */
+int vine_abi_struct_size(int which);
+
 #ifdef __cplusplus
 }
 #endif

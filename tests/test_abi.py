@@ -42,6 +42,12 @@ def test_struct_layout_matches_library(lib):
     assert lib.vine_abi_version() == abi.ABI_VERSION
 
 
+def test_ppo_argument_structs_match_the_library(lib):
+    for i, st in enumerate(abi.PPO_STRUCTS):
+        assert lib.vine_abi_struct_size(i) == C.sizeof(st), (st.__name__, lib.vine_abi_struct_size(i), C.sizeof(st))
+    assert lib.vine_abi_struct_size(len(abi.PPO_STRUCTS)) < 0
+
+
 def test_observation_widths(lib):
     for name, t in abi.OBSERVATION_TYPES.items():
         assert lib.vine_num_observations(t) == abi.NUM_OBSERVATIONS[t]

@@ -138,7 +138,7 @@ EXPORTED_SYMBOLS = [
     "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
     "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
     "vine_lstm_cell_fwd", "vine_lstm_cell_bwd", "vine_lstm_pack", "vine_lstm_step", "vine_lstm_mask", "vine_lstm_head", "vine_lstm_head_train", "vine_lstm_cell_bwd_tiles", "vine_lstm_bwd_gemm",
-    "vine_lstm_gather", "vine_lstm_num_params", "vine_lstm_wgrad", "vine_lstm_reduce", "vine_lstm_adam",
+    "vine_lstm_gather", "vine_abi_struct_size", "vine_lstm_num_params", "vine_lstm_wgrad", "vine_lstm_reduce", "vine_lstm_adam",
 ]
 METRIC_SUMS, METRIC_MAXES = 45, 30
 METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limit_hit", "abs_tip_y", "tip_z", "tip_velocities",
@@ -223,6 +223,10 @@ class VinePpoMinibatch(C.Structure):
                                     "lr_min", "lr_max", "reserved_f")]
         + [("dh3_ext", C.c_void_p)])
 
+# argument structs of the PPO entry points in the order of vine_abi_struct_size()
+PPO_STRUCTS = [VinePolicyAct, VineRolloutPost, VinePpoPrologue, VinePpoMinibatch, VineLstmStep, VineLstmHead, VineLstmHeadTrain,
+               VineLstmCellBwd, VineLstmBwdGemm, VineLstmWgrad, VineLstmGather]
+
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libvine_b200.so")
 _lib = None
@@ -271,6 +275,7 @@ def _declare(lib):
     lib.vine_lstm_cell_bwd_tiles.argtypes = [C.POINTER(VineLstmCellBwd), vp]
     lib.vine_lstm_bwd_gemm.argtypes = [C.POINTER(VineLstmBwdGemm), vp]
     lib.vine_lstm_gather.argtypes = [C.POINTER(VineLstmGather), vp]
+    lib.vine_abi_struct_size.argtypes = [C.c_int]
     lib.vine_lstm_num_params.argtypes = [C.c_int]
     lib.vine_lstm_wgrad.argtypes = [C.POINTER(VineLstmWgrad), vp]
     lib.vine_lstm_reduce.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]

@@ -949,6 +949,23 @@ int vine_lstm_bwd_gemm(const VineLstmBwdGemm* a, void* stream) {
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
+int vine_abi_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(VinePolicyAct);
+    case 1: return (int)sizeof(VineRolloutPost);
+    case 2: return (int)sizeof(VinePpoPrologue);
+    case 3: return (int)sizeof(VinePpoMinibatch);
+    case 4: return (int)sizeof(VineLstmStep);
+    case 5: return (int)sizeof(VineLstmHead);
+    case 6: return (int)sizeof(VineLstmHeadTrain);
+    case 7: return (int)sizeof(VineLstmCellBwd);
+    case 8: return (int)sizeof(VineLstmBwdGemm);
+    case 9: return (int)sizeof(VineLstmWgrad);
+    case 10: return (int)sizeof(VineLstmGather);
+    default: return VINE_ERR_INVALID_ARG;
+  }
+}
+
 int vine_lstm_gather(const VineLstmGather* a, void* stream) {
   if (!a || !a->obs || !a->scalars || !a->not_done || !a->c_saved || !a->hh_saved || !a->mb_obs || !a->mb_scalars || !a->mb_not_done ||
       !a->c0 || !a->hm0 || a->seq_len < 1 || a->chunks < 1 || a->env_count < 1 || a->env_begin < 0 ||
