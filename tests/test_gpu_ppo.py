@@ -190,3 +190,17 @@ def test_native_paths_run_on_the_default_task_config():
         assert all(x == x and abs(x) < 1e6 for x in (st["a_loss"], st["c_loss"], st["kl"]))
         assert all(torch.isfinite(p).all() for p in agent.model.parameters())
         assert not torch.equal(w0, agent.model.actor_mlp[0].weight)
+
+
+@pytest.mark.parametrize("extra", [[], MLP], ids=["reference_network", "mlp"])
+def test_fstr_training_reaches_the_success_band(extra):
+    """Learning check (the only parity available for the PPO side: rl_games is not vendored): FSTR, 4096 envs, 250 iterations
+    on the kernel-only paths.  Band: the torch-update agent reaches 0.80-0.85 success at this point
+    (profiles/ppo_fstr_r01_training*.log); the kernel paths must be within 0.10 of that, i.e. >= 0.72, with episodes getting
+    shorter than the 100-step time-out."""
+    cfg = vcfg.compose(vcfg.FSTR_OVERRIDES + ["num_envs=4096", "headless=True"] + extra)
+    agent = PPOAgent(vine.make(cfg=cfg), cfg["train"], seed=42, use_graphs=True)
+    hist = agent.train(250, log_every=50, log=None)
+    last = hist[-1]
+    assert last["success_rate"] >= 0.72 and last["mean_length"] < 60 and last["mean_return"] > 600, last
+    assert hist[0]["success_rate"] < last["success_rate"]
