@@ -26,6 +26,9 @@ VDEV uint4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32
   return make_uint4(c0, c1, c2, c3);
 }
 
+// 1/x as one MUFU.RCP (__fdividef(1, x) adds a range check and a scaling multiply per call; the pivots of the SPD system
+// matrix and squared edge lengths are far inside the normal range)
+VDEV float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 VDEV float u01(uint32_t x) { return __fmul_rn((float)(x >> 8), 5.9604644775390625e-08f); }  // [0,1)
 VDEV float uniform_ab(uint32_t x, float lo, float rng) { return __fmaf_rn(u01(x), rng, lo); }
 
@@ -242,7 +245,7 @@ VDEV void capsule_rect(const VineParams& p, const Rect& R, float Ay, float Az, f
   }
   // (ii) rectangle corners against the capsule segment
   const float ey = By - Ay, ez = Bz - Az;
-  const float inv_ee = __fdividef(1.f, ey * ey + ez * ez);
+  const float inv_ee = rcp_approx(ey * ey + ez * ez);
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     const float sa = (c & 1) ? 1.f : -1.f, sn = (c & 2) ? 1.f : -1.f;
@@ -401,7 +404,7 @@ VDEV void substep(const VineParams& p, const JointImp& J, float rail_force, cons
   }
   // LDL^T (row-wise): u_q = A_jq - sum_{r<q} u_r L_qr ; L_jq = u_q / d_q ; d_j = A_jj - sum_q u_q L_jq
   float dinv[6];
-  dinv[0] = __fdividef(1.f, M[0][0]);
+  dinv[0] = rcp_approx(M[0][0]);
 #pragma unroll
   for (int j = 1; j < 6; ++j) {
     float u[5];
@@ -416,11 +419,9 @@ VDEV void substep(const VineParams& p, const JointImp& J, float rail_force, cons
       M[j][q] = l;
       dj = fmaf(-uq, l, dj);
     }
-    dinv[j] = __fdividef(1.f, dj);
+    dinv[j] = rcp_approx(dj);
   }
-  // solve M dv = h f
-#pragma unroll
-  for (int i = 0; i < 6; ++i) f[i] *= p.h;
+  // solve M a = f (dv = h a is folded into the velocity update)
 #pragma unroll
   for (int i = 1; i < 6; ++i)
 #pragma unroll
@@ -431,16 +432,17 @@ VDEV void substep(const VineParams& p, const JointImp& J, float rail_force, cons
   for (int i = 4; i >= 0; --i)
 #pragma unroll
     for (int q = i + 1; q < 6; ++q) f[i] = fmaf(-M[q][i], f[q], f[i]);
-  d.v[0] += f[0]; d.x[0] = fmaf(p.h, d.v[0], d.x[0]);
+  d.v[0] = fmaf(p.h, f[0], d.v[0]); d.x[0] = fmaf(p.h, d.v[0], d.x[0]);
 #pragma unroll
   for (int j = 0; j < VINE_NL; ++j) {
-    d.v[j + 1] += f[j + 1];
+    d.v[j + 1] = fmaf(p.h, f[j + 1], d.v[j + 1]);
     const float dl = p.h * d.v[j + 1];
     d.x[j + 1] += dl;
-    // rotate (S,C) by dl: sin dl ~ dl (1 - dl^2/6), cos dl ~ 1 - dl^2/2 + dl^4/24  (|dl| << 1)
+    // rotate (S,C) by dl: sin dl ~ dl (1 - dl^2/6), cos dl ~ 1 - dl^2/2. |dl| = h |w| < 0.03 for |w| < 36 rad/s, where the
+    // dropped dl^4/24 < 3.4e-8 is below half an ulp of 1; the exact sin/cos is re-evaluated every sim step (refresh_trig)
     const float d2 = dl * dl;
     const float sd = dl * fmaf(-0.16666667f, d2, 1.f);
-    const float cd = fmaf(d2, fmaf(0.041666668f, d2, -0.5f), 1.f);
+    const float cd = fmaf(-0.5f, d2, 1.f);
     const float s = d.S[j], c = d.C[j];
     d.S[j] = fmaf(s, cd, c * sd);
     d.C[j] = fmaf(c, cd, -s * sd);
