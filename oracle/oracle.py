@@ -55,6 +55,8 @@ def lib():
         for f in (L.oracle_uniform4, L.oracle_normal4):
             f.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _fp]
             f.restype = None
+        L.oracle_dynamics_uniforms.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _fp]
+        L.oracle_dynamics_uniforms.restype = None
         L.oracle_step.argtypes = [C.POINTER(abi.VineConfig), C.POINTER(OracleArrays), C.c_int, C.c_int]
         L.oracle_init.argtypes = [C.POINTER(abi.VineConfig), C.POINTER(OracleArrays)]
         L.oracle_reset_idx.argtypes = [C.POINTER(abi.VineConfig), C.POINTER(OracleArrays), _i64p, C.c_int64]
@@ -102,6 +104,13 @@ def philox(seed, gid, site, step, block):
 def uniform4(seed, gid, site, step, block):
     out = (C.c_float * 4)()
     lib().oracle_uniform4(seed, gid, site, step, block, out)
+    return np.array(list(out), dtype=np.float32)
+
+
+def dynamics_uniforms(seed, gid, step, sim_i):
+    """The 24 16-bit uniforms of one sim step's dynamics-scaling draw (3 Philox blocks)."""
+    out = (C.c_float * 24)()
+    lib().oracle_dynamics_uniforms(seed, gid, step, sim_i, out)
     return np.array(list(out), dtype=np.float32)
 
 

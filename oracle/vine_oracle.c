@@ -135,6 +135,19 @@ void oracle_uniform4(uint64_t seed, uint32_t gid, uint32_t site, uint32_t step, 
   for (int i = 0; i < 4; ++i) out[i] = u01(r[i]);
 }
 
+/* The 24 uniforms of one sim step's dynamics draw (V5:1053-1055 needs 20, the accel scaling 1): 16 random bits each, two per
+ * Philox word of blocks 8 i .. 8 i + 2, low half first. */
+void oracle_dynamics_uniforms(uint64_t seed, uint32_t gid, uint32_t step, uint32_t sim_i, float out[24]) {
+  for (uint32_t b = 0; b < 3; ++b) {
+    uint32_t r[4];
+    oracle_philox(seed, gid, SITE_DYNAMICS, step, sim_i * 8u + b, r);
+    for (int w = 0; w < 4; ++w) {
+      out[8 * b + 2 * w] = (float)(r[w] & 0xffffu) * 1.52587890625e-05f;      /* 2^-16: [0,1) */
+      out[8 * b + 2 * w + 1] = (float)(r[w] >> 16) * 1.52587890625e-05f;
+    }
+  }
+}
+
 /* Box-Muller: 4 u32 -> 4 standard normals. */
 void oracle_normal4(uint64_t seed, uint32_t gid, uint32_t site, uint32_t step, uint32_t block,
                     float out[4]) {
@@ -493,7 +506,7 @@ static void step_env(const VineConfig* c, const Derived* d, OracleArrays* A, int
     float scale[20]; const float* sp = NULL; float acc_scale = 1.0f;
     if (c->vine_randomize) { /* V5:1053-1055: redrawn every sim step */
       float u[24];
-      for (uint32_t b = 0; b < 6; ++b) oracle_uniform4(A->seed, gid, SITE_DYNAMICS, step, (uint32_t)i * 8u + b, &u[4 * b]);
+      oracle_dynamics_uniforms(A->seed, gid, step, (uint32_t)i, u);
       for (int k = 0; k < 20; ++k) scale[k] = uniform_ab(u[k], d->dyn_min, d->dyn_max);
       acc_scale = uniform_ab(u[20], d->acc_min, d->acc_max);
       sp = scale;

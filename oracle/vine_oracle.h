@@ -67,6 +67,7 @@ void oracle_config_defaults(VineConfig* cfg);
 void oracle_philox(uint64_t seed, uint32_t gid, uint32_t site, uint32_t step, uint32_t block,
                    uint32_t out[4]);
 /* Same uniform / normal conversions the product uses; for fixture generation. */
+void oracle_dynamics_uniforms(uint64_t seed, uint32_t gid, uint32_t step, uint32_t sim_i, float out[24]);
 void oracle_uniform4(uint64_t seed, uint32_t gid, uint32_t site, uint32_t step, uint32_t block,
                      float out[4]);
 void oracle_normal4(uint64_t seed, uint32_t gid, uint32_t site, uint32_t step, uint32_t block,

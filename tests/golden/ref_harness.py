@@ -130,9 +130,12 @@ class PhiloxFeed:
                 if len(shape) == 3:      # V5:1054 dynamics scaling [N,5,20]
                     out = torch.ones(*shape, dtype=torch.float32)
                     sc = np.ones((feed.n, 5, 4), np.float32)
+                    a32 = np.float32(a)
+                    rng = np.float32(np.float32(b) - a32)
                     for e in range(feed.n):
-                        vals = np.concatenate([feed._uniform_ab(feed.off + e, O.SITE_DYNAMICS, feed.step,
-                                                                feed.sim_i * 8 + blk, a, b) for blk in range(5)])
+                        u = O.dynamics_uniforms(feed.seed, feed.off + e, feed.step, feed.sim_i)[:20]
+                        # fmaf(u, rng, a) evaluated exactly: a 16-bit u times an f32 is exact in f64
+                        vals = np.array([np.float32(np.float64(x) * np.float64(rng) + np.float64(a32)) for x in u], np.float32)
                         sc[e] = vals.reshape(5, 4)
                     for j in range(5):
                         for term in range(4):

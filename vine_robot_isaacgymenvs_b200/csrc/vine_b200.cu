@@ -144,29 +144,34 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
     float rail_force = 0.f;
 #pragma unroll
     for (int i = 0; i < VINE_MAX_CFI; ++i) in.contact[i] = 0.f;
+    const float dyn_rng16 = p.dyn_rng * 1.52587890625e-05f, acc_rng16 = p.acc_rng * 1.52587890625e-05f;   // 2^-16
 #pragma unroll 1
     for (int i = 0; i < p.C; ++i) {
-      if (i > 0) refresh_trig(p, d);  // exact sin/cos once per sim step; substeps rotate incrementally
+      // exact sin/cos: once per control step in free space (the incremental rotation drifts < 1e-6 over the 40 substeps at
+      // |w| < 36 rad/s), once per sim step with obstacles (impacts can spin a link an order of magnitude faster)
+      if (CONTACT && i > 0) refresh_trig(p, d);
       if (i > 0 && i == p.C - 1 && reset_in != 0 && p.stale) {  // only needed by V5:797 on reset steps
         float vy, vz; tip_fk(d, tipb_y, tipb_z, vy, vz);
       }
       JointLaw law; joint_law_unscaled(law);
       float acc_scale = 1.f;
       if (p.randomize) {  // V5:1053-1055: 20 multipliers re-drawn every sim step (+1 for accel scaling)
-        uint32_t u[24];
+        // 16 random bits per multiplier (two per Philox word): 3 Philox calls per sim step instead of 6; multiplier k uses
+        // half k of the 24 halves of blocks 8 i .. 8 i + 2, low half first
+        uint32_t u[12];
 #pragma unroll
-        for (uint32_t b = 0; b < 6; ++b) {
+        for (uint32_t b = 0; b < 3; ++b) {
           const uint4 r = philox4x32(a.k0, a.k1, gid, VINE_SITE_DYNAMICS, step, (uint32_t)i * 8u + b);
           u[4 * b] = r.x; u[4 * b + 1] = r.y; u[4 * b + 2] = r.z; u[4 * b + 3] = r.w;
         }
 #pragma unroll
         for (int j = 0; j < VINE_NL; ++j) {
-          law.K[j] = __fmul_rn(law.K[j], uniform_ab(u[4 * j], p.dyn_min, p.dyn_rng));
-          law.Cd[j] = __fmul_rn(law.Cd[j], uniform_ab(u[4 * j + 1], p.dyn_min, p.dyn_rng));
-          law.b[j] = __fmul_rn(law.b[j], uniform_ab(u[4 * j + 2], p.dyn_min, p.dyn_rng));
-          law.B[j] = __fmul_rn(law.B[j], uniform_ab(u[4 * j + 3], p.dyn_min, p.dyn_rng));
+          law.K[j] = __fmul_rn(law.K[j], uniform_ab16(u[2 * j] & 0xffffu, p.dyn_min, dyn_rng16));
+          law.Cd[j] = __fmul_rn(law.Cd[j], uniform_ab16(u[2 * j] >> 16, p.dyn_min, dyn_rng16));
+          law.b[j] = __fmul_rn(law.b[j], uniform_ab16(u[2 * j + 1] & 0xffffu, p.dyn_min, dyn_rng16));
+          law.B[j] = __fmul_rn(law.B[j], uniform_ab16(u[2 * j + 1] >> 16, p.dyn_min, dyn_rng16));
         }
-        acc_scale = uniform_ab(u[20], p.acc_min, p.acc_rng);
+        acc_scale = uniform_ab16(u[10] & 0xffffu, p.acc_min, acc_rng16);
       }
       // rigid-body cart velocity: stale on the first sim step after a reset (V5:1069)
       const float cart_vel = (i == 0) ? cart_body_vy : d.v[0];

@@ -31,6 +31,9 @@ VDEV uint4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32
 VDEV float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 VDEV float u01(uint32_t x) { return __fmul_rn((float)(x >> 8), 5.9604644775390625e-08f); }  // [0,1)
 VDEV float uniform_ab(uint32_t x, float lo, float rng) { return __fmaf_rn(u01(x), rng, lo); }
+// 16-bit draw h in [0, 65536) -> lo + (h 2^-16) rng with rng16 = rng * 2^-16 (the power-of-two scaling of either factor
+// leaves the exact product, hence the fused result, unchanged)
+VDEV float uniform_ab16(uint32_t h, float lo, float rng16) { return __fmaf_rn((float)h, rng16, lo); }
 
 // sin/cos for |x| up to a few thousand (Cody-Waite reduction + Cephes minimax kernels)
 VDEV void vine_sincos(float x, float& s, float& c) {
