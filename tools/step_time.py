@@ -1,0 +1,25 @@
+"""Time env.step at a given preset/size with CUDA events: python tools/step_time.py PRESET N [override ...]"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+import vine_robot_isaacgymenvs_b200 as vine  # noqa: E402
+from vine_robot_isaacgymenvs_b200 import config as vcfg  # noqa: E402
+
+preset = getattr(vcfg, sys.argv[1])
+n = int(sys.argv[2])
+env = vine.make(cfg=vcfg.compose(preset + [f"num_envs={n}", "headless=True"] + sys.argv[3:]))
+g = torch.Generator(device="cuda").manual_seed(0)
+acts = [torch.rand(n, 2, device="cuda", generator=g) * 2 - 1 for _ in range(8)]
+for t in range(40):
+    env.step(acts[t % 8])
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for t in range(40):
+    env.step(acts[t % 8])
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 40
+print(f"{sys.argv[1]} n={n} {' '.join(sys.argv[3:])}: {ms:.4f} ms/step  {n / ms / 1e3:.4g} env-steps/s")

@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(CONTACT ? VINE_BLOCK_CONTACT : VINE_BLOCK, CON
 vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
   constexpr int BLOCK = CONTACT ? VINE_BLOCK_CONTACT : VINE_BLOCK;
   __shared__ float s_obs[BLOCK * (VINE_MAX_OBS + 1)];
+  __shared__ ContactScratch s_contact[CONTACT ? BLOCK / 32 : 1];
+  ContactScratch* cs = &s_contact[CONTACT ? threadIdx.x >> 5 : 0];
   const int64_t e = a.first + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (e < a.end) {
     const float4 s0 = a.S0[e], s1 = a.S1[e], s2 = a.S2[e], s3 = a.S3[e], s4 = a.S4[e], s5 = a.S5[e];
@@ -135,8 +137,9 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
     in.prev_u_rail = u_rail;                                               // V5:945
     const float u_use = p.use_smoothed ? smoothed : u_fpam;                // V5:1059
 
-    Obstacles ob;
-    if (CONTACT) build_obstacles(p, target[1], target[2], obj[0], obj[1], ob);
+    Obstacles ob = {0, -1, 0.f, 0.f, 0.f, 0.f};
+    ContactCache cc = {0u, 1e30f};   // no candidate pairs yet: the first substep culls
+    if (CONTACT) build_obstacles(p, target[1], target[2], obj[0], obj[1], cs, ob);
 
     // ---- controlFrequencyInv x {forces, contact sample, simulate}  VT:338-356 ----
     Dyn d; rel_to_abs(p, q, qd, d);
@@ -192,7 +195,7 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
       in.contact[i] = lip;  // VT:348-351: force of the PREVIOUS simulate
       JointImp J; joint_implicit_consts(p, law, u_use, efforts, J);
 #pragma unroll 1
-      for (int s = 0; s < p.S; ++s) substep<CONTACT>(p, J, rail_force, &ob, d, lip);
+      for (int s = 0; s < p.S; ++s) substep<CONTACT>(p, J, rail_force, ob, cs, cc, d, lip);
     }
     float tipvel_y, tipvel_z;
     tip_fk(d, tip_y, tip_z, tipvel_y, tipvel_z);
@@ -445,6 +448,8 @@ __global__ void vine_actuation_kernel(const __grid_constant__ VineParams p, int6
 
 template <bool CONTACT>
 __global__ void __launch_bounds__(VINE_BLOCK) vine_simulate_kernel(const __grid_constant__ VineParams p, int64_t n, const VineSimulateIO io) {
+  __shared__ ContactScratch s_contact[CONTACT ? VINE_BLOCK / 32 : 1];
+  ContactScratch* cs = &s_contact[CONTACT ? threadIdx.x >> 5 : 0];
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   float q[6], qd[6], efforts[6];
@@ -458,14 +463,15 @@ __global__ void __launch_bounds__(VINE_BLOCK) vine_simulate_kernel(const __grid_
     }
   }
   const float u_use = io.u_fpam_to_use ? io.u_fpam_to_use[e] : 0.f;
-  Obstacles ob;
+  Obstacles ob = {0, -1, 0.f, 0.f, 0.f, 0.f};
+  ContactCache cc = {0u, 1e30f};
   if (CONTACT) build_obstacles(p, io.target_positions[3 * e + 1], io.target_positions[3 * e + 2],
-                               io.object_info[2 * e], io.object_info[2 * e + 1], ob);
+                               io.object_info[2 * e], io.object_info[2 * e + 1], cs, ob);
   Dyn d; rel_to_abs(p, q, qd, d);
   JointImp J; joint_implicit_consts(p, law, u_use, efforts, J);
   float lip = 0.f;
 #pragma unroll 1
-  for (int s = 0; s < p.S; ++s) substep<CONTACT>(p, J, efforts[0], &ob, d, lip);
+  for (int s = 0; s < p.S; ++s) substep<CONTACT>(p, J, efforts[0], ob, cs, cc, d, lip);
   float ty, tz, vy, vz; tip_fk(d, ty, tz, vy, vz);
   abs_to_rel(d, q, qd);
   for (int i = 0; i < 6; ++i) { io.dof_pos[6 * e + i] = q[i]; io.dof_vel[6 * e + i] = qd[i]; }

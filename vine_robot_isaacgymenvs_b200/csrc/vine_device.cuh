@@ -123,20 +123,34 @@ VDEV float rail_controller(const VineParams& p, float cart_vel_y, float u_rail, 
 // Obstacles: rectangles in the (y,z) plane of motion (custom_shelf.urdf:82-93,139-152 placed by
 // V5:818-829; pipe tube V5:841-885 with the STL's dimensions).
 // ------------------------------------------------------------------------------------------
-struct Rect { float cy, cz, ay, az, ha, hn; };
-struct Obstacles {
-  Rect r[VINE_MAX_RECTS];
-  int n, lip;                        // lip = index of the sensing shelf_link rectangle or -1
-  float lo_y, hi_y, lo_z, hi_z;      // bounding box of all rectangles
+// Per-warp shared scratch of the contact variant (dynamic indexing by link / rectangle without local memory):
+//   rect:  six floats per rectangle and env: centre (cy, cz), unit axis (ay, az), half extents along the axis (ha) and the
+//          normal (hn); fixed for the control step
+//   chain: joint positions / velocities, sin/cos and spin of the links of an env with candidate contacts, rewritten by
+//          that env's lane in the substeps in which it has any
+enum { CH_PY = 0, CH_PZ = 6, CH_VY = 12, CH_VZ = 18, CH_S = 24, CH_C = 29, CH_W = 34, CH_FIELDS = 39 };
+struct ContactScratch {
+  float rect[32][VINE_MAX_RECTS * 6 + 1];   // [lane][6 r + field]; odd row stride keeps the lanes on different banks
+  float chain[CH_FIELDS][32];               // [field][lane]
 };
+// rectangle count and index of the sensing shelf_link rectangle (-1: none), the same for all envs; bounding box of this env's
+struct Obstacles { int n, lip; float lo_y, hi_y, lo_z, hi_z; };
+// candidate (link, rectangle) pairs of one env (bit 5 r + j) and a bound on how far any point of the chain has moved since
+// they were culled (negative: distance still to go before the chain can reach the obstacles' bounding box); registers
+struct ContactCache { unsigned pm; float disp; };
+#define VINE_CULL_SLACK 0.02f
 
-VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, float theta, Obstacles& ob) {
+VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, float theta, ContactScratch* cs, Obstacles& ob) {
+  float* R = cs->rect[threadIdx.x & 31];
+  auto put = [&](int i, float cy, float cz, float ay, float az, float ha, float hn) {
+    R[6 * i] = cy; R[6 * i + 1] = cz; R[6 * i + 2] = ay; R[6 * i + 3] = az; R[6 * i + 4] = ha; R[6 * i + 5] = hn;
+  };
   ob.n = 0; ob.lip = -1;
   if (p.shelf) {
     const float ry = ty + (-0.2f + depth), rz = tz - 0.01f;
-    ob.r[0] = {ry - 0.001f, rz, 1.f, 0.f, 0.1995f, 0.005f};
-    ob.r[1] = {ry, rz + 0.2f, 1.f, 0.f, 0.2f, 0.005f};
-    ob.r[2] = {ry + 0.199f, rz, 1.f, 0.f, 0.001f, 0.005f};
+    put(0, ry - 0.001f, rz, 1.f, 0.f, 0.1995f, 0.005f);
+    put(1, ry, rz + 0.2f, 1.f, 0.f, 0.2f, 0.005f);
+    put(2, ry + 0.199f, rz, 1.f, 0.f, 0.001f, 0.005f);
     ob.lip = 2; ob.n = 3;
   }
   if (p.pipe) {
@@ -146,15 +160,16 @@ VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, 
     const float ey = ty + depth * ct + off * st, ez = tz + depth * st - off * ct;
     const float ay = -ct, az = -st, ny = -az, nz = ay;
     const float mid = 0.5f * (win + wout), hn = 0.5f * (wout - win), ha = 0.5f * 0.34125f;
-    ob.r[ob.n++] = {ey + ay * ha - mid * ny, ez + az * ha - mid * nz, ay, az, ha, hn};
-    ob.r[ob.n++] = {ey + ay * ha + mid * ny, ez + az * ha + mid * nz, ay, az, ha, hn};
+    put(ob.n, ey + ay * ha - mid * ny, ez + az * ha - mid * nz, ay, az, ha, hn);
+    put(ob.n + 1, ey + ay * ha + mid * ny, ez + az * ha + mid * nz, ay, az, ha, hn);
+    ob.n += 2;
   }
   ob.lo_y = ob.lo_z = 1e30f; ob.hi_y = ob.hi_z = -1e30f;
   for (int i = 0; i < ob.n; ++i) {
-    const Rect& R = ob.r[i];
-    const float ey = fabsf(R.ay) * R.ha + fabsf(R.az) * R.hn, ez = fabsf(R.az) * R.ha + fabsf(R.ay) * R.hn;
-    ob.lo_y = fminf(ob.lo_y, R.cy - ey); ob.hi_y = fmaxf(ob.hi_y, R.cy + ey);
-    ob.lo_z = fminf(ob.lo_z, R.cz - ez); ob.hi_z = fmaxf(ob.hi_z, R.cz + ez);
+    const float ey = fabsf(R[6 * i + 2]) * R[6 * i + 4] + fabsf(R[6 * i + 3]) * R[6 * i + 5];
+    const float ez = fabsf(R[6 * i + 3]) * R[6 * i + 4] + fabsf(R[6 * i + 2]) * R[6 * i + 5];
+    ob.lo_y = fminf(ob.lo_y, R[6 * i] - ey); ob.hi_y = fmaxf(ob.hi_y, R[6 * i] + ey);
+    ob.lo_z = fminf(ob.lo_z, R[6 * i + 1] - ez); ob.hi_z = fmaxf(ob.hi_z, R[6 * i + 1] + ez);
   }
 }
 
@@ -200,11 +215,18 @@ VDEV void tip_fk(const Dyn& d, float& ty, float& tz, float& tvy, float& tvz) {
 }
 
 // ---- penalty contact, frictionless (V5:477,491,499) ----
-struct LinkLoad { float fy, fz, t; };  // net force and torque about the link's proximal joint
+// Contacts are rare per env but common per warp, and everything an env does about them runs with ~1 of 32 lanes active,
+// i.e. at the latency of one dependent instruction chain.  So the chain is kept short: each env carries a conservative
+// candidate mask of (link, rectangle) pairs that is re-culled only after the chain has moved VINE_CULL_SLACK since the
+// last cull (a substep without candidates costs 12 instructions), and there is ONE copy of the narrow phase, entered per
+// candidate pair with the link picked by a run-time index into shared memory, its 2 capsules x (2 end points + 4 rectangle
+// corners) unrolled so the twelve independent point tests overlap.
 
-VDEV void contact_point(const VineParams& p, float Py, float Pz, float ny, float nz, float dist, float radius,
-                        float jy, float jz, float jvy, float jvz, float w, LinkLoad& L, float& ofy, float& ofz) {
-  const float pen = radius + p.rest - dist;
+struct PairLoad { float fy, fz, t; };  // net force and torque about the link's proximal joint of one (link, rectangle) pair
+
+VDEV void contact_point(const VineParams& p, float Py, float Pz, float ny, float nz, float dist, float reach,
+                        float jy, float jz, float jvy, float jvz, float w, PairLoad& L) {
+  const float pen = reach - dist;
   if (!(pen > 0.f)) return;
   const float ry = Py - jy, rz = Pz - jz;
   const float vy = jvy - w * rz, vz = jvz + w * ry;
@@ -212,47 +234,41 @@ VDEV void contact_point(const VineParams& p, float Py, float Pz, float ny, float
   if (!(f > 0.f)) return;
   const float Fy = f * ny, Fz = f * nz;
   L.fy += Fy; L.fz += Fz; L.t += ry * Fz - rz * Fy;
-  ofy -= Fy; ofz -= Fz;
 }
 
 // capsule (core A-B, radius r) of a link whose proximal joint is at (jy,jz) moving with (jvy,jvz), spin w
-// The two inner loops are kept rolled on purpose: with everything unrolled the ten inlined copies (5 links x 2 capsules)
-// made the contact kernel 140 KB of code and the instruction cache its bottleneck (ncu: 3.2 warps per issue slot stalled
-// on "no instruction"); a non-inlined function fixed that but cost latency at small env counts (argument spills).
-VDEV void capsule_rect(const VineParams& p, const Rect& R, float Ay, float Az, float By, float Bz, float radius,
-                       bool test_a, bool closed_end, float jy, float jz, float jvy, float jvz, float w,
-                       LinkLoad& L, float& ofy, float& ofz) {
-  const float ay = R.ay, az = R.az, ny = -az, nz = ay;
-  {
-    // separating-axis cull in the rectangle's frame (exact: every distance used below is >= the separation along either
-    // rectangle axis, and a contact needs distance < radius + rest)
-    const float laA = (Ay - R.cy) * ay + (Az - R.cz) * az, lnA = (Ay - R.cy) * ny + (Az - R.cz) * nz;
-    const float laB = (By - R.cy) * ay + (Bz - R.cz) * az, lnB = (By - R.cy) * ny + (Bz - R.cz) * nz;
-    const float reach = radius + p.rest;
-    if (fminf(lnA, lnB) >= R.hn + reach || fmaxf(lnA, lnB) <= -(R.hn + reach) || fminf(laA, laB) >= R.ha + reach ||
-        fmaxf(laA, laB) <= -(R.ha + reach))
-      return;
-  }
+VDEV void capsule_rect(const VineParams& p, const float* R, float Ay, float Az, float By, float Bz, float radius,
+                       bool test_a, bool closed_end, float jy, float jz, float jvy, float jvz, float w, PairLoad& L) {
+  const float cy = R[0], cz = R[1], ay = R[2], az = R[3], ha = R[4], hn = R[5];
+  const float ny = -az, nz = ay;
+  const float reach = radius + p.rest;
+  // separating-axis cull in the rectangle's frame (exact: every distance used below is >= the separation along either
+  // rectangle axis, and a contact needs distance < radius + rest)
+  const float laA = (Ay - cy) * ay + (Az - cz) * az, lnA = (Ay - cy) * ny + (Az - cz) * nz;
+  const float laB = (By - cy) * ay + (Bz - cz) * az, lnB = (By - cy) * ny + (Bz - cz) * nz;
+  if (fminf(lnA, lnB) >= hn + reach || fmaxf(lnA, lnB) <= -(hn + reach) || fminf(laA, laB) >= ha + reach ||
+      fmaxf(laA, laB) <= -(ha + reach))
+    return;
   // (i) capsule end points against the rectangle's faces
-#pragma unroll 1
+#pragma unroll
   for (int e = 0; e < 2; ++e) {
     if (e == 0 && !test_a) continue;
     const float Py = e == 0 ? Ay : By, Pz = e == 0 ? Az : Bz;
-    const float la = (Py - R.cy) * ay + (Pz - R.cz) * az, ln = (Py - R.cy) * ny + (Pz - R.cz) * nz;
-    const float qa = fabsf(la) - R.ha, qn = fabsf(ln) - R.hn;
+    const float la = e == 0 ? laA : laB, ln = e == 0 ? lnA : lnB;
+    const float qa = fabsf(la) - ha, qn = fabsf(ln) - hn;
     if (qa > 0.f && qn > 0.f) continue;  // corner region: handled by (ii)
     float dist, gy, gz;
-    if (qa > qn) { dist = qa; const float s = la < 0.f ? -1.f : 1.f; gy = s * ay; gz = s * az; }
-    else { dist = qn; const float s = ln < 0.f ? -1.f : 1.f; gy = s * ny; gz = s * nz; }
-    contact_point(p, Py, Pz, gy, gz, dist, radius, jy, jz, jvy, jvz, w, L, ofy, ofz);
+    if (qa > qn) { dist = qa; const float sg = la < 0.f ? -1.f : 1.f; gy = sg * ay; gz = sg * az; }
+    else { dist = qn; const float sg = ln < 0.f ? -1.f : 1.f; gy = sg * ny; gz = sg * nz; }
+    contact_point(p, Py, Pz, gy, gz, dist, reach, jy, jz, jvy, jvz, w, L);
   }
   // (ii) rectangle corners against the capsule segment
   const float ey = By - Ay, ez = Bz - Az;
   const float inv_ee = rcp_approx(ey * ey + ez * ez);
-#pragma unroll 1
+#pragma unroll
   for (int c = 0; c < 4; ++c) {
     const float sa = (c & 1) ? 1.f : -1.f, sn = (c & 2) ? 1.f : -1.f;
-    const float Vy = R.cy + sa * R.ha * ay + sn * R.hn * ny, Vz = R.cz + sa * R.ha * az + sn * R.hn * nz;
+    const float Vy = cy + sa * ha * ay + sn * hn * ny, Vz = cz + sa * ha * az + sn * hn * nz;
     float t = ((Vy - Ay) * ey + (Vz - Az) * ez) * inv_ee;
     t = fminf(fmaxf(t, 0.f), 1.f);
     if (t >= 1.f && !closed_end) continue;  // shared joint point belongs to the next link
@@ -261,71 +277,108 @@ VDEV void capsule_rect(const VineParams& p, const Rect& R, float Ay, float Az, f
     const float d2 = dy * dy + dz * dz;
     if (!(d2 > 1e-18f)) continue;
     const float inv = rsqrtf(d2);
-    contact_point(p, Py, Pz, dy * inv, dz * inv, d2 * inv, radius, jy, jz, jvy, jvz, w, L, ofy, ofz);
+    contact_point(p, Py, Pz, dy * inv, dz * inv, d2 * inv, reach, jy, jz, jvy, jvz, w, L);
   }
 }
 
+// conservative per-env cull: link j (both capsules + rest offset lie within `reach` of its midpoint) against rectangle r
+VDEV unsigned cull_pairs(const VineParams& p, const Obstacles& ob, const float* R, const float py[VINE_NL + 1],
+                         const float pz[VINE_NL + 1]) {
+  const float reach = 0.09f + p.rest + VINE_CULL_SLACK;   // sqrt(0.04425^2 + 0.055^2) + 0.0169 = 0.0875 (FPAM side), 0.0824 (main)
+  unsigned pm = 0;
+#pragma unroll 1
+  for (int r = 0; r < ob.n; ++r) {
+    const float cy = R[6 * r], cz = R[6 * r + 1], ay = R[6 * r + 2], az = R[6 * r + 3];
+    const float ta = R[6 * r + 4] + reach, tn = R[6 * r + 5] + reach;
+    unsigned bits = 0;
+#pragma unroll
+    for (int j = 0; j < VINE_NL; ++j) {
+      const float dy = 0.5f * (py[j] + py[j + 1]) - cy, dz = 0.5f * (pz[j] + pz[j + 1]) - cz;
+      if (!(fabsf(dy * ay + dz * az) > ta || fabsf(dz * ay - dy * az) > tn)) bits |= 1u << j;
+    }
+    pm |= bits << (5 * r);
+  }
+  return pm;
+}
+
 // all link-vs-obstacle contacts of one substep; adds generalized forces to f[6], returns |F_lip|
-VDEV float contact_forces(const VineParams& p, const Obstacles& ob, const Dyn& d, float f[6]) {
-  float py[VINE_NL + 1], pz[VINE_NL + 1], vy[VINE_NL + 1], vz[VINE_NL + 1];
-  py[0] = d.x[0]; pz[0] = VINE_PIVOT_Z; vy[0] = d.v[0]; vz[0] = 0.f;
-  float lo_y = py[0], hi_y = py[0], lo_z = pz[0], hi_z = pz[0];
+VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScratch* cs, ContactCache& cc, const Dyn& d, float f[6]) {
+  {
+    // every point of the chain moved at most h (|v_y| + rho sum |w|) in the last substep (rho: farthest point from a joint)
+    float ws = 0.f;
+#pragma unroll
+    for (int j = 0; j < VINE_NL; ++j) ws += fabsf(d.v[j + 1]);
+    cc.disp = fmaf(p.h, fmaf(VINE_LINK_LEN + 0.1f, ws, fabsf(d.v[0])), cc.disp);
+  }
+  const bool stale = !(cc.disp <= VINE_CULL_SLACK);
+  if (!stale && cc.pm == 0u) return 0.f;
+
+  const int lane = threadIdx.x & 31;
+  float py[VINE_NL + 1], pz[VINE_NL + 1];
+  py[0] = d.x[0]; pz[0] = VINE_PIVOT_Z;
 #pragma unroll
   for (int j = 0; j < VINE_NL; ++j) {
     py[j + 1] = fmaf(-VINE_LINK_LEN, d.S[j], py[j]); pz[j + 1] = fmaf(VINE_LINK_LEN, d.C[j], pz[j]);
-    const float lw = VINE_LINK_LEN * d.v[j + 1];
-    vy[j + 1] = fmaf(-lw, d.C[j], vy[j]); vz[j + 1] = fmaf(-lw, d.S[j], vz[j]);
-    lo_y = fminf(lo_y, py[j + 1]); hi_y = fmaxf(hi_y, py[j + 1]);
-    lo_z = fminf(lo_z, pz[j + 1]); hi_z = fmaxf(hi_z, pz[j + 1]);
   }
-  // conservative cull: chain inflated by the widest cross-section (FPAM offset + radius + rest)
-  const float m = VINE_FPAM_OFFSET + VINE_FPAM_RADIUS + p.rest + 1e-3f;
-  if (hi_y + m < ob.lo_y || lo_y - m > ob.hi_y || hi_z + m < ob.lo_z || lo_z - m > ob.hi_z) return 0.f;
-
-  LinkLoad L[VINE_NL];
-  float lfy = 0.f, lfz = 0.f;
+  const float* R = cs->rect[lane];
+  if (stale) {
+    float lo_y = py[0], hi_y = py[0], lo_z = pz[0], hi_z = pz[0];
 #pragma unroll
-  for (int j = 0; j < VINE_NL; ++j) {
-    L[j] = {0.f, 0.f, 0.f};
-    const bool last = (j == VINE_NL - 1);
-    // main cylinder URDF:95-99 as a capsule; the last one is shortened so its cap ends at the tip
-    const float By = last ? fmaf(VINE_LINK_RADIUS, d.S[j], py[j + 1]) : py[j + 1];
-    const float Bz = last ? fmaf(-VINE_LINK_RADIUS, d.C[j], pz[j + 1]) : pz[j + 1];
-    // FPAM cylinder URDF:110-114, offset along the link's local +y = (cos phi, sin phi)
-    const float oy = VINE_FPAM_OFFSET * d.C[j], oz = VINE_FPAM_OFFSET * d.S[j];
-    const float FBy = py[j + 1] + oy + (last ? VINE_FPAM_RADIUS * d.S[j] : 0.f);
-    const float FBz = pz[j + 1] + oz - (last ? VINE_FPAM_RADIUS * d.C[j] : 0.f);
-    // per (link, rectangle) cull in the rectangle's frame: everything of this link (both capsules + rest offset) lies
-    // within `reach` of the link's midpoint, so a pair farther than that from the rectangle contributes exactly zero
-    const float my = 0.5f * (py[j] + py[j + 1]), mz = 0.5f * (pz[j] + pz[j + 1]);
-    const float reach = 0.09f + p.rest;   // sqrt(0.04425^2 + 0.055^2) + 0.0169 = 0.0875 (FPAM side), 0.0824 (main)
-#pragma unroll 1
-    for (int r = 0; r < ob.n; ++r) {
-      {
-        const Rect& R = ob.r[r];
-        const float dy = my - R.cy, dz = mz - R.cz;
-        if (fabsf(dy * R.ay + dz * R.az) > R.ha + reach || fabsf(dz * R.ay - dy * R.az) > R.hn + reach) continue;
-      }
-      float ofy = 0.f, ofz = 0.f;
-#pragma unroll 1
-      for (int cap = 0; cap < 2; ++cap) {   // main cylinder, FPAM cylinder: one rolled copy of the narrow phase (code size)
-        const bool fp = cap != 0;
-        capsule_rect(p, ob.r[r], fp ? py[j] + oy : py[j], fp ? pz[j] + oz : pz[j], fp ? FBy : By, fp ? FBz : Bz,
-                     fp ? VINE_FPAM_RADIUS : VINE_LINK_RADIUS, fp || j == 0, fp || last, py[j], pz[j], vy[j], vz[j], d.v[j + 1],
-                     L[j], ofy, ofz);
-      }
-      if (r == ob.lip) { lfy += ofy; lfz += ofz; }
+    for (int j = 1; j <= VINE_NL; ++j) {
+      lo_y = fminf(lo_y, py[j]); hi_y = fmaxf(hi_y, py[j]); lo_z = fminf(lo_z, pz[j]); hi_z = fmaxf(hi_z, pz[j]);
+    }
+    // chain inflated by the widest cross-section (FPAM offset + radius) + rest + slack against the obstacles' bounding box:
+    // with a gap between the two no contact is possible until the chain has moved gap + slack
+    const float m = VINE_FPAM_OFFSET + VINE_FPAM_RADIUS + p.rest + 1e-3f + VINE_CULL_SLACK;
+    const float gap = fmaxf(fmaxf(lo_y - m - ob.hi_y, ob.lo_y - (hi_y + m)), fmaxf(lo_z - m - ob.hi_z, ob.lo_z - (hi_z + m)));
+    if (gap > 0.f) { cc.pm = 0u; cc.disp = -gap; }
+    else { cc.pm = cull_pairs(p, ob, R, py, pz); cc.disp = 0.f; }
+    if (cc.pm == 0u) return 0.f;
+  }
+  // publish this env's chain in its column of the warp's scratch: the narrow phase picks its link by a run-time index
+  {
+    float* ch = &cs->chain[0][lane];
+    float vy = d.v[0], vz = 0.f;
+    ch[32 * CH_PY] = py[0]; ch[32 * CH_PZ] = pz[0]; ch[32 * CH_VY] = vy; ch[32 * CH_VZ] = vz;
+#pragma unroll
+    for (int j = 0; j < VINE_NL; ++j) {
+      const float lw = VINE_LINK_LEN * d.v[j + 1];
+      vy = fmaf(-lw, d.C[j], vy); vz = fmaf(-lw, d.S[j], vz);
+      ch[32 * (CH_PY + j + 1)] = py[j + 1]; ch[32 * (CH_PZ + j + 1)] = pz[j + 1];
+      ch[32 * (CH_VY + j + 1)] = vy; ch[32 * (CH_VZ + j + 1)] = vz;
+      ch[32 * (CH_S + j)] = d.S[j]; ch[32 * (CH_C + j)] = d.C[j]; ch[32 * (CH_W + j)] = d.v[j + 1];
     }
   }
-  // generalized forces: Q_y = sum F;  Q_j = T_j + (p_{j+1} - p_j) x sum_{m>j} F_m
-  float sy = 0.f, sz = 0.f;
+  float lfy = 0.f, lfz = 0.f;
+  unsigned pm = cc.pm;
+#pragma unroll 1
+  while (pm) {
+    const int b = __ffs(pm) - 1;
+    pm &= pm - 1;
+    const int r = b / 5, j = b - 5 * r;
+    const float* ch = &cs->chain[j][lane];
+    const float jy = ch[32 * CH_PY], jz = ch[32 * CH_PZ], ty = ch[32 * (CH_PY + 1)], tz = ch[32 * (CH_PZ + 1)];
+    const float jvy = ch[32 * CH_VY], jvz = ch[32 * CH_VZ], S = ch[32 * CH_S], C = ch[32 * CH_C], w = ch[32 * CH_W];
+    const bool last = j == VINE_NL - 1;
+    PairLoad L = {0.f, 0.f, 0.f};
+    // main cylinder URDF:95-99 as a capsule; the last link's capsules are shortened so that their caps end at the tip
+    capsule_rect(p, R + 6 * r, jy, jz, last ? fmaf(VINE_LINK_RADIUS, S, ty) : ty, last ? fmaf(-VINE_LINK_RADIUS, C, tz) : tz,
+                 VINE_LINK_RADIUS, j == 0, last, jy, jz, jvy, jvz, w, L);
+    // FPAM cylinder URDF:110-114, offset along the link's local +y = (cos phi, sin phi)
+    const float oy = VINE_FPAM_OFFSET * C, oz = VINE_FPAM_OFFSET * S;
+    capsule_rect(p, R + 6 * r, jy + oy, jz + oz, ty + oy + (last ? VINE_FPAM_RADIUS * S : 0.f),
+                 tz + oz - (last ? VINE_FPAM_RADIUS * C : 0.f), VINE_FPAM_RADIUS, true, true, jy, jz, jvy, jvz, w, L);
+    if (L.fy != 0.f || L.fz != 0.f) {
+      // generalized forces: Q_y = F;  Q_j = T_j;  Q_m = (p_{m+1} - p_m) x F for the links m < j below the contact
+      f[0] += L.fy;
 #pragma unroll
-  for (int j = VINE_NL - 1; j >= 0; --j) {
-    const float ry = py[j + 1] - py[j], rz = pz[j + 1] - pz[j];
-    f[j + 1] += L[j].t + (ry * sz - rz * sy);
-    sy += L[j].fy; sz += L[j].fz;
+      for (int m = 0; m < VINE_NL; ++m) {
+        const float q = m == j ? L.t : (py[m + 1] - py[m]) * L.fz - (pz[m + 1] - pz[m]) * L.fy;
+        if (m <= j) f[m + 1] += q;
+      }
+      if (r == ob.lip) { lfy -= L.fy; lfz -= L.fz; }
+    }
   }
-  f[0] += sy;
   return sqrtf(lfy * lfy + lfz * lfz);
 }
 
@@ -358,7 +411,8 @@ VDEV void joint_implicit_consts(const VineParams& p, const JointLaw& law, float 
 //   P_j = sum_{m>j} L beta_m a_m + L beta_j sum_{m<j} a_m  (Q_j likewise with b):
 //   f_j = S_j (g beta_j - P_j) + C_j Q_j ,   f_y = F - D v_y - (1/L) sum_m L beta_m b_m
 template <bool CONTACT>
-VDEV void substep(const VineParams& p, const JointImp& J, float rail_force, const Obstacles* ob, Dyn& d, float& lip) {
+VDEV void substep(const VineParams& p, const JointImp& J, float rail_force, const Obstacles& ob, ContactScratch* cs, ContactCache& cc,
+                  Dyn& d, float& lip) {
   float a[VINE_NL], b[VINE_NL], As[VINE_NL], Bs[VINE_NL];
 #pragma unroll
   for (int j = 0; j < VINE_NL; ++j) { const float w2 = d.v[j + 1] * d.v[j + 1]; a[j] = d.C[j] * w2; b[j] = d.S[j] * w2; }
@@ -391,7 +445,7 @@ VDEV void substep(const VineParams& p, const JointImp& J, float rail_force, cons
       tn = t;
     }
   }
-  if (CONTACT) lip = contact_forces(p, *ob, d, f);
+  if (CONTACT) lip = contact_forces(p, ob, cs, cc, d, f);
   // lower triangle of the SPD system matrix; rows/cols: 0 = cart, 1..5 = links
   float M[6][6];
   M[0][0] = J.m00;
