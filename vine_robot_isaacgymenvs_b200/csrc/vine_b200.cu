@@ -11,6 +11,7 @@
 // VecTask buffers (obs/rew/reset/progress/timeout) are torch-owned row-major tensors (VT:260-283).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "vine_device.cuh"
 
@@ -34,6 +35,9 @@ struct StepArgs {
   float* obs; float* obs_clamped; float* rew;
   int64_t* reset; int64_t* progress; uint8_t* timeout;
   float* dbg;  // [N, VINE_DBG_W] or nullptr
+  // contact variant only (else nullptr): per-env "had contact candidates in its last step" flag, the env order of this launch
+  // (envs with the flag first, so that they share warps) and the two cursors the binning kernel fills it with
+  uint8_t* near; int32_t* perm; int32_t* bin_cursor;
 };
 
 struct VineEnv {
@@ -96,8 +100,10 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
   __shared__ float s_obs[BLOCK * (VINE_MAX_OBS + 1)];
   __shared__ ContactScratch s_contact[CONTACT ? BLOCK / 32 : 1];
   ContactScratch* cs = &s_contact[CONTACT ? threadIdx.x >> 5 : 0];
-  const int64_t e = a.first + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (e < a.end) {
+  const int64_t slot = a.first + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  const bool live = slot < a.end;
+  const int64_t e = (CONTACT && a.perm && live) ? (int64_t)a.perm[slot] : slot;
+  if (live) {
     const float4 s0 = a.S0[e], s1 = a.S1[e], s2 = a.S2[e], s3 = a.S3[e], s4 = a.S4[e], s5 = a.S5[e];
     float q[6] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y};
     float qd[6] = {s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
@@ -138,7 +144,7 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
     const float u_use = p.use_smoothed ? smoothed : u_fpam;                // V5:1059
 
     Obstacles ob = {0, -1, 0.f, 0.f, 0.f, 0.f};
-    ContactCache cc = {0u, 1e30f};   // no candidate pairs yet: the first substep culls
+    ContactCache cc = {0u, 1e30f, 0u};   // no candidate pairs yet: the first substep culls
     if (CONTACT) build_obstacles(p, target[1], target[2], obj[0], obj[1], cs, ob);
 
     // ---- controlFrequencyInv x {forces, contact sample, simulate}  VT:338-356 ----
@@ -256,6 +262,7 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
     a.reset[e] = o.reset;
     a.progress[e] = progress;
     a.timeout[e] = o.timeout;
+    if (CONTACT && a.near) a.near[e] = cc.seen != 0u;
     float* row = s_obs + threadIdx.x * (VINE_MAX_OBS + 1);
 #pragma unroll
     for (int i = 0; i < VINE_MAX_OBS; ++i) if (i < p.O) row[i] = o.obs[i];
@@ -268,7 +275,51 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
     }
   }
   __syncthreads();
-  store_obs_block<BLOCK>(s_obs, p.O, a.first, a.end, p.clip_obs, a.obs, a.obs_clamped);
+  if (CONTACT && a.perm) {
+    // binned launch: the block's rows belong to scattered envs; one row (O <= 32 floats) per warp-wide store
+    const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+    const int64_t mine = live ? e : -1;
+#pragma unroll 1
+    for (int r = 0; r < 32; ++r) {
+      const int64_t er = __shfl_sync(0xffffffffu, mine, r);
+      if (er >= 0 && lane < p.O) {
+        float v = s_obs[(w0 + r) * (VINE_MAX_OBS + 1) + lane];
+        a.obs[er * p.O + lane] = v;
+        if (a.obs_clamped) a.obs_clamped[er * p.O + lane] = fminf(fmaxf(v, -p.clip_obs), p.clip_obs);
+      }
+    }
+  } else {
+    store_obs_block<BLOCK>(s_obs, p.O, a.first, a.end, p.clip_obs, a.obs, a.obs_clamped);
+  }
+}
+
+// Env order of a binned launch of the contact variant: envs that had contact candidates in their last step first, the others
+// from the back. A warp then runs the narrow phase with most of its lanes or none; per-env results do not depend on the
+// order (no cross-lane arithmetic), so the unordered cursors are fine.
+__global__ void __launch_bounds__(1024) vine_bin_kernel(const StepArgs a) {
+  __shared__ int s_near[32], s_far[32], s_base[2];
+  const int64_t e = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  const bool valid = e < a.n, nr = valid && a.near[e] != 0;
+  const unsigned bn = __ballot_sync(0xffffffffu, nr), bf = __ballot_sync(0xffffffffu, valid && !nr);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_near[warp] = __popc(bn); s_far[warp] = __popc(bf); }
+  __syncthreads();
+  if (warp == 0) {
+    const int cn = s_near[lane], cf = s_far[lane];
+    int in = cn, jf = cf;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int tn = __shfl_up_sync(0xffffffffu, in, off), tf = __shfl_up_sync(0xffffffffu, jf, off);
+      if (lane >= off) { in += tn; jf += tf; }
+    }
+    s_near[lane] = in - cn; s_far[lane] = jf - cf;   // exclusive prefix over the warps of this block
+    if (lane == 31) { s_base[0] = atomicAdd(a.bin_cursor, in); s_base[1] = atomicAdd(a.bin_cursor + 1, jf); }
+  }
+  __syncthreads();
+  if (!valid) return;
+  const unsigned lt = (1u << lane) - 1u;
+  if (nr) a.perm[s_base[0] + s_near[warp] + __popc(bn & lt)] = (int32_t)e;
+  else a.perm[a.n - 1 - (s_base[1] + s_far[warp] + __popc(bf & lt))] = (int32_t)e;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -464,7 +515,7 @@ __global__ void __launch_bounds__(VINE_BLOCK) vine_simulate_kernel(const __grid_
   }
   const float u_use = io.u_fpam_to_use ? io.u_fpam_to_use[e] : 0.f;
   Obstacles ob = {0, -1, 0.f, 0.f, 0.f, 0.f};
-  ContactCache cc = {0u, 1e30f};
+  ContactCache cc = {0u, 1e30f, 0u};
   if (CONTACT) build_obstacles(p, io.target_positions[3 * e + 1], io.target_positions[3 * e + 2],
                                io.object_info[2 * e], io.object_info[2 * e + 1], cs, ob);
   Dyn d; rel_to_abs(p, q, qd, d);
@@ -566,6 +617,7 @@ void vine_destroy(VineEnv* env) {
   cudaSetDevice(env->device);
   cudaFree(env->a.S0); cudaFree(env->a.S1); cudaFree(env->a.S2); cudaFree(env->a.S3); cudaFree(env->a.S4);
   cudaFree(env->a.S5); cudaFree(env->a.ring); cudaFree(env->a.ctr); cudaFree(env->a.dbg);
+  cudaFree(env->a.near); cudaFree(env->a.perm); cudaFree(env->a.bin_cursor);
   delete env;
 }
 
@@ -591,6 +643,14 @@ int vine_create(const VineConfig* cfg, int64_t num_envs, int64_t global_env_offs
   if (e == cudaSuccess) e = cudaMalloc(&a.S5, n * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&a.ring, n * sizeof(float2) * (size_t)(p.D > 0 ? p.D : 1));
   if (e == cudaSuccess) e = cudaMalloc(&a.ctr, n * sizeof(uint32_t));
+  // contact variant: bin the envs by "had contact candidates" before every full step (VINE_CONTACT_BINNING=0 turns it off)
+  const char* binning = getenv("VINE_CONTACT_BINNING");
+  if ((p.shelf || p.pipe) && !(binning && binning[0] == '0')) {
+    if (e == cudaSuccess) e = cudaMalloc(&a.near, n);
+    if (e == cudaSuccess) e = cudaMemset(a.near, 0, n);
+    if (e == cudaSuccess) e = cudaMalloc(&a.perm, n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&a.bin_cursor, 2 * sizeof(int32_t));
+  }
   if (e == cudaSuccess) {
     vine_init_kernel<<<grid_for(num_envs, 256), 256>>>(env->p, env->a);
     e = cudaGetLastError();
@@ -742,12 +802,27 @@ int vine_metrics(VineEnv* env, double* sums, float* maxes, void* stream) {
   return VINE_OK;
 }
 
+// The contact variant bins its envs (vine_bin_kernel) only for large launches: small ones are latency-bound (one wave, the
+// slowest warp sets the time) and a warp full of envs with candidates is the slowest there is. Putting fewer envs into each
+// warp of a small launch was measured too and changes nothing: the time is one env's own contact chain, not the lanes' sum.
+#define VINE_BIN_MIN_ENVS 98304   // measured crossover on B200: binning pays from ~100 k envs per launch (shelf and pipe presets)
+
 int vine_step(VineEnv* env, void* stream) {
   if (!env) return VINE_ERR_INVALID_ARG;
   if (!env->bound) { snprintf(env->err, 256, "vine_step: call vine_bind_io first"); return VINE_ERR_NOT_BOUND; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (env->p.shelf || env->p.pipe) vine_step_kernel<true><<<grid_for(env->a.n, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, st>>>(env->p, env->a);
-  else vine_step_kernel<false><<<grid_for(env->a.n, VINE_BLOCK), VINE_BLOCK, 0, st>>>(env->p, env->a);
+  if (env->p.shelf || env->p.pipe) {
+    StepArgs a = env->a;
+    if (a.perm && a.n >= VINE_BIN_MIN_ENVS) {
+      CUDA_TRY(env, cudaMemsetAsync(a.bin_cursor, 0, 2 * sizeof(int32_t), st));
+      vine_bin_kernel<<<grid_for(a.n, 1024), 1024, 0, st>>>(a);
+    } else {
+      a.perm = nullptr;
+    }
+    vine_step_kernel<true><<<grid_for(a.n, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, st>>>(env->p, a);
+  } else {
+    vine_step_kernel<false><<<grid_for(env->a.n, VINE_BLOCK), VINE_BLOCK, 0, st>>>(env->p, env->a);
+  }
   CUDA_TRY(env, cudaGetLastError());
   return VINE_OK;
 }
@@ -761,6 +836,7 @@ int vine_step_range(VineEnv* env, int64_t first, int64_t count, void* stream) {
   }
   StepArgs a = env->a;
   a.first = first; a.end = first + count;
+  a.perm = nullptr;   // chunked launches keep the identity order (the near flags are still maintained)
   if (env->p.shelf || env->p.pipe) vine_step_kernel<true><<<grid_for(count, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, (cudaStream_t)stream>>>(env->p, a);
   else vine_step_kernel<false><<<grid_for(count, VINE_BLOCK), VINE_BLOCK, 0, (cudaStream_t)stream>>>(env->p, a);
   CUDA_TRY(env, cudaGetLastError());

@@ -137,7 +137,7 @@ struct ContactScratch {
 struct Obstacles { int n, lip; float lo_y, hi_y, lo_z, hi_z; };
 // candidate (link, rectangle) pairs of one env (bit 5 r + j) and a bound on how far any point of the chain has moved since
 // they were culled (negative: distance still to go before the chain can reach the obstacles' bounding box); registers
-struct ContactCache { unsigned pm; float disp; };
+struct ContactCache { unsigned pm; float disp; unsigned seen; };   // seen: OR of every mask of this control step
 #define VINE_CULL_SLACK 0.02f
 
 VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, float theta, ContactScratch* cs, Obstacles& ob) {
@@ -332,7 +332,7 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScrat
     const float m = VINE_FPAM_OFFSET + VINE_FPAM_RADIUS + p.rest + 1e-3f + VINE_CULL_SLACK;
     const float gap = fmaxf(fmaxf(lo_y - m - ob.hi_y, ob.lo_y - (hi_y + m)), fmaxf(lo_z - m - ob.hi_z, ob.lo_z - (hi_z + m)));
     if (gap > 0.f) { cc.pm = 0u; cc.disp = -gap; }
-    else { cc.pm = cull_pairs(p, ob, R, py, pz); cc.disp = 0.f; }
+    else { cc.pm = cull_pairs(p, ob, R, py, pz); cc.disp = 0.f; cc.seen |= cc.pm; }
     if (cc.pm == 0u) return 0.f;
   }
   // publish this env's chain in its column of the warp's scratch: the narrow phase picks its link by a run-time index
