@@ -152,11 +152,15 @@ def test_long_random_rollout_stays_physical():
     assert float(tip[:, 2].max()) < 1.42 and float(tip[:, 2].min()) > 0.5      # within the chain's reach of the pivot
 
 
-@pytest.mark.parametrize("preset,n", [("SHELF_OVERRIDES", 16384), ("PIPE_DR_OVERRIDES", 65536)], ids=["configs2_shelf", "configs3_pipe_dr"])
+@pytest.mark.parametrize("preset,n", [("SHELF_OVERRIDES", 16384), ("PIPE_DR_OVERRIDES", 65536), ("SHELF_OVERRIDES", 131072),
+                                      ("PIPE_DR_OVERRIDES", 131072)],
+                         ids=["configs2_shelf", "configs3_pipe_dr", "shelf_binned_launch", "pipe_dr_binned_launch"])
 def test_contact_configs_at_baseline_sizes_are_deterministic_shard_invariant_and_physical(preset, n):
     """BASELINE configs[2] / configs[3] at their full env counts, through size-independent properties: bit-identical
     reruns, bit-identical under 4-way sharding by global env id (the 8-GPU layout of configs[3]), finite and bounded
-    state after a random rollout that pushes half the envs into the obstacles."""
+    state after a random rollout that pushes half the envs into the obstacles. At 131072 envs the whole-batch launches bin
+    the envs by contact candidates (vine_bin_kernel) while the four 32768-env shards step in identity order, so the same
+    comparison pins the binned launch bit for bit against the unbinned one."""
     import vine_robot_isaacgymenvs_b200 as vine
     from vine_robot_isaacgymenvs_b200 import config as vcfg
     ov = getattr(vcfg, preset) + ["headless=True", "task.env.maxEpisodeLength=40"]
