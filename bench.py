@@ -400,7 +400,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         cores = host_threads()
         cn = 65536
-        rate, steps, dt = cpu_oracle_rate(cn, budget_s=12.0)
+        rate, steps, dt = cpu_oracle_rate(cn, budget_s=12.0, max_steps=512)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{cn} envs x {steps} control steps ({dt:.1f} s), oracle f32 dynamics, OpenMP x{cores}"}
 
