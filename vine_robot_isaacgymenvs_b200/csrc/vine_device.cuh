@@ -138,7 +138,6 @@ struct Obstacles { int n, lip; float lo_y, hi_y, lo_z, hi_z; };
 // candidate (link, rectangle) pairs of one env (bit 5 r + j) and a bound on how far any point of the chain has moved since
 // they were culled (negative: distance still to go before the chain can reach the obstacles' bounding box); registers
 struct ContactCache { unsigned pm; float disp; unsigned seen; };   // seen: OR of every mask of this control step
-#define VINE_CULL_SLACK 0.02f
 
 VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, float theta, ContactScratch* cs, Obstacles& ob) {
   float* R = cs->rect[threadIdx.x & 31];
@@ -217,7 +216,7 @@ VDEV void tip_fk(const Dyn& d, float& ty, float& tz, float& tvy, float& tvz) {
 // ---- penalty contact, frictionless (V5:477,491,499) ----
 // Contacts are rare per env but common per warp, and everything an env does about them runs with ~1 of 32 lanes active,
 // i.e. at the latency of one dependent instruction chain.  So the chain is kept short: each env carries a conservative
-// candidate mask of (link, rectangle) pairs that is re-culled only after the chain has moved VINE_CULL_SLACK since the
+// candidate mask of (link, rectangle) pairs that is re-culled only after the chain has moved p.cull_slack since the
 // last cull (a substep without candidates costs 12 instructions), and there is ONE copy of the narrow phase, entered per
 // candidate pair with the link picked by a run-time index into shared memory, its 2 capsules x (2 end points + 4 rectangle
 // corners) unrolled so the twelve independent point tests overlap.
@@ -284,7 +283,7 @@ VDEV void capsule_rect(const VineParams& p, const float* R, float Ay, float Az, 
 // conservative per-env cull: link j (both capsules + rest offset lie within `reach` of its midpoint) against rectangle r
 VDEV unsigned cull_pairs(const VineParams& p, const Obstacles& ob, const float* R, const float py[VINE_NL + 1],
                          const float pz[VINE_NL + 1]) {
-  const float reach = 0.09f + p.rest + VINE_CULL_SLACK;   // sqrt(0.04425^2 + 0.055^2) + 0.0169 = 0.0875 (FPAM side), 0.0824 (main)
+  const float reach = 0.09f + p.rest + p.cull_slack;   // sqrt(0.04425^2 + 0.055^2) + 0.0169 = 0.0875 (FPAM side), 0.0824 (main)
   unsigned pm = 0;
 #pragma unroll 1
   for (int r = 0; r < ob.n; ++r) {
@@ -310,7 +309,7 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScrat
     for (int j = 0; j < VINE_NL; ++j) ws += fabsf(d.v[j + 1]);
     cc.disp = fmaf(p.h, fmaf(VINE_LINK_LEN + 0.1f, ws, fabsf(d.v[0])), cc.disp);
   }
-  const bool stale = !(cc.disp <= VINE_CULL_SLACK);
+  const bool stale = !(cc.disp <= p.cull_slack);
   if (!stale && cc.pm == 0u) return 0.f;
 
   const int lane = threadIdx.x & 31;
@@ -329,7 +328,7 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScrat
     }
     // chain inflated by the widest cross-section (FPAM offset + radius) + rest + slack against the obstacles' bounding box:
     // with a gap between the two no contact is possible until the chain has moved gap + slack
-    const float m = VINE_FPAM_OFFSET + VINE_FPAM_RADIUS + p.rest + 1e-3f + VINE_CULL_SLACK;
+    const float m = VINE_FPAM_OFFSET + VINE_FPAM_RADIUS + p.rest + 1e-3f + p.cull_slack;
     const float gap = fmaxf(fmaxf(lo_y - m - ob.hi_y, ob.lo_y - (hi_y + m)), fmaxf(lo_z - m - ob.hi_z, ob.lo_z - (hi_z + m)));
     if (gap > 0.f) { cc.pm = 0u; cc.disp = -gap; }
     else { cc.pm = cull_pairs(p, ob, R, py, pz); cc.disp = 0.f; cc.seen |= cc.pm; }

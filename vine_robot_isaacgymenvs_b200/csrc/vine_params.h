@@ -35,6 +35,7 @@ struct VineParams {
   // controller (V5:1064-1098)
   float dt, control_dt, rail_force_max, rail_accel, p_gain, d_gain;
   float dyn_min, dyn_rng, acc_min, acc_rng;
+  float cull_slack;   // contact variant: how far a chain may move before its candidate pairs are re-culled (m)
   // reward / reset (V5:1218-1248)
   float soft_limit, success_dist;
   float w[VINE_NUM_REWARDS];
