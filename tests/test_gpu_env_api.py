@@ -188,6 +188,25 @@ def test_contact_configs_at_baseline_sizes_are_deterministic_shard_invariant_and
     assert early_resets > 0
 
 
+def test_binned_contact_launch_with_a_ragged_tail_equals_unbinned_shards():
+    """98,341 envs (not a multiple of the warp or of the 1024-env binning block) step through the binned launch; two shards
+    below the binning threshold cover the same global env ids in identity order. Bit-identical outputs and state."""
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    n, n0 = 98304 + 37, 49152
+    ov = vcfg.SHELF_OVERRIDES + ["headless=True", "task.env.maxEpisodeLength=30"]
+    make = lambda m, off=0: vine.make(cfg=vcfg.compose(ov + [f"num_envs={m}"]), global_env_offset=off)  # noqa: E731
+    whole, lo, hi = make(n), make(n0), make(n - n0, n0)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(45):
+        act = torch.rand(n, 2, device="cuda", generator=g) * 2.4 - 1.2
+        act[: n // 2, 1] = act[: n // 2, 1].abs()
+        whole.step(act); lo.step(act[:n0]); hi.step(act[n0:])
+    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "timeout_buf", "dof_pos", "dof_vel", "tip_positions"):
+        assert torch.equal(getattr(whole, name), torch.cat([getattr(lo, name), getattr(hi, name)])), name
+    assert int((whole.reset_buf != 0).sum()) > 0
+
+
 def test_metrics_kernel_matches_the_reference_wandb_formulas():
     """vine_metrics vs the formulas of compute_reward's wandb_dict (V5:1250-1322) evaluated with torch on the exposed state."""
     import vine_robot_isaacgymenvs_b200 as vine
