@@ -207,6 +207,31 @@ def test_binned_contact_launch_with_a_ragged_tail_equals_unbinned_shards():
     assert int((whole.reset_buf != 0).sum()) > 0
 
 
+@pytest.mark.parametrize("preset", ["FSTR_OVERRIDES", "SHELF_OVERRIDES", "PIPE_DR_OVERRIDES"])
+def test_ragged_and_single_env_batches_equal_the_head_of_a_larger_batch(preset):
+    """Edge sizes: 1 env and 33 envs (one lane past a warp) produce, bit for bit, what envs 0 and 0..32 of a 200-env batch
+    produce (same global env ids, same actions); reset_idx accepts an empty id list and a full one."""
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    ov = getattr(vcfg, preset) + ["headless=True", "task.env.maxEpisodeLength=7"]
+    make = lambda m: vine.make(cfg=vcfg.compose(ov + [f"num_envs={m}"]))  # noqa: E731
+    big, one, ragged = make(200), make(1), make(33)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(20):
+        act = torch.rand(200, 2, device="cuda", generator=g) * 2.4 - 1.2
+        act[:, 1] = act[:, 1].abs()
+        big.step(act); one.step(act[:1]); ragged.step(act[:33])
+        if t == 9:   # an explicit reset of everything, and an empty one, in all three
+            for env, m in ((big, 200), (one, 1), (ragged, 33)):
+                env.reset_idx(torch.zeros(0, dtype=torch.long, device="cuda"))
+                env.reset_idx(torch.arange(m, device="cuda"))
+    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "timeout_buf", "dof_pos", "dof_vel", "target_positions"):
+        b = getattr(big, name)
+        assert torch.equal(getattr(one, name), b[:1]), (name, "1 env")
+        assert torch.equal(getattr(ragged, name), b[:33]), (name, "33 envs")
+    assert bool(torch.isfinite(big.obs_buf).all())
+
+
 def test_metrics_kernel_matches_the_reference_wandb_formulas():
     """vine_metrics vs the formulas of compute_reward's wandb_dict (V5:1250-1322) evaluated with torch on the exposed state."""
     import vine_robot_isaacgymenvs_b200 as vine
