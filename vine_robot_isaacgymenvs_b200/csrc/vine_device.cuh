@@ -29,6 +29,15 @@ VDEV uint4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32
 // 1/x as one MUFU.RCP (__fdividef(1, x) adds a range check and a scaling multiply per call; the pivots of the SPD system
 // matrix and squared edge lengths are far inside the normal range)
 VDEV float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// IEEE a / b (round to nearest) for the task logic that must match torch bit for bit. div.rn's fast path (FCHK) sends the whole
+// warp through a ~50-instruction subroutine whenever one lane's numerator is zero, and the observation row is full of exact
+// zeros (x components, depth and angle without an obstacle): ncu showed 20 such calls per warp and step, 17 % of the stall
+// samples. 0 / b = 0 with the sign of a xor b for every finite non-zero b, so those lanes divide 1 by b and select.
+VDEV float div_rn(float a, float b) {
+  const bool bypass = a == 0.f && fabsf(b) > 0.f && fabsf(b) < __int_as_float(0x7f800000);
+  const float q = __fdiv_rn(bypass ? 1.f : a, b);
+  return bypass ? __int_as_float(__float_as_int(a) ^ (__float_as_int(b) & (int)0x80000000)) : q;
+}
 VDEV float u01(uint32_t x) { return __fmul_rn((float)(x >> 8), 5.9604644775390625e-08f); }  // [0,1)
 VDEV float uniform_ab(uint32_t x, float lo, float rng) { return __fmaf_rn(u01(x), rng, lo); }
 // 16-bit draw h in [0, 65536) -> lo + (h 2^-16) rng with rng16 = rng * 2^-16 (the power-of-two scaling of either factor
@@ -72,7 +81,7 @@ VDEV void normal4(uint4 r, float out[4]) {
 // ------------------------------------------------------------------------------------------
 VDEV void rescale_actions(const VineParams& p, float a0, float a1, float& new_rail, float& new_fpam) {
   new_rail = __fmul_rn(a0, p.rail_scale);
-  new_fpam = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(a1, 1.0f), 2.0f), p.fpam_range), p.fpam_min);
+  new_fpam = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(a1, 1.0f), 0.5f), p.fpam_range), p.fpam_min);   // x / 2 == x * 0.5 exactly
 }
 
 VDEV void apply_overrides_and_smooth(const VineParams& p, float& u_rail, float& u_fpam, float& smoothed) {
@@ -110,7 +119,7 @@ VDEV float rail_controller(const VineParams& p, float cart_vel_y, float u_rail, 
                            float& prev_cart_vel, float& prev_err) {
   const float err = __fsub_rn(u_rail, cart_vel_y);
   float minmax = (err > 0.0f) ? p.rail_force_max : -p.rail_force_max;
-  const float accel = __fdiv_rn(__fsub_rn(cart_vel_y, prev_cart_vel), p.dt);          // V5:1079
+  const float accel = div_rn(__fsub_rn(cart_vel_y, prev_cart_vel), p.dt);          // V5:1079
   float accel_target = (err > 0.0f) ? p.rail_accel : -p.rail_accel;
   accel_target = __fmul_rn(accel_target, acc_scale);                                   // README.md:63 knob
   minmax = __fadd_rn(minmax, __fmul_rn(0.30f, __fsub_rn(accel_target, accel)));       // V5:1083-1087
@@ -527,9 +536,9 @@ struct PostOut { float obs[VINE_MAX_OBS]; float rew; float r[VINE_NUM_REWARDS]; 
 VDEV void observation_row(const VineParams& p, const PostIn& in, float raw[VINE_MAX_OBS]) {
   float fdq[6], fdt[3];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) fdq[i] = __fdiv_rn(__fsub_rn(in.q[i], in.prev_q[i]), p.control_dt);      // V5:1347
+  for (int i = 0; i < 6; ++i) fdq[i] = div_rn(__fsub_rn(in.q[i], in.prev_q[i]), p.control_dt);      // V5:1347
 #pragma unroll
-  for (int i = 0; i < 3; ++i) fdt[i] = __fdiv_rn(__fsub_rn(in.tip[i], in.prev_tip[i]), p.control_dt);  // V5:1348
+  for (int i = 0; i < 3; ++i) fdt[i] = div_rn(__fsub_rn(in.tip[i], in.prev_tip[i]), p.control_dt);  // V5:1348
   const int t = p.obs_type;
   int k = 0;
 #pragma unroll
@@ -572,7 +581,7 @@ VDEV void post_physics(const VineParams& p, const PostIn& in, const float* noise
   observation_row(p, in, raw);
 #pragma unroll
   for (int i = 0; i < VINE_MAX_OBS; ++i) {
-    float v = __fdiv_rn(raw[i], p.obs_scale[i]);                            // V5:1385
+    float v = div_rn(raw[i], p.obs_scale[i]);                            // V5:1385
     if (noise != nullptr && i < p.O) v = __fadd_rn(v, __fmul_rn(p.obs_noise, noise[i]));  // V5:1388-1390
     o.obs[i] = v;
   }
@@ -586,7 +595,7 @@ VDEV void post_physics(const VineParams& p, const PostIn& in, const float* noise
     float s = in.contact[0];
 #pragma unroll
     for (int i = 1; i < VINE_MAX_CFI; ++i) if (i < p.C) s = __fadd_rn(s, in.contact[i]);
-    contact = __fdiv_rn(s, (float)p.C);
+    contact = div_rn(s, (float)p.C);
     nonzero = contact > 0.f;
   }
   float* r = o.r;
