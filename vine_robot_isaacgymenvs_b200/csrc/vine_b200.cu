@@ -71,8 +71,10 @@ __device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64
   const int count2 = rows * O / 2;  // O is even for every ObservationType
   float2* g = reinterpret_cast<float2*>(obs + row0 * O);
   float2* gc = obs_clamped ? reinterpret_cast<float2*>(obs_clamped + row0 * O) : nullptr;
+  const float inv_O = 1.0f / (float)O;
   for (int i = threadIdx.x; i < count2; i += BLOCK) {
-    const int e0 = 2 * i, r0 = e0 / O, c0 = e0 - r0 * O;  // c0 even, c0+1 < O
+    // r0 = e0 / O without the 20-instruction integer division (exact: e0 < 128 * 32, the quotient is far from a rounding boundary)
+    const int e0 = 2 * i, r0 = (int)(((float)e0 + 0.5f) * inv_O), c0 = e0 - r0 * O;  // c0 even, c0+1 < O
     float2 v;
     v.x = s_obs[r0 * (VINE_MAX_OBS + 1) + c0];
     v.y = s_obs[r0 * (VINE_MAX_OBS + 1) + c0 + 1];
