@@ -34,7 +34,7 @@ WORKLOAD = "FSTR (README.md:63 / BASELINE configs[1] knobs) env step, U(-1,1) ac
 UNIT = "env-steps/s"
 # Algorithmic work per env-step of the FSTR workload (derivations: DESIGN.md §6)
 HBM_BYTES_PER_ENV_STEP = 273.0      # O=18, ACTION_DELAY=1
-FLOPS_PER_ENV_STEP = 17.53e3        # ncu ffma*2+fmul+fadd thread-inst per env-step of the shipped kernel (profiles/step_kernel_r01e_raw.csv)
+FLOPS_PER_ENV_STEP = 17.61e3        # ncu ffma*2+fmul+fadd thread-inst per env-step of the shipped kernel (profiles/step_kernel_r01g_raw.csv)
 
 
 def fstr_cfg(num_envs, extra=()):
