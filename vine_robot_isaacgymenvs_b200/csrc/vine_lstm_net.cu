@@ -353,6 +353,11 @@ __global__ void __launch_bounds__(256, 2) vine_lstm_head_train_kernel(const Vine
   float sc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // lane 0: dbh[3], dlogstd[2], a_loss, c_loss, kl, b_loss
   const float ls0 = a.logstd[0], ls1 = a.logstd[1], lso0 = a.logstd_old[0], lso1 = a.logstd_old[1];
   const float sig0 = __expf(ls0), sig1 = __expf(ls1), sigo0 = __expf(lso0), sigo1 = __expf(lso1);
+  // sigma is a parameter, not a per-row quantity: every division of the row math below is by one of these constants, so the
+  // eight IEEE divisions per row (~17 dependent instructions each, in all 32 lanes) become multiplications
+  const float inv_sig0 = 1.f / sig0, inv_sig1 = 1.f / sig1;
+  const float klc0 = __logf(sig0 / sigo0 + 1e-5f) - 0.5f, klc1 = __logf(sig1 / sigo1 + 1e-5f) - 0.5f;
+  const float klq0 = 1.f / (2.f * (sig0 * sig0 + 1e-5f)), klq1 = 1.f / (2.f * (sig1 * sig1 + 1e-5f));
   for (int64_t s = warp0; s < a.n; s += nwarps) {
     const int64_t tile = s / TILE;
     const int row = (int)(s % TILE), unit = 8 * lane;
@@ -385,14 +390,14 @@ __global__ void __launch_bounds__(256, 2) vine_lstm_head_train_kernel(const Vine
     const float* q = a.scalars + 8 * s;
     const float4 q0 = *reinterpret_cast<const float4*>(q), q1 = *reinterpret_cast<const float4*>(q + 4);
     const float act0 = q0.x, act1 = q0.y, muo0 = q0.z, muo1 = q0.w, nlpo = q1.x, vo = q1.y, ret = q1.z, adv = q1.w;
-    const float e0 = (act0 - mu0) / sig0, e1 = (act1 - mu1) / sig1;
+    const float e0 = (act0 - mu0) * inv_sig0, e1 = (act1 - mu1) * inv_sig1;
     const float nlp = 0.5f * (e0 * e0 + e1 * e1) + 1.8378770664093453f + ls0 + ls1;
     const float ratio = __expf(nlpo - nlp);
     const float lo = 1.f - a.e_clip, hi = 1.f + a.e_clip;
     const float t1 = -adv * ratio, t2 = -adv * fminf(fmaxf(ratio, lo), hi);
     const bool inside = ratio >= lo && ratio <= hi;
     const float g_nlp = ((inside || t1 > t2) ? -adv : 0.f) * (-ratio);
-    float dmu0 = g_nlp * (-e0 / sig0), dmu1 = g_nlp * (-e1 / sig1);
+    float dmu0 = g_nlp * (-e0 * inv_sig0), dmu1 = g_nlp * (-e1 * inv_sig1);
     const float dls0 = g_nlp * (1.f - e0 * e0) - a.entropy_coef, dls1 = g_nlp * (1.f - e1 * e1) - a.entropy_coef;
     const float dvo = v - vo, vclip = vo + fminf(fmaxf(dvo, -a.e_clip), a.e_clip);
     const float r1 = v - ret, r2 = vclip - ret, c1 = r1 * r1, c2 = r2 * r2;
@@ -403,8 +408,7 @@ __global__ void __launch_bounds__(256, 2) vine_lstm_head_train_kernel(const Vine
     dmu0 += a.bounds_loss_coef * 2.f * (bh0 + bl0);
     dmu1 += a.bounds_loss_coef * 2.f * (bh1 + bl1);
     const float m0 = mu0 - muo0, m1 = mu1 - muo1;
-    const float kl = __logf(sig0 / sigo0 + 1e-5f) + (sigo0 * sigo0 + m0 * m0) / (2.f * (sig0 * sig0 + 1e-5f)) - 0.5f +
-                     __logf(sig1 / sigo1 + 1e-5f) + (sigo1 * sigo1 + m1 * m1) / (2.f * (sig1 * sig1 + 1e-5f)) - 0.5f;
+    const float kl = klc0 + (sigo0 * sigo0 + m0 * m0) * klq0 + klc1 + (sigo1 * sigo1 + m1 * m1) * klq1;
     dmu0 *= a.inv_B, dmu1 *= a.inv_B, dv *= a.inv_B;
     if (lane == 0) {
       sc[0] += dmu0, sc[1] += dmu1, sc[2] += dv;

@@ -138,6 +138,10 @@ __global__ void __launch_bounds__(128 * Q, 1) vine_ppo_minibatch_kernel(const Mb
   const int64_t ntiles = (B + TILE - 1) / TILE;
   const float ls0 = a.logstd[0], ls1 = a.logstd[1], lso0 = a.logstd_old[0], lso1 = a.logstd_old[1];
   const float sig0 = __expf(ls0), sig1 = __expf(ls1), sigo0 = __expf(lso0), sigo1 = __expf(lso1);
+  // sigma is a parameter: the row math divides only by these constants, so its eight IEEE divisions become multiplications
+  const float inv_sig0 = 1.f / sig0, inv_sig1 = 1.f / sig1;
+  const float klc0 = __logf(sig0 / sigo0 + 1e-5f) - 0.5f, klc1 = __logf(sig1 / sigo1 + 1e-5f) - 0.5f;
+  const float klq0 = 1.f / (2.f * (sig0 * sig0 + 1e-5f)), klq1 = 1.f / (2.f * (sig1 * sig1 + 1e-5f));
   bool first = true;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
@@ -175,15 +179,15 @@ __global__ void __launch_bounds__(128 * Q, 1) vine_ppo_minibatch_kernel(const Mb
       const float mu0 = __uint_as_float(r[0]) + bh[0], mu1 = __uint_as_float(r[1]) + bh[1], v = __uint_as_float(r[2]) + bh[2];
       float dmu0 = 0.f, dmu1 = 0.f, dv = 0.f;
       if (valid) {
-        const float d0 = (act0 - mu0) / sig0, d1 = (act1 - mu1) / sig1;
+        const float d0 = (act0 - mu0) * inv_sig0, d1 = (act1 - mu1) * inv_sig1;
         const float nlp = 0.5f * (d0 * d0 + d1 * d1) + 1.8378770664093453f + ls0 + ls1;
         const float ratio = __expf(nlpo - nlp);
         const float lo = 1.f - a.e_clip, hi = 1.f + a.e_clip;
         const float t1 = -adv * ratio, t2 = -adv * fminf(fmaxf(ratio, lo), hi);
         const bool inside = ratio >= lo && ratio <= hi;
         const float g_nlp = ((inside || t1 > t2) ? -adv : 0.f) * (-ratio);
-        dmu0 = g_nlp * (-d0 / sig0);
-        dmu1 = g_nlp * (-d1 / sig1);
+        dmu0 = g_nlp * (-d0 * inv_sig0);
+        dmu1 = g_nlp * (-d1 * inv_sig1);
         float dls0 = g_nlp * (1.f - d0 * d0) - a.entropy_coef, dls1 = g_nlp * (1.f - d1 * d1) - a.entropy_coef;
         // clipped value loss (clip_value: True), both on normalised values
         const float dvo = v - vo, vclip = vo + fminf(fmaxf(dvo, -a.e_clip), a.e_clip);
@@ -197,8 +201,7 @@ __global__ void __launch_bounds__(128 * Q, 1) vine_ppo_minibatch_kernel(const Mb
         dmu1 += a.bounds_coef * 2.f * (bh1 + bl1);
         // KL(old || new) of the diagonal Gaussians, rl_games policy_kl
         const float m0 = mu0 - muo0, m1 = mu1 - muo1;
-        const float kl = __logf(sig0 / sigo0 + 1e-5f) + (sigo0 * sigo0 + m0 * m0) / (2.f * (sig0 * sig0 + 1e-5f)) - 0.5f +
-                         __logf(sig1 / sigo1 + 1e-5f) + (sigo1 * sigo1 + m1 * m1) / (2.f * (sig1 * sig1 + 1e-5f)) - 0.5f;
+        const float kl = klc0 + (sigo0 * sigo0 + m0 * m0) * klq0 + klc1 + (sigo1 * sigo1 + m1 * m1) * klq1;
         st[0] += fmaxf(t1, t2) * a.inv_B;
         st[1] += fmaxf(c1, c2) * a.inv_B;
         st[2] += kl * a.inv_B;
