@@ -387,7 +387,10 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScrat
       if (r == ob.lip) { lfy -= L.fy; lfz -= L.fz; }
     }
   }
-  return sqrtf(lfy * lfy + lfz * lfz);
+  // |F_lip| is zero in almost every substep, and sqrt's zero argument sends the warp through its slow-path subroutine
+  const float l2 = lfy * lfy + lfz * lfz;
+  const float l = sqrtf(l2 > 0.f ? l2 : 1.f);
+  return l2 > 0.f ? l : 0.f;
 }
 
 // per-sim-step joint constants for the implicit integrator:
