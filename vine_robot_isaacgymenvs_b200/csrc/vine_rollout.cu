@@ -307,8 +307,10 @@ static int prologue_ok(const VinePpoPrologue* a) {
 
 int vine_ppo_moments(const VinePpoPrologue* a, void* stream) {
   if (!prologue_ok(a)) return VINE_ERR_INVALID_ARG;
-  int64_t blocks = (a->count + 2047) / 2048;
-  if (blocks > 296) blocks = 296;
+  // one block per SM at most: the row loop is latency-bound (a warp reads one 72-byte observation row per load), so it wants
+  // as many blocks as there are SMs, and no more (every block ends in ~40 f64 atomics on the same addresses)
+  int64_t blocks = (a->count + 255) / 256;
+  if (blocks > 148) blocks = 148;
   vine_ppo_moments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
