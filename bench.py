@@ -283,9 +283,12 @@ def run_ours(args, rank, world, local_rank):
     # ---- PPO frames/s (second half of BASELINE.json's metric): BASELINE configs[1] literally ----
     # FSTR, 4096 envs per GPU, horizon 16, minibatch 32768, 4 mini-epochs; one iteration = rollout
     # (16 x {policy, fused env step}) + GAE + update; frames = T * N * ranks per iteration.
-    def measure_ppo(num_envs, iters, warmup, extra, use_graphs=True, fused_update=True):
+    def measure_ppo(num_envs, iters, warmup, extra, use_graphs=True, fused_update=True, preset=None):
         from vine_robot_isaacgymenvs_b200.ppo.ppo import PPOAgent
-        pcfg = fstr_cfg(num_envs, [f"sim_device={dev}", f"rl_device={dev}"] + list(extra))
+        from vine_robot_isaacgymenvs_b200 import config as vcfg
+        devs = [f"sim_device={dev}", f"rl_device={dev}"]
+        pcfg = (fstr_cfg(num_envs, devs + list(extra)) if preset is None else
+                vcfg.compose(preset + [f"num_envs={num_envs}", "headless=True"] + devs + list(extra)))
         penv = vine.make(cfg=pcfg, global_env_offset=rank * num_envs)
         agent = PPOAgent(penv, pcfg["train"], device=dev, seed=42 + rank, use_graphs=use_graphs,
                          use_fused_update=fused_update)
@@ -342,8 +345,12 @@ def run_ours(args, rank, world, local_rank):
                "mlp_only_torch_update": measure_ppo(4096, args.ppo_iters, 5, ["train.params.network.rnn=null"],
                                                     fused_update=False)}
         if not args.no_sweep:
+            from vine_robot_isaacgymenvs_b200.config import SHELF_OVERRIDES as shelf_preset
             ppo["reference_network_65536_envs"] = measure_ppo(65536, max(3, args.ppo_iters // 4), 3,
                                                               ["train.params.config.minibatch_size=131072"])
+            # BASELINE configs[2]: shelf + contact-force resets at its own env count (minibatch = the whole 16384 x 16 batch / 2)
+            ppo["reference_network_configs2_shelf_16384_envs"] = measure_ppo(
+                16384, max(3, args.ppo_iters // 2), 3, ["train.params.config.minibatch_size=131072"], preset=shelf_preset)
             ppo["mlp_only_65536_envs"] = measure_ppo(65536, max(3, args.ppo_iters // 4), 3,
                                                      ["train.params.network.rnn=null",
                                                       "train.params.config.minibatch_size=131072"])
