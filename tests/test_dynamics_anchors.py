@@ -1,0 +1,279 @@
+"""Independent anchors of the dynamics + contact model that stands in for PhysX.
+
+PhysX itself cannot be run (closed Isaac Gym binary), so the oracle's restatement is pinned against
+things that do NOT share its derivation:
+  * tests/independent_model.py — Cartesian FK of the URDF + torch-autograd Lagrangian + scipy DOP853; it reproduces
+    SURVEY Appendix E.3's survey-time float64 probe (mass-matrix diagonal, both static equilibria, all five modal
+    frequencies), which was made before any oracle or kernel existed;
+  * the oracle's mass matrix, its free-motion trajectories, its small-oscillation frequencies, its convergence order
+    and its energy behaviour are then checked against that model;
+  * contact: momentum balance at rest (sum of contact forces = applied rail force), the penalty law's penetration
+    (pen = F / k per contact point) from independently computed geometry, and the face-contact force law.
+All CPU, float64 oracle path (`oracle_simulate(..., use_f64=1)`).
+"""
+import numpy as np
+import pytest
+import torch
+
+import independent_model as IM
+from vine_robot_isaacgymenvs_b200 import abi
+
+SURVEY_E3_MODAL = np.array([8.55, 64.2, 168.5, 446.3, 778.7])       # rad/s, cart free, u = 0
+SURVEY_E3_MDIAG = np.array([0.52, 1.68e-2, 1.01e-2, 5.1e-3, 1.9e-3, 3.0e-4])
+
+
+def _simulate(O, vc, q, qd, efforts, scale=None, u=None, target=None, obj=None, steps=1):
+    """`steps` sim steps of the f64 oracle from (q, qd) [n,6] with constant efforts; returns q, qd, lip force."""
+    n = q.shape[0]
+    f = np.float32
+    arr = {"dof_pos": np.ascontiguousarray(q, f), "dof_vel": np.ascontiguousarray(qd, f),
+           "dof_efforts": np.ascontiguousarray(efforts, f),
+           "dynamics_scaling": None if scale is None else np.ascontiguousarray(scale, f),
+           "u_fpam_to_use": np.zeros(n, f) if u is None else np.ascontiguousarray(u, f),
+           "target_positions": np.zeros((n, 3), f) if target is None else np.ascontiguousarray(target, f),
+           "object_info": np.zeros((n, 2), f) if obj is None else np.ascontiguousarray(obj, f),
+           "tip_positions": np.zeros((n, 3), f), "tip_velocities": np.zeros((n, 3), f), "shelf_contact_force": np.zeros(n, f)}
+    for _ in range(steps):
+        O.call_io("oracle_simulate", vc, n, abi.VineSimulateIO, arr, 1)
+    return arr["dof_pos"].astype(np.float64), arr["dof_vel"].astype(np.float64), arr["shelf_contact_force"].astype(np.float64)
+
+
+def _free_cfg(O, zoh=True, damping=2e-2, dt=0.00833, substeps=10):
+    vc = O.default_config()
+    vc.create_pipe = 0; vc.create_shelf = 0
+    vc.torque_law_integration = 0 if zoh else 1
+    vc.damping = damping; vc.dt = dt; vc.substeps = substeps
+    return vc
+
+
+def test_independent_model_reproduces_the_survey_probe():
+    """SURVEY Appendix E.3 (float64 Lagrangian probe made at survey time): M(0) diagonal, equilibria, modal frequencies."""
+    np.testing.assert_allclose(np.diag(IM.mass_matrix(np.zeros(6))), SURVEY_E3_MDIAG, rtol=2e-2)
+    q0 = IM.equilibrium(0.0)
+    py, pz, _ = IM.joint_points(torch.as_tensor(q0))
+    np.testing.assert_allclose([float(py[-1]), float(pz[-1])], [-0.0076, 0.5227], atol=1e-4)
+    q3 = IM.equilibrium(3.0)
+    np.testing.assert_allclose(q3[1:], [-0.001, -0.076, -0.137, -0.092, -0.170], atol=1e-3)
+    py, pz, _ = IM.joint_points(torch.as_tensor(q3))
+    np.testing.assert_allclose([float(py[-1]), float(pz[-1])], [-0.093, 0.539], atol=1e-3)
+    w, _, _ = IM.modal_frequencies(q0)
+    assert w[0] < 1e-4                                                   # the free cart: one rigid-body mode
+    np.testing.assert_allclose(w[1:], SURVEY_E3_MODAL, rtol=1e-2)
+
+
+def test_oracle_mass_matrix_equals_the_autograd_lagrangian(oracle_lib):
+    rng = np.random.default_rng(0)
+    for _ in range(25):
+        q = np.concatenate([rng.uniform(-0.3, 0.3, 1), rng.normal(0, 0.6, 5)])
+        np.testing.assert_allclose(oracle_lib.mass_matrix(q), IM.mass_matrix(q), rtol=0, atol=1e-12)
+
+
+def test_oracle_static_equilibria_are_the_lagrangian_ones(oracle_lib):
+    """Hold the torque law at u = 0 and u = 3 (implicit mode) until the chain rests: the rest pose is the root of
+    dV/dq + K q + b + B u = 0 found by Newton on the independent model."""
+    for u in (0.0, 3.0):
+        vc = _free_cfg(oracle_lib, zoh=False, damping=0.3)   # extra joint damping: faster settling, same rest pose
+        q, qd, _ = _simulate(oracle_lib, vc, np.zeros((1, 6)), np.zeros((1, 6)), np.zeros((1, 6)), u=np.full(1, u), steps=1500)
+        assert np.abs(qd).max() < 1e-5
+        np.testing.assert_allclose(q[0, 1:], IM.equilibrium(u)[1:], atol=2e-6)
+
+
+def test_oracle_small_oscillations_have_the_survey_modal_frequencies(oracle_lib):
+    """Release the oracle from equilibrium + a small displacement along each mode shape of the independent model
+    (torque-law damping scaled to 0, PhysX damping 0) and read the frequency of that modal coordinate off its zero
+    crossings: SURVEY E.3's 8.55 / 64.2 / 168.5 / 446.3 / 778.7 rad/s within 1 %."""
+    q_eq = IM.equilibrium(0.0)
+    w_ref, vec, M = IM.modal_frequencies(q_eq)
+    scale = np.ones((1, 5, 4)); scale[:, :, 1] = 0.0                       # (K, C, b, B): no C q' term
+    for i in range(1, 6):
+        w = w_ref[i]
+        per_period = 64
+        dt = 2 * np.pi / w / per_period                                   # sample the oracle 64 times per period
+        vc = _free_cfg(oracle_lib, zoh=False, damping=0.0, dt=dt, substeps=20)   # h = period / 1280
+        shape = vec[:, i] / np.abs(vec[:, i]).max()
+        q = (q_eq + 2e-3 * shape)[None].copy(); qd = np.zeros((1, 6))
+        coord = []
+        for _ in range(per_period * 6):
+            q, qd, _ = _simulate(oracle_lib, vc, q, qd, np.zeros((1, 6)), scale=scale)
+            coord.append(float(shape @ M @ (q[0] - q_eq)))
+        coord = np.array(coord)
+        sign = np.sign(coord)
+        idx = np.nonzero(sign[1:] != sign[:-1])[0]
+        assert len(idx) >= 8, f"mode {i}: no oscillation"
+        t_cross = (idx + coord[idx] / (coord[idx] - coord[idx + 1]) + 1) * dt    # linear interpolation
+        w_meas = np.pi / np.mean(np.diff(t_cross))
+        assert abs(w_meas / SURVEY_E3_MODAL[i - 1] - 1) < 1e-2, f"mode {i}: {w_meas:.2f} vs {SURVEY_E3_MODAL[i - 1]}"
+        assert abs(w_meas / w - 1) < 3e-3
+
+
+def _ode_reference(q0, qd0, efforts, damping, duration):
+    force = lambda q, qd: efforts - damping * qd                          # noqa: E731  constant efforts + DOF damping (V5:504)
+    return IM.integrate(q0, qd0, duration, force)
+
+
+def test_oracle_trajectory_converges_to_the_lagrangian_ode_with_order_one(oracle_lib):
+    """One 8.33 ms sim step with constant efforts (the literal VT:346-356 semantics) from random moving states:
+    the semi-implicit Euler of the oracle converges to the continuous-time solution of the autograd model, error
+    proportional to h (order 1)."""
+    rng = np.random.default_rng(3)
+    dt = 0.00833
+    for case in range(3):
+        q0 = np.concatenate([rng.uniform(-0.2, 0.2, 1), rng.normal(0, 0.15, 5)]).astype(np.float32).astype(np.float64)
+        qd0 = np.concatenate([rng.normal(0, 0.3, 1), rng.normal(0, 1.0, 5)]).astype(np.float32).astype(np.float64)
+        eff = np.concatenate([rng.uniform(-3, 3, 1), rng.normal(0, 0.02, 5)]).astype(np.float32).astype(np.float64)
+        q_ref, qd_ref = _ode_reference(q0, qd0, eff, 2e-2, dt)
+        errs = []
+        for sub in (10, 20, 40, 80, 2000):
+            vc = _free_cfg(oracle_lib, zoh=True, substeps=sub)
+            q, qd, _ = _simulate(oracle_lib, vc, q0[None], qd0[None], eff[None])
+            errs.append((np.abs(q[0] - q_ref).max(), np.abs(qd[0] - qd_ref).max()))
+        errs = np.array(errs)
+        # fine limit: the oracle IS the Lagrangian model (f32 state at the ABI boundary bounds what can be resolved)
+        assert errs[-1, 0] < 2e-6 and errs[-1, 1] < 3e-4, errs[-1]
+        # order of convergence from the velocity error (well above the f32 floor): halving h halves the error
+        order = np.log2(errs[0, 1] / errs[2, 1]) / 2.0
+        assert 0.8 < order < 1.25, (order, errs)
+        # shipped step size h = dt/10 (the reference's own substeps, YT:103-104; PhysX integrates with the same h and a
+        # first-order scheme too): discretisation error against the continuous-time solution, for the record
+        print(f"\n[anchor] case {case}: h = dt/10 vs continuous time: |dq| {errs[0, 0]:.2e}, |dqd| {errs[0, 1]:.2e} "
+              f"(max |qd| {np.abs(qd_ref).max():.2f}); order {order:.2f}; h = dt/2000: |dq| {errs[-1, 0]:.1e}, |dqd| {errs[-1, 1]:.1e}")
+        assert errs[0, 0] < 1e-3 * max(np.abs(q_ref).max(), 0.1)
+        assert errs[0, 1] < 5e-2 * max(np.abs(qd_ref).max(), 1.0)
+
+
+def test_oracle_energy_without_dissipation(oracle_lib):
+    """D = 0, no torque law, no actuation: a conservative double-pendulum-like swing. The independent model's energy,
+    evaluated on the oracle's trajectory, drifts by O(h): bounded and halving with h."""
+    q0 = np.array([0.05, 0.5, 0.3, -0.2, 0.25, 0.4]); qd0 = np.zeros(6)
+    drift = []
+    for sub in (10, 20):
+        vc = _free_cfg(oracle_lib, zoh=True, damping=0.0, substeps=sub)
+        q, qd = q0[None].copy(), qd0[None].copy()
+        e0 = IM.energy(q[0], qd[0]); emin = emax = e0
+        kin_max = 0.0
+        for _ in range(40):                                                # a third of a second: ~1.5 swings of the slow mode
+            q, qd, _ = _simulate(oracle_lib, vc, q, qd, np.zeros((1, 6)))
+            e = IM.energy(q[0], qd[0])
+            emin, emax = min(emin, e), max(emax, e)
+            kin_max = max(kin_max, float(IM.kinetic(torch.as_tensor(q[0]), torch.as_tensor(qd[0]))))
+        assert kin_max > 1e-3                                              # it really moved
+        drift.append((emax - emin) / kin_max)
+    assert drift[0] < 0.05, drift                                          # shipped step size: a few % of the exchanged energy
+    assert 1.5 < drift[0] / drift[1] < 2.6, drift                          # O(h)
+
+
+# ---------------------------------------------------------------------------------------------- contact
+def _shelf_cfg(O):
+    vc = O.default_config()
+    vc.create_pipe = 0; vc.create_shelf = 1
+    vc.torque_law_integration = 1
+    return vc
+
+
+def _segment_point_distance(ay, az, by, bz, py, pz):
+    ey, ez = by - ay, bz - az
+    t = np.clip(((py - ay) * ey + (pz - az) * ez) / (ey * ey + ez * ez), 0.0, 1.0)
+    cy, cz = ay + t * ey, az + t * ez
+    return float(np.hypot(cy - py, cz - pz)), (cy, cz)
+
+
+def test_contact_rest_state_balances_the_applied_rail_force(oracle_lib):
+    """Push the cart toward -y with a constant 1 N rail force until the chain rests against the shelf's sensing lip
+    (custom_shelf.urdf:139-152).  The rail is frictionless along y and gravity is along z, so at rest the contact
+    forces' y-components must sum to exactly the applied force; the lip is the only thing touched, so the sampled
+    |F(shelf_link)| (VT:348-351) has that magnitude, and each touching lip corner sits pen = F_i / k inside the
+    capsule (independent geometry from the rest pose)."""
+    O = oracle_lib
+    vc = _shelf_cfg(O)
+    vc.damping = 0.3                                                     # settles faster; statics do not depend on it
+    F = 1.0
+    # lip centre at target + (0, depth - 0.001, -0.01); put it 0.115 m below the first joint (link 1) so the top board
+    # (0.2 m above the middle board) is above the rail and cannot be reached
+    depth, tz = 0.0, 0.86
+    target = np.array([[0.0, -0.1, tz]]); obj = np.array([[depth, 0.0]])
+    q = np.zeros((1, 6)); q[0, 0] = -0.1 + 0.0381 + 0.03                   # cart starts 3 cm in front of the lip face
+    qd = np.zeros((1, 6))
+    eff = np.zeros((1, 6)); eff[0, 0] = -F
+    lip = None
+    for _ in range(60):
+        q, qd, lip = _simulate(O, vc, q, qd, eff, u=np.zeros(1), target=target, obj=obj, steps=25)
+        if np.abs(qd).max() < 1e-6:
+            break
+    assert np.abs(qd).max() < 1e-5, "did not come to rest"
+    # independent geometry: the lip's two front corners against every collision capsule of the chain
+    # (main cylinder r = 0.0381 on the link axis, FPAM cylinder r = 0.0169 offset 0.055 along the link's local +y;
+    # URDF:95-115) with the rest offset added to the radius
+    py, pz, phi = IM.joint_points(torch.as_tensor(q[0]))
+    py, pz, phi = py.numpy(), pz.numpy(), phi.numpy()
+    lip_front_y = target[0, 1] + depth - 0.2 + 0.199 + 0.001
+    lip_z = tz - 0.01
+    k, rest = vc.contact_stiffness, vc.contact_rest_offset
+    total_y = total_z = 0.0
+    n_touch = 0
+    for cz in (lip_z - 0.005, lip_z + 0.005):
+        for j in range(5):
+            for radius, off in ((0.0381, 0.0), (0.0169, 0.055)):
+                oy, oz = off * np.cos(phi[j]), off * np.sin(phi[j])
+                d, (cy_, cz_) = _segment_point_distance(py[j] + oy, pz[j] + oz, py[j + 1] + oy, pz[j + 1] + oz, lip_front_y, cz)
+                pen = radius + rest - d
+                if pen > 0:                                               # force on the capsule: k pen along corner -> axis
+                    total_y += k * pen * (cy_ - lip_front_y) / d
+                    total_z += k * pen * (cz_ - cz) / d
+                    n_touch += 1
+    assert n_touch >= 1
+    # momentum balance along the frictionless rail: sum of contact forces in y == applied force
+    assert abs(total_y - F) < 5e-3 * F, f"sum k pen n_y = {total_y} vs applied {F}"
+    # what the task samples (VT:348-351) is the NORM of the force on shelf_link: the link leans, so the normals tilt
+    assert abs(lip[0] - np.hypot(total_y, total_z)) < 5e-3 * F, (lip[0], total_y, total_z)
+    assert lip[0] >= F * (1 - 1e-3)
+    print(f"\n[anchor] contact statics: applied {F} N, sum k pen n_y = {total_y:.5f} N, |F_lip| oracle {lip[0]:.5f} vs geometry "
+          f"{np.hypot(total_y, total_z):.5f}")
+
+
+def test_penalty_force_law_on_a_face(oracle_lib):
+    """The last link held horizontal (q5 = -90 deg), its end cap pressed `pen` into the front face of the sensing lip:
+    contact features are the cap's centre against the face plus the lip's two front corners against the cap
+    (vertex-edge decomposition), each with f = max(0, k pen_i - c v_n,i).  Expected values from plain
+    geometry; closing speed adds c v, separation faster than k pen / c gives exactly zero (no adhesion), and motion
+    ALONG a face changes nothing (zero friction, V5:477,491,499)."""
+    O = oracle_lib
+    vc = _shelf_cfg(O)
+    vc.substeps = 1                                                      # the sampled force is that of the first (only) substep
+    k, c, rest, r = vc.contact_stiffness, vc.contact_damping, vc.contact_rest_offset, 0.0381
+    q = np.zeros((1, 6)); q[0, 5] = -np.pi / 2
+    py, pz, phi = IM.joint_points(torch.as_tensor(q[0]))
+    tip_y, tip_z = float(py[-1]), float(pz[-1])
+    dirn = np.array([-np.sin(float(phi[-1])), np.cos(float(phi[-1]))])    # link direction, ~(-1, 0)
+    B = np.array([tip_y, tip_z]) - r * dirn                              # centre of the end cap (the cap ends at the tip)
+    pen = 0.002
+    face_y = B[0] - (r + rest - pen)
+    # lip centre (face_y - 0.001, B_z): target + (0, depth - 0.001, -0.01) with depth = 0
+    target = np.array([[0.0, face_y, B[1] + 0.01]]); obj = np.zeros((1, 2))
+
+    def expected(v_close):
+        total = np.zeros(2)
+        f = k * pen + c * v_close                                        # cap centre vs face, normal +y
+        total += max(f, 0.0) * np.array([1.0, 0.0])
+        for dz in (-0.005, 0.005):                                       # the lip's front corners vs the cap centre
+            corner = np.array([face_y, B[1] + dz])
+            dvec = B - corner; dist = np.linalg.norm(dvec); n = dvec / dist
+            f = k * (r + rest - dist) + c * v_close * n[0]
+            total += max(f, 0.0) * n
+        return float(np.linalg.norm(total))
+
+    for v_cart, label in ((0.0, "static"), (-0.05, "closing"), (5.0, "separating")):
+        qd = np.zeros((1, 6)); qd[0, 0] = v_cart                          # the whole chain translates with the cart
+        _, _, lip = _simulate(O, vc, q, qd, np.zeros((1, 6)), target=target, obj=obj)
+        want = expected(-v_cart)
+        assert abs(lip[0] - want) < 1e-3 * max(want, 1.0), (label, lip[0], want)
+    assert expected(0.0) > k * pen and expected(-5.0) == 0.0
+    # frictionless: sliding ALONG the top face of the lip (tip cap resting on it from above, chain hanging straight)
+    q = np.zeros((1, 6))
+    py, pz, _ = IM.joint_points(torch.as_tensor(q[0]))
+    target = np.array([[0.0, float(py[-1]) + 0.001, float(pz[-1]) - rest + pen - 0.005 + 0.01]])
+    forces = []
+    for v_cart in (0.0, 0.5):
+        qd = np.zeros((1, 6)); qd[0, 0] = v_cart
+        _, _, lip = _simulate(O, vc, q, qd, np.zeros((1, 6)), target=target, obj=obj)
+        forces.append(lip[0])
+    assert forces[0] > k * pen * 0.99 and abs(forces[1] - forces[0]) < 2e-3 * forces[0], forces

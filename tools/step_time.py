@@ -15,11 +15,14 @@ acts = [torch.rand(n, 2, device="cuda", generator=g) * 2 - 1 for _ in range(8)]
 for t in range(40):
     env.step(acts[t % 8])
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for t in range(40):
-    env.step(acts[t % 8])
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 40
-print(f"{sys.argv[1]} n={n} {' '.join(sys.argv[3:])}: {ms:.4f} ms/step  {n / ms / 1e3:.4g} env-steps/s")
+best = 1e9
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(40):
+        env.actions.copy_(acts[t % 8])
+        env.step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1) / 40)
+print(f"{sys.argv[1]} n={n} {' '.join(sys.argv[3:])}: {best:.4f} ms/step  {n / best / 1e3:.4g} env-steps/s", flush=True)

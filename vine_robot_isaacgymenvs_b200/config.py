@@ -520,4 +520,8 @@ def task_cfg_to_vine_config(cfg):
     c.contact_stiffness = float(vc.get("stiffness", 2000.0))
     c.contact_damping = float(vc.get("damping", 2.0))
     c.contact_rest_offset = float(sim.get("physx", {}).get("rest_offset", 0.001))
+    # launch tuning of the library (no counterpart in the reference; results do not depend on it)
+    c.contact_cull_slack = float(vc.get("cull_slack", 0.01))
+    c.contact_binning = int(bool(vc.get("binning", True)))
+    c.step_kernel_variant = abi.STEP_KERNEL_VARIANT[str(sim.get("vine_step_kernel", "auto")).lower()]
     return c

@@ -22,6 +22,9 @@
 #ifndef VINE_STEP_MIN_BLOCKS_CONTACT
 #define VINE_STEP_MIN_BLOCKS_CONTACT 12  // contact variant (1-warp blocks): 160 registers (no spills) instead of 200 -> 12 warps/SM; measured
 #endif                                   // +14 % (shelf) / +11 % (pipe): hides the per-warp load imbalance of the narrow phase
+#ifndef VINE_STEP2_MIN_BLOCKS
+#define VINE_STEP2_MIN_BLOCKS 0  // two-envs-per-thread kernel: the compiler's own register choice
+#endif
 #define VINE_DBG_W 20  // u_rail,u_fpam,prev_u_rail,rail_force,tipvel y,z, reward_matrix[13], pad
 
 struct StepArgs {
@@ -63,17 +66,17 @@ static char g_create_err[256] = "";
 // ------------------------------------------------------------------------------------------
 // coalesced store of a block's observation rows staged in shared memory
 // ------------------------------------------------------------------------------------------
-template <int BLOCK>
+template <int ROWS, int THREADS>
 __device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64_t first, int64_t end, float clip,
                                                 float* __restrict__ obs, float* __restrict__ obs_clamped) {
-  const int64_t row0 = first + (int64_t)blockIdx.x * BLOCK;
-  const int rows = (int)min((int64_t)BLOCK, end - row0);
+  const int64_t row0 = first + (int64_t)blockIdx.x * ROWS;
+  const int rows = (int)min((int64_t)ROWS, end - row0);
   const int count2 = rows * O / 2;  // O is even for every ObservationType
   float2* g = reinterpret_cast<float2*>(obs + row0 * O);
   float2* gc = obs_clamped ? reinterpret_cast<float2*>(obs_clamped + row0 * O) : nullptr;
   const float inv_O = 1.0f / (float)O;
-  for (int i = threadIdx.x; i < count2; i += BLOCK) {
-    // r0 = e0 / O without the 20-instruction integer division (exact: e0 < 128 * 32, the quotient is far from a rounding boundary)
+  for (int i = threadIdx.x; i < count2; i += THREADS) {
+    // r0 = e0 / O without the 20-instruction integer division (exact: e0 < 256 * 32, the quotient is far from a rounding boundary)
     const int e0 = 2 * i, r0 = (int)(((float)e0 + 0.5f) * inv_O), c0 = e0 - r0 * O;  // c0 even, c0+1 < O
     float2 v;
     v.x = s_obs[r0 * (VINE_MAX_OBS + 1) + c0];
@@ -87,7 +90,187 @@ __device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64
 }
 
 // ------------------------------------------------------------------------------------------
-// THE fused control step == VecTask.step (VT:319-380)
+// The control step of ONE environment, cut at the points where the integrator runs, so that the one-env-per-thread
+// kernel (contact variant) and the two-envs-per-thread kernel (free space, packed FP32) share every line of task logic.
+// ------------------------------------------------------------------------------------------
+struct EnvStep {   // what one env carries in registers across the sim steps of a control step
+  float smoothed, prev_cart_vel, prev_err, lip, cart_body_vy;
+  float u_rail, u_fpam, u_use, rail_force;
+  float tipb_y, tipb_z;             // rigid-body tip as of the refresh before the LAST simulate (V5:797 on reset steps)
+  float contact[VINE_MAX_CFI];      // VT:348-351 samples (shelf only)
+  uint32_t step, gid;
+  bool reset_in;
+};
+
+// load + VT:333 + pre_physics_step V5:922-945; returns the env's dynamics state in absolute coordinates
+__device__ __forceinline__ void env_begin(const VineParams& p, const StepArgs& a, int64_t e, EnvStep& E, Dyn& d) {
+  const float4 s0 = a.S0[e], s1 = a.S1[e], s2 = a.S2[e], s3 = a.S3[e], s4 = a.S4[e];
+  const float q[6] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y};
+  const float qd[6] = {s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
+  E.smoothed = s3.x; E.prev_cart_vel = s3.y; E.prev_err = s3.z; E.lip = s3.w;
+  E.tipb_y = s4.x; E.tipb_z = s4.y; E.cart_body_vy = s4.z;
+  E.step = a.ctr[e];
+  E.gid = (uint32_t)(a.gid0 + e);
+  const float2 act = a.actions[e];
+  E.reset_in = a.reset[e] != 0;
+  float a0 = fminf(fmaxf(act.x, -p.clip_act), p.clip_act);
+  float a1 = fminf(fmaxf(act.y, -p.clip_act), p.clip_act);
+  if (p.randomize && p.act_noise != 0.f) {  // V5:930-932 (noise after the clamp)
+    float nz[4];
+    normal4(philox4x32(a.k0, a.k1, E.gid, VINE_SITE_ACTION_NOISE, E.step, 0), nz);
+    a0 = __fadd_rn(a0, __fmul_rn(p.act_noise, nz[0]));
+    a1 = __fadd_rn(a1, __fmul_rn(p.act_noise, nz[1]));
+  }
+  rescale_actions(p, a0, a1, E.u_rail, E.u_fpam);
+  if (p.D > 0) {  // V5:936-937 FIFO of ACTION_DELAY control steps
+    float2* slot = a.ring + (int64_t)(E.step % (uint32_t)p.D) * a.n + e;
+    const float2 old = *slot;
+    *slot = make_float2(E.u_rail, E.u_fpam);
+    E.u_rail = old.x; E.u_fpam = old.y;
+  }
+  apply_overrides_and_smooth(p, E.u_rail, E.u_fpam, E.smoothed);
+  E.u_use = p.use_smoothed ? E.smoothed : E.u_fpam;                // V5:1059
+  E.rail_force = 0.f;
+#pragma unroll
+  for (int i = 0; i < VINE_MAX_CFI; ++i) E.contact[i] = 0.f;
+  rel_to_abs(p, q, qd, d);
+}
+
+// head of sim step i (VT:338-351): dynamics-scaling draws, rail controller, contact sample, integrator constants
+__device__ __forceinline__ void env_sim_step_begin(const VineParams& p, const StepArgs& a, int i, EnvStep& E, const Dyn& d, JointImp& J) {
+  if (i > 0 && i == p.C - 1 && E.reset_in && p.stale) {  // only needed by V5:797 on reset steps
+    float vy, vz; tip_fk(d, E.tipb_y, E.tipb_z, vy, vz);
+  }
+  JointLaw law; joint_law_unscaled(law);
+  float acc_scale = 1.f;
+  if (p.randomize) {  // V5:1053-1055: 20 multipliers re-drawn every sim step (+1 for accel scaling)
+    // 16 random bits per multiplier (two per Philox word): 3 Philox calls per sim step instead of 6; multiplier k uses
+    // half k of the 24 halves of blocks 8 i .. 8 i + 2, low half first
+    const float dyn_rng16 = p.dyn_rng * 1.52587890625e-05f, acc_rng16 = p.acc_rng * 1.52587890625e-05f;   // 2^-16
+    uint32_t u[12];
+#pragma unroll
+    for (uint32_t b = 0; b < 3; ++b) {
+      const uint4 r = philox4x32(a.k0, a.k1, E.gid, VINE_SITE_DYNAMICS, E.step, (uint32_t)i * 8u + b);
+      u[4 * b] = r.x; u[4 * b + 1] = r.y; u[4 * b + 2] = r.z; u[4 * b + 3] = r.w;
+    }
+#pragma unroll
+    for (int j = 0; j < VINE_NL; ++j) {
+      law.K[j] = __fmul_rn(law.K[j], uniform_ab16(u[2 * j] & 0xffffu, p.dyn_min, dyn_rng16));
+      law.Cd[j] = __fmul_rn(law.Cd[j], uniform_ab16(u[2 * j] >> 16, p.dyn_min, dyn_rng16));
+      law.b[j] = __fmul_rn(law.b[j], uniform_ab16(u[2 * j + 1] & 0xffffu, p.dyn_min, dyn_rng16));
+      law.B[j] = __fmul_rn(law.B[j], uniform_ab16(u[2 * j + 1] >> 16, p.dyn_min, dyn_rng16));
+    }
+    acc_scale = uniform_ab16(u[10] & 0xffffu, p.acc_min, acc_rng16);
+  }
+  // rigid-body cart velocity: stale on the first sim step after a reset (V5:1069)
+  const float cart_vel = (i == 0) ? E.cart_body_vy : d.v[0];
+  float efforts[6];
+  efforts[0] = rail_controller(p, cart_vel, E.u_rail, acc_scale, E.prev_cart_vel, E.prev_err);
+  E.rail_force = efforts[0];
+  if (!p.implicit_law) {
+#pragma unroll
+    for (int j = 0; j < VINE_NL; ++j) {
+      const float th = j == 0 ? d.x[1] : d.x[j + 1] - d.x[j];
+      const float thd = j == 0 ? d.v[1] : d.v[j + 1] - d.v[j];
+      efforts[j + 1] = joint_torque(law, j, th, thd, E.u_use);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < VINE_NL; ++j) efforts[j + 1] = 0.f;
+  }
+  if (p.shelf) {
+#pragma unroll
+    for (int k = 0; k < VINE_MAX_CFI; ++k) if (k == i) E.contact[k] = E.lip;  // VT:348-351: force of the PREVIOUS simulate
+  }
+  joint_implicit_consts(p, law, E.u_use, efforts, J);
+}
+
+// post_physics_step V5:1110-1120 + VT:366-374 + write-back; the observation row goes to `row` (shared memory).
+// Values that the step only needs here (the joint positions and rigid-body tip at the start of the step = prev_dof_pos /
+// prev_tip_positions V5:943-944, targets, object info, progress, the reward sum) are re-read from their planes instead of
+// being carried in registers across the 40 substeps: the planes still hold the step's input until the write-back below.
+__device__ __forceinline__ void env_end(const VineParams& p, const StepArgs& a, int64_t e, EnvStep& E, const Dyn& d, float* row) {
+  float q[6], qd[6];
+  float tip_y, tip_z, tipvel_y, tipvel_z;
+  tip_fk(d, tip_y, tip_z, tipvel_y, tipvel_z);
+  float cart_y_body = d.x[0];
+  float cart_body_vy = d.v[0];
+  abs_to_rel(d, q, qd);
+  const float4 s0 = a.S0[e], s1 = a.S1[e], s4 = a.S4[e], s5 = a.S5[e];
+  float target[3] = {0.f, s5.x, s5.y};
+  float obj[2] = {s5.z, s5.w};
+  float agg = s4.w;
+  PostIn in;
+  in.prev_q[0] = s0.x; in.prev_q[1] = s0.y; in.prev_q[2] = s0.z; in.prev_q[3] = s0.w; in.prev_q[4] = s1.x; in.prev_q[5] = s1.y;  // V5:943
+  in.prev_tip[0] = 0.f; in.prev_tip[1] = s4.x; in.prev_tip[2] = s4.y;     // V5:944
+  in.prev_u_rail = E.u_rail;                                             // V5:945
+  int64_t progress = a.progress[e] + 1;                                  // V5:1111
+  int64_t reset_in = E.reset_in ? 1 : 0;
+  if (E.reset_in) {  // deferred reset of envs flagged at the end of the previous step (V5:1114-1116)
+    reset_env(p, a.k0, a.k1, E.gid, E.step, q, qd, target, obj);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) in.prev_q[i] = q[i];                     // V5:794
+    if (p.stale) {                                                       // V5:796-797 stale rigid-body views
+      in.prev_tip[1] = E.tipb_y; in.prev_tip[2] = E.tipb_z;
+    } else {                                                             // "as if FK were done": clean episode boundary
+      Dyn dn; rel_to_abs(p, q, qd, dn);
+      tip_fk(dn, tip_y, tip_z, tipvel_y, tipvel_z);
+      in.prev_tip[1] = tip_y; in.prev_tip[2] = tip_z;
+      cart_y_body = q[0]; cart_body_vy = 0.f; E.lip = 0.f; E.prev_cart_vel = 0.f;
+#pragma unroll
+      for (int i = 0; i < VINE_MAX_CFI; ++i) E.contact[i] = 0.f;
+    }
+    in.prev_u_rail = 0.f;                                                // V5:798
+    E.prev_err = 0.f;                                                    // V5:799
+    reset_in = 0; progress = 0; agg = 0.f;                               // V5:807-810
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { in.q[i] = q[i]; in.qd[i] = qd[i]; }
+  in.tip[0] = 0.f; in.tip[1] = tip_y; in.tip[2] = tip_z;
+  in.tipvel[0] = 0.f; in.tipvel[1] = tipvel_y; in.tipvel[2] = tipvel_z;
+  in.target[0] = target[0]; in.target[1] = target[1]; in.target[2] = target[2];
+  in.target_vel[0] = in.target_vel[1] = in.target_vel[2] = 0.f;          // V5:916-918
+  in.obj[0] = obj[0]; in.obj[1] = obj[1];
+  in.cart_y = cart_y_body; in.smoothed = E.smoothed; in.u_fpam = E.u_fpam; in.u_rail = E.u_rail;
+#pragma unroll
+  for (int i = 0; i < VINE_MAX_CFI; ++i) in.contact[i] = E.contact[i];
+  in.reset_in = reset_in; in.progress = progress;
+  float noise[VINE_MAX_OBS];
+  const bool noisy = p.randomize && p.obs_noise != 0.f;
+  if (noisy) {
+#pragma unroll
+    for (uint32_t b = 0; b < VINE_MAX_OBS / 4; ++b) {
+      if ((int)(4 * b) < p.O) normal4(philox4x32(a.k0, a.k1, E.gid, VINE_SITE_OBS_NOISE, E.step, b), &noise[4 * b]);
+    }
+  }
+  PostOut o;
+  post_physics(p, in, noisy ? noise : nullptr, o);
+  agg = __fadd_rn(agg, o.rew);                                           // V5:1278
+
+  a.S0[e] = make_float4(q[0], q[1], q[2], q[3]);
+  a.S1[e] = make_float4(q[4], q[5], qd[0], qd[1]);
+  a.S2[e] = make_float4(qd[2], qd[3], qd[4], qd[5]);
+  a.S3[e] = make_float4(E.smoothed, E.prev_cart_vel, E.prev_err, E.lip);
+  a.S4[e] = make_float4(tip_y, tip_z, cart_body_vy, agg);
+  if (E.reset_in) a.S5[e] = make_float4(target[1], target[2], obj[0], obj[1]);
+  a.ctr[e] = E.step + 1u;
+  a.rew[e] = o.rew;
+  a.reset[e] = o.reset;
+  a.progress[e] = progress;
+  a.timeout[e] = o.timeout;
+#pragma unroll
+  for (int i = 0; i < VINE_MAX_OBS; ++i) if (i < p.O) row[i] = o.obs[i];
+  if (a.dbg) {
+    float* dbg = a.dbg + e * VINE_DBG_W;
+    dbg[0] = E.u_rail; dbg[1] = E.u_fpam; dbg[2] = in.prev_u_rail; dbg[3] = E.rail_force;
+    dbg[4] = tipvel_y; dbg[5] = tipvel_z;
+#pragma unroll
+    for (int i = 0; i < VINE_NUM_REWARDS; ++i) dbg[6 + i] = o.r[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// THE fused control step == VecTask.step (VT:319-380), one environment per thread
 // ------------------------------------------------------------------------------------------
 // Block size: 128 for the free-space variant.  The contact variant uses one warp per block: its warps finish at very
 // different times (the narrow phase runs only where something touches), and a block holds its registers until its slowest
@@ -106,175 +289,25 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
   const bool live = slot < a.end;
   const int64_t e = (CONTACT && a.perm && live) ? (int64_t)a.perm[slot] : slot;
   if (live) {
-    const float4 s0 = a.S0[e], s1 = a.S1[e], s2 = a.S2[e], s3 = a.S3[e], s4 = a.S4[e], s5 = a.S5[e];
-    float q[6] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y};
-    float qd[6] = {s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
-    float smoothed = s3.x, prev_cart_vel = s3.y, prev_err = s3.z, lip = s3.w;
-    float tip_y = s4.x, tip_z = s4.y, cart_body_vy = s4.z, agg = s4.w;
-    float target[3] = {0.f, s5.x, s5.y};
-    float obj[2] = {s5.z, s5.w};
-    const uint32_t step = a.ctr[e];
-    const uint32_t gid = (uint32_t)(a.gid0 + e);
-    const float2 act = a.actions[e];
-    int64_t reset_in = a.reset[e];
-    const bool was_reset = reset_in != 0;
-    int64_t progress = a.progress[e];
-
-    // ---- VT:333 + pre_physics_step V5:922-945 ----
-    float a0 = fminf(fmaxf(act.x, -p.clip_act), p.clip_act);
-    float a1 = fminf(fmaxf(act.y, -p.clip_act), p.clip_act);
-    if (p.randomize && p.act_noise != 0.f) {  // V5:930-932 (noise after the clamp)
-      float nz[4];
-      normal4(philox4x32(a.k0, a.k1, gid, VINE_SITE_ACTION_NOISE, step, 0), nz);
-      a0 = __fadd_rn(a0, __fmul_rn(p.act_noise, nz[0]));
-      a1 = __fadd_rn(a1, __fmul_rn(p.act_noise, nz[1]));
-    }
-    float u_rail, u_fpam;
-    rescale_actions(p, a0, a1, u_rail, u_fpam);
-    if (p.D > 0) {  // V5:936-937 FIFO of ACTION_DELAY control steps
-      float2* slot = a.ring + (int64_t)(step % (uint32_t)p.D) * a.n + e;
-      const float2 old = *slot;
-      *slot = make_float2(u_rail, u_fpam);
-      u_rail = old.x; u_fpam = old.y;
-    }
-    apply_overrides_and_smooth(p, u_rail, u_fpam, smoothed);
-    PostIn in;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) in.prev_q[i] = q[i];                       // V5:943
-    in.prev_tip[0] = 0.f; in.prev_tip[1] = tip_y; in.prev_tip[2] = tip_z;  // V5:944
-    in.prev_u_rail = u_rail;                                               // V5:945
-    const float u_use = p.use_smoothed ? smoothed : u_fpam;                // V5:1059
-
+    EnvStep E; Dyn d;
+    env_begin(p, a, e, E, d);
     Obstacles ob = {0, -1, 0.f, 0.f, 0.f, 0.f};
     ContactCache cc = {0u, 1e30f, 0u};   // no candidate pairs yet: the first substep culls
-    if (CONTACT) build_obstacles(p, target[1], target[2], obj[0], obj[1], cs, ob);
-
+    if (CONTACT) { const float4 s5 = a.S5[e]; build_obstacles(p, s5.x, s5.y, s5.z, s5.w, cs, ob); }
+    const float m00 = fmaf(p.h, p.damping, p.mtot), m00inv = rcp_approx(m00);
     // ---- controlFrequencyInv x {forces, contact sample, simulate}  VT:338-356 ----
-    Dyn d; rel_to_abs(p, q, qd, d);
-    float tipb_y = tip_y, tipb_z = tip_z;  // rigid-body tip as of the refresh before the LAST simulate
-    float rail_force = 0.f;
-#pragma unroll
-    for (int i = 0; i < VINE_MAX_CFI; ++i) in.contact[i] = 0.f;
-    const float dyn_rng16 = p.dyn_rng * 1.52587890625e-05f, acc_rng16 = p.acc_rng * 1.52587890625e-05f;   // 2^-16
 #pragma unroll 1
     for (int i = 0; i < p.C; ++i) {
       // exact sin/cos: once per control step in free space (the incremental rotation drifts < 1e-6 over the 40 substeps at
       // |w| < 36 rad/s), once per sim step with obstacles (impacts can spin a link an order of magnitude faster)
       if (CONTACT && i > 0) refresh_trig(p, d);
-      if (i > 0 && i == p.C - 1 && reset_in != 0 && p.stale) {  // only needed by V5:797 on reset steps
-        float vy, vz; tip_fk(d, tipb_y, tipb_z, vy, vz);
-      }
-      JointLaw law; joint_law_unscaled(law);
-      float acc_scale = 1.f;
-      if (p.randomize) {  // V5:1053-1055: 20 multipliers re-drawn every sim step (+1 for accel scaling)
-        // 16 random bits per multiplier (two per Philox word): 3 Philox calls per sim step instead of 6; multiplier k uses
-        // half k of the 24 halves of blocks 8 i .. 8 i + 2, low half first
-        uint32_t u[12];
-#pragma unroll
-        for (uint32_t b = 0; b < 3; ++b) {
-          const uint4 r = philox4x32(a.k0, a.k1, gid, VINE_SITE_DYNAMICS, step, (uint32_t)i * 8u + b);
-          u[4 * b] = r.x; u[4 * b + 1] = r.y; u[4 * b + 2] = r.z; u[4 * b + 3] = r.w;
-        }
-#pragma unroll
-        for (int j = 0; j < VINE_NL; ++j) {
-          law.K[j] = __fmul_rn(law.K[j], uniform_ab16(u[2 * j] & 0xffffu, p.dyn_min, dyn_rng16));
-          law.Cd[j] = __fmul_rn(law.Cd[j], uniform_ab16(u[2 * j] >> 16, p.dyn_min, dyn_rng16));
-          law.b[j] = __fmul_rn(law.b[j], uniform_ab16(u[2 * j + 1] & 0xffffu, p.dyn_min, dyn_rng16));
-          law.B[j] = __fmul_rn(law.B[j], uniform_ab16(u[2 * j + 1] >> 16, p.dyn_min, dyn_rng16));
-        }
-        acc_scale = uniform_ab16(u[10] & 0xffffu, p.acc_min, acc_rng16);
-      }
-      // rigid-body cart velocity: stale on the first sim step after a reset (V5:1069)
-      const float cart_vel = (i == 0) ? cart_body_vy : d.v[0];
-      float efforts[6];
-      efforts[0] = rail_controller(p, cart_vel, u_rail, acc_scale, prev_cart_vel, prev_err);
-      rail_force = efforts[0];
-      if (!p.implicit_law) {
-#pragma unroll
-        for (int j = 0; j < VINE_NL; ++j) {
-          const float th = j == 0 ? d.x[1] : d.x[j + 1] - d.x[j];
-          const float thd = j == 0 ? d.v[1] : d.v[j + 1] - d.v[j];
-          efforts[j + 1] = joint_torque(law, j, th, thd, u_use);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < VINE_NL; ++j) efforts[j + 1] = 0.f;
-      }
-      in.contact[i] = lip;  // VT:348-351: force of the PREVIOUS simulate
-      JointImp J; joint_implicit_consts(p, law, u_use, efforts, J);
+      JointImp J;
+      env_sim_step_begin(p, a, i, E, d, J);
 #pragma unroll 1
-      for (int s = 0; s < p.S; ++s) substep<CONTACT>(p, J, rail_force, ob, cs, cc, d, lip);
+      for (int s = 0; s < p.S; ++s) substep<CONTACT, float>(p, J, m00, m00inv, E.rail_force, ob, cs, cc, d, E.lip);
     }
-    float tipvel_y, tipvel_z;
-    tip_fk(d, tip_y, tip_z, tipvel_y, tipvel_z);
-    float cart_y_body = d.x[0];
-    cart_body_vy = d.v[0];
-    abs_to_rel(d, q, qd);
-
-    // ---- post_physics_step V5:1110-1120 ----
-    progress += 1;
-    if (reset_in != 0) {  // deferred reset of envs flagged at the end of the previous step (V5:1114-1116)
-      reset_env(p, a.k0, a.k1, gid, step, q, qd, target, obj);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) in.prev_q[i] = q[i];                     // V5:794
-      if (p.stale) {                                                       // V5:796-797 stale rigid-body views
-        in.prev_tip[1] = tipb_y; in.prev_tip[2] = tipb_z;
-      } else {                                                             // "as if FK were done": clean episode boundary
-        Dyn dn; rel_to_abs(p, q, qd, dn);
-        tip_fk(dn, tip_y, tip_z, tipvel_y, tipvel_z);
-        in.prev_tip[1] = tip_y; in.prev_tip[2] = tip_z;
-        cart_y_body = q[0]; cart_body_vy = 0.f; lip = 0.f; prev_cart_vel = 0.f;
-#pragma unroll
-        for (int i = 0; i < VINE_MAX_CFI; ++i) in.contact[i] = 0.f;
-      }
-      in.prev_u_rail = 0.f;                                                // V5:798
-      prev_err = 0.f;                                                      // V5:799
-      reset_in = 0; progress = 0; agg = 0.f;                               // V5:807-810
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { in.q[i] = q[i]; in.qd[i] = qd[i]; }
-    in.tip[0] = 0.f; in.tip[1] = tip_y; in.tip[2] = tip_z;
-    in.tipvel[0] = 0.f; in.tipvel[1] = tipvel_y; in.tipvel[2] = tipvel_z;
-    in.target[0] = target[0]; in.target[1] = target[1]; in.target[2] = target[2];
-    in.target_vel[0] = in.target_vel[1] = in.target_vel[2] = 0.f;          // V5:916-918
-    in.obj[0] = obj[0]; in.obj[1] = obj[1];
-    in.cart_y = cart_y_body; in.smoothed = smoothed; in.u_fpam = u_fpam; in.u_rail = u_rail;
-    in.reset_in = reset_in; in.progress = progress;
-    float noise[VINE_MAX_OBS];
-    const bool noisy = p.randomize && p.obs_noise != 0.f;
-    if (noisy) {
-#pragma unroll
-      for (uint32_t b = 0; b < VINE_MAX_OBS / 4; ++b) {
-        if ((int)(4 * b) < p.O) normal4(philox4x32(a.k0, a.k1, gid, VINE_SITE_OBS_NOISE, step, b), &noise[4 * b]);
-      }
-    }
-    PostOut o;
-    post_physics(p, in, noisy ? noise : nullptr, o);
-    agg = __fadd_rn(agg, o.rew);                                           // V5:1278
-
-    // ---- write back ----
-    a.S0[e] = make_float4(q[0], q[1], q[2], q[3]);
-    a.S1[e] = make_float4(q[4], q[5], qd[0], qd[1]);
-    a.S2[e] = make_float4(qd[2], qd[3], qd[4], qd[5]);
-    a.S3[e] = make_float4(smoothed, prev_cart_vel, prev_err, lip);
-    a.S4[e] = make_float4(tip_y, tip_z, cart_body_vy, agg);
-    if (was_reset) a.S5[e] = make_float4(target[1], target[2], obj[0], obj[1]);
-    a.ctr[e] = step + 1u;
-    a.rew[e] = o.rew;
-    a.reset[e] = o.reset;
-    a.progress[e] = progress;
-    a.timeout[e] = o.timeout;
+    env_end(p, a, e, E, d, s_obs + threadIdx.x * (VINE_MAX_OBS + 1));
     if (CONTACT && a.near) a.near[e] = cc.seen != 0u;
-    float* row = s_obs + threadIdx.x * (VINE_MAX_OBS + 1);
-#pragma unroll
-    for (int i = 0; i < VINE_MAX_OBS; ++i) if (i < p.O) row[i] = o.obs[i];
-    if (a.dbg) {
-      float* dbg = a.dbg + e * VINE_DBG_W;
-      dbg[0] = u_rail; dbg[1] = u_fpam; dbg[2] = in.prev_u_rail; dbg[3] = rail_force;
-      dbg[4] = tipvel_y; dbg[5] = tipvel_z;
-#pragma unroll
-      for (int i = 0; i < VINE_NUM_REWARDS; ++i) dbg[6 + i] = o.r[i];
-    }
   }
   __syncthreads();
   if (CONTACT && a.perm) {
@@ -291,8 +324,57 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
       }
     }
   } else {
-    store_obs_block<BLOCK>(s_obs, p.O, a.first, a.end, p.clip_obs, a.obs, a.obs_clamped);
+    store_obs_block<BLOCK, BLOCK>(s_obs, p.O, a.first, a.end, p.clip_obs, a.obs, a.obs_clamped);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// The free-space control step with TWO environments per thread: thread t of a block owns envs base + t and
+// base + VINE_BLOCK2 + t (both coalesced), integrates them in the two lanes of FFMA2/FMUL2/FADD2 (substep<false, float2>)
+// and runs the scalar task logic (bit-exact to the reference's torch kernels) once per env.
+// ------------------------------------------------------------------------------------------
+#define VINE_BLOCK2 128
+__global__ void __launch_bounds__(VINE_BLOCK2, VINE_STEP2_MIN_BLOCKS)
+vine_step2_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
+  __shared__ float s_obs[2 * VINE_BLOCK2 * (VINE_MAX_OBS + 1)];
+  const int64_t eA = a.first + (int64_t)blockIdx.x * (2 * VINE_BLOCK2) + threadIdx.x;
+  const int64_t eB0 = eA + VINE_BLOCK2;
+  const bool liveA = eA < a.end, liveB = eB0 < a.end;
+  const int64_t eB = liveB ? eB0 : eA;   // a ragged tail integrates env A in both lanes and stores it once
+  if (liveA) {
+    EnvStep EA, EB;
+    DynT<float2> d2;
+    {
+      Dyn dA, dB;
+      env_begin(p, a, eA, EA, dA);
+      env_begin(p, a, eB, EB, dB);
+      pack2(dA, dB, d2);
+    }
+    Obstacles ob = {0, -1, 0.f, 0.f, 0.f, 0.f};
+    ContactCache cc = {0u, 1e30f, 0u};
+    float lip_unused = 0.f;
+    const float m00 = fmaf(p.h, p.damping, p.mtot), m00inv = rcp_approx(m00);
+#pragma unroll 1
+    for (int i = 0; i < p.C; ++i) {
+      JointImpT<float2> J2;
+      float2 rail;
+      {
+        Dyn dA, dB; unpack2(d2, dA, dB);
+        JointImp JA, JB;
+        env_sim_step_begin(p, a, i, EA, dA, JA);
+        env_sim_step_begin(p, a, i, EB, dB, JB);
+        pack2(JA, JB, J2);
+        rail = make_float2(EA.rail_force, EB.rail_force);
+      }
+#pragma unroll 1
+      for (int s = 0; s < p.S; ++s) substep<false, float2>(p, J2, m00, m00inv, rail, ob, nullptr, cc, d2, lip_unused);
+    }
+    Dyn dA, dB; unpack2(d2, dA, dB);
+    env_end(p, a, eA, EA, dA, s_obs + threadIdx.x * (VINE_MAX_OBS + 1));
+    if (liveB) env_end(p, a, eB, EB, dB, s_obs + (VINE_BLOCK2 + threadIdx.x) * (VINE_MAX_OBS + 1));
+  }
+  __syncthreads();
+  store_obs_block<2 * VINE_BLOCK2, VINE_BLOCK2>(s_obs, p.O, a.first, a.end, p.clip_obs, a.obs, a.obs_clamped);
 }
 
 // Env order of a binned launch of the contact variant: envs that had contact candidates in their last step first, the others
@@ -523,8 +605,9 @@ __global__ void __launch_bounds__(VINE_BLOCK) vine_simulate_kernel(const __grid_
   Dyn d; rel_to_abs(p, q, qd, d);
   JointImp J; joint_implicit_consts(p, law, u_use, efforts, J);
   float lip = 0.f;
+  const float m00 = fmaf(p.h, p.damping, p.mtot), m00inv = rcp_approx(m00);
 #pragma unroll 1
-  for (int s = 0; s < p.S; ++s) substep<CONTACT>(p, J, efforts[0], ob, cs, cc, d, lip);
+  for (int s = 0; s < p.S; ++s) substep<CONTACT, float>(p, J, m00, m00inv, efforts[0], ob, cs, cc, d, lip);
   float ty, tz, vy, vz; tip_fk(d, ty, tz, vy, vz);
   abs_to_rel(d, q, qd);
   for (int i = 0; i < 6; ++i) { io.dof_pos[6 * e + i] = q[i]; io.dof_vel[6 * e + i] = qd[i]; }
@@ -607,6 +690,7 @@ int vine_config_defaults(VineConfig* c) {  // YT:7-134
   c->revolute_lower = -3.4e38; c->revolute_upper = 3.4e38;
   c->prismatic_lower = -3.4e38; c->prismatic_upper = 3.4e38;
   c->contact_stiffness = 2000.0; c->contact_damping = 2.0; c->contact_rest_offset = 0.001;
+  c->contact_cull_slack = 0.01; c->contact_binning = 1; c->step_kernel_variant = VINE_STEP_KERNEL_AUTO;
   return VINE_OK;
 }
 
@@ -632,10 +716,10 @@ int vine_create(const VineConfig* cfg, int64_t num_envs, int64_t global_env_offs
   if (rc != VINE_OK) { snprintf(g_create_err, 256, "%s", why); return rc; }
   VineEnv* env = new VineEnv();
   memset(env, 0, sizeof(*env));
-  {  // contact variant: re-cull slack in metres (measured on B200: 0.005-0.01 best, 0.04 is 5-10 % slower)
-    const char* sl = getenv("VINE_CULL_SLACK");
-    p.cull_slack = sl ? (float)atof(sl) : 0.01f;
-    if (!(p.cull_slack > 0.f)) p.cull_slack = 0.01f;
+  // contact variant: re-cull slack in metres (measured on B200: 0.005-0.01 best, 0.04 is 5-10 % slower)
+  p.cull_slack = cfg->contact_cull_slack > 0.0 ? (float)cfg->contact_cull_slack : 0.01f;
+  if (cfg->step_kernel_variant < VINE_STEP_KERNEL_AUTO || cfg->step_kernel_variant > VINE_STEP_KERNEL_TWO_ENVS_PACKED) {
+    snprintf(g_create_err, 256, "unknown step_kernel_variant"); return VINE_ERR_INVALID_ARG;
   }
   env->p = p; env->cfg = *cfg; env->device = device;
   StepArgs& a = env->a;
@@ -650,9 +734,8 @@ int vine_create(const VineConfig* cfg, int64_t num_envs, int64_t global_env_offs
   if (e == cudaSuccess) e = cudaMalloc(&a.S5, n * sizeof(float4));
   if (e == cudaSuccess) e = cudaMalloc(&a.ring, n * sizeof(float2) * (size_t)(p.D > 0 ? p.D : 1));
   if (e == cudaSuccess) e = cudaMalloc(&a.ctr, n * sizeof(uint32_t));
-  // contact variant: bin the envs by "had contact candidates" before every full step (VINE_CONTACT_BINNING=0 turns it off)
-  const char* binning = getenv("VINE_CONTACT_BINNING");
-  if ((p.shelf || p.pipe) && !(binning && binning[0] == '0')) {
+  // contact variant: bin the envs by "had contact candidates" before every full step
+  if ((p.shelf || p.pipe) && cfg->contact_binning) {
     if (e == cudaSuccess) e = cudaMalloc(&a.near, n);
     if (e == cudaSuccess) e = cudaMemset(a.near, 0, n);
     if (e == cudaSuccess) e = cudaMalloc(&a.perm, n * sizeof(int32_t));
@@ -814,6 +897,15 @@ int vine_metrics(VineEnv* env, double* sums, float* maxes, void* stream) {
 // warp of a small launch was measured too and changes nothing: the time is one env's own contact chain, not the lanes' sum.
 #define VINE_BIN_MIN_ENVS 98304   // measured crossover on B200: binning pays from ~100 k envs per launch (shelf and pipe presets)
 
+// free space: two envs per thread on the packed FP32 instructions unless the config asks for the scalar kernel
+static void launch_free_step(const VineEnv* env, const StepArgs& a, cudaStream_t st) {
+  const int64_t count = a.end - a.first;
+  if (env->cfg.step_kernel_variant == VINE_STEP_KERNEL_ONE_ENV_PER_THREAD)
+    vine_step_kernel<false><<<grid_for(count, VINE_BLOCK), VINE_BLOCK, 0, st>>>(env->p, a);
+  else
+    vine_step2_kernel<<<grid_for(count, 2 * VINE_BLOCK2), VINE_BLOCK2, 0, st>>>(env->p, a);
+}
+
 int vine_step(VineEnv* env, void* stream) {
   if (!env) return VINE_ERR_INVALID_ARG;
   if (!env->bound) { snprintf(env->err, 256, "vine_step: call vine_bind_io first"); return VINE_ERR_NOT_BOUND; }
@@ -828,7 +920,7 @@ int vine_step(VineEnv* env, void* stream) {
     }
     vine_step_kernel<true><<<grid_for(a.n, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, st>>>(env->p, a);
   } else {
-    vine_step_kernel<false><<<grid_for(env->a.n, VINE_BLOCK), VINE_BLOCK, 0, st>>>(env->p, env->a);
+    launch_free_step(env, env->a, st);
   }
   CUDA_TRY(env, cudaGetLastError());
   return VINE_OK;
@@ -845,7 +937,7 @@ int vine_step_range(VineEnv* env, int64_t first, int64_t count, void* stream) {
   a.first = first; a.end = first + count;
   a.perm = nullptr;   // chunked launches keep the identity order (the near flags are still maintained)
   if (env->p.shelf || env->p.pipe) vine_step_kernel<true><<<grid_for(count, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, (cudaStream_t)stream>>>(env->p, a);
-  else vine_step_kernel<false><<<grid_for(count, VINE_BLOCK), VINE_BLOCK, 0, (cudaStream_t)stream>>>(env->p, a);
+  else launch_free_step(env, a, (cudaStream_t)stream);
   CUDA_TRY(env, cudaGetLastError());
   return VINE_OK;
 }

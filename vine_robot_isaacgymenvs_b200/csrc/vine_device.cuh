@@ -186,7 +186,35 @@ VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, 
 // ------------------------------------------------------------------------------------------
 // S/C = sin/cos of the absolute link angles phi_k = 3.1415 + phi'_k, carried in registers: refreshed
 // exactly once per sim step (refresh_trig) and rotated incrementally by h*w_k in every substep.
-struct Dyn { float x[6], v[6], S[VINE_NL], C[VINE_NL]; };
+template <typename T> struct DynT { T x[6], v[6], S[VINE_NL], C[VINE_NL]; };
+typedef DynT<float> Dyn;
+
+// Arithmetic of the integrator, written once for two value types:
+//   float  : one environment per thread (contact variant, function-level entry points)
+//   float2 : TWO environments per thread on Blackwell's packed FP32 instructions (fma/mul/add.rn.f32x2 -> SASS
+//            FFMA2/FMUL2/FADD2): lane .x = env A, .y = env B, half the issue slots per environment. Scalar constants
+//            enter as broadcast operands (`R.F32` / `UR.F32` / immediates in SASS), negations as operand modifiers.
+// Every operation is an explicit round-to-nearest intrinsic (nvcc cannot contract or re-associate them), so both
+// instantiations compute bit-identical results per environment.
+template <typename T> struct Ops;
+template <> struct Ops<float> {
+  static VDEV float bc(float a) { return a; }
+  static VDEV float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+  static VDEV float mul(float a, float b) { return __fmul_rn(a, b); }
+  static VDEV float add(float a, float b) { return __fadd_rn(a, b); }
+  static VDEV float sub(float a, float b) { return __fsub_rn(a, b); }
+  static VDEV float neg(float a) { return -a; }
+  static VDEV float rcp(float a) { return rcp_approx(a); }
+};
+template <> struct Ops<float2> {
+  static VDEV float2 bc(float a) { return make_float2(a, a); }
+  static VDEV float2 fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+  static VDEV float2 mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+  static VDEV float2 add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+  static VDEV float2 neg(float2 a) { return make_float2(-a.x, -a.y); }
+  static VDEV float2 sub(float2 a, float2 b) { return __fadd2_rn(a, neg(b)); }
+  static VDEV float2 rcp(float2 a) { return make_float2(rcp_approx(a.x), rcp_approx(a.y)); }
+};
 
 VDEV void refresh_trig(const VineParams& p, Dyn& d) {
 #pragma unroll
@@ -396,7 +424,8 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScrat
 // per-sim-step joint constants for the implicit integrator:
 //   t_j = tc_j - kk_j theta_j - ek_j thetadot_j  (ek = dd + h kk),  gam_j = h dd_j + h^2 kk_j + armature,
 //   diag_j = alpha_j + gam_j + gam_{j+1} (constant part of the system matrix diagonal)
-struct JointImp { float kk[VINE_NL], ek[VINE_NL], tc[VINE_NL], gam[VINE_NL], diag[VINE_NL], m00; };
+template <typename T> struct JointImpT { T kk[VINE_NL], ek[VINE_NL], tc[VINE_NL], gam[VINE_NL], diag[VINE_NL]; };
+typedef JointImpT<float> JointImp;
 
 VDEV void joint_implicit_consts(const VineParams& p, const JointLaw& law, float u_use, const float efforts[6], JointImp& J) {
 #pragma unroll
@@ -413,7 +442,27 @@ VDEV void joint_implicit_consts(const VineParams& p, const JointLaw& law, float 
   }
 #pragma unroll
   for (int j = 0; j < VINE_NL; ++j) J.diag[j] = p.alpha[j] + J.gam[j] + (j + 1 < VINE_NL ? J.gam[j + 1] : 0.f);
-  J.m00 = fmaf(p.h, p.damping, p.mtot);
+}
+
+// (A, B) of two environments -> lanes (.x, .y)
+VDEV void pack2(const Dyn& A, const Dyn& B, DynT<float2>& d) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { d.x[i] = make_float2(A.x[i], B.x[i]); d.v[i] = make_float2(A.v[i], B.v[i]); }
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) { d.S[j] = make_float2(A.S[j], B.S[j]); d.C[j] = make_float2(A.C[j], B.C[j]); }
+}
+VDEV void unpack2(const DynT<float2>& d, Dyn& A, Dyn& B) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { A.x[i] = d.x[i].x; B.x[i] = d.x[i].y; A.v[i] = d.v[i].x; B.v[i] = d.v[i].y; }
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) { A.S[j] = d.S[j].x; B.S[j] = d.S[j].y; A.C[j] = d.C[j].x; B.C[j] = d.C[j].y; }
+}
+VDEV void pack2(const JointImp& A, const JointImp& B, JointImpT<float2>& J) {
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    J.kk[j] = make_float2(A.kk[j], B.kk[j]); J.ek[j] = make_float2(A.ek[j], B.ek[j]); J.tc[j] = make_float2(A.tc[j], B.tc[j]);
+    J.gam[j] = make_float2(A.gam[j], B.gam[j]); J.diag[j] = make_float2(A.diag[j], B.diag[j]);
+  }
 }
 
 // One substep of the semi-implicit integrator (equations of motion: DESIGN.md §4):
@@ -421,99 +470,104 @@ VDEV void joint_implicit_consts(const VineParams& p, const JointLaw& law, float 
 // Velocity-product terms in O(n): with a_m = C_m w_m^2, b_m = S_m w_m^2,
 //   P_j = sum_{m>j} L beta_m a_m + L beta_j sum_{m<j} a_m  (Q_j likewise with b):
 //   f_j = S_j (g beta_j - P_j) + C_j Q_j ,   f_y = F - D v_y - (1/L) sum_m L beta_m b_m
-template <bool CONTACT>
-VDEV void substep(const VineParams& p, const JointImp& J, float rail_force, const Obstacles& ob, ContactScratch* cs, ContactCache& cc,
-                  Dyn& d, float& lip) {
-  float a[VINE_NL], b[VINE_NL], As[VINE_NL], Bs[VINE_NL];
+// m00 = M_tot + h D (cart row of the system matrix), m00inv its reciprocal: the same for every env and substep.
+template <bool CONTACT, typename T>
+VDEV void substep(const VineParams& p, const JointImpT<T>& J, float m00, float m00inv, T rail_force, const Obstacles& ob,
+                  ContactScratch* cs, ContactCache& cc, DynT<T>& d, float& lip) {
+  typedef Ops<T> O;
+  T a[VINE_NL], b[VINE_NL], As[VINE_NL], Bs[VINE_NL];
 #pragma unroll
-  for (int j = 0; j < VINE_NL; ++j) { const float w2 = d.v[j + 1] * d.v[j + 1]; a[j] = d.C[j] * w2; b[j] = d.S[j] * w2; }
-  As[VINE_NL - 1] = 0.f; Bs[VINE_NL - 1] = 0.f;
+  for (int j = 0; j < VINE_NL; ++j) { const T w2 = O::mul(d.v[j + 1], d.v[j + 1]); a[j] = O::mul(d.C[j], w2); b[j] = O::mul(d.S[j], w2); }
+  As[VINE_NL - 2] = O::mul(O::bc(p.Lbeta[VINE_NL - 1]), a[VINE_NL - 1]);
+  Bs[VINE_NL - 2] = O::mul(O::bc(p.Lbeta[VINE_NL - 1]), b[VINE_NL - 1]);
 #pragma unroll
-  for (int j = VINE_NL - 2; j >= 0; --j) {
-    As[j] = fmaf(p.Lbeta[j + 1], a[j + 1], As[j + 1]);
-    Bs[j] = fmaf(p.Lbeta[j + 1], b[j + 1], Bs[j + 1]);
+  for (int j = VINE_NL - 3; j >= 0; --j) {
+    As[j] = O::fma(O::bc(p.Lbeta[j + 1]), a[j + 1], As[j + 1]);
+    Bs[j] = O::fma(O::bc(p.Lbeta[j + 1]), b[j + 1], Bs[j + 1]);
   }
-  float f[6];
-  f[0] = fmaf(-p.inv_L, fmaf(p.Lbeta[0], b[0], Bs[0]), fmaf(-p.damping, d.v[0], rail_force));
+  T f[6];
+  f[0] = O::fma(O::bc(-p.inv_L), O::fma(O::bc(p.Lbeta[0]), b[0], Bs[0]), O::fma(O::bc(-p.damping), d.v[0], rail_force));
   {
-    float Ap = 0.f, Bp = 0.f;
+    T Ap = a[0], Bp = b[0];
+    f[1] = O::fma(d.C[0], Bs[0], O::mul(d.S[0], O::sub(O::bc(p.gbeta[0]), As[0])));
 #pragma unroll
-    for (int j = 0; j < VINE_NL; ++j) {
-      const float P = fmaf(p.Lbeta[j], Ap, As[j]), Q = fmaf(p.Lbeta[j], Bp, Bs[j]);
-      f[j + 1] = fmaf(d.C[j], Q, d.S[j] * (p.gbeta[j] - P));
-      Ap += a[j]; Bp += b[j];
+    for (int j = 1; j < VINE_NL; ++j) {
+      const T P = j == VINE_NL - 1 ? O::mul(O::bc(p.Lbeta[j]), Ap) : O::fma(O::bc(p.Lbeta[j]), Ap, As[j]);
+      const T Q = j == VINE_NL - 1 ? O::mul(O::bc(p.Lbeta[j]), Bp) : O::fma(O::bc(p.Lbeta[j]), Bp, Bs[j]);
+      f[j + 1] = O::fma(d.C[j], Q, O::mul(d.S[j], O::sub(O::bc(p.gbeta[j]), P)));
+      if (j + 1 < VINE_NL) { Ap = O::add(Ap, a[j]); Bp = O::add(Bp, b[j]); }
     }
   }
   // joint torques (relative coordinates) -> absolute: Q_j = t_j - t_{j+1}
   {
-    float tn = 0.f;
+    T tn = O::bc(0.f);
 #pragma unroll
     for (int j = VINE_NL - 1; j >= 0; --j) {
-      const float th = j == 0 ? d.x[1] : d.x[j + 1] - d.x[j];
-      const float thd = j == 0 ? d.v[1] : d.v[j + 1] - d.v[j];
-      const float t = fmaf(-J.ek[j], thd, fmaf(-J.kk[j], th, J.tc[j]));
-      f[j + 1] += t - tn;
+      const T th = j == 0 ? d.x[1] : O::sub(d.x[j + 1], d.x[j]);
+      const T thd = j == 0 ? d.v[1] : O::sub(d.v[j + 1], d.v[j]);
+      const T t = O::fma(O::neg(J.ek[j]), thd, O::fma(O::neg(J.kk[j]), th, J.tc[j]));
+      f[j + 1] = O::add(f[j + 1], j == VINE_NL - 1 ? t : O::sub(t, tn));
       tn = t;
     }
   }
-  if (CONTACT) lip = contact_forces(p, ob, cs, cc, d, f);
+  if constexpr (CONTACT) lip = contact_forces(p, ob, cs, cc, d, f);
   // lower triangle of the SPD system matrix; rows/cols: 0 = cart, 1..5 = links
-  float M[6][6];
-  M[0][0] = J.m00;
+  T M[6][6];
 #pragma unroll
   for (int j = 0; j < VINE_NL; ++j) {
-    M[j + 1][0] = -p.beta[j] * d.C[j];
+    M[j + 1][0] = O::mul(O::bc(-p.beta[j]), d.C[j]);
     M[j + 1][j + 1] = J.diag[j];
 #pragma unroll
     for (int m = 0; m < j; ++m) {
-      const float c = p.Lbeta[j] * fmaf(d.C[j], d.C[m], d.S[j] * d.S[m]);
-      M[j + 1][m + 1] = (m == j - 1) ? c - J.gam[j] : c;
+      const T c = O::fma(d.C[j], d.C[m], O::mul(d.S[j], d.S[m]));
+      M[j + 1][m + 1] = (m == j - 1) ? O::fma(O::bc(p.Lbeta[j]), c, O::neg(J.gam[j])) : O::mul(O::bc(p.Lbeta[j]), c);
     }
   }
   // LDL^T (row-wise): u_q = A_jq - sum_{r<q} u_r L_qr ; L_jq = u_q / d_q ; d_j = A_jj - sum_q u_q L_jq
-  float dinv[6];
-  dinv[0] = rcp_approx(M[0][0]);
+  T dinv[6];
+  dinv[0] = O::bc(m00inv);
 #pragma unroll
   for (int j = 1; j < 6; ++j) {
-    float u[5];
-    float dj = M[j][j];
+    T u[5];
+    T dj = M[j][j];
 #pragma unroll
     for (int q = 0; q < j; ++q) {
-      float uq = M[j][q];
+      T uq = M[j][q];
 #pragma unroll
-      for (int r = 0; r < q; ++r) uq = fmaf(-u[r], M[q][r], uq);
+      for (int r = 0; r < q; ++r) uq = O::fma(O::neg(u[r]), M[q][r], uq);
       u[q] = uq;
-      const float l = uq * dinv[q];
+      const T l = O::mul(uq, dinv[q]);
       M[j][q] = l;
-      dj = fmaf(-uq, l, dj);
+      dj = O::fma(O::neg(uq), l, dj);
     }
-    dinv[j] = rcp_approx(dj);
+    dinv[j] = O::rcp(dj);
   }
+  (void)m00;
   // solve M a = f (dv = h a is folded into the velocity update)
 #pragma unroll
   for (int i = 1; i < 6; ++i)
 #pragma unroll
-    for (int q = 0; q < i; ++q) f[i] = fmaf(-M[i][q], f[q], f[i]);
+    for (int q = 0; q < i; ++q) f[i] = O::fma(O::neg(M[i][q]), f[q], f[i]);
 #pragma unroll
-  for (int i = 0; i < 6; ++i) f[i] *= dinv[i];
+  for (int i = 0; i < 6; ++i) f[i] = O::mul(f[i], dinv[i]);
 #pragma unroll
   for (int i = 4; i >= 0; --i)
 #pragma unroll
-    for (int q = i + 1; q < 6; ++q) f[i] = fmaf(-M[q][i], f[q], f[i]);
-  d.v[0] = fmaf(p.h, f[0], d.v[0]); d.x[0] = fmaf(p.h, d.v[0], d.x[0]);
+    for (int q = i + 1; q < 6; ++q) f[i] = O::fma(O::neg(M[q][i]), f[q], f[i]);
+  d.v[0] = O::fma(O::bc(p.h), f[0], d.v[0]); d.x[0] = O::fma(O::bc(p.h), d.v[0], d.x[0]);
 #pragma unroll
   for (int j = 0; j < VINE_NL; ++j) {
-    d.v[j + 1] = fmaf(p.h, f[j + 1], d.v[j + 1]);
-    const float dl = p.h * d.v[j + 1];
-    d.x[j + 1] += dl;
+    d.v[j + 1] = O::fma(O::bc(p.h), f[j + 1], d.v[j + 1]);
+    const T dl = O::mul(O::bc(p.h), d.v[j + 1]);
+    d.x[j + 1] = O::add(d.x[j + 1], dl);
     // rotate (S,C) by dl: sin dl ~ dl (1 - dl^2/6), cos dl ~ 1 - dl^2/2. |dl| = h |w| < 0.03 for |w| < 36 rad/s, where the
     // dropped dl^4/24 < 3.4e-8 is below half an ulp of 1; the exact sin/cos is re-evaluated every sim step (refresh_trig)
-    const float d2 = dl * dl;
-    const float sd = dl * fmaf(-0.16666667f, d2, 1.f);
-    const float cd = fmaf(-0.5f, d2, 1.f);
-    const float s = d.S[j], c = d.C[j];
-    d.S[j] = fmaf(s, cd, c * sd);
-    d.C[j] = fmaf(c, cd, -s * sd);
+    const T d2 = O::mul(dl, dl);
+    const T sd = O::mul(dl, O::fma(O::bc(-0.16666667f), d2, O::bc(1.f)));
+    const T cd = O::fma(O::bc(-0.5f), d2, O::bc(1.f));
+    const T s = d.S[j], c = d.C[j];
+    d.S[j] = O::fma(s, cd, O::mul(c, sd));
+    d.C[j] = O::fma(c, cd, O::neg(O::mul(s, sd)));
   }
 }
 
