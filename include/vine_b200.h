@@ -550,6 +550,10 @@ typedef struct VineLstmHeadTrain {
   float* debug_out;              /* NULL or [n, 4]: mu0, mu1, normalised value, neglogp */
   int64_t n;
   float e_clip, critic_coef, entropy_coef, bounds_loss_coef, inv_B, reserved_f;
+  /* rl_games dataset.update_mu_sigma: NULL, or the [T, N, 8] scalars buffer this minibatch was gathered from; the kernel
+   * stores this pass's mu into columns 2,3 of the source row of every minibatch row (rows = [step in chunk][chunk][env]) */
+  float* mu_writeback;
+  int64_t wb_seq_len, wb_chunks, wb_num_envs, wb_env_begin, wb_env_count;
 } VineLstmHeadTrain;
 int vine_lstm_head_train(const VineLstmHeadTrain* args, void* stream);
 
@@ -673,7 +677,8 @@ typedef struct VinePpoMinibatch {
   const void* packed;            /* VINE_MLP_PACKED_BYTES */
   const float* obs;              /* [T, N, O] raw observations */
   const float* actions;          /* [T, N, 2] */
-  const float* mu_old;           /* [T, N, 2] */
+  float* mu_old;                 /* [T, N, 2] in: mean of the policy the row was last evaluated with (rollout, or the previous
+                                    mini-epoch); out: this pass's mean (rl_games dataset.update_mu_sigma) */
   const float* neglogp_old;      /* [T, N] */
   const float* values_old;       /* [T, N] normalised */
   const float* returns;          /* [T, N] normalised */
@@ -681,7 +686,7 @@ typedef struct VinePpoMinibatch {
   const float* obs_mean;         /* [O] */
   const float* obs_inv_std;      /* [O] */
   const float* logstd;           /* [2] current (points into the flat parameter vector) */
-  const float* logstd_old;       /* [2] at rollout time */
+  const float* logstd_old;       /* [2] log-std these rows were last evaluated with (see vine_ppo_reduce) */
   float* workspace;              /* [workspace_ctas][VINE_PPO_WS_FLOATS] gradient partials, 16-B aligned */
   float* state;                  /* device optimiser state, see above */
   float* debug_out;              /* NULL or [T*env_count, 4]: mu0, mu1, normalised value, neglogp per sample */
@@ -696,8 +701,11 @@ int vine_ppo_num_params(int num_obs);
 int vine_ppo_max_ctas(void);     /* upper bound of gradient partials one vine_ppo_minibatch call writes */
 /* returns the number of partials written (> 0) or a negative error */
 int vine_ppo_minibatch(const VinePpoMinibatch* batch, void* stream);
-/* flat[p] = sum of the partials in parameter order, flat[P..P+3] = a_loss, c_loss, kl, b_loss (means) */
-int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* flat, void* stream);
+/* flat[p] = sum of the partials in parameter order, flat[P..P+3] = a_loss, c_loss, kl, b_loss (means).
+ * logstd_old_out (NULL or [2]) receives a copy of logstd (the parameter, [2]): the sigma half of rl_games'
+ * dataset.update_mu_sigma -- this launch sits between the minibatch kernel (last reader) and Adam (writer). */
+int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* flat, const float* logstd,
+                    float* logstd_old_out, void* stream);
 /* Adam step with g = flat * grad_scale (1/world after an all-reduce); updates params, moments, packed, state */
 /* bookkeeping != 0: also record the loss statistics / pending KL in `state` (0 when vine_lstm_adam does it) */
 int vine_ppo_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq,

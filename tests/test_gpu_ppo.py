@@ -37,6 +37,7 @@ def test_ppo_iterations_are_finite_and_learn_something(variant, graphs):
     assert all(torch.isfinite(p).all() for p in agent.model.parameters())
     assert any(not torch.equal(a, b) for a, b in zip(before, agent.model.parameters()))
     assert float(agent.obs_rms.count) > 1.0 and agent.frames == (6 + (3 if graphs else 0)) * 16 * 512  # +3: graph warm-up
+    assert agent.epoch == 6 + (3 if graphs else 0)          # warm-up iterations are real training iterations and are counted
 
 
 def test_fused_update_moves_the_parameters_like_the_torch_update():
@@ -61,6 +62,45 @@ def test_fused_update_moves_the_parameters_like_the_torch_update():
     for k in ("a_loss", "c_loss", "kl"):
         assert abs(sa[k] - sb[k]) <= 3e-2 * abs(sb[k]) + 1e-4, (k, sa[k], sb[k])
     assert torch.allclose(a.obs_rms.running_mean, b.obs_rms.running_mean, atol=1e-6)
+
+
+@pytest.mark.parametrize("net", ["mlp", "lstm"])
+def test_full_update_kl_and_learning_rate_follow_the_torch_update(net):
+    """A whole update (4 mini-epochs x 2 minibatches) from the same rollout: the kernel paths and the torch path apply rl_games'
+    update_mu_sigma after every minibatch (mini-epoch k measures its KL against mini-epoch k-1, not against the rollout), use
+    the same policy_kl argument order, and therefore report the same mean KL and take the same adaptive-lr decisions."""
+    two = ["train.params.config.minibatch_size=4096"]
+    extra = (MLP if net == "mlp" else []) + two
+    a = make_agent(extra, False, use_fused_update=True)
+    b = make_agent(extra, False, use_fused_update=False)
+    b.load_state_dict(a.state_dict())
+    for _ in range(2):                                   # a second iteration: non-trivial normalisers and sigma
+        a._rollout()
+        for name in ("b_obs", "b_act", "b_mu", "b_nlp", "b_val", "b_ret", "b_adv", "b_done"):
+            getattr(b, name).copy_(getattr(a, name))
+        if net == "lstm":
+            from vine_robot_isaacgymenvs_b200.ppo.tiles import from_tiles
+            for ck in range(a.T // a.seq_len):
+                b.b_h[ck].copy_(from_tiles(a._HH_saved[ck], a.n))
+                b.b_c[ck].copy_(a._C_saved[ck])
+        mu_rollout = a.b_mu.clone()
+        a.pop_stats(); b.pop_stats()
+        a._update_any()
+        b._update_any()
+        torch.cuda.synchronize()
+        sa, sb = a.pop_stats(), b.pop_stats()
+        assert sb["kl"] > 0
+        assert abs(sa["kl"] - sb["kl"]) <= 0.15 * sb["kl"] + 2e-5, (sa["kl"], sb["kl"])
+        # same number of x1.5 / /1.5 decisions (bf16 GEMMs may move one borderline minibatch across a threshold)
+        import math
+        assert abs(math.log(a.lr / b.lr) / math.log(1.5)) <= 1.01, (a.lr, b.lr)
+        # update_mu_sigma happened: the "old" mean of the rows now is the last mini-epoch's, in both paths
+        mu_a = a._scal[..., 2:4] if net == "lstm" else a.b_mu
+        assert float((mu_a - mu_rollout).abs().max()) > 1e-4
+        assert float((mu_a - b.b_mu).abs().mean()) < 3e-2
+        # the sigma snapshot of every minibatch slot is the log-std BEFORE the last Adam step of that slot
+        assert a._logstd_old.shape == (2, 2) and float((a._logstd_old - a.model.sigma).abs().max()) < 2e-2
+        b.load_state_dict(a.state_dict())
 
 
 def test_native_lstm_update_moves_the_parameters_like_the_torch_update():
@@ -102,6 +142,9 @@ def test_checkpoint_roundtrip_uses_rl_games_layout(tmp_path):
     sd = a.state_dict()
     assert "a2c_network.rnn.rnn.weight_hh_l0" in sd["model"] and "running_mean_std.running_mean" in sd["model"]
     assert "value_mean_std.running_var" in sd["model"] and {"epoch", "frame", "optimizer", "last_lr"} <= set(sd)
+    # rl_games 1.5.2 RunningMeanStd((value_size,)): the value normaliser is [1], its count a scalar
+    assert sd["model"]["value_mean_std.running_mean"].shape == (1,) and sd["model"]["value_mean_std.count"].shape == ()
+    assert sd["model"]["running_mean_std.running_mean"].shape == (18,) and "vine_rng_counter" in sd
     torch.save(sd, tmp_path / "ck.pth")
     b = make_agent([], False)
     b.load_state_dict(torch.load(tmp_path / "ck.pth", map_location="cuda:0"))

@@ -61,8 +61,10 @@ def reference(W, buf, mean, inv_std, logstd_old, e0, E, hyp, bf16_weights=True):
     entropy = (0.5 + 0.5 * math.log(2 * math.pi) + logstd).sum()
     loss = a_loss + 0.5 * c_loss * hyp["critic_coef"] - hyp["entropy_coef"] * entropy + b_loss * hyp["bounds_loss_coef"]
     loss.backward()
+    # rl_games torch_ext.policy_kl(p0 = current, p1 = old), the restatement the torch update path calls
+    from vine_robot_isaacgymenvs_b200.ppo.ppo import policy_kl
     so = torch.exp(logstd_old)
-    kl = (torch.log(sigma / so + 1e-5) + (so ** 2 + (mu - sl(buf["mu_old"])) ** 2) / (2 * (sigma ** 2 + 1e-5)) - 0.5).sum(-1).mean()
+    kl = policy_kl(mu.detach(), sigma.detach().expand_as(mu), sl(buf["mu_old"]), so.expand_as(mu))
     return [l.grad for l in leaves], dict(a_loss=a_loss.item(), c_loss=c_loss.item(), kl=kl.item(), b_loss=b_loss.item()), \
         mu.detach(), v.detach()
 
@@ -86,11 +88,22 @@ def run_kernel(lib, W, buf, mean, inv_std, logstd_old, e0, E, hyp, O, T, N, debu
         logstd=logstd.data_ptr(), logstd_old=logstd_old.data_ptr(), workspace=ws.data_ptr(), state=state.data_ptr(),
         debug_out=dbg.data_ptr() if debug else None, horizon=T, num_envs=N, env_begin=e0, env_count=E, num_obs=O,
         workspace_ctas=ctas, adaptive_lr=1, kl_threshold=0.008, lr_min=1e-6, lr_max=1e-2, **hyp)
+    mu_before = buf["mu_old"].clone()
     n_part = lib.vine_ppo_minibatch(C.byref(mb), None)
     assert n_part > 0, n_part
     out = torch.zeros(P + 4, device="cuda")
-    assert lib.vine_ppo_reduce(p(ws), n_part, O, p(out), None) == 0
+    ls_snapshot = torch.full((2,), 7.0, device="cuda")
+    assert lib.vine_ppo_reduce(p(ws), n_part, O, p(out), p(logstd), p(ls_snapshot), None) == 0
     torch.cuda.synchronize()
+    # rl_games dataset.update_mu_sigma: the kernel leaves this pass's mu in the minibatch's rows of mu_old (only there) and
+    # the reduce launch snapshots the log-std the minibatch was evaluated with
+    buf["mu_after"] = buf["mu_old"].clone()
+    buf["mu_old"].copy_(mu_before)
+    assert torch.equal(ls_snapshot, logstd)
+    outside = torch.ones(N, dtype=torch.bool, device="cuda"); outside[e0:e0 + E] = False
+    assert torch.equal(buf["mu_after"][:, outside], mu_before[:, outside])
+    if debug:
+        assert torch.equal(buf["mu_after"][:, e0:e0 + E].reshape(-1, 2), dbg[:, :2])
     return flat, packed, state, out, dbg, n_part
 
 

@@ -34,7 +34,7 @@ def test_player_reproduces_the_network_and_carries_lstm_state(tmp_path):
 
 def test_control_model_rescales_to_hardware_ranges(tmp_path):
     ck, m, rms = _checkpoint(False)
-    cm = VineRobotControlModel(ck, x_range=(-2.0, 2.0), u_range=(0.0, 3.0), num_obs=18)
+    cm = VineRobotControlModel(ck, x_range=(-2.0, 2.0), u_range=(0.0, 3.0), num_obs=18, deterministic=True)
     assert not cm.player.model.has_rnn
     parts = [torch.randn(6), torch.randn(6), torch.randn(3), torch.randn(3)]
     out = cm.get_action(*parts)

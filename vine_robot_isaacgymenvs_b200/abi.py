@@ -178,7 +178,9 @@ class VineLstmHead(C.Structure):
 class VineLstmHeadTrain(C.Structure):
     _fields_ = ([(n, C.c_void_p) for n in ("params", "hh", "scalars", "logstd", "logstd_old", "dh", "grads", "debug_out")]
                 + [("n", C.c_int64)]
-                + [(n, C.c_float) for n in ("e_clip", "critic_coef", "entropy_coef", "bounds_loss_coef", "inv_B", "reserved_f")])
+                + [(n, C.c_float) for n in ("e_clip", "critic_coef", "entropy_coef", "bounds_loss_coef", "inv_B", "reserved_f")]
+                + [("mu_writeback", C.c_void_p)]
+                + [(n, C.c_int64) for n in ("wb_seq_len", "wb_chunks", "wb_num_envs", "wb_env_begin", "wb_env_count")])
 
 
 class VineLstmCellBwd(C.Structure):
@@ -285,7 +287,7 @@ def _declare(lib):
     lib.vine_ppo_num_params.argtypes = [C.c_int]
     lib.vine_ppo_max_ctas.argtypes = []
     lib.vine_ppo_minibatch.argtypes = [C.POINTER(VinePpoMinibatch), vp]
-    lib.vine_ppo_reduce.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    lib.vine_ppo_reduce.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.vine_ppo_adam.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)

@@ -356,8 +356,9 @@ __global__ void __launch_bounds__(256, 2) vine_lstm_head_train_kernel(const Vine
   // sigma is a parameter, not a per-row quantity: every division of the row math below is by one of these constants, so the
   // eight IEEE divisions per row (~17 dependent instructions each, in all 32 lanes) become multiplications
   const float inv_sig0 = 1.f / sig0, inv_sig1 = 1.f / sig1;
-  const float klc0 = __logf(sig0 / sigo0 + 1e-5f) - 0.5f, klc1 = __logf(sig1 / sigo1 + 1e-5f) - 0.5f;
-  const float klq0 = 1.f / (2.f * (sig0 * sig0 + 1e-5f)), klq1 = 1.f / (2.f * (sig1 * sig1 + 1e-5f));
+  // rl_games policy_kl(p0 = current policy, p1 = the policy the rows were last evaluated with), as in vine_ppo_minibatch_kernel
+  const float klc0 = __logf(sigo0 / sig0 + 1e-5f) - 0.5f, klc1 = __logf(sigo1 / sig1 + 1e-5f) - 0.5f;
+  const float klq0 = 1.f / (2.f * (sigo0 * sigo0 + 1e-5f)), klq1 = 1.f / (2.f * (sigo1 * sigo1 + 1e-5f));
   for (int64_t s = warp0; s < a.n; s += nwarps) {
     const int64_t tile = s / TILE;
     const int row = (int)(s % TILE), unit = 8 * lane;
@@ -408,9 +409,15 @@ __global__ void __launch_bounds__(256, 2) vine_lstm_head_train_kernel(const Vine
     dmu0 += a.bounds_loss_coef * 2.f * (bh0 + bl0);
     dmu1 += a.bounds_loss_coef * 2.f * (bh1 + bl1);
     const float m0 = mu0 - muo0, m1 = mu1 - muo1;
-    const float kl = klc0 + (sigo0 * sigo0 + m0 * m0) * klq0 + klc1 + (sigo1 * sigo1 + m1 * m1) * klq1;
+    const float kl = klc0 + (sig0 * sig0 + m0 * m0) * klq0 + klc1 + (sig1 * sig1 + m1 * m1) * klq1;
     dmu0 *= a.inv_B, dmu1 *= a.inv_B, dv *= a.inv_B;
     if (lane == 0) {
+      if (a.mu_writeback) {   // dataset.update_mu_sigma: row s = [step l][chunk c][env e] of the minibatch -> row (c L + l, e0 + e) of [T, N, 8]
+        const int64_t per_step = a.wb_chunks * a.wb_env_count;
+        const int64_t l = s / per_step, rem = s - l * per_step, c = rem / a.wb_env_count, e = rem - c * a.wb_env_count;
+        float* dst = a.mu_writeback + ((c * a.wb_seq_len + l) * a.wb_num_envs + a.wb_env_begin + e) * 8 + 2;
+        *reinterpret_cast<float2*>(dst) = make_float2(mu0, mu1);
+      }
       sc[0] += dmu0, sc[1] += dmu1, sc[2] += dv;
       sc[3] += dls0 * a.inv_B, sc[4] += dls1 * a.inv_B;
       sc[5] += fmaxf(t1, t2) * a.inv_B, sc[6] += fmaxf(c1, c2) * a.inv_B, sc[7] += kl * a.inv_B;

@@ -53,7 +53,8 @@ constexpr int ST_LR = 0, ST_STEP = 1, ST_KL = 2, ST_PENDING = 3, ST_SUMS = 4 /* 
 
 struct MbArgs {
   const uint8_t* packed;
-  const float *obs, *act, *mu_old, *nlp_old, *val_old, *ret, *adv, *obs_mean, *obs_inv_std, *logstd, *logstd_old;
+  const float *obs, *act, *nlp_old, *val_old, *ret, *adv, *obs_mean, *obs_inv_std, *logstd, *logstd_old;
+  float* mu_old;   // in: the policy mean these rows were last evaluated with; out: this pass's mean (rl_games dataset.update_mu_sigma)
   float *ws, *state, *debug;
   const float* dh3_ext;   // recurrent network: d(loss)/d(h3) comes from the LSTM backward instead of the MLP heads
   int T, N, e0, E, O;
@@ -140,8 +141,10 @@ __global__ void __launch_bounds__(128 * Q, 1) vine_ppo_minibatch_kernel(const Mb
   const float sig0 = __expf(ls0), sig1 = __expf(ls1), sigo0 = __expf(lso0), sigo1 = __expf(lso1);
   // sigma is a parameter: the row math divides only by these constants, so its eight IEEE divisions become multiplications
   const float inv_sig0 = 1.f / sig0, inv_sig1 = 1.f / sig1;
-  const float klc0 = __logf(sig0 / sigo0 + 1e-5f) - 0.5f, klc1 = __logf(sig1 / sigo1 + 1e-5f) - 0.5f;
-  const float klq0 = 1.f / (2.f * (sig0 * sig0 + 1e-5f)), klq1 = 1.f / (2.f * (sig1 * sig1 + 1e-5f));
+  // rl_games torch_ext.policy_kl(p0 = current policy, p1 = the policy the rows were last evaluated with):
+  //   log(sigma1 / sigma0 + 1e-5) + (sigma0^2 + (mu1 - mu0)^2) / (2 (sigma1^2 + 1e-5)) - 1/2, summed over the actions
+  const float klc0 = __logf(sigo0 / sig0 + 1e-5f) - 0.5f, klc1 = __logf(sigo1 / sig1 + 1e-5f) - 0.5f;
+  const float klq0 = 1.f / (2.f * (sigo0 * sigo0 + 1e-5f)), klq1 = 1.f / (2.f * (sigo1 * sigo1 + 1e-5f));
   bool first = true;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
@@ -199,9 +202,10 @@ __global__ void __launch_bounds__(128 * Q, 1) vine_ppo_minibatch_kernel(const Mb
         const float bh0 = fmaxf(mu0 - 1.1f, 0.f), bl0 = fminf(mu0 + 1.1f, 0.f), bh1 = fmaxf(mu1 - 1.1f, 0.f), bl1 = fminf(mu1 + 1.1f, 0.f);
         dmu0 += a.bounds_coef * 2.f * (bh0 + bl0);
         dmu1 += a.bounds_coef * 2.f * (bh1 + bl1);
-        // KL(old || new) of the diagonal Gaussians, rl_games policy_kl
         const float m0 = mu0 - muo0, m1 = mu1 - muo1;
-        const float kl = klc0 + (sigo0 * sigo0 + m0 * m0) * klq0 + klc1 + (sigo1 * sigo1 + m1 * m1) * klq1;
+        const float kl = klc0 + (sig0 * sig0 + m0 * m0) * klq0 + klc1 + (sig1 * sig1 + m1 * m1) * klq1;
+        // the next mini-epoch measures its KL against THIS pass (a2c_common train_epoch: dataset.update_mu_sigma(cmu, csigma))
+        *reinterpret_cast<float2*>(a.mu_old + 2 * grow) = make_float2(mu0, mu1);
         st[0] += fmaxf(t1, t2) * a.inv_B;
         st[1] += fmaxf(c1, c2) * a.inv_B;
         st[2] += kl * a.inv_B;
@@ -415,7 +419,11 @@ __device__ inline int ws_to_param(int w, int O) {
 // One workspace slot per (x) thread so the partial reads are coalesced, RED_SPLIT threads share a slot's partials.
 constexpr int RED_SLOTS = 64, RED_SPLIT = 4;
 __global__ void __launch_bounds__(RED_SLOTS* RED_SPLIT) vine_ppo_reduce_kernel(const float* __restrict__ ws, int n_partials, int O,
-                                                                               float* __restrict__ flat) {
+                                                                               float* __restrict__ flat, const float* __restrict__ logstd,
+                                                                               float* __restrict__ logstd_old_out) {
+  // sigma half of dataset.update_mu_sigma: the log-std this minibatch was evaluated with becomes its rows' "old" one. Done
+  // here because this launch sits between the last reader (the minibatch kernel) and the writer (Adam) of the parameter.
+  if (logstd_old_out && blockIdx.x == 0 && threadIdx.x < 2) logstd_old_out[threadIdx.x] = logstd[threadIdx.x];
   __shared__ float part[RED_SPLIT][RED_SLOTS];
   const int lane = threadIdx.x % RED_SLOTS, grp = threadIdx.x / RED_SLOTS;
   const int w = blockIdx.x * RED_SLOTS + lane;
@@ -521,11 +529,12 @@ int vine_ppo_minibatch(const VinePpoMinibatch* b, void* stream) {
   return grid;   // number of gradient partials written (>= 1)
 }
 
-int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* flat, void* stream) {
-  if (!workspace || !flat || n_partials < 1 || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
+int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* flat, const float* logstd, float* logstd_old_out,
+                    void* stream) {
+  if (!workspace || !flat || n_partials < 1 || num_obs < 1 || num_obs >= K1 || (logstd_old_out && !logstd)) return VINE_ERR_INVALID_ARG;
   const int slots = WS_STATS + 8;
-  vine_ppo_reduce_kernel<<<(slots + RED_SLOTS - 1) / RED_SLOTS, RED_SLOTS * RED_SPLIT, 0, (cudaStream_t)stream>>>(workspace, n_partials,
-                                                                                                          num_obs, flat);
+  vine_ppo_reduce_kernel<<<(slots + RED_SLOTS - 1) / RED_SLOTS, RED_SLOTS * RED_SPLIT, 0, (cudaStream_t)stream>>>(
+      workspace, n_partials, num_obs, flat, logstd, logstd_old_out);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 

@@ -66,8 +66,12 @@ class PolicyPlayer:
 class VineRobotControlModel(torch.nn.Module):
     """vine_robot_test_model.py:143-177: actions rescaled from [-1, 1] to the hardware ranges."""
 
-    def __init__(self, checkpoint_path, x_range, u_range, num_obs, device="cpu", **player_kw):
+    def __init__(self, checkpoint_path, x_range, u_range, num_obs, device="cpu", deterministic=False, **player_kw):
+        """``deterministic=False`` is what the reference script does: its ``forward`` calls ``get_action(obs)`` whose
+        ``is_determenistic`` defaults to False, i.e. it SAMPLES (vine_robot_test_model.py:112-131,170-171).  Pass True to act
+        with the mean."""
         super().__init__()
+        self.deterministic = bool(deterministic)
         self.rail_force_min, self.rail_force_max = x_range
         self.u_min, self.u_max = u_range
         self.player = PolicyPlayer(num_obs, device=device, **player_kw).restore(checkpoint_path)
@@ -77,7 +81,7 @@ class VineRobotControlModel(torch.nn.Module):
         return (x + 1) * (high - low) / 2 + low
 
     def forward(self, obs):
-        return self.player.get_action(obs, is_deterministic=True)
+        return self.player.get_action(obs, is_deterministic=self.deterministic)
 
     def get_action(self, *parts):
         """``parts``: the observation pieces in the order the policy was trained on (the reference's script passes

@@ -49,9 +49,11 @@ class NativeLstmPath:
 
     # ------------------------------------------------------------------ forward + backward of one minibatch
     def gradients(self, packed_mlp, packed_lstm, obs, scalars, not_done, obs_mean, obs_inv_std, value_stats, logstd, logstd_old,
-                  state, debug_out=None):
+                  state, debug_out=None, writeback=None):
         """obs f32 [L, S, O], scalars f32 [L, S, 8], not_done f32 [L, S]; self.HM[0] (masked initial hidden state tiles) and
-        self.C0 must already hold the initial LSTM state.  Leaves the gradients in flat_g_mlp / flat_g_lstm."""
+        self.C0 must already hold the initial LSTM state.  Leaves the gradients in flat_g_mlp / flat_g_lstm.
+        ``writeback`` = (scalars_src [T, N, 8], seq_len, chunks, num_envs, env_begin, env_count): rl_games'
+        dataset.update_mu_sigma -- this pass's mu goes back into the source rows and ``logstd_old`` receives ``logstd``."""
         lib, L, S, tl, st = self.lib, self.L, self.S, self.tiles, self._stream()
         n = L * S
         act = abi.VinePolicyAct(packed=_ptr(packed_mlp), obs=_ptr(obs), obs_mean=_ptr(obs_mean), obs_inv_std=_ptr(obs_inv_std),
@@ -70,6 +72,9 @@ class NativeLstmPath:
                                    debug_out=_ptr(debug_out) if debug_out is not None else None, n=n, inv_B=1.0 / n,
                                    e_clip=h["e_clip"], critic_coef=h["critic_coef"], entropy_coef=h["entropy_coef"],
                                    bounds_loss_coef=h["bounds_loss_coef"])
+        if writeback is not None:
+            src, wl, wc, wn, wb, we = writeback
+            ht.mu_writeback, ht.wb_seq_len, ht.wb_chunks, ht.wb_num_envs, ht.wb_env_begin, ht.wb_env_count = _ptr(src), wl, wc, wn, wb, we
         hparts = lib.vine_lstm_head_train(C.byref(ht), st)
         assert hparts > 0, hparts
         for t in range(L - 1, -1, -1):
@@ -90,7 +95,9 @@ class NativeLstmPath:
                                   bounds_loss_coef=h["bounds_loss_coef"], dh3_ext=_ptr(self.DH3))
         n_part = lib.vine_ppo_minibatch(C.byref(mb), st)
         assert n_part > 0, n_part
-        assert lib.vine_ppo_reduce(C.c_void_p(_ptr(self.mlp_ws)), n_part, self.O, C.c_void_p(_ptr(self.flat_g_mlp)), st) == 0
+        wb = writeback is not None   # sigma half of update_mu_sigma: after the last reader of logstd_old, before Adam
+        assert lib.vine_ppo_reduce(C.c_void_p(_ptr(self.mlp_ws)), n_part, self.O, C.c_void_p(_ptr(self.flat_g_mlp)),
+                                   C.c_void_p(_ptr(logstd)) if wb else None, C.c_void_p(_ptr(logstd_old)) if wb else None, st) == 0
         wg = abi.VineLstmWgrad(u=_ptr(self.U), hm=_ptr(self.HM), dg=_ptr(self.DG), workspace=_ptr(self.wg_ws), ntiles=L * tl,
                                splits=self.splits)
         assert lib.vine_lstm_wgrad(C.byref(wg), st) == 0

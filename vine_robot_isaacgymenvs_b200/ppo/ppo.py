@@ -182,6 +182,10 @@ class PPOAgent:
         self.normalize_advantage = bool(c["normalize_advantage"])
         self.truncate_grads, self.grad_norm = bool(c.get("truncate_grads", False)), float(c.get("grad_norm", 1.0))
         self.bf16 = bool(c.get("mixed_precision", False))
+        # an episode counts as a success when the "Position Success" term (1000 x its weight, V5:1507, V5:186-203) fired in
+        # its last step: half of that bonus separates it from every other term at any weight; no weight, no success signal
+        w_succ = float(env.cfg["env"].get("POSITION_SUCCESS_REWARD_WEIGHT", 1.0)) if hasattr(env, "cfg") else 1.0
+        self.success_threshold = 500.0 * w_succ if w_succ > 0 else float("inf")
         units = net["mlp"]["units"]
         torch.manual_seed(seed)
         dev = self.device
@@ -190,26 +194,32 @@ class PPOAgent:
         self.seq_len = int(c.get("seq_len", 4)) if self.has_rnn else 1
         assert self.T % self.seq_len == 0, "horizon_length must be a multiple of seq_len"
         self.obs_rms = RunningMeanStd((self.O,)).to(dev)
-        self.val_rms = RunningMeanStd(()).to(dev)
+        self.val_rms = RunningMeanStd((1,)).to(dev)     # rl_games: RunningMeanStd((value_size,)) -> checkpoint shape [1]
         self.world = vd.rank_world()[1]
         if self.world > 1:  # hvd.setup_algo equivalent: identical parameters on every rank
             for p in self.model.parameters():
                 torch.distributed.broadcast(p.data, 0)
         self._want_graphs = bool(use_graphs)
         self._lib = abi.load_library()
-        # The MLP-only network runs entirely on hand-written sm_100a kernels: vine_mlp_forward for the rollout and
-        # vine_ppo_minibatch / vine_ppo_reduce / vine_ppo_adam for the update (tcgen05/TMEM); anything else (the LSTM
-        # variant) falls back to torch autograd + cuBLAS/cuDNN for the update.
-        self.fused = (bool(use_fused_policy) and not self.has_rnn and list(units) == [256, 128, 64] and self.A == 2
-                      and self.O <= 31 and self.normalize_input and self.normalize_value)
-        self.fused_update = self.fused and bool(use_fused_update) and not self.truncate_grads
-        # the reference network (MLP -> LSTM 256 -> LayerNorm -> heads) on hand-written kernels as well (ppo/lstm_native.py)
+        # Both networks run entirely on hand-written sm_100a kernels (tcgen05/TMEM): vine_policy_act / vine_lstm_* for the
+        # rollout, vine_ppo_minibatch / vine_lstm_* / vine_ppo_adam for the update.  There is NO silent dispatch: a
+        # configuration the kernels do not cover raises here.  torch autograd + cuBLAS/cuDNN + torch Adam exist only as the
+        # explicit baseline `use_fused_update=False` (`use_fused_policy=False` additionally takes the policy forward to torch).
         rnn_cfg = net.get("rnn") or {}
-        self.native_lstm = (self.has_rnn and bool(use_fused_update) and bool(use_fused_policy) and not self.truncate_grads
-                            and list(units) == [256, 128, 64] and self.A == 2 and self.O <= 30 and self.normalize_input
-                            and self.normalize_value and int(rnn_cfg.get("units", 0)) == 256 and bool(rnn_cfg.get("concat_input"))
-                            and bool(rnn_cfg.get("layer_norm")) and self.n % 128 == 0 and self.mb_envs % 128 == 0)
-        self.fused_update = self.fused_update or self.native_lstm
+        self.fused = self.native_lstm = self.fused_update = False
+        if use_fused_update:
+            if not use_fused_policy:
+                raise ValueError("use_fused_update=True needs use_fused_policy=True (the kernel update reads the kernel rollout's buffers)")
+            why = self._kernel_path_gaps(units, rnn_cfg)
+            if why:
+                raise NotImplementedError(
+                    "PPO kernel path does not cover this configuration: " + "; ".join(why) +
+                    ". Pass use_fused_update=False for the torch autograd + cuBLAS baseline, or change the configuration.")
+            self.native_lstm = self.has_rnn
+            self.fused = not self.has_rnn
+            self.fused_update = True
+        elif use_fused_policy and not self.has_rnn and not self._kernel_path_gaps(units, rnn_cfg, update=False):
+            self.fused = True   # baseline update, kernel policy forward (asked for explicitly: use_fused_update=False)
         # CUDA graphs: single GPU always; multi-GPU only for the kernel-only path (its NCCL all-reduces are captured too)
         self.use_graphs = self._want_graphs and (self.world == 1 or (self.fused_update and bool(c.get("graph_nccl", True))))
         if self.native_lstm:
@@ -250,6 +260,27 @@ class PPOAgent:
             self._mu_buf, self._val_buf = f(n, self.A), f(n)
             self._refresh_fused(pack=True)
 
+    def _kernel_path_gaps(self, units, rnn_cfg, update=True):
+        """Why the hand-written kernel path cannot run this configuration (empty list: it can)."""
+        why = []
+        if list(units) != [256, 128, 64]:
+            why.append(f"network.mlp.units {list(units)} (kernels are built for [256, 128, 64])")
+        if self.A != 2:
+            why.append(f"{self.A} actions (kernels: 2)")
+        if self.O > (30 if self.has_rnn else 31):
+            why.append(f"{self.O} observations (kernels: <= {30 if self.has_rnn else 31})")
+        if not (self.normalize_input and self.normalize_value):
+            why.append("normalize_input / normalize_value must both be True")
+        if update and self.truncate_grads:
+            why.append("truncate_grads=True (gradient-norm clipping is not in the kernel update)")
+        if self.has_rnn:
+            if int(rnn_cfg.get("units", 0)) != 256 or not rnn_cfg.get("concat_input") or not rnn_cfg.get("layer_norm"):
+                why.append("network.rnn must be the reference's block: units 256, concat_input True, layer_norm True")
+            if self.n % 128 or self.mb_envs % 128:
+                why.append(f"num_envs ({self.n}) and minibatch_size / horizon_length ({self.mb_envs}) must be multiples of 128 "
+                           "for the recurrent kernels (128-row tensor-core tiles)")
+        return why
+
     def _param_order(self):
         """The flat parameter order of include/vine_b200.h (vine_ppo_*)."""
         m = self.model
@@ -274,7 +305,7 @@ class PPOAgent:
         self._ctas = lib.vine_ppo_max_ctas()
         self._ws = torch.empty(self._ctas, abi.PPO_WS_FLOATS, device=dev)
         self._flat_grads = torch.zeros(P + 4, device=dev)
-        self._logstd_old = torch.zeros(2, device=dev)
+        self._logstd_old = torch.zeros(self.n // self.mb_envs, 2, device=dev)   # per minibatch slot (update_mu_sigma)
         z = lambda: torch.zeros(self.T, self.n, device=dev)  # noqa: E731
         self._val_old_n, self._ret_n, self._adv_n = z(), z(), z()
         self._mb_structs = self._roll_structs = None
@@ -316,7 +347,7 @@ class PPOAgent:
         self.ppo_state = torch.zeros(abi.PPO_STATE_FLOATS, device=dev)
         self.ppo_state[0] = lr
         self.lr_t = self.ppo_state[0]
-        self._logstd_old = z(2)
+        self._logstd_old = z(self.n // self.mb_envs, 2)                           # per minibatch slot (update_mu_sigma)
         zz = lambda: z(self.T, self.n)  # noqa: E731
         self._val_old_n, self._ret_n, self._adv_n = zz(), zz(), zz()
         self._mb_structs = self._roll_structs = None
@@ -381,7 +412,7 @@ class PPOAgent:
                                        values=ptr(self.b_val[t]), shaped_rewards=ptr(self.b_rew[t]), dones_next=ptr(self._done_ext[t + 1]),
                                        ep_return=ptr(self.ep_ret), ep_length=ptr(self.ep_len), ep_stats=ptr(self.ep_stats),
                                        rng_counter=ptr(self._rng_counter), n=n, reward_scale=self.reward_scale, gamma=self.gamma,
-                                       value_bootstrap=int(self.value_bootstrap), success_reward_threshold=500.0,
+                                       value_bootstrap=int(self.value_bootstrap), success_reward_threshold=self.success_threshold,
                                        not_done_next=ptr(self._nd_ext[t + 1]))
             assert lib.vine_rollout_post(C.byref(post), stream) == 0
         if self._r_cur != 0:   # odd horizon: keep the persistent state in buffer 0 so a captured graph can be replayed
@@ -416,7 +447,7 @@ class PPOAgent:
         if self.world > 1:
             torch.distributed.all_reduce(self._moments)
         assert lib.vine_ppo_finalize(C.byref(self._prologue), stream) == 0
-        self._logstd_old.copy_(self.model.sigma)
+        self._logstd_old.copy_(self.model.sigma.expand_as(self._logstd_old))
         # per-row scalars of the loss, once per iteration: action(2), mu_old(2), neglogp_old, value_old, return, advantage
         torch.cat([self.b_act, self.b_mu, self.b_nlp.unsqueeze(-1), self._val_old_n.unsqueeze(-1), self._ret_n.unsqueeze(-1),
                    self._adv_n.unsqueeze(-1)], dim=-1, out=self._scal)
@@ -431,7 +462,8 @@ class PPOAgent:
                                         num_obs=self.O)
                 assert lib.vine_lstm_gather(C.byref(ga), stream) == 0
                 path.gradients(self._packed, self._lpacked, self._mb_obs, self._mb_scal, self._mb_nd, self._obs_mean_f,
-                               self._obs_inv_std_f, self._val_stats, self.model.sigma, self._logstd_old, self.ppo_state)
+                               self._obs_inv_std_f, self._val_stats, self.model.sigma, self._logstd_old[e0 // E], self.ppo_state,
+                               writeback=(self._scal, L, chunks, n, e0, E))
                 if self.world > 1:   # ONE collective per minibatch: gradients + loss statistics (incl. the KL) of both halves
                     torch.distributed.all_reduce(path.flat_g)
                 sc = 1.0 / self.world
@@ -446,8 +478,8 @@ class PPOAgent:
         operand layout) -- only needed when something other than vine_ppo_adam changed them."""
         self._obs_mean_f.copy_(self.obs_rms.running_mean.float())
         self._obs_inv_std_f.copy_(torch.rsqrt(self.obs_rms.running_var.float() + self.obs_rms.eps))
-        self._val_stats.copy_(torch.stack([self.val_rms.running_mean.float(),
-                                           torch.sqrt(self.val_rms.running_var.float() + self.val_rms.eps)]))
+        self._val_stats.copy_(torch.cat([self.val_rms.running_mean.float().reshape(1),
+                                         torch.sqrt(self.val_rms.running_var.float() + self.val_rms.eps).reshape(1)]))
         if pack:
             p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -504,7 +536,7 @@ class PPOAgent:
                                          ep_length=ptr(self.ep_len), ep_stats=ptr(self.ep_stats),
                                          rng_counter=ptr(self._rng_counter), n=n, reward_scale=self.reward_scale,
                                          gamma=self.gamma, value_bootstrap=int(self.value_bootstrap),
-                                         success_reward_threshold=500.0) for t in range(T)]
+                                         success_reward_threshold=self.success_threshold) for t in range(T)]
             last = abi.VinePolicyAct(mu=ptr(self._mu_buf), value=ptr(self.last_value), **common)
             self._roll_structs = (acts, posts, last)
         acts, posts, last = self._roll_structs
@@ -549,7 +581,7 @@ class PPOAgent:
             self.ep_ret += rew
             self.ep_len += 1
             d = dones.to(torch.float32)
-            self.ep_stats += torch.stack([d.sum(), (d * (rew > 500.0)).sum(), (d * self.ep_ret).sum(),
+            self.ep_stats += torch.stack([d.sum(), (d * (rew > self.success_threshold)).sum(), (d * self.ep_ret).sum(),
                                           (d * self.ep_len).sum()]).double()
             self.ep_ret *= 1.0 - d
             self.ep_len *= 1.0 - d
@@ -573,6 +605,24 @@ class PPOAgent:
         else:
             self._rollout()
         self.frames += self.T * self.n * self.world
+
+    @torch.no_grad()
+    def evaluate(self, steps, deterministic=True):
+        """Play mode (reference: train.py test=True -> rl_games player.run, `deterministic: True` by default): roll the policy
+        without learning; deterministic = act with the mean.  The rollout kernels sample mu + exp(logstd) eps, so the mean
+        action is obtained by running them with logstd = -40 (sigma = 4e-18, below f32 resolution of any mu)."""
+        sigma = self.model.sigma.data
+        keep = sigma.clone()
+        if deterministic:
+            sigma.fill_(-40.0)
+        try:
+            self.pop_stats()
+            for _ in range(max(1, steps // self.T)):
+                self._rollout()
+            torch.cuda.synchronize(self.device)
+        finally:
+            sigma.copy_(keep)
+        return self.pop_stats()
 
     # ------------------------------------------------------------------ learning
     def _update_lr(self, kl):
@@ -603,7 +653,8 @@ class PPOAgent:
                 mean = s[0] / cnt
                 std = torch.sqrt(torch.clamp((s[1] - cnt * mean * mean) / (cnt - 1.0), min=0.0))
                 adv = (adv - mean.float()) / (std.float() + 1e-8)
-            sigma_old = torch.exp(self.model.sigma.detach()).clone()
+            # sigma of the policy each row was last evaluated with, per minibatch slot (rl_games dataset.update_mu_sigma)
+            sigma_old = torch.exp(self.model.sigma.detach()).clone().expand(n // self.mb_envs, -1).clone()
             not_done = 1.0 - self.b_done
         params = [p for p in self.model.parameters()]
         E = self.mb_envs
@@ -639,7 +690,11 @@ class PPOAgent:
                 self.opt.zero_grad(set_to_none=False)
                 loss.backward()
                 with torch.no_grad():
-                    kl = policy_kl(mu.detach(), sigma.detach(), flat(mu_old), sigma_old.expand_as(mu))
+                    kl = policy_kl(mu.detach(), sigma.detach(), flat(mu_old), sigma_old[e0 // E].expand_as(mu))
+                    # a2c_common.train_epoch: dataset.update_mu_sigma(cmu, csigma) -- the next mini-epoch's KL is against this pass
+                    unmb = mu.detach().reshape(L, T // L, E, -1).transpose(0, 1).reshape(T, E, -1)
+                    mu_old[:, e0:e0 + E] = unmb
+                    sigma_old[e0 // E] = sigma.detach()[0]
                     if self.world > 1:  # ONE collective per minibatch: gradients + KL
                         g = torch.cat([p.grad.reshape(-1) for p in params])
                         g, extra = vd.allreduce_mean_(g, kl.reshape(1))
@@ -680,24 +735,26 @@ class PPOAgent:
         if self.world > 1:
             torch.distributed.all_reduce(self._moments)
         assert lib.vine_ppo_finalize(C.byref(self._prologue), stream) == 0
-        self._logstd_old.copy_(self.model.sigma)
+        self._logstd_old.copy_(self.model.sigma.expand_as(self._logstd_old))
         if self._mb_structs is None:
             ptr = lambda x: x.data_ptr()  # noqa: E731
             self._mb_structs = [abi.VinePpoMinibatch(
                 packed=ptr(self._packed), obs=ptr(self.b_obs), actions=ptr(self.b_act), mu_old=ptr(self.b_mu),
                 neglogp_old=ptr(self.b_nlp), values_old=ptr(self._val_old_n), returns=ptr(self._ret_n),
                 advantages=ptr(self._adv_n), obs_mean=ptr(self._obs_mean_f), obs_inv_std=ptr(self._obs_inv_std_f),
-                logstd=ptr(self.model.sigma), logstd_old=ptr(self._logstd_old), workspace=ptr(self._ws),
+                logstd=ptr(self.model.sigma), logstd_old=ptr(self._logstd_old[e0 // self.mb_envs]), workspace=ptr(self._ws),
                 state=ptr(self.ppo_state), debug_out=None, horizon=T, num_envs=n, env_begin=e0, env_count=self.mb_envs,
                 num_obs=self.O, workspace_ctas=self._ctas, adaptive_lr=int(self.adaptive), e_clip=self.e_clip,
                 critic_coef=self.critic_coef, entropy_coef=self.entropy_coef, bounds_loss_coef=self.bounds_coef,
                 kl_threshold=self.kl_threshold, lr_min=1e-6, lr_max=1e-2) for e0 in range(0, n, self.mb_envs)]
         p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
         for _ in range(self.mini_epochs):
-            for mb in self._mb_structs:
+            for slot, mb in enumerate(self._mb_structs):
+                # forward + losses + backward; writes this pass's mu over the rows' mu_old (rl_games dataset.update_mu_sigma)
                 n_part = lib.vine_ppo_minibatch(C.byref(mb), stream)
                 assert n_part > 0, n_part
-                assert lib.vine_ppo_reduce(p(self._ws), n_part, self.O, p(self._flat_grads), stream) == 0
+                assert lib.vine_ppo_reduce(p(self._ws), n_part, self.O, p(self._flat_grads), p(self.model.sigma),
+                                           p(self._logstd_old[slot]), stream) == 0
                 if self.world > 1:   # ONE collective per minibatch: gradients + loss statistics (incl. the KL)
                     torch.distributed.all_reduce(self._flat_grads)
                 assert lib.vine_ppo_adam(p(self._flat_grads), 1.0 / self.world, p(self.flat), p(self.adam_m), p(self.adam_v),
@@ -711,7 +768,7 @@ class PPOAgent:
             for _ in range(warmup):
                 self._rollout()
                 self._update_any()
-                self.frames += self.T * self.n
+                self.frames += self.T * self.n * self.world   # real training iterations: counted like any other
                 self.epoch += 1
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
@@ -754,13 +811,17 @@ class PPOAgent:
         return {"episodes": int(e[0]), "success_rate": e[1] / eps, "mean_return": e[2] / eps, "mean_length": e[3] / eps,
                 "a_loss": l[0] / nmb, "c_loss": l[1] / nmb, "kl": l[2] / nmb}
 
-    def train(self, max_epochs, log_every=25, log=print):
+    def train(self, max_epochs, log_every=25, log=print, on_epoch=None):
         hist = []
         torch.cuda.synchronize(self.device)
         t0, f0 = time.perf_counter(), self.frames
-        for ep in range(max_epochs):
+        last = self.epoch + max_epochs      # the CUDA-graph warm-up iterations of the first call count against max_epochs
+        while self.epoch < last:
+            before = self.epoch
             self.train_epoch()
-            if (ep + 1) % log_every == 0 or ep == max_epochs - 1:
+            if on_epoch is not None:
+                on_epoch(self)
+            if any(e % log_every == 0 for e in range(before + 1, self.epoch + 1)) or self.epoch >= last:
                 torch.cuda.synchronize(self.device)
                 st = self.pop_stats()
                 st.update({"epoch": self.epoch, "frames": self.frames, "lr": self.lr,
@@ -790,8 +851,11 @@ class PPOAgent:
         return self.opt.state_dict()
 
     def state_dict(self):
-        return {"model": self.rlgames_model_state(), "optimizer": self._optimizer_state(), "epoch": self.epoch,
-                "frame": self.frames, "last_lr": self.lr, "last_mean_rewards": 0.0, "env_state": None}
+        sd = {"model": self.rlgames_model_state(), "optimizer": self._optimizer_state(), "epoch": self.epoch,
+              "frame": self.frames, "last_lr": self.lr, "last_mean_rewards": 0.0, "env_state": None}
+        if self.fused_update:   # Philox stream position of the action noise: a resumed run must not replay it
+            sd["vine_rng_counter"] = int(self._rng_counter.item())
+        return sd
 
     def load_state_dict(self, sd):
         model = sd["model"]
@@ -805,8 +869,9 @@ class PPOAgent:
             sub = {k[len(name) + 1:]: v for k, v in model.items() if k.startswith(name + ".")}
             if not sub and name in sd:          # older layout: normalisers stored beside 'model'
                 sub = sd[name]
-            if sub:
-                rms.load_state_dict({k: v.to(rms.running_mean.dtype) for k, v in sub.items()})
+            if sub:   # value_mean_std is [1] in rl_games files; older files of this trainer stored it 0-dim
+                own = rms.state_dict()
+                rms.load_state_dict({k: v.to(own[k].dtype).reshape(own[k].shape) for k, v in sub.items()})
         opt = sd.get("optimizer")
         if opt and self.fused_update and "fused_adam" in opt:
             self.adam_m.copy_(opt["fused_adam"]["exp_avg"])
@@ -817,6 +882,8 @@ class PPOAgent:
                 self.adam_vl.copy_(opt["fused_adam"]["exp_avg_sq_lstm"])
         elif opt and not self.fused_update and "fused_adam" not in opt:
             self.opt.load_state_dict(opt)
+        if self.fused_update and "vine_rng_counter" in sd:
+            self._rng_counter.fill_(int(sd["vine_rng_counter"]))
         self.epoch, self.frames = sd.get("epoch", 0), sd.get("frame", 0)
         self.lr_t.fill_(float(sd.get("last_lr", self.lr)))
         if self.fused or self.native_lstm:
