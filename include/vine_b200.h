@@ -239,6 +239,10 @@ typedef struct VineStateView {
   float* rail_force;           /* [N] */
   float* tip_velocities;       /* [N,3] */
   float* reward_matrix;        /* [N,13] unweighted terms of the last step (V5:1500) */
+  float* finite_difference_dof_vel;          /* [N,6] (q - prev_q) / control_dt (V5:1347) */
+  float* finite_difference_tip_velocities;   /* [N,3] (tip - prev_tip) / control_dt (V5:1348) */
+  float* cart_body_pos_y;                    /* [N] cart_positions[:,1], the rigid-body view the reward reads (V5:1231): equals
+                                                dof_pos[:,0] except on a reset step, where it is still the old episode's */
 } VineStateView;
 
 int vine_get_state(VineEnv* env, const VineStateView* view, void* stream);
@@ -631,10 +635,12 @@ typedef struct VineLstmWgrad {
 } VineLstmWgrad;
 int vine_lstm_num_params(int num_obs);
 int vine_lstm_wgrad(const VineLstmWgrad* args, void* stream);
+/* head_grads: the partials of vine_lstm_head_train; its last row is scratch for their sum.  p2p_channel (NULL on one GPU):
+ * see "gradient all-reduce over peer memory" below */
 int vine_lstm_reduce(const float* workspace, int splits, float* head_grads, int head_parts, int num_obs, float* flat,
-                     void* stream);   /* head_grads: the partials of vine_lstm_head_train; its last row is scratch for their sum */
+                     void* p2p_channel, void* stream);
 int vine_lstm_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq, void* packed,
-                   float* state, int num_obs, float beta1, float beta2, float eps, void* stream);
+                   float* state, int num_obs, float beta1, float beta2, float eps, void* p2p_channel, void* stream);
 
 /*
  * Pointwise half of the LSTM layer of the reference's network (Vine5LinkMovingBasePPO.yaml:32-38; rl_games
@@ -705,12 +711,35 @@ int vine_ppo_minibatch(const VinePpoMinibatch* batch, void* stream);
  * logstd_old_out (NULL or [2]) receives a copy of logstd (the parameter, [2]): the sigma half of rl_games'
  * dataset.update_mu_sigma -- this launch sits between the minibatch kernel (last reader) and Adam (writer). */
 int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* flat, const float* logstd,
-                    float* logstd_old_out, void* stream);
+                    float* logstd_old_out, void* p2p_channel, void* stream);
 /* Adam step with g = flat * grad_scale (1/world after an all-reduce); updates params, moments, packed, state */
 /* bookkeeping != 0: also record the loss statistics / pending KL in `state` (0 when vine_lstm_adam does it) */
 int vine_ppo_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq,
                   void* packed, float* state, int num_obs, float beta1, float beta2, float eps, int bookkeeping,
-                  void* stream);
+                  void* p2p_channel, void* stream);
+
+/*
+ * Gradient all-reduce over peer memory (multi-GPU PPO; replaces the per-minibatch all-reduce of the flattened gradients the
+ * reference gets from rl_games / Horovod: learning/common_agent.py:125-126,219).  One process per GPU of ONE node:
+ *   vine_p2p_alloc(count, &region, handle)   cudaMalloc of this rank's region (two buffers of `count` f32 + flags) and its
+ *                                            64-byte CUDA IPC handle; the caller exchanges the handles (torch.distributed);
+ *   vine_p2p_open(peer_handle, &region)      maps a peer's region (NVLink peer access);
+ *   vine_p2p_channel_create(regions[world] in rank order (own region at [rank]), world, rank, count, &channel)
+ * and the channel is passed to the producer (vine_ppo_reduce / vine_lstm_reduce: the rank's gradient sum goes into its own
+ * region; `flat` may then be NULL) and to the consumer (vine_ppo_adam / vine_lstm_adam: waits until every rank has
+ * published, adds the `world` buffers in rank order -- bit-identical sums, hence bit-identical parameters, on all ranks --
+ * and applies Adam to the sum; grad_scale = 1 / world gives the mean).  One channel per (producer, consumer) pair; every
+ * rank must issue the same launches.  No host synchronisation, CUDA-graph capturable; csrc/vine_p2p.cuh has the protocol.
+ */
+#define VINE_P2P_HANDLE_BYTES 64
+#define VINE_P2P_MAX_WORLD 16
+int vine_p2p_alloc(int64_t count, void** region, void* ipc_handle_out);
+int vine_p2p_open(const void* ipc_handle, void** region);
+int vine_p2p_close(void* region);      /* a region obtained from vine_p2p_open */
+int vine_p2p_free(void* region);       /* a region obtained from vine_p2p_alloc */
+int vine_p2p_channel_create(void* const* regions, int world, int rank, int64_t count, void** channel);
+int vine_p2p_channel_status(const void* channel, uint32_t* exchanges_done, uint32_t* timed_out);   /* synchronises */
+int vine_p2p_channel_destroy(void* channel);
 
 /* sizeof of the argument structs of the PPO entry points, in declaration order (VinePolicyAct = 0, VineRolloutPost,
  * VinePpoPrologue, VinePpoMinibatch, VineLstmStep, VineLstmHead, VineLstmHeadTrain, VineLstmCellBwd, VineLstmBwdGemm,

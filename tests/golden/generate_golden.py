@@ -75,6 +75,10 @@ STEP_SCENARIOS = {
 }
 
 
+# scenarios whose rollout also freezes the reference's wandb_dict of every step (metrics_<name>.npz)
+METRIC_SCENARIOS = ("c2_fstr", "c3_shelf")
+
+
 def make_actions(mode, rng, T, n):
     a = rng.uniform(-1.3, 1.3, (T, n, 2)).astype(np.float32)   # beyond +-1: exercises clipActions
     if mode == "reach":  # half the envs drive toward -y with high pressure so obstacles get touched
@@ -94,12 +98,18 @@ def gen_step(name, overrides, n, T, mode, seed=42):
             "aggregated_rew_buf"]
     rec = {k: [] for k in keys}
     contact = []
+    wandb_rows, wandb_keys = [], None
     for t in range(T):
         rt.step(actions[t])
         s = rt.snapshot()
         for k in keys:
             rec[k].append(s[k])
         contact.append(rt.gym.c_lip.copy())
+        if name in METRIC_SCENARIOS:   # the reference's own per-step wandb dict (compute_reward, V5:1250-1322)
+            wd = {k: float(v) for k, v in rt.task.wandb_dict.items()}
+            wandb_keys = wandb_keys or sorted(wd)
+            assert sorted(wd) == wandb_keys
+            wandb_rows.append([wd[k] for k in wandb_keys])
         if name == "delay0" and t == 9:   # VT:412-427 reset_done path: reset_idx outside step
             rt.reset_done_ids(np.arange(0, n, 3))
     out = {k: np.stack(v) for k, v in rec.items()}
@@ -110,6 +120,10 @@ def gen_step(name, overrides, n, T, mode, seed=42):
     out["reset_done_at"] = np.array(9 if name == "delay0" else -1)
     path = os.path.join(HERE, "step_%s.npz" % name)
     np.savez_compressed(path, **out)
+    if wandb_rows:
+        np.savez_compressed(os.path.join(HERE, "metrics_%s.npz" % name), keys=np.array(json.dumps(wandb_keys)),
+                            values=np.array(wandb_rows, np.float64), index_to_view=np.array(int(rt.task.index_to_view)),
+                            overrides=out["overrides"], seed=out["seed"], actions=actions)
     print("%-22s n=%3d T=%3d  resets=%5d  timeouts=%4d  max|contact|=%.3g  %d KB" % (
         name, n, T, int(out["reset_buf"].sum()), int(out["timeout_buf"].sum()), float(out["contact"].max()),
         os.path.getsize(path) // 1024))

@@ -34,8 +34,15 @@ def test_cuda_arm_line():
     assert BASE | {"roofline", "clocks", "gpu_launches", "ppo", "ppo_frames_per_s"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] >= 3 and d["gpu_launches"] == 5 and d["scaling"] == "weak"
     assert d["value"] > 1e8 and d["e2e"]["value"] > 1e7 and d["e2e"]["h2d_bytes_per_step"] == 65536 * 8
-    r = d["roofline"]
-    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "GB/s"
+    r = d["roofline"]          # the BINDING resource of the env step (FP32); HBM rides along as roofline_hbm
+    assert r["bound"] == "fp32_fma" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] == "TFLOP/s"
+    assert 0.1 < r["frac"] < 1.0 and r["flops_per_env_step"] > 1e4
+    h = d["roofline_hbm"]
+    assert h["bound"] == "hbm" and h["unit"] == "GB/s" and abs(h["frac"] - h["achieved"] / h["peak"]) < 1e-9
+    c1 = d["cpu_baseline_c1"]  # reference's unmodified Python step, configs[0] (committed build-container record on the GPU box)
+    assert c1 and c1["value"] > 0 and "64 envs x 200 control steps" in c1["sample"] and c1["measured_on"]
+    u = d["ppo"]["reference_network"]["update_roofline"]
+    assert u["bound"] == "tensor" and abs(u["frac"] - u["achieved"] / u["peak"]) < 1e-9
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert "hw_slowdown" not in d["clocks"]["reasons"]
     p = d["ppo"]["reference_network"]

@@ -188,6 +188,35 @@ def test_contact_configs_at_baseline_sizes_are_deterministic_shard_invariant_and
     assert early_resets > 0
 
 
+@pytest.mark.parametrize("preset,n", [("SHELF_OVERRIDES", 3000), ("PIPE_DR_OVERRIDES", 20000 + 13)], ids=["shelf", "pipe_dr"])
+def test_routed_obstacle_step_equals_the_single_launch_bit_for_bit(preset, n):
+    """Obstacle variants: the routed step (bin -> near pass || far pass with the free-space integrator -> redo pass of the envs
+    the far pass gave up) against ONE launch of the contact variant over all envs in identity order: every buffer and every
+    state plane identical at every step, while envs keep crossing between far and near (half of them are driven into the
+    obstacle, episodes end and restart)."""
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    ov = getattr(vcfg, preset) + ["headless=True", "task.env.maxEpisodeLength=30", f"num_envs={n}"]
+    routed = vine.make(cfg=vcfg.compose(ov + ["+task.sim.vine_contact.binning=2"]))
+    single = vine.make(cfg=vcfg.compose(ov + ["+task.sim.vine_contact.binning=0"]))
+    g = torch.Generator(device="cuda").manual_seed(n)
+    touched = 0
+    for t in range(70):
+        act = torch.rand(n, 2, device="cuda", generator=g) * 2.4 - 1.2
+        act[: n // 2, 1] = act[: n // 2, 1].abs()
+        act[: n // 2, 0] = -act[: n // 2, 0].abs()                  # toward -y, where the obstacles are
+        routed.step(act); single.step(act)
+        for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "timeout_buf"):
+            assert torch.equal(getattr(routed, name), getattr(single, name)), (name, t)
+        assert torch.equal(routed.obs_dict["obs"], single.obs_dict["obs"])
+        if preset == "SHELF_OVERRIDES":
+            touched += int((routed.get_state_dict()["shelf_contact_force"] > 0).sum())
+    sa, sb = routed.get_state_dict(), single.get_state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert preset != "SHELF_OVERRIDES" or touched > 0
+
+
 def test_binned_contact_launch_with_a_ragged_tail_equals_unbinned_shards():
     """98,341 envs (not a multiple of the warp or of the 1024-env binning block) step through the binned launch; two shards
     below the binning threshold cover the same global env ids in identity order. Bit-identical outputs and state."""
@@ -291,3 +320,52 @@ def test_mat_trajectory_replay_overwrites_state_like_the_reference(tmp_path):
     assert torch.allclose(q[:, 1:], torch.tensor(mat["Q"][:, i], dtype=torch.float32, device="cuda").expand(64, 5))
     assert float(env.dof_vel.abs().max()) == 0.0
     assert torch.allclose(env.target_positions[:, 1:], torch.tensor(mat["moving_target_pos"][1:, i], dtype=torch.float32, device="cuda").expand(64, 2))
+
+
+def test_state_attributes_write_through_like_the_reference_views():
+    """The reference pokes simulator state through tensor views: ``self.dof_pos[env_ids, idx] = ...`` / ``self.dof_vel[env_ids] = 0``
+    (V5:780-793) before ``set_dof_state_tensor_indexed``; ``cart_velocities`` (V5:362) feeds the rail controller (V5:1069).
+    Here the attributes are snapshots that write in-place modifications back to the library state."""
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    n = 300
+    make = lambda: vine.make(cfg=vcfg.compose(vcfg.FSTR_OVERRIDES + [f"num_envs={n}", "headless=True"]))  # noqa: E731
+    env, ref = make(), make()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.rand(n, 2, device="cuda", generator=g) * 2 - 1
+    for e in (env, ref):
+        e.step(a); e.step(a)
+    ids = torch.tensor([3, 17, 256], device="cuda")
+    new_q = torch.rand(3, 6, device="cuda", generator=g) * 0.2 - 0.1
+    # the reference idiom, in place through the attribute
+    env.dof_pos[ids] = new_q
+    env.dof_vel[ids] = 0.0
+    env.dof_pos[ids, 0] += 0.01
+    env.smoothed_u_fpam[ids] = 1.5
+    cv = env.cart_velocities
+    assert cv.shape == (n, 3) and float(cv[:, 0].abs().max()) == 0.0 and float(cv[:, 2].abs().max()) == 0.0
+    env.cart_velocities[ids, 1] = 0.25
+    # the same through the explicit state API
+    st = ref.get_state_dict()
+    st["dof_pos"][ids] = new_q
+    st["dof_pos"][ids, 0] += 0.01
+    st["dof_vel"][ids] = 0.0
+    st["smoothed_u_fpam"][ids] = 1.5
+    st["cart_body_vel_y"][ids] = 0.25
+    ref.set_state_dict(st)
+    assert torch.equal(env.dof_pos, ref.dof_pos) and torch.equal(env.dof_pos[ids, 1:], new_q[:, 1:])
+    assert torch.equal(env.cart_velocities[:, 1], ref.get_state_dict()["cart_body_vel_y"])
+    untouched = torch.ones(n, dtype=torch.bool, device="cuda"); untouched[ids] = False
+    for e in (env, ref):
+        e.step(a)
+    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf"):
+        assert torch.equal(getattr(env, name), getattr(ref, name)), name
+    assert not torch.equal(env.obs_buf[ids], make().obs_buf[ids])
+    # outputs of the last step are read-only: an in-place write raises instead of silently doing nothing
+    env.enable_debug_outputs(True); env.step(a)
+    with pytest.raises(RuntimeError):
+        env.rail_force[ids] = 0.0
+    with pytest.raises(RuntimeError):
+        env.cart_positions[ids, 1] = 0.0
+    kept = env.progress_buf > 0                       # an env reset in this step still shows the old episode's body position
+    assert env.cart_positions.shape == (n, 3) and torch.equal(env.cart_positions[kept, 1], env.dof_pos[kept, 0])

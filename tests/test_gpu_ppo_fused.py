@@ -93,7 +93,7 @@ def run_kernel(lib, W, buf, mean, inv_std, logstd_old, e0, E, hyp, O, T, N, debu
     assert n_part > 0, n_part
     out = torch.zeros(P + 4, device="cuda")
     ls_snapshot = torch.full((2,), 7.0, device="cuda")
-    assert lib.vine_ppo_reduce(p(ws), n_part, O, p(out), p(logstd), p(ls_snapshot), None) == 0
+    assert lib.vine_ppo_reduce(p(ws), n_part, O, p(out), p(logstd), p(ls_snapshot), None, None) == 0
     torch.cuda.synchronize()
     # rl_games dataset.update_mu_sigma: the kernel leaves this pass's mu in the minibatch's rows of mu_old (only there) and
     # the reduce launch snapshots the log-std the minibatch was evaluated with
@@ -154,7 +154,7 @@ def test_adam_kernel_matches_torch_adam_and_repacks_the_weights():
             state[1] += 1.0
         ref.grad = out[:P].clone()
         opt.step()
-        assert lib.vine_ppo_adam(p(out), 1.0, p(flat), p(m), p(v), p(packed), p(state), O, 0.9, 0.999, 1e-8, 1, None) == 0
+        assert lib.vine_ppo_adam(p(out), 1.0, p(flat), p(m), p(v), p(packed), p(state), O, 0.9, 0.999, 1e-8, 1, None, None) == 0
         torch.cuda.synchronize()
         assert float((flat - ref.detach()).abs().max()) < 1e-6
     assert float(state[3]) == 1.0 and abs(float(state[2]) - float(out[P + 2])) < 1e-7 and float(state[8]) == 3.0
@@ -274,3 +274,46 @@ def test_update_prologue_matches_running_mean_std():
         assert torch.allclose(mean_f, ref_obs.running_mean.float(), atol=1e-5)
         assert torch.allclose(inv_f, torch.rsqrt(ref_obs.running_var.float() + 1e-5), rtol=1e-5)
         assert float(moments.abs().max()) == 0.0
+
+
+def test_p2p_channel_on_one_rank_is_transparent():
+    """world = 1: the peer-memory all-reduce (csrc/vine_p2p.cuh) degenerates to "the reduce kernel writes into the region's
+    buffer seq & 1, the Adam kernel reads it back": parameters after several optimiser steps are bit-identical to the plain
+    path, the sequence number advances once per exchange, nothing times out."""
+    from vine_robot_isaacgymenvs_b200 import distributed as vd
+    lib = abi.load_library()
+    T, N, O = 16, 512, 18
+    W, buf, mean, inv_std, logstd_old = make_problem(T, N, O, seed=9)
+    results = []
+    for use_channel in (False, True):
+        flat = torch.cat([w.reshape(-1) for w in W]).contiguous()
+        P = flat.numel()
+        packed = torch.zeros(abi.MLP_PACKED_BYTES, dtype=torch.uint8, device="cuda")
+        assert lib.vine_mlp_pack(*[p(w.contiguous()) for w in split(flat, W)[:10]], O, p(packed), None) == 0
+        ctas = lib.vine_ppo_max_ctas()
+        ws = torch.zeros(ctas, abi.PPO_WS_FLOATS, device="cuda")
+        state = torch.zeros(abi.PPO_STATE_FLOATS, device="cuda"); state[0] = 3e-4
+        m, v, out = torch.zeros(P, device="cuda"), torch.zeros(P, device="cuda"), torch.zeros(P + 4, device="cuda")
+        ch = vd.P2PChannel(lib, P + 4, "cuda") if use_channel else None
+        mu_old = buf["mu_old"].clone()
+        for k in range(5):                                   # 5 exchanges: both buffers of the region get reused
+            e0 = (k % 2) * 256
+            mb = abi.VinePpoMinibatch(
+                packed=packed.data_ptr(), obs=buf["obs"].data_ptr(), actions=buf["act"].data_ptr(), mu_old=mu_old.data_ptr(),
+                neglogp_old=buf["nlp_old"].data_ptr(), values_old=buf["val_old"].data_ptr(), returns=buf["ret"].data_ptr(),
+                advantages=buf["adv"].data_ptr(), obs_mean=mean.data_ptr(), obs_inv_std=inv_std.data_ptr(),
+                logstd=flat[P - 2:].data_ptr(), logstd_old=logstd_old.data_ptr(), workspace=ws.data_ptr(), state=state.data_ptr(),
+                debug_out=None, horizon=T, num_envs=N, env_begin=e0, env_count=256, num_obs=O, workspace_ctas=ctas, adaptive_lr=1,
+                kl_threshold=0.008, lr_min=1e-6, lr_max=1e-2, **HYP)
+            n_part = lib.vine_ppo_minibatch(C.byref(mb), None)
+            assert n_part > 0
+            assert lib.vine_ppo_reduce(p(ws), n_part, O, p(out), None, None, ch.ptr if ch else None, None) == 0
+            assert lib.vine_ppo_adam(p(out), 1.0, p(flat), p(m), p(v), p(packed), p(state), O, 0.9, 0.999, 1e-8, 1,
+                                     ch.ptr if ch else None, None) == 0
+        torch.cuda.synchronize()
+        if ch is not None:
+            assert ch.status() == (5, False)
+            ch.close()
+        results.append((flat.clone(), m.clone(), v.clone(), packed.clone(), state.clone()))
+    for a, b in zip(*results):
+        assert torch.equal(a, b)

@@ -200,3 +200,44 @@ def test_packed_two_env_kernel_equals_one_env_per_thread_kernel_bit_for_bit(n):
     for k in s0:
         assert torch.equal(s0[k], s1[k]), k
     assert int(envs[0].progress_buf.max()) < 45    # resets did happen
+
+
+@pytest.mark.parametrize("name", ["c2_fstr", "c3_shelf"])
+def test_wandb_dict_matches_the_reference_key_by_key(name, oracle_lib):
+    """tests/golden/metrics_<name>.npz holds what the reference's own compute_reward put into ``self.wandb_dict`` at every
+    step of the step_<name> rollout (V5:1250-1322: 19 aggregate scalars, 3 aggregated-reward entries, 54 reward-term
+    statistics and the per-view-env traces).  ``env.wandb_dict()`` (one reduction launch + one state read) must have exactly
+    those keys and, stepping from the reference's state, those values (means of f32 per-env quantities that match to ~1e-5)."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, f"metrics_{name}.npz"))
+    keys, values, actions = json.loads(str(z["keys"])), z["values"], z["actions"]
+    overrides = json.loads(str(z["overrides"]))
+    T, n = actions.shape[:2]
+    task_cfg = vcfg.task_config(overrides)
+    vc = vcfg.task_cfg_to_vine_config(task_cfg)
+    from vine_robot_isaacgymenvs_b200.tasks import isaacgym_task_map
+    env = isaacgym_task_map["Vine5LinkMovingBase"](
+        cfg={**task_cfg, "seed": int(z["seed"])}, rl_device="cuda:0", sim_device="cuda:0", graphics_device_id=-1,
+        headless=True, virtual_screen_capture=False, force_render=False)
+    env.enable_debug_outputs(True)
+    assert env.index_to_view == int(z["index_to_view"])
+    ora = oracle_lib.OracleEnv(vc, n, seed=int(z["seed"]), use_f64=True)
+    worst = {}
+    for t in range(T):
+        env.step(torch.from_numpy(actions[t]).cuda())
+        ora.step(actions[t])
+        got = env.wandb_dict()
+        assert sorted(got) == keys, (sorted(set(got) ^ set(keys)))
+        for k, ref in zip(keys, values[t]):
+            g = got[k]
+            loose = "qd" in k or "vel" in k.lower() or "Velocity" in k        # velocities: the stated 1e-2 dynamics tolerance
+            tol = (2e-2 * abs(ref) + 5e-3) if loose else (2e-3 * abs(ref) + 2e-4)
+            if "nonzero_contact" in k or k in ("target_reached", "limit_hit", "tip_limit_hit"):
+                tol = 1.0 / n + 1e-6                                          # a mask mean: at most one env at a threshold tie
+            assert abs(g - ref) <= tol, (t, k, g, ref)
+            worst[k] = max(worst.get(k, 0.0), abs(g - ref))
+        sync_env_to_oracle(env, ora)
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:3]
+    print(f"\n[wandb_dict {name}] {len(keys)} keys x {T} steps; largest |difference|: " + ", ".join(f"{k}: {v:.2e}" for k, v in top))

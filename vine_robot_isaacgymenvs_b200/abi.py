@@ -98,7 +98,7 @@ class VineStateView(C.Structure):
         "smoothed_u_fpam", "prev_cart_vel", "prev_cart_vel_error", "shelf_contact_force",
         "actions_history", "aggregated_rew_buf")] + [("step_count", _i64p)] + [(n, _fp) for n in (
         "u_rail_velocity", "u_fpam", "prev_u_rail_velocity", "rail_force", "tip_velocities",
-        "reward_matrix")]
+        "reward_matrix", "finite_difference_dof_vel", "finite_difference_tip_velocities", "cart_body_pos_y")]
 
 
 class VinePostPhysicsIO(C.Structure):
@@ -138,6 +138,8 @@ EXPORTED_SYMBOLS = [
     "vine_pre_physics", "vine_actuation", "vine_simulate", "vine_philox_debug", "vine_gae",
     "vine_mlp_pack", "vine_mlp_forward",
     "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
+    "vine_p2p_alloc", "vine_p2p_open", "vine_p2p_close", "vine_p2p_free", "vine_p2p_channel_create", "vine_p2p_channel_status",
+    "vine_p2p_channel_destroy",
     "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
     "vine_lstm_cell_fwd", "vine_lstm_cell_bwd", "vine_lstm_pack", "vine_lstm_step", "vine_lstm_mask", "vine_lstm_head", "vine_lstm_head_train", "vine_lstm_cell_bwd_tiles", "vine_lstm_bwd_gemm",
     "vine_lstm_gather", "vine_abi_struct_size", "vine_lstm_num_params", "vine_lstm_wgrad", "vine_lstm_reduce", "vine_lstm_adam",
@@ -282,13 +284,20 @@ def _declare(lib):
     lib.vine_abi_struct_size.argtypes = [C.c_int]
     lib.vine_lstm_num_params.argtypes = [C.c_int]
     lib.vine_lstm_wgrad.argtypes = [C.POINTER(VineLstmWgrad), vp]
-    lib.vine_lstm_reduce.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
-    lib.vine_lstm_adam.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, vp]
+    lib.vine_lstm_reduce.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]
+    lib.vine_lstm_adam.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp]
     lib.vine_ppo_num_params.argtypes = [C.c_int]
     lib.vine_ppo_max_ctas.argtypes = []
     lib.vine_ppo_minibatch.argtypes = [C.POINTER(VinePpoMinibatch), vp]
-    lib.vine_ppo_reduce.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp]
-    lib.vine_ppo_adam.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, vp]
+    lib.vine_ppo_reduce.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    lib.vine_ppo_adam.argtypes = [vp, C.c_float, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp]
+    lib.vine_p2p_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p), vp]
+    lib.vine_p2p_open.argtypes = [vp, C.POINTER(C.c_void_p)]
+    lib.vine_p2p_close.argtypes = [vp]
+    lib.vine_p2p_free.argtypes = [vp]
+    lib.vine_p2p_channel_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
+    lib.vine_p2p_channel_status.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.vine_p2p_channel_destroy.argtypes = [vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("vine_destroy", "vine_last_error"):

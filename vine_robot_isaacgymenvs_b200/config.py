@@ -522,6 +522,7 @@ def task_cfg_to_vine_config(cfg):
     c.contact_rest_offset = float(sim.get("physx", {}).get("rest_offset", 0.001))
     # launch tuning of the library (no counterpart in the reference; results do not depend on it)
     c.contact_cull_slack = float(vc.get("cull_slack", 0.01))
-    c.contact_binning = int(bool(vc.get("binning", True)))
+    b = vc.get("binning", 1)                    # 0 = one launch in identity order, 1 = routed from 4096 envs, 2 = always routed
+    c.contact_binning = int(b) if not isinstance(b, bool) else int(b)
     c.step_kernel_variant = abi.STEP_KERNEL_VARIANT[str(sim.get("vine_step_kernel", "auto")).lower()]
     return c

@@ -25,7 +25,7 @@
 #ifndef VINE_STEP2_MIN_BLOCKS
 #define VINE_STEP2_MIN_BLOCKS 0  // two-envs-per-thread kernel: the compiler's own register choice
 #endif
-#define VINE_DBG_W 20  // u_rail,u_fpam,prev_u_rail,rail_force,tipvel y,z, reward_matrix[13], pad
+#define VINE_DBG_W 28  // u_rail,u_fpam,prev_u_rail,rail_force,tipvel y,z, reward_matrix[13], pad, fd dof vel[6], fd tip vel y,z
 
 struct StepArgs {
   int64_t n, gid0;
@@ -41,6 +41,10 @@ struct StepArgs {
   // contact variant only (else nullptr): per-env "had contact candidates in its last step" flag, the env order of this launch
   // (envs with the flag first, so that they share warps) and the two cursors the binning kernel fills it with
   uint8_t* near; int32_t* perm; int32_t* bin_cursor;
+  // obstacle variants, routed step: the launch takes its envs from list[0 .. *list_count) (list_reversed: from the END of the
+  // n-entry array backwards); the far pass appends the envs it had to give up to redo_list / redo_count
+  const int32_t* list; const int32_t* list_count; int list_reversed;
+  int32_t* redo_list; int32_t* redo_count;
 };
 
 struct VineEnv {
@@ -49,6 +53,10 @@ struct VineEnv {
   StepArgs a;
   int device;
   int bound;
+  // routed step of the obstacle variants: the near pass runs beside the far pass on this stream (forked from and joined back
+  // into the caller's stream with the two events, so the whole step stays one capturable unit of the caller's stream)
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
   char err[256];
 };
 
@@ -96,6 +104,7 @@ __device__ __forceinline__ void store_obs_block(const float* s_obs, int O, int64
 struct EnvStep {   // what one env carries in registers across the sim steps of a control step
   float smoothed, prev_cart_vel, prev_err, lip, cart_body_vy;
   float u_rail, u_fpam, u_use, rail_force;
+  float new_rail, new_fpam;         // this step's command, pushed into the delay ring at the end of the step
   float tipb_y, tipb_z;             // rigid-body tip as of the refresh before the LAST simulate (V5:797 on reset steps)
   float contact[VINE_MAX_CFI];      // VT:348-351 samples (shelf only)
   uint32_t step, gid;
@@ -122,10 +131,9 @@ __device__ __forceinline__ void env_begin(const VineParams& p, const StepArgs& a
     a1 = __fadd_rn(a1, __fmul_rn(p.act_noise, nz[1]));
   }
   rescale_actions(p, a0, a1, E.u_rail, E.u_fpam);
-  if (p.D > 0) {  // V5:936-937 FIFO of ACTION_DELAY control steps
-    float2* slot = a.ring + (int64_t)(E.step % (uint32_t)p.D) * a.n + e;
-    const float2 old = *slot;
-    *slot = make_float2(E.u_rail, E.u_fpam);
+  E.new_rail = E.u_rail; E.new_fpam = E.u_fpam;
+  if (p.D > 0) {  // V5:936-937 FIFO of ACTION_DELAY control steps; the push happens in env_end (nothing is written before the
+    const float2 old = a.ring[(int64_t)(E.step % (uint32_t)p.D) * a.n + e];   // step is complete, so a pass may give an env up)
     E.u_rail = old.x; E.u_fpam = old.y;
   }
   apply_overrides_and_smooth(p, E.u_rail, E.u_fpam, E.smoothed);
@@ -253,6 +261,7 @@ __device__ __forceinline__ void env_end(const VineParams& p, const StepArgs& a, 
   a.S3[e] = make_float4(E.smoothed, E.prev_cart_vel, E.prev_err, E.lip);
   a.S4[e] = make_float4(tip_y, tip_z, cart_body_vy, agg);
   if (E.reset_in) a.S5[e] = make_float4(target[1], target[2], obj[0], obj[1]);
+  if (p.D > 0) a.ring[(int64_t)(E.step % (uint32_t)p.D) * a.n + e] = make_float2(E.new_rail, E.new_fpam);
   a.ctr[e] = E.step + 1u;
   a.rew[e] = o.rew;
   a.reset[e] = o.reset;
@@ -264,8 +273,15 @@ __device__ __forceinline__ void env_end(const VineParams& p, const StepArgs& a, 
     float* dbg = a.dbg + e * VINE_DBG_W;
     dbg[0] = E.u_rail; dbg[1] = E.u_fpam; dbg[2] = in.prev_u_rail; dbg[3] = E.rail_force;
     dbg[4] = tipvel_y; dbg[5] = tipvel_z;
+    dbg[19] = cart_y_body;   // rigid-body cart position: the pre-reset one on a reset step (stale body views, V5:796)
 #pragma unroll
     for (int i = 0; i < VINE_NUM_REWARDS; ++i) dbg[6 + i] = o.r[i];
+    // finite_difference_dof_vel / finite_difference_tip_velocities (V5:1347-1348), what the reference's per-view-env wandb
+    // traces show (V5:1283-1300): the same two expressions compute_observations uses
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dbg[20 + i] = div_rn(__fsub_rn(in.q[i], in.prev_q[i]), p.control_dt);
+    dbg[26] = div_rn(__fsub_rn(in.tip[1], in.prev_tip[1]), p.control_dt);
+    dbg[27] = div_rn(__fsub_rn(in.tip[2], in.prev_tip[2]), p.control_dt);
   }
 }
 
@@ -278,6 +294,27 @@ __device__ __forceinline__ void env_end(const VineParams& p, const StepArgs& a, 
 #ifndef VINE_BLOCK_CONTACT
 #define VINE_BLOCK_CONTACT 32
 #endif
+
+// one observation row (O <= 32 floats) per warp-wide store: for launches whose envs are not consecutive
+__device__ __forceinline__ void store_obs_rows_scattered(const VineParams& p, const StepArgs& a, const float* s_obs, int64_t mine) {
+  const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+#pragma unroll 1
+  for (int r = 0; r < 32; ++r) {
+    const int64_t er = __shfl_sync(0xffffffffu, mine, r);
+    if (er >= 0 && lane < p.O) {
+      const float v = s_obs[(w0 + r) * (VINE_MAX_OBS + 1) + lane];
+      a.obs[er * p.O + lane] = v;
+      if (a.obs_clamped) a.obs_clamped[er * p.O + lane] = fminf(fmaxf(v, -p.clip_obs), p.clip_obs);
+    }
+  }
+}
+
+// env id of launch slot `slot` (< count): consecutive, or through the launch's list
+__device__ __forceinline__ int64_t slot_env(const StepArgs& a, int64_t slot) {
+  if (!a.list) return a.first + slot;
+  return (int64_t)(a.list_reversed ? a.list[a.n - 1 - slot] : a.list[slot]);
+}
+
 template <bool CONTACT>
 __global__ void __launch_bounds__(CONTACT ? VINE_BLOCK_CONTACT : VINE_BLOCK, CONTACT ? VINE_STEP_MIN_BLOCKS_CONTACT : VINE_STEP_MIN_BLOCKS)
 vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
@@ -285,47 +322,100 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
   __shared__ float s_obs[BLOCK * (VINE_MAX_OBS + 1)];
   __shared__ ContactScratch s_contact[CONTACT ? BLOCK / 32 : 1];
   ContactScratch* cs = &s_contact[CONTACT ? threadIdx.x >> 5 : 0];
-  const int64_t slot = a.first + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  const bool live = slot < a.end;
-  const int64_t e = (CONTACT && a.perm && live) ? (int64_t)a.perm[slot] : slot;
+  const int64_t count = a.list_count ? (int64_t)*a.list_count : a.end - a.first;
+  // Listed launches (near / redo pass) hold nothing but envs with contact work, and the lanes of a warp wait for each other's
+  // narrow phases; when the list is short enough for the grid, each warp takes only 8 of them (lanes 0..7)
+  const int lanes = (CONTACT && a.list && count <= (int64_t)gridDim.x * 8) ? 8 : BLOCK;
+  // grid-stride over the launch's slots: listed launches are sized without knowing the list length
+#pragma unroll 1
+  for (int64_t base = (int64_t)blockIdx.x * lanes; base < count; base += (int64_t)gridDim.x * lanes) {
+    const int64_t slot = base + threadIdx.x;
+    const bool live = slot < count && (int)threadIdx.x < lanes;
+    const int64_t e = live ? slot_env(a, slot) : -1;
+    if (live) {
+      EnvStep E; Dyn d;
+      env_begin(p, a, e, E, d);
+      Obstacles ob = {0, -1, 0.f, 0.f, 0.f, 0.f};
+      ContactCache cc = {0u, 1e30f, 0u};   // no candidate pairs yet: the first substep culls
+      if (CONTACT) { const float4 s5 = a.S5[e]; build_obstacles(p, s5.x, s5.y, s5.z, s5.w, cs, ob); }
+      const float m00 = fmaf(p.h, p.damping, p.mtot), m00inv = rcp_approx(m00);
+      // ---- controlFrequencyInv x {forces, contact sample, simulate}  VT:338-356 ----
+#pragma unroll 1
+      for (int i = 0; i < p.C; ++i) {
+        // exact sin/cos: once per control step in free space (the incremental rotation drifts < 1e-6 over the 40 substeps at
+        // |w| < 36 rad/s), once per sim step with obstacles (impacts can spin a link an order of magnitude faster)
+        if (CONTACT && i > 0) refresh_trig(p, d);
+        JointImp J;
+        env_sim_step_begin(p, a, i, E, d, J);
+#pragma unroll 1
+        for (int s = 0; s < p.S; ++s) substep<CONTACT, float>(p, J, m00, m00inv, E.rail_force, ob, cs, cc, d, E.lip);
+      }
+      env_end(p, a, e, E, d, s_obs + threadIdx.x * (VINE_MAX_OBS + 1));
+      if (CONTACT && a.near) a.near[e] = cc.seen != 0u;
+    }
+    __syncthreads();
+    if (CONTACT && a.list) store_obs_rows_scattered(p, a, s_obs, e);
+    else store_obs_block<BLOCK, BLOCK>(s_obs, p.O, a.first + base - (int64_t)blockIdx.x * BLOCK, a.end, p.clip_obs, a.obs, a.obs_clamped);   // unlisted: lanes == BLOCK
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Far pass of the obstacle variants.  Most envs of a step are nowhere near their obstacle (random actions: ~2 % with the
+// shelf, ~8 % with the pipe), and the contact variant charges them its 155 registers, its one-warp blocks and its 20 KB
+// sim-step loop anyway.  So a routed step (vine_step with obstacles) sends the envs that were not near in their last step
+// through THIS kernel: the free-space integrator (substep<false>) plus a bound on how far the chain has moved since its
+// bounding box last had a gap to the obstacles' (7 instructions per substep).  An env whose boxes come to overlap is given up
+// -- nothing has been written for it -- and appended to the redo list, which the contact variant runs afterwards.  An env
+// that finishes here never had a contact candidate, so it computed exactly what the contact variant would have (same
+// explicit round-to-nearest arithmetic, same per-sim-step trig refresh): results do not depend on the routing.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VINE_BLOCK) vine_step_far_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
+  __shared__ float s_obs[VINE_BLOCK * (VINE_MAX_OBS + 1)];
+  const int64_t count = a.list_count ? a.n - (int64_t)*a.list_count : a.n;   // list_count = number of NEAR envs at the front
+  const int64_t slot = (int64_t)blockIdx.x * VINE_BLOCK + threadIdx.x;
+  if ((int64_t)blockIdx.x * VINE_BLOCK >= count) return;
+  const bool live = slot < count;
+  int64_t e = live ? slot_env(a, slot) : -1;
   if (live) {
     EnvStep E; Dyn d;
     env_begin(p, a, e, E, d);
-    Obstacles ob = {0, -1, 0.f, 0.f, 0.f, 0.f};
-    ContactCache cc = {0u, 1e30f, 0u};   // no candidate pairs yet: the first substep culls
-    if (CONTACT) { const float4 s5 = a.S5[e]; build_obstacles(p, s5.x, s5.y, s5.z, s5.w, cs, ob); }
+    Obstacles ob;
+    { const float4 s5 = a.S5[e]; obstacle_bbox(p, s5.x, s5.y, s5.z, s5.w, ob); }
+    float gap = chain_obstacle_gap(p, ob, d);
+    bool given_up = !(gap > 0.f);
+    float disp = -gap;
+    ContactCache cc = {0u, 0.f, 0u};
     const float m00 = fmaf(p.h, p.damping, p.mtot), m00inv = rcp_approx(m00);
-    // ---- controlFrequencyInv x {forces, contact sample, simulate}  VT:338-356 ----
 #pragma unroll 1
-    for (int i = 0; i < p.C; ++i) {
-      // exact sin/cos: once per control step in free space (the incremental rotation drifts < 1e-6 over the 40 substeps at
-      // |w| < 36 rad/s), once per sim step with obstacles (impacts can spin a link an order of magnitude faster)
-      if (CONTACT && i > 0) refresh_trig(p, d);
+    for (int i = 0; i < p.C && !given_up; ++i) {
+      if (i > 0) refresh_trig(p, d);        // like the contact variant: exact sin/cos once per sim step
       JointImp J;
       env_sim_step_begin(p, a, i, E, d, J);
 #pragma unroll 1
-      for (int s = 0; s < p.S; ++s) substep<CONTACT, float>(p, J, m00, m00inv, E.rail_force, ob, cs, cc, d, E.lip);
+      for (int s = 0; s < p.S; ++s) {
+        substep<false, float>(p, J, m00, m00inv, E.rail_force, ob, nullptr, cc, d, E.lip);
+        disp += chain_displacement_bound(p, d);
+        if (disp > p.cull_slack) {          // the chain may have reached the boxes' gap: measure it again
+          gap = chain_obstacle_gap(p, ob, d);
+          if (!(gap > 0.f)) { given_up = true; break; }
+          disp = -gap;
+        }
+      }
+      E.lip = 0.f;                          // nothing touched during this simulate (VT:348-351 samples it next sim step)
     }
-    env_end(p, a, e, E, d, s_obs + threadIdx.x * (VINE_MAX_OBS + 1));
-    if (CONTACT && a.near) a.near[e] = cc.seen != 0u;
+    if (given_up) {
+      a.redo_list[atomicAdd(a.redo_count, 1)] = (int32_t)e;
+      e = -1;                               // no observation row
+    } else {
+      env_end(p, a, e, E, d, s_obs + threadIdx.x * (VINE_MAX_OBS + 1));
+      // (marking envs near ahead of time -- within one step's reach of the gap, or just reset -- was measured: the near pass
+      // grows faster than the redo pass shrinks, 0.97 -> 1.13 ms per 1 M shelf envs)
+      a.near[e] = 0;
+    }
   }
   __syncthreads();
-  if (CONTACT && a.perm) {
-    // binned launch: the block's rows belong to scattered envs; one row (O <= 32 floats) per warp-wide store
-    const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
-    const int64_t mine = live ? e : -1;
-#pragma unroll 1
-    for (int r = 0; r < 32; ++r) {
-      const int64_t er = __shfl_sync(0xffffffffu, mine, r);
-      if (er >= 0 && lane < p.O) {
-        float v = s_obs[(w0 + r) * (VINE_MAX_OBS + 1) + lane];
-        a.obs[er * p.O + lane] = v;
-        if (a.obs_clamped) a.obs_clamped[er * p.O + lane] = fminf(fmaxf(v, -p.clip_obs), p.clip_obs);
-      }
-    }
-  } else {
-    store_obs_block<BLOCK, BLOCK>(s_obs, p.O, a.first, a.end, p.clip_obs, a.obs, a.obs_clamped);
-  }
+  store_obs_rows_scattered(p, a, s_obs, e);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -506,6 +596,12 @@ __global__ void vine_state_kernel(const __grid_constant__ VineParams p, const St
     if (v.rail_force) v.rail_force[e] = dbg[3];
     if (v.tip_velocities) { v.tip_velocities[3 * e] = 0.f; v.tip_velocities[3 * e + 1] = dbg[4]; v.tip_velocities[3 * e + 2] = dbg[5]; }
     if (v.reward_matrix) for (int i = 0; i < VINE_NUM_REWARDS; ++i) v.reward_matrix[VINE_NUM_REWARDS * e + i] = dbg[6 + i];
+    if (v.cart_body_pos_y) v.cart_body_pos_y[e] = dbg[19];
+    if (v.finite_difference_dof_vel) for (int i = 0; i < 6; ++i) v.finite_difference_dof_vel[6 * e + i] = dbg[20 + i];
+    if (v.finite_difference_tip_velocities) {
+      v.finite_difference_tip_velocities[3 * e] = 0.f;
+      v.finite_difference_tip_velocities[3 * e + 1] = dbg[26]; v.finite_difference_tip_velocities[3 * e + 2] = dbg[27];
+    }
   }
 }
 
@@ -703,7 +799,10 @@ void vine_destroy(VineEnv* env) {
   cudaSetDevice(env->device);
   cudaFree(env->a.S0); cudaFree(env->a.S1); cudaFree(env->a.S2); cudaFree(env->a.S3); cudaFree(env->a.S4);
   cudaFree(env->a.S5); cudaFree(env->a.ring); cudaFree(env->a.ctr); cudaFree(env->a.dbg);
-  cudaFree(env->a.near); cudaFree(env->a.perm); cudaFree(env->a.bin_cursor);
+  cudaFree(env->a.near); cudaFree(env->a.perm); cudaFree(env->a.bin_cursor); cudaFree(env->a.redo_list);
+  if (env->side) cudaStreamDestroy(env->side);
+  if (env->ev_fork) cudaEventDestroy(env->ev_fork);
+  if (env->ev_join) cudaEventDestroy(env->ev_join);
   delete env;
 }
 
@@ -739,7 +838,15 @@ int vine_create(const VineConfig* cfg, int64_t num_envs, int64_t global_env_offs
     if (e == cudaSuccess) e = cudaMalloc(&a.near, n);
     if (e == cudaSuccess) e = cudaMemset(a.near, 0, n);
     if (e == cudaSuccess) e = cudaMalloc(&a.perm, n * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&a.bin_cursor, 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&a.redo_list, n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&a.bin_cursor, 4 * sizeof(int32_t));   // near cursor, far cursor, redo count, pad
+    if (e == cudaSuccess) {   // the near pass (few, slow warps) gets its blocks placed ahead of the far pass's: it then runs beside it
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      e = cudaStreamCreateWithPriority(&env->side, cudaStreamNonBlocking, hi);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_join, cudaEventDisableTiming);
   }
   if (e == cudaSuccess) {
     vine_init_kernel<<<grid_for(num_envs, 256), 256>>>(env->p, env->a);
@@ -892,18 +999,31 @@ int vine_metrics(VineEnv* env, double* sums, float* maxes, void* stream) {
   return VINE_OK;
 }
 
-// The contact variant bins its envs (vine_bin_kernel) only for large launches: small ones are latency-bound (one wave, the
-// slowest warp sets the time) and a warp full of envs with candidates is the slowest there is. Putting fewer envs into each
-// warp of a small launch was measured too and changes nothing: the time is one env's own contact chain, not the lanes' sum.
-#define VINE_BIN_MIN_ENVS 98304   // measured crossover on B200: binning pays from ~100 k envs per launch (shelf and pipe presets)
-
-// free space: two envs per thread on the packed FP32 instructions unless the config asks for the scalar kernel
+// free space: one env per thread (AUTO: as fast at 1 M envs and 1.5x faster at 4096) unless the config asks for
+// the packed two-envs-per-thread kernel
 static void launch_free_step(const VineEnv* env, const StepArgs& a, cudaStream_t st) {
   const int64_t count = a.end - a.first;
-  if (env->cfg.step_kernel_variant == VINE_STEP_KERNEL_ONE_ENV_PER_THREAD)
-    vine_step_kernel<false><<<grid_for(count, VINE_BLOCK), VINE_BLOCK, 0, st>>>(env->p, a);
-  else
+  if (env->cfg.step_kernel_variant == VINE_STEP_KERNEL_TWO_ENVS_PACKED)
     vine_step2_kernel<<<grid_for(count, 2 * VINE_BLOCK2), VINE_BLOCK2, 0, st>>>(env->p, a);
+  else
+    vine_step_kernel<false><<<grid_for(count, VINE_BLOCK), VINE_BLOCK, 0, st>>>(env->p, a);
+}
+
+// Routed step of the obstacle variants (contact_binning != 0), per control step:
+//   1. vine_bin_kernel          orders the envs: "near" (chain box overlapped the obstacles' box in the last step) first, the
+//                               rest from the back; the near count stays on the device
+//   2. vine_step_kernel<true>   over the near list, on the side stream           } concurrently: the near pass is a handful
+//      vine_step_far_kernel     over the rest (free-space integrator + gap bound)  } of latency-bound warps
+//   3. vine_step_kernel<true>   over the envs the far pass gave up (boxes came to overlap during this step)
+// Per-env results do not depend on the routing (see vine_step_far_kernel).  contact_binning: 0 = one contact-variant launch
+// over all envs in identity order, 1 = routed from VINE_ROUTE_MIN_ENVS envs (measured crossover on B200: 131,072 envs 0.37 vs
+// 0.42 ms, 262,144 envs 0.63 vs 0.49 ms; below it the step is bounded by its slowest warp either way and the routed step pays
+// that latency twice, near pass + redo pass), 2 = always routed.
+#define VINE_ROUTE_MIN_ENVS 196608
+
+static unsigned listed_grid(int64_t n, int max_blocks) {
+  const int64_t b = (n + VINE_BLOCK_CONTACT - 1) / VINE_BLOCK_CONTACT;
+  return (unsigned)(b < max_blocks ? b : max_blocks);
 }
 
 int vine_step(VineEnv* env, void* stream) {
@@ -912,13 +1032,28 @@ int vine_step(VineEnv* env, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (env->p.shelf || env->p.pipe) {
     StepArgs a = env->a;
-    if (a.perm && a.n >= VINE_BIN_MIN_ENVS) {
-      CUDA_TRY(env, cudaMemsetAsync(a.bin_cursor, 0, 2 * sizeof(int32_t), st));
+    const bool routed = a.perm && (env->cfg.contact_binning >= 2 || a.n >= VINE_ROUTE_MIN_ENVS);
+    if (routed) {
+      CUDA_TRY(env, cudaMemsetAsync(a.bin_cursor, 0, 4 * sizeof(int32_t), st));
       vine_bin_kernel<<<grid_for(a.n, 1024), 1024, 0, st>>>(a);
+      CUDA_TRY(env, cudaEventRecord(env->ev_fork, st));
+      CUDA_TRY(env, cudaStreamWaitEvent(env->side, env->ev_fork, 0));
+      StepArgs nr = a;
+      nr.list = a.perm; nr.list_count = a.bin_cursor; nr.list_reversed = 0;
+      vine_step_kernel<true><<<listed_grid(a.n, 148 * 12), VINE_BLOCK_CONTACT, 0, env->side>>>(env->p, nr);
+      CUDA_TRY(env, cudaEventRecord(env->ev_join, env->side));
+      StepArgs fr = a;
+      fr.list = a.perm; fr.list_count = a.bin_cursor; fr.list_reversed = 1;
+      fr.redo_list = a.redo_list; fr.redo_count = a.bin_cursor + 2;
+      vine_step_far_kernel<<<grid_for(a.n, VINE_BLOCK), VINE_BLOCK, 0, st>>>(env->p, fr);
+      CUDA_TRY(env, cudaStreamWaitEvent(st, env->ev_join, 0));
+      StepArgs rd = a;
+      rd.list = a.redo_list; rd.list_count = a.bin_cursor + 2; rd.list_reversed = 0;
+      vine_step_kernel<true><<<listed_grid(a.n, 148 * 6), VINE_BLOCK_CONTACT, 0, st>>>(env->p, rd);
     } else {
       a.perm = nullptr;
+      vine_step_kernel<true><<<grid_for(a.n, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, st>>>(env->p, a);
     }
-    vine_step_kernel<true><<<grid_for(a.n, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, st>>>(env->p, a);
   } else {
     launch_free_step(env, env->a, st);
   }

@@ -148,18 +148,16 @@ struct Obstacles { int n, lip; float lo_y, hi_y, lo_z, hi_z; };
 // they were culled (negative: distance still to go before the chain can reach the obstacles' bounding box); registers
 struct ContactCache { unsigned pm; float disp; unsigned seen; };   // seen: OR of every mask of this control step
 
-VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, float theta, ContactScratch* cs, Obstacles& ob) {
-  float* R = cs->rect[threadIdx.x & 31];
-  auto put = [&](int i, float cy, float cz, float ay, float az, float ha, float hn) {
-    R[6 * i] = cy; R[6 * i + 1] = cz; R[6 * i + 2] = ay; R[6 * i + 3] = az; R[6 * i + 4] = ha; R[6 * i + 5] = hn;
-  };
-  ob.n = 0; ob.lip = -1;
+// the obstacle rectangles of one env: put(index, centre y, centre z, axis y, axis z, half extent along the axis, along the normal)
+template <class Put>
+VDEV void for_each_obstacle_rect(const VineParams& p, float ty, float tz, float depth, float theta, int& n, int& lip, Put&& put) {
+  n = 0; lip = -1;
   if (p.shelf) {
     const float ry = ty + (-0.2f + depth), rz = tz - 0.01f;
     put(0, ry - 0.001f, rz, 1.f, 0.f, 0.1995f, 0.005f);
     put(1, ry, rz + 0.2f, 1.f, 0.f, 0.2f, 0.005f);
     put(2, ry + 0.199f, rz, 1.f, 0.f, 0.001f, 0.005f);
-    ob.lip = 2; ob.n = 3;
+    lip = 2; n = 3;
   }
   if (p.pipe) {
     float st, ct; vine_sincos(theta, st, ct);
@@ -168,17 +166,31 @@ VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, 
     const float ey = ty + depth * ct + off * st, ez = tz + depth * st - off * ct;
     const float ay = -ct, az = -st, ny = -az, nz = ay;
     const float mid = 0.5f * (win + wout), hn = 0.5f * (wout - win), ha = 0.5f * 0.34125f;
-    put(ob.n, ey + ay * ha - mid * ny, ez + az * ha - mid * nz, ay, az, ha, hn);
-    put(ob.n + 1, ey + ay * ha + mid * ny, ez + az * ha + mid * nz, ay, az, ha, hn);
-    ob.n += 2;
+    put(n, ey + ay * ha - mid * ny, ez + az * ha - mid * nz, ay, az, ha, hn);
+    put(n + 1, ey + ay * ha + mid * ny, ez + az * ha + mid * nz, ay, az, ha, hn);
+    n += 2;
   }
+}
+
+VDEV void build_obstacles(const VineParams& p, float ty, float tz, float depth, float theta, ContactScratch* cs, Obstacles& ob) {
+  float* R = cs->rect[threadIdx.x & 31];
   ob.lo_y = ob.lo_z = 1e30f; ob.hi_y = ob.hi_z = -1e30f;
-  for (int i = 0; i < ob.n; ++i) {
-    const float ey = fabsf(R[6 * i + 2]) * R[6 * i + 4] + fabsf(R[6 * i + 3]) * R[6 * i + 5];
-    const float ez = fabsf(R[6 * i + 3]) * R[6 * i + 4] + fabsf(R[6 * i + 2]) * R[6 * i + 5];
-    ob.lo_y = fminf(ob.lo_y, R[6 * i] - ey); ob.hi_y = fmaxf(ob.hi_y, R[6 * i] + ey);
-    ob.lo_z = fminf(ob.lo_z, R[6 * i + 1] - ez); ob.hi_z = fmaxf(ob.hi_z, R[6 * i + 1] + ez);
-  }
+  for_each_obstacle_rect(p, ty, tz, depth, theta, ob.n, ob.lip, [&](int i, float cy, float cz, float ay, float az, float ha, float hn) {
+    R[6 * i] = cy; R[6 * i + 1] = cz; R[6 * i + 2] = ay; R[6 * i + 3] = az; R[6 * i + 4] = ha; R[6 * i + 5] = hn;
+    const float ey = fabsf(ay) * ha + fabsf(az) * hn, ez = fabsf(az) * ha + fabsf(ay) * hn;
+    ob.lo_y = fminf(ob.lo_y, cy - ey); ob.hi_y = fmaxf(ob.hi_y, cy + ey);
+    ob.lo_z = fminf(ob.lo_z, cz - ez); ob.hi_z = fmaxf(ob.hi_z, cz + ez);
+  });
+}
+
+// bounding box of the obstacles only (the far pass of the obstacle variants keeps nothing else)
+VDEV void obstacle_bbox(const VineParams& p, float ty, float tz, float depth, float theta, Obstacles& ob) {
+  ob.lo_y = ob.lo_z = 1e30f; ob.hi_y = ob.hi_z = -1e30f;
+  for_each_obstacle_rect(p, ty, tz, depth, theta, ob.n, ob.lip, [&](int, float cy, float cz, float ay, float az, float ha, float hn) {
+    const float ey = fabsf(ay) * ha + fabsf(az) * hn, ez = fabsf(az) * ha + fabsf(ay) * hn;
+    ob.lo_y = fminf(ob.lo_y, cy - ey); ob.hi_y = fmaxf(ob.hi_y, cy + ey);
+    ob.lo_z = fminf(ob.lo_z, cz - ez); ob.hi_z = fmaxf(ob.hi_z, cz + ez);
+  });
 }
 
 // ------------------------------------------------------------------------------------------
@@ -337,15 +349,39 @@ VDEV unsigned cull_pairs(const VineParams& p, const Obstacles& ob, const float* 
   return pm;
 }
 
+// every point of the chain moved at most h (|v_y| + rho sum |w|) in the last substep (rho: farthest point from a joint)
+VDEV float chain_displacement_bound(const VineParams& p, const Dyn& d) {
+  float ws = 0.f;
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) ws += fabsf(d.v[j + 1]);
+  return p.h * fmaf(VINE_LINK_LEN + 0.1f, ws, fabsf(d.v[0]));
+}
+
+// Chain inflated by the widest cross-section (FPAM offset + radius) + rest + slack against the obstacles' bounding box: with a
+// gap > 0 between the two no contact is possible until some point of the chain has moved `gap`.
+VDEV float chain_obstacle_gap(const VineParams& p, const Obstacles& ob, const float py[VINE_NL + 1], const float pz[VINE_NL + 1]) {
+  float lo_y = py[0], hi_y = py[0], lo_z = pz[0], hi_z = pz[0];
+#pragma unroll
+  for (int j = 1; j <= VINE_NL; ++j) {
+    lo_y = fminf(lo_y, py[j]); hi_y = fmaxf(hi_y, py[j]); lo_z = fminf(lo_z, pz[j]); hi_z = fmaxf(hi_z, pz[j]);
+  }
+  const float m = VINE_FPAM_OFFSET + VINE_FPAM_RADIUS + p.rest + 1e-3f + p.cull_slack;
+  return fmaxf(fmaxf(lo_y - m - ob.hi_y, ob.lo_y - (hi_y + m)), fmaxf(lo_z - m - ob.hi_z, ob.lo_z - (hi_z + m)));
+}
+
+VDEV float chain_obstacle_gap(const VineParams& p, const Obstacles& ob, const Dyn& d) {
+  float py[VINE_NL + 1], pz[VINE_NL + 1];
+  py[0] = d.x[0]; pz[0] = VINE_PIVOT_Z;
+#pragma unroll
+  for (int j = 0; j < VINE_NL; ++j) {
+    py[j + 1] = fmaf(-VINE_LINK_LEN, d.S[j], py[j]); pz[j + 1] = fmaf(VINE_LINK_LEN, d.C[j], pz[j]);
+  }
+  return chain_obstacle_gap(p, ob, py, pz);
+}
+
 // all link-vs-obstacle contacts of one substep; adds generalized forces to f[6], returns |F_lip|
 VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScratch* cs, ContactCache& cc, const Dyn& d, float f[6]) {
-  {
-    // every point of the chain moved at most h (|v_y| + rho sum |w|) in the last substep (rho: farthest point from a joint)
-    float ws = 0.f;
-#pragma unroll
-    for (int j = 0; j < VINE_NL; ++j) ws += fabsf(d.v[j + 1]);
-    cc.disp = fmaf(p.h, fmaf(VINE_LINK_LEN + 0.1f, ws, fabsf(d.v[0])), cc.disp);
-  }
+  cc.disp += chain_displacement_bound(p, d);
   const bool stale = !(cc.disp <= p.cull_slack);
   if (!stale && cc.pm == 0u) return 0.f;
 
@@ -358,17 +394,9 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScrat
   }
   const float* R = cs->rect[lane];
   if (stale) {
-    float lo_y = py[0], hi_y = py[0], lo_z = pz[0], hi_z = pz[0];
-#pragma unroll
-    for (int j = 1; j <= VINE_NL; ++j) {
-      lo_y = fminf(lo_y, py[j]); hi_y = fmaxf(hi_y, py[j]); lo_z = fminf(lo_z, pz[j]); hi_z = fmaxf(hi_z, pz[j]);
-    }
-    // chain inflated by the widest cross-section (FPAM offset + radius) + rest + slack against the obstacles' bounding box:
-    // with a gap between the two no contact is possible until the chain has moved gap + slack
-    const float m = VINE_FPAM_OFFSET + VINE_FPAM_RADIUS + p.rest + 1e-3f + p.cull_slack;
-    const float gap = fmaxf(fmaxf(lo_y - m - ob.hi_y, ob.lo_y - (hi_y + m)), fmaxf(lo_z - m - ob.hi_z, ob.lo_z - (hi_z + m)));
+    const float gap = chain_obstacle_gap(p, ob, py, pz);
     if (gap > 0.f) { cc.pm = 0u; cc.disp = -gap; }
-    else { cc.pm = cull_pairs(p, ob, R, py, pz); cc.disp = 0.f; cc.seen |= cc.pm; }
+    else { cc.pm = cull_pairs(p, ob, R, py, pz); cc.disp = 0.f; cc.seen |= cc.pm | 0x80000000u; }   // bit 31: the boxes overlapped
     if (cc.pm == 0u) return 0.f;
   }
   // publish this env's chain in its column of the warp's scratch: the narrow phase picks its link by a run-time index

@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include "vine_device.cuh"
+#include "vine_p2p.cuh"
 #include "vine_mlp_common.cuh"
 
 namespace {
@@ -763,7 +764,8 @@ __global__ void __launch_bounds__(128) vine_lstm_head_sum_kernel(const float* __
 // flat gradient vector from the weight-gradient partials: one thread per workspace slot (coalesced reads over the K splits),
 // scattered write to the slot's parameter; the parameters fed by the head kernel come from the summed head buffer.
 __global__ void __launch_bounds__(256) vine_lstm_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ hsum, int O,
-                                                               float* __restrict__ flat) {
+                                                               float* __restrict__ flat, const VineP2PChannel* ch) {
+  if (ch) flat = p2p_local_buffer(ch);   // multi-GPU: straight into this rank's peer-visible buffer (vine_p2p.cuh)
   const LstmSeg sg = lstm_segments(O);
   const int PL = sg.end;
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -804,20 +806,21 @@ __global__ void __launch_bounds__(256) vine_lstm_reduce_kernel(const float* __re
 
 __global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scale, float* __restrict__ params, float* __restrict__ m,
                                       float* __restrict__ v, uint8_t* __restrict__ packed, float* __restrict__ state, int O, float beta1,
-                                      float beta2, float eps) {
+                                      float beta2, float eps, VineP2PChannel* ch) {
   const int PL = lstm_num_params(O);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= PL) {
-    if (p == PL) {   // loss statistics + the KL that drives the adaptive learning rate (state layout: vine_ppo_adam)
-      for (int j = 0; j < 4; ++j) state[4 + j] += flat[PL + j] * scale;
-      state[8] += 1.f;
-      state[2] = flat[PL + 2] * scale;
-      state[3] = 1.f;
-    }
-    return;
+  // multi-GPU: wait for every rank's gradient buffer, then read the sum over the ranks instead of `flat` (vine_p2p.cuh)
+  const unsigned seq = ch ? p2p_exchange_begin(ch) : 0u;
+  auto grad = [&](int i) { return (ch ? p2p_sum(ch, seq, i) : flat[i]) * scale; };
+  if (p == PL) {   // loss statistics + the KL that drives the adaptive learning rate (state layout: vine_ppo_adam)
+    for (int j = 0; j < 4; ++j) state[4 + j] += grad(PL + j);
+    state[8] += 1.f;
+    state[2] = grad(PL + 2);
+    state[3] = 1.f;
   }
+  if (p < PL) {
   const float lr = state[0], step = state[1];
-  const float g = flat[p] * scale;
+  const float g = grad(p);
   const float mn = beta1 * m[p] + (1.f - beta1) * g;
   const float vn = beta2 * v[p] + (1.f - beta2) * g * g;
   m[p] = mn;
@@ -849,6 +852,8 @@ __global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scal
     else if (p < sg.ls) f32 = reinterpret_cast<float*>(packed + LP_BH) + 2;
     if (f32) *f32 = w;
   }
+  }
+  if (ch) p2p_exchange_end(ch);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1006,8 +1011,9 @@ int vine_lstm_wgrad(const VineLstmWgrad* a, void* stream) {
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
-int vine_lstm_reduce(const float* workspace, int splits, float* head_grads, int head_parts, int num_obs, float* flat, void* stream) {
-  if (!workspace || !head_grads || !flat || splits < 1 || head_parts < 1 || head_parts > VINE_LSTM_HEAD_GRAD_PARTS || num_obs < 1 ||
+int vine_lstm_reduce(const float* workspace, int splits, float* head_grads, int head_parts, int num_obs, float* flat, void* p2p_channel,
+                     void* stream) {
+  if (!workspace || !head_grads || (!flat && !p2p_channel) || splits < 1 || head_parts < 1 || head_parts > VINE_LSTM_HEAD_GRAD_PARTS || num_obs < 1 ||
       num_obs >= K1)
     return VINE_ERR_INVALID_ARG;
   const int n = lstm_num_params(num_obs) + 4;
@@ -1016,16 +1022,17 @@ int vine_lstm_reduce(const float* workspace, int splits, float* head_grads, int 
   vine_lstm_head_sum_kernel<<<HG_FLOATS / 4, 128, 0, (cudaStream_t)stream>>>(head_grads, head_parts, hsum);
   const int threads = WG_BLOCKS * WG_BLOCK_FLOATS + 5 * HID + 9;
   (void)n;
-  vine_lstm_reduce_kernel<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, splits, hsum, num_obs, flat);
+  vine_lstm_reduce_kernel<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, splits, hsum, num_obs, flat,
+                                                                                   (const VineP2PChannel*)p2p_channel);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
 int vine_lstm_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq, void* packed, float* state,
-                   int num_obs, float beta1, float beta2, float eps, void* stream) {
-  if (!flat || !params || !exp_avg || !exp_avg_sq || !packed || !state || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
+                   int num_obs, float beta1, float beta2, float eps, void* p2p_channel, void* stream) {
+  if ((!flat && !p2p_channel) || !params || !exp_avg || !exp_avg_sq || !packed || !state || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
   const int n = lstm_num_params(num_obs) + 1;
   vine_lstm_adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(flat, grad_scale, params, exp_avg, exp_avg_sq, (uint8_t*)packed,
-                                                                         state, num_obs, beta1, beta2, eps);
+                                                                         state, num_obs, beta1, beta2, eps, (VineP2PChannel*)p2p_channel);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "vine_mlp_common.cuh"
+#include "vine_p2p.cuh"
 
 namespace {
 using namespace vine_mlp;
@@ -420,7 +421,8 @@ __device__ inline int ws_to_param(int w, int O) {
 constexpr int RED_SLOTS = 64, RED_SPLIT = 4;
 __global__ void __launch_bounds__(RED_SLOTS* RED_SPLIT) vine_ppo_reduce_kernel(const float* __restrict__ ws, int n_partials, int O,
                                                                                float* __restrict__ flat, const float* __restrict__ logstd,
-                                                                               float* __restrict__ logstd_old_out) {
+                                                                               float* __restrict__ logstd_old_out, const VineP2PChannel* ch) {
+  if (ch) flat = p2p_local_buffer(ch);   // multi-GPU: the sum goes straight into this rank's peer-visible buffer (vine_p2p.cuh)
   // sigma half of dataset.update_mu_sigma: the log-std this minibatch was evaluated with becomes its rows' "old" one. Done
   // here because this launch sits between the last reader (the minibatch kernel) and the writer (Adam) of the parameter.
   if (logstd_old_out && blockIdx.x == 0 && threadIdx.x < 2) logstd_old_out[threadIdx.x] = logstd[threadIdx.x];
@@ -447,34 +449,37 @@ __global__ void __launch_bounds__(RED_SLOTS* RED_SPLIT) vine_ppo_reduce_kernel(c
 // torch.optim.Adam (no weight decay, no amsgrad) on the flat parameter vector + re-pack for the tensor cores
 __global__ void vine_ppo_adam_kernel(const float* __restrict__ flat, float scale, float* __restrict__ params, float* __restrict__ m,
                                      float* __restrict__ v, uint8_t* __restrict__ packed, float* __restrict__ state, int O,
-                                     float beta1, float beta2, float eps, int bookkeeping) {
+                                     float beta1, float beta2, float eps, int bookkeeping, VineP2PChannel* ch) {
   const int P = num_params(O);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) {
-    if (p == P && bookkeeping) {   // bookkeeping by exactly one thread
-      for (int j = 0; j < 4; ++j) state[ST_SUMS + j] += flat[P + j] * scale;
-      state[ST_COUNT] += 1.f;
-      state[ST_KL] = flat[P + 2] * scale;
-      state[ST_PENDING] = 1.f;
+  // multi-GPU: wait for every rank's gradient buffer, then read the sum over the ranks instead of `flat` (vine_p2p.cuh)
+  const unsigned seq = ch ? p2p_exchange_begin(ch) : 0u;
+  auto grad = [&](int i) { return (ch ? p2p_sum(ch, seq, i) : flat[i]) * scale; };
+  if (p == P && bookkeeping) {   // bookkeeping by exactly one thread
+    for (int j = 0; j < 4; ++j) state[ST_SUMS + j] += grad(P + j);
+    state[ST_COUNT] += 1.f;
+    state[ST_KL] = grad(P + 2);
+    state[ST_PENDING] = 1.f;
+  }
+  if (p < P) {
+    const float lr = state[ST_LR], step = state[ST_STEP];
+    const float g = grad(p);
+    const float mn = beta1 * m[p] + (1.f - beta1) * g;
+    const float vn = beta2 * v[p] + (1.f - beta2) * g * g;
+    m[p] = mn;
+    v[p] = vn;
+    const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
+    const float w = params[p] - (lr / bc1) * mn / (sqrtf(vn) / sqrtf(bc2) + eps);
+    params[p] = w;
+    int ws_off, pk_off;
+    bool f32;
+    param_map(p, O, ws_off, pk_off, f32);
+    if (pk_off >= 0) {
+      if (f32) *reinterpret_cast<float*>(packed + pk_off) = w;
+      else *reinterpret_cast<__nv_bfloat16*>(packed + pk_off) = __float2bfloat16_rn(w);
     }
-    return;
   }
-  const float lr = state[ST_LR], step = state[ST_STEP];
-  const float g = flat[p] * scale;
-  const float mn = beta1 * m[p] + (1.f - beta1) * g;
-  const float vn = beta2 * v[p] + (1.f - beta2) * g * g;
-  m[p] = mn;
-  v[p] = vn;
-  const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
-  const float w = params[p] - (lr / bc1) * mn / (sqrtf(vn) / sqrtf(bc2) + eps);
-  params[p] = w;
-  int ws_off, pk_off;
-  bool f32;
-  param_map(p, O, ws_off, pk_off, f32);
-  if (pk_off >= 0) {
-    if (f32) *reinterpret_cast<float*>(packed + pk_off) = w;
-    else *reinterpret_cast<__nv_bfloat16*>(packed + pk_off) = __float2bfloat16_rn(w);
-  }
+  if (ch) p2p_exchange_end(ch);
 }
 
 }  // namespace
@@ -530,22 +535,81 @@ int vine_ppo_minibatch(const VinePpoMinibatch* b, void* stream) {
 }
 
 int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* flat, const float* logstd, float* logstd_old_out,
-                    void* stream) {
-  if (!workspace || !flat || n_partials < 1 || num_obs < 1 || num_obs >= K1 || (logstd_old_out && !logstd)) return VINE_ERR_INVALID_ARG;
+                    void* p2p_channel, void* stream) {
+  if (!workspace || (!flat && !p2p_channel) || n_partials < 1 || num_obs < 1 || num_obs >= K1 || (logstd_old_out && !logstd))
+    return VINE_ERR_INVALID_ARG;
   const int slots = WS_STATS + 8;
   vine_ppo_reduce_kernel<<<(slots + RED_SLOTS - 1) / RED_SLOTS, RED_SLOTS * RED_SPLIT, 0, (cudaStream_t)stream>>>(
-      workspace, n_partials, num_obs, flat, logstd, logstd_old_out);
+      workspace, n_partials, num_obs, flat, logstd, logstd_old_out, (const VineP2PChannel*)p2p_channel);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
 int vine_ppo_adam(const float* flat, float grad_scale, float* params, float* exp_avg, float* exp_avg_sq, void* packed,
-                  float* state, int num_obs, float beta1, float beta2, float eps, int bookkeeping, void* stream) {
-  if (!flat || !params || !exp_avg || !exp_avg_sq || !packed || !state || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
+                  float* state, int num_obs, float beta1, float beta2, float eps, int bookkeeping, void* p2p_channel, void* stream) {
+  if ((!flat && !p2p_channel) || !params || !exp_avg || !exp_avg_sq || !packed || !state || num_obs < 1 || num_obs >= K1)
+    return VINE_ERR_INVALID_ARG;
   const int n = num_params(num_obs) + 1;
   vine_ppo_adam_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(flat, grad_scale, params, exp_avg, exp_avg_sq,
                                                                          (uint8_t*)packed, state, num_obs, beta1, beta2, eps,
-                                                                         bookkeeping);
+                                                                         bookkeeping, (VineP2PChannel*)p2p_channel);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// peer-memory regions and channels of the gradient all-reduce (vine_p2p.cuh)
+// ------------------------------------------------------------------------------------------
+static size_t p2p_region_bytes(int64_t count) { return (size_t)VINE_P2P_FLAG_BYTES + 2u * (size_t)count * sizeof(float); }
+
+int vine_p2p_alloc(int64_t count, void** region, void* ipc_handle_out) {
+  if (count < 1 || !region || !ipc_handle_out) return VINE_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == VINE_P2P_HANDLE_BYTES, "handle size");
+  void* p = nullptr;
+  if (cudaMalloc(&p, p2p_region_bytes(count)) != cudaSuccess) return VINE_ERR_CUDA;
+  if (cudaMemset(p, 0, p2p_region_bytes(count)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { cudaFree(p); return VINE_ERR_CUDA; }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); return VINE_ERR_CUDA; }
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  *region = p;
+  return VINE_OK;
+}
+
+int vine_p2p_open(const void* ipc_handle, void** region) {
+  if (!ipc_handle || !region) return VINE_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  return cudaIpcOpenMemHandle(region, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+int vine_p2p_close(void* region) { return cudaIpcCloseMemHandle(region) == cudaSuccess ? VINE_OK : VINE_ERR_CUDA; }
+int vine_p2p_free(void* region) { return cudaFree(region) == cudaSuccess ? VINE_OK : VINE_ERR_CUDA; }
+
+int vine_p2p_channel_create(void* const* regions, int world, int rank, int64_t count, void** channel) {
+  if (!regions || !channel || world < 1 || world > VINE_P2P_MAX_RANKS || rank < 0 || rank >= world || count < 1) return VINE_ERR_INVALID_ARG;
+  VineP2PChannel h;
+  memset(&h, 0, sizeof(h));
+  for (int r = 0; r < world; ++r) {
+    if (!regions[r]) return VINE_ERR_INVALID_ARG;
+    h.peer_base[r] = (unsigned long long)(uintptr_t)regions[r];
+  }
+  h.world = world; h.rank = rank; h.count = count;
+  void* d = nullptr;
+  if (cudaMalloc(&d, sizeof(h)) != cudaSuccess) return VINE_ERR_CUDA;
+  if (cudaMemcpy(d, &h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return VINE_ERR_CUDA; }
+  *channel = d;
+  return VINE_OK;
+}
+
+// exchanges completed and the timeout flag of a channel (synchronises the device: for tests and error reporting)
+int vine_p2p_channel_status(const void* channel, uint32_t* seq, uint32_t* error) {
+  if (!channel) return VINE_ERR_INVALID_ARG;
+  VineP2PChannel h;
+  if (cudaMemcpy(&h, channel, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return VINE_ERR_CUDA;
+  if (seq) *seq = h.seq;
+  if (error) *error = h.error;
+  return VINE_OK;
+}
+
+int vine_p2p_channel_destroy(void* channel) { return cudaFree(channel) == cudaSuccess ? VINE_OK : VINE_ERR_CUDA; }
 
 }  // extern "C"

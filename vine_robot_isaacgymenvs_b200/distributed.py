@@ -80,3 +80,72 @@ def merge_moments(count, mean, m2):
     local = m2.double() + c[0] * (mean.double() - gmean) ** 2   # c[0]: keeps 0-dim statistics 0-dim
     dist.all_reduce(local)
     return tot.to(torch.float64), gmean.to(mean.dtype), local.to(m2.dtype)
+
+
+class P2PChannel:
+    """One channel of the gradient all-reduce over NVLink peer memory (include/vine_b200.h "Gradient all-reduce over peer
+    memory", csrc/vine_p2p.cuh): this rank's region (two buffers of ``count`` f32 + flags) is allocated by the library and
+    exported as a CUDA IPC handle; the handles are exchanged with ONE all_gather at construction; every peer region is mapped;
+    ``ptr`` is the device-side channel the producer / consumer kernels take.  world == 1 works too (the channel then only
+    exercises the buffers and the sequence logic).  NCCL is used for nothing but the handle exchange."""
+
+    def __init__(self, lib, count, device):
+        import ctypes as C
+        self.lib, self.count, self.device = lib, int(count), torch.device(device)
+        rank, world, _ = rank_world()
+        if not (dist.is_available() and dist.is_initialized()):
+            rank, world = 0, 1
+        self.rank, self.world = rank, world
+        region, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            rc = lib.vine_p2p_alloc(self.count, C.byref(region), handle)
+        if rc != 0:
+            raise RuntimeError(f"vine_p2p_alloc failed ({rc})")
+        self._own = region
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        handles = [torch.empty_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(handles, mine)
+        else:
+            handles = [mine]
+        self._opened = []
+        regions = (C.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                regions[r] = region.value
+                continue
+            peer = C.c_void_p()
+            raw = (C.c_ubyte * 64)(*handles[r].cpu().tolist())
+            with torch.cuda.device(self.device):
+                rc = lib.vine_p2p_open(raw, C.byref(peer))
+            if rc != 0:
+                raise RuntimeError(f"vine_p2p_open failed for rank {r} ({rc}): CUDA IPC / NVLink peer access is required "
+                                   "(one process per GPU on ONE node); pass grad_allreduce='nccl' to use NCCL instead")
+            self._opened.append(peer)
+            regions[r] = peer.value
+        ch = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = lib.vine_p2p_channel_create(regions, world, rank, self.count, C.byref(ch))
+        if rc != 0:
+            raise RuntimeError(f"vine_p2p_channel_create failed ({rc})")
+        self.ptr = ch
+        if world > 1:
+            dist.barrier()          # nobody launches before every rank has mapped every region
+
+    def status(self):
+        """(exchanges completed, timed_out) -- synchronises the device."""
+        import ctypes as C
+        seq, err = C.c_uint32(), C.c_uint32()
+        assert self.lib.vine_p2p_channel_status(self.ptr, C.byref(seq), C.byref(err)) == 0
+        return int(seq.value), bool(err.value)
+
+    def close(self):
+        if getattr(self, "ptr", None) is not None:
+            torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                dist.barrier()      # peers may still be reading this rank's region
+            self.lib.vine_p2p_channel_destroy(self.ptr)
+            for peer in self._opened:
+                self.lib.vine_p2p_close(peer)
+            self.lib.vine_p2p_free(self._own)
+            self.ptr = None

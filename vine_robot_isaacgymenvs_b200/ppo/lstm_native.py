@@ -49,11 +49,13 @@ class NativeLstmPath:
 
     # ------------------------------------------------------------------ forward + backward of one minibatch
     def gradients(self, packed_mlp, packed_lstm, obs, scalars, not_done, obs_mean, obs_inv_std, value_stats, logstd, logstd_old,
-                  state, debug_out=None, writeback=None):
+                  state, debug_out=None, writeback=None, p2p=(None, None)):
         """obs f32 [L, S, O], scalars f32 [L, S, 8], not_done f32 [L, S]; self.HM[0] (masked initial hidden state tiles) and
         self.C0 must already hold the initial LSTM state.  Leaves the gradients in flat_g_mlp / flat_g_lstm.
         ``writeback`` = (scalars_src [T, N, 8], seq_len, chunks, num_envs, env_begin, env_count): rl_games'
-        dataset.update_mu_sigma -- this pass's mu goes back into the source rows and ``logstd_old`` receives ``logstd``."""
+        dataset.update_mu_sigma -- this pass's mu goes back into the source rows and ``logstd_old`` receives ``logstd``.
+        ``p2p`` = (MLP channel, LSTM channel) device pointers: multi-GPU, the two gradient sums go into this rank's peer-visible
+        buffers instead of flat_g_* (distributed.P2PChannel)."""
         lib, L, S, tl, st = self.lib, self.L, self.S, self.tiles, self._stream()
         n = L * S
         act = abi.VinePolicyAct(packed=_ptr(packed_mlp), obs=_ptr(obs), obs_mean=_ptr(obs_mean), obs_inv_std=_ptr(obs_inv_std),
@@ -97,9 +99,9 @@ class NativeLstmPath:
         assert n_part > 0, n_part
         wb = writeback is not None   # sigma half of update_mu_sigma: after the last reader of logstd_old, before Adam
         assert lib.vine_ppo_reduce(C.c_void_p(_ptr(self.mlp_ws)), n_part, self.O, C.c_void_p(_ptr(self.flat_g_mlp)),
-                                   C.c_void_p(_ptr(logstd)) if wb else None, C.c_void_p(_ptr(logstd_old)) if wb else None, st) == 0
+                                   C.c_void_p(_ptr(logstd)) if wb else None, C.c_void_p(_ptr(logstd_old)) if wb else None, p2p[0], st) == 0
         wg = abi.VineLstmWgrad(u=_ptr(self.U), hm=_ptr(self.HM), dg=_ptr(self.DG), workspace=_ptr(self.wg_ws), ntiles=L * tl,
                                splits=self.splits)
         assert lib.vine_lstm_wgrad(C.byref(wg), st) == 0
         assert lib.vine_lstm_reduce(C.c_void_p(_ptr(self.wg_ws)), self.splits, C.c_void_p(_ptr(self.head_grads)), hparts, self.O,
-                                    C.c_void_p(_ptr(self.flat_g_lstm)), st) == 0
+                                    C.c_void_p(_ptr(self.flat_g_lstm)), p2p[1], st) == 0

@@ -155,9 +155,20 @@ def policy_kl(p0_mu, p0_sigma, p1_mu, p1_sigma):
     return (c1 + c2 - 0.5).sum(-1).mean()
 
 
+def rlgames_model_state(model, obs_rms, val_rms):
+    """The ``model`` entry of an rl-games 1.5.2 checkpoint (``A2CBase.get_full_state_weights`` -> ``model.state_dict()`` of
+    ``ModelA2CContinuousLogStd.Network``): the network under ``a2c_network.*``, the input normaliser under
+    ``running_mean_std.*`` ([O], [O], []) and the value normaliser under ``value_mean_std.*`` ([1], [1], [])."""
+    sd = {"a2c_network." + k: v.detach().clone() for k, v in model.state_dict().items()}
+    for name, rms in (("running_mean_std", obs_rms), ("value_mean_std", val_rms)):
+        for k, v in rms.state_dict().items():
+            sd[f"{name}.{k}"] = v.detach().clone()
+    return sd
+
+
 class PPOAgent:
     def __init__(self, env, train_cfg, device=None, seed=42, use_graphs=False, use_fused_policy=True,
-                 use_fused_update=True):
+                 use_fused_update=True, grad_allreduce="p2p"):
         c = train_cfg["params"]["config"]
         net = train_cfg["params"]["network"]
         self.env, self.c = env, c
@@ -222,10 +233,20 @@ class PPOAgent:
             self.fused = True   # baseline update, kernel policy forward (asked for explicitly: use_fused_update=False)
         # CUDA graphs: single GPU always; multi-GPU only for the kernel-only path (its NCCL all-reduces are captured too)
         self.use_graphs = self._want_graphs and (self.world == 1 or (self.fused_update and bool(c.get("graph_nccl", True))))
+        # multi-GPU gradient all-reduce of the kernel paths: "p2p" = one-shot over NVLink peer memory inside the reduce / Adam
+        # kernels (csrc/vine_p2p.cuh; bit-identical parameters on all ranks), "nccl" = one NCCL all-reduce per minibatch (baseline)
+        if grad_allreduce not in ("p2p", "nccl"):
+            raise ValueError("grad_allreduce must be 'p2p' or 'nccl'")
+        self.grad_allreduce = grad_allreduce if (self.world > 1 and self.fused_update) else "none"
+        self._p2p_mlp = self._p2p_lstm = None
         if self.native_lstm:
             self._init_native_lstm(float(c["learning_rate"]))
         elif self.fused_update:
             self._init_fused_update(float(c["learning_rate"]))
+        if self.grad_allreduce == "p2p":
+            self._p2p_mlp = vd.P2PChannel(self._lib, self._lib.vine_ppo_num_params(self.O) + 4, dev)
+            if self.native_lstm:
+                self._p2p_lstm = vd.P2PChannel(self._lib, self._lib.vine_lstm_num_params(self.O) + 4, dev)
         else:
             self.lr_t = torch.tensor(float(c["learning_rate"]), device=dev)   # device-side: no sync in the schedule
             self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t, eps=1e-8, capturable=True)
@@ -452,6 +473,8 @@ class PPOAgent:
         torch.cat([self.b_act, self.b_mu, self.b_nlp.unsqueeze(-1), self._val_old_n.unsqueeze(-1), self._ret_n.unsqueeze(-1),
                    self._adv_n.unsqueeze(-1)], dim=-1, out=self._scal)
         path = self._path
+        pm = self._p2p_mlp.ptr if self._p2p_mlp is not None else None
+        pl = self._p2p_lstm.ptr if self._p2p_lstm is not None else None
         for _ in range(self.mini_epochs):
             for e0 in range(0, n, E):
                 # rows of the minibatch ordered [step in chunk][chunk, env] + the initial LSTM state of every sequence: one launch
@@ -463,14 +486,14 @@ class PPOAgent:
                 assert lib.vine_lstm_gather(C.byref(ga), stream) == 0
                 path.gradients(self._packed, self._lpacked, self._mb_obs, self._mb_scal, self._mb_nd, self._obs_mean_f,
                                self._obs_inv_std_f, self._val_stats, self.model.sigma, self._logstd_old[e0 // E], self.ppo_state,
-                               writeback=(self._scal, L, chunks, n, e0, E))
-                if self.world > 1:   # ONE collective per minibatch: gradients + loss statistics (incl. the KL) of both halves
+                               writeback=(self._scal, L, chunks, n, e0, E), p2p=(pm, pl))
+                if self.grad_allreduce == "nccl":   # baseline: ONE NCCL all-reduce per minibatch (gradients + loss statistics)
                     torch.distributed.all_reduce(path.flat_g)
-                sc = 1.0 / self.world
+                sc = 1.0 / self.world                # p2p: the Adam kernels add the ranks' buffers themselves (vine_p2p.cuh)
                 assert lib.vine_ppo_adam(p(path.flat_g_mlp), sc, p(self.flat), p(self.adam_m), p(self.adam_v), p(self._packed),
-                                         p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, 0, stream) == 0
+                                         p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, 0, pm, stream) == 0
                 assert lib.vine_lstm_adam(p(path.flat_g_lstm), sc, p(self.flat_l), p(self.adam_ml), p(self.adam_vl), p(self._lpacked),
-                                          p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, stream) == 0
+                                          p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, pl, stream) == 0
 
     @torch.no_grad()
     def _refresh_fused(self, pack=False):
@@ -748,17 +771,19 @@ class PPOAgent:
                 critic_coef=self.critic_coef, entropy_coef=self.entropy_coef, bounds_loss_coef=self.bounds_coef,
                 kl_threshold=self.kl_threshold, lr_min=1e-6, lr_max=1e-2) for e0 in range(0, n, self.mb_envs)]
         p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        pm = self._p2p_mlp.ptr if self._p2p_mlp is not None else None
         for _ in range(self.mini_epochs):
             for slot, mb in enumerate(self._mb_structs):
                 # forward + losses + backward; writes this pass's mu over the rows' mu_old (rl_games dataset.update_mu_sigma)
                 n_part = lib.vine_ppo_minibatch(C.byref(mb), stream)
                 assert n_part > 0, n_part
                 assert lib.vine_ppo_reduce(p(self._ws), n_part, self.O, p(self._flat_grads), p(self.model.sigma),
-                                           p(self._logstd_old[slot]), stream) == 0
-                if self.world > 1:   # ONE collective per minibatch: gradients + loss statistics (incl. the KL)
+                                           p(self._logstd_old[slot]), pm, stream) == 0
+                if self.grad_allreduce == "nccl":   # baseline: ONE NCCL all-reduce per minibatch (gradients + loss statistics)
                     torch.distributed.all_reduce(self._flat_grads)
+                # p2p: the Adam kernel waits for every rank's buffer and adds them in rank order itself (vine_p2p.cuh)
                 assert lib.vine_ppo_adam(p(self._flat_grads), 1.0 / self.world, p(self.flat), p(self.adam_m), p(self.adam_v),
-                                         p(self._packed), p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, 1, stream) == 0
+                                         p(self._packed), p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, 1, pm, stream) == 0
 
     def capture_graphs(self, warmup=3):
         """Warm up eagerly on a side stream, then capture the rollout and the update as two graphs."""
@@ -828,7 +853,11 @@ class PPOAgent:
                            "fps_total": (self.frames - f0) / (time.perf_counter() - t0)})
                 hist.append(st)
                 if log:
-                    log(" ".join(f"{k}={v:.4g}" if isinstance(v, float) else f"{k}={v}" for k, v in st.items()))
+                    line = " ".join(f"{k}={v:.4g}" if isinstance(v, float) else f"{k}={v}" for k, v in st.items())
+                    try:
+                        log(line, st)          # loggers that also want the numbers (train.py: scalar writer + observer)
+                    except TypeError:
+                        log(line)
         return hist
 
     # ------------------------------------------------------------------ checkpoints
@@ -836,11 +865,7 @@ class PPOAgent:
     # runs/<name>/nn/*.pth and what isaacgymenvs/vine_robot_test_model.py:135-139 reads back: ``model`` holds the
     # network under ``a2c_network.*`` plus the input/value normalisers as ``running_mean_std.*`` / ``value_mean_std.*``.
     def rlgames_model_state(self):
-        sd = {"a2c_network." + k: v.detach().clone() for k, v in self.model.state_dict().items()}
-        for name, rms in (("running_mean_std", self.obs_rms), ("value_mean_std", self.val_rms)):
-            for k, v in rms.state_dict().items():
-                sd[f"{name}.{k}"] = v.detach().clone()
-        return sd
+        return rlgames_model_state(self.model, self.obs_rms, self.val_rms)
 
     def _optimizer_state(self):
         if self.fused_update:

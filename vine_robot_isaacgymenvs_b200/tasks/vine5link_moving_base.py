@@ -249,7 +249,8 @@ class Vine5LinkMovingBase(VecTask):
         "shelf_contact_force": (), "aggregated_rew_buf": (),
     }
     _DEBUG_FIELDS = {"u_rail_velocity": (), "u_fpam": (), "prev_u_rail_velocity": (), "rail_force": (),
-                     "tip_velocities": (3,), "reward_matrix": (13,)}
+                     "tip_velocities": (3,), "reward_matrix": (13,), "finite_difference_dof_vel": (6,),
+                     "finite_difference_tip_velocities": (3,), "cart_body_pos_y": ()}
 
     def get_state_dict(self, debug=False):
         """Snapshot of the private SoA state as torch tensors named like the reference attributes."""
@@ -324,32 +325,134 @@ class Vine5LinkMovingBase(VecTask):
         out["Aggregated Reward 1 Std Up"], out["Aggregated Reward 1 Std Down"] = mean + std ** 0.5, mean - std ** 0.5
         return out
 
+    def view_traces(self, index=None):
+        """The per-env traces the reference logs for ONE env, ``self.index_to_view`` (V5:1283-1312), with its key names:
+        joint positions / velocities / finite-difference velocities, tip / cart / target positions and velocities, the
+        commands, the rail force and the shelf contact force of the last step.  One state read, one host copy."""
+        if not getattr(self, "_debug_enabled", False):
+            self.enable_debug_outputs(True)
+            raise RuntimeError("view traces need the debug plane: enabled now, call again after the next step()")
+        i = self.index_to_view if index is None else int(index)
+        st = {k: v[i].tolist() if v.dim() > 1 else float(v[i]) for k, v in self.get_state_dict(debug=True).items()
+              if k not in ("actions_history", "step_count")}
+        at = " at self.index_to_view"
+        out = {f"prismatic_q0{at}": st["dof_pos"][0], f"prismatic_qd0{at}": st["dof_vel"][0],
+               f"prismatic_finite_diff_qd0{at}": st["finite_difference_dof_vel"][0]}
+        for j in range(N_REVOLUTE_DOFS):
+            out[f"q{j}{at}"], out[f"qd{j}{at}"] = st["dof_pos"][j + 1], st["dof_vel"][j + 1]
+            out[f"finite_diff_qd{j}{at}"] = st["finite_difference_dof_vel"][j + 1]
+        cart_pos, cart_vel = [0.0, st["cart_body_pos_y"], 0.975], [0.0, st["cart_body_vel_y"], 0.0]
+        for k, d in enumerate("xyz"):
+            out[f"tip_vel_{d}{at}"], out[f"cart_vel_{d}{at}"], out[f"target_vel_{d}{at}"] = st["tip_velocities"][k], cart_vel[k], 0.0
+            out[f"finite_diff_tip_vel_{d}{at}"] = st["finite_difference_tip_velocities"][k]
+            out[f"tip_pos_{d}{at}"], out[f"cart_pos_{d}{at}"] = st["tip_positions"][k], cart_pos[k]
+            out[f"target_pos_{d}{at}"] = st["target_positions"][k]
+        contact = -st["reward_matrix"][12]                      # Contact Force term = -contact [contact > 0] (V5:1531)
+        out.update({f"u_fpam{at}": st["u_fpam"], f"smoothed u_fpam{at}": st["smoothed_u_fpam"],
+                    f"u_rail_velocity{at}": st["u_rail_velocity"], f"rail_force{at}": st["rail_force"],
+                    f"contact_force{at}": contact, f"nonzero_contact_force{at}": float(contact > 0)})
+        return out
+
+    def wandb_dict(self):
+        """Everything the reference's compute_reward puts into ``self.wandb_dict`` each step (V5:1250-1322), same keys:
+        the aggregate entries (one reduction launch, ``metrics()``) plus the per-view-env traces (``view_traces()``)."""
+        out = self.metrics()
+        out.update(self.view_traces())
+        return out
+
     def _get(self, name):
         return self.get_state_dict(debug=name in self._DEBUG_FIELDS)[name]
 
-    dof_pos = property(lambda s: s._get("dof_pos"), lambda s, v: s.set_state_dict({"dof_pos": v}))
-    dof_vel = property(lambda s: s._get("dof_vel"), lambda s, v: s.set_state_dict({"dof_vel": v}))
-    tip_positions = property(lambda s: s._get("tip_positions"), lambda s, v: s.set_state_dict({"tip_positions": v}))
-    target_positions = property(lambda s: s._get("target_positions"), lambda s, v: s.set_state_dict({"target_positions": v}))
-    object_info = property(lambda s: s._get("object_info"), lambda s, v: s.set_state_dict({"object_info": v}))
-    smoothed_u_fpam = property(lambda s: s._get("smoothed_u_fpam").unsqueeze(-1),
+    def _view(self, name, shape=None, field=None, readonly=False):
+        """The reference's state attributes are torch views of the simulator's tensors; here the state lives in the library's
+        SoA planes, so an attribute read is a snapshot (one small kernel) wrapped in ``StateView``: reading works like a
+        tensor, and the reference's in-place idioms -- ``env.dof_pos[ids] = x`` (V5:791-793), ``.copy_()``, ``.zero_()``,
+        ``+=`` -- write THROUGH to the library state (``vine_set_state``).  A snapshot does not follow later steps: read the
+        attribute again after ``step()``."""
+        t = self._get(field or name)
+        if shape is not None:
+            t = t.reshape(shape)
+        return StateView.wrap(t, self, field or name, readonly)
+
+    dof_pos = property(lambda s: s._view("dof_pos"), lambda s, v: s.set_state_dict({"dof_pos": v}))
+    dof_vel = property(lambda s: s._view("dof_vel"), lambda s, v: s.set_state_dict({"dof_vel": v}))
+    tip_positions = property(lambda s: s._view("tip_positions"), lambda s, v: s.set_state_dict({"tip_positions": v}))
+    target_positions = property(lambda s: s._view("target_positions"), lambda s, v: s.set_state_dict({"target_positions": v}))
+    object_info = property(lambda s: s._view("object_info"), lambda s, v: s.set_state_dict({"object_info": v}))
+    smoothed_u_fpam = property(lambda s: s._view("smoothed_u_fpam", (-1, 1)),
                                lambda s, v: s.set_state_dict({"smoothed_u_fpam": v.reshape(-1)}))
-    prev_cart_vel = property(lambda s: s._get("prev_cart_vel").unsqueeze(-1))
-    prev_cart_vel_error = property(lambda s: s._get("prev_cart_vel_error").unsqueeze(-1))
-    aggregated_rew_buf = property(lambda s: s._get("aggregated_rew_buf"))
-    u_rail_velocity = property(lambda s: s._get("u_rail_velocity").unsqueeze(-1))
-    u_fpam = property(lambda s: s._get("u_fpam").unsqueeze(-1))
-    prev_u_rail_velocity = property(lambda s: s._get("prev_u_rail_velocity").unsqueeze(-1))
-    rail_force = property(lambda s: s._get("rail_force").unsqueeze(-1))
-    tip_velocities = property(lambda s: s._get("tip_velocities"))
+    prev_cart_vel = property(lambda s: s._view("prev_cart_vel", (-1, 1)),
+                             lambda s, v: s.set_state_dict({"prev_cart_vel": v.reshape(-1)}))
+    prev_cart_vel_error = property(lambda s: s._view("prev_cart_vel_error", (-1, 1)),
+                                   lambda s, v: s.set_state_dict({"prev_cart_vel_error": v.reshape(-1)}))
+    aggregated_rew_buf = property(lambda s: s._view("aggregated_rew_buf"), lambda s, v: s.set_state_dict({"aggregated_rew_buf": v}))
+    # outputs of the last step (debug plane): read-only, an in-place write raises instead of silently doing nothing
+    u_rail_velocity = property(lambda s: s._view("u_rail_velocity", (-1, 1), readonly=True))
+    u_fpam = property(lambda s: s._view("u_fpam", (-1, 1), readonly=True))
+    prev_u_rail_velocity = property(lambda s: s._view("prev_u_rail_velocity", (-1, 1), readonly=True))
+    rail_force = property(lambda s: s._view("rail_force", (-1, 1), readonly=True))
+    tip_velocities = property(lambda s: s._view("tip_velocities", readonly=True))
 
     @property
     def cart_positions(self):
-        q = self._get("dof_pos")
+        """Rigid-body view V5:359: (0, cart y, 0.975) (URDF:275); read-only (write dof_pos).  With the debug
+        outputs enabled it is the body position the last step's reward used -- on a reset step still the old episode's (stale body
+        views, V5:796) -- otherwise dof_pos[:, 0], which differs from it only on reset steps."""
+        dbg = getattr(self, "_debug_enabled", False)
+        y = self._get("cart_body_pos_y") if dbg else self._get("dof_pos")[:, 0]
         out = torch.zeros(self.num_envs, 3, device=self.device)
-        out[:, 1] = q[:, 0]
-        out[:, 2] = 0.975  # URDF:275
-        return out
+        out[:, 1] = y
+        out[:, 2] = 0.975
+        return StateView.wrap(out, self, "cart_positions", True)
+
+    @property
+    def cart_velocities(self):
+        """Rigid-body view V5:362, read by the rail controller at V5:1069: (0, cart body velocity as of the last simulate, 0).
+        Writable: the y column is the library's ``cart_body_vel_y`` plane (stale after a reset like the reference's)."""
+        v = self._get("cart_body_vel_y")
+        out = torch.zeros(self.num_envs, 3, device=self.device)
+        out[:, 1] = v
+        return StateView.wrap(out, self, "cart_body_vel_y", False, post=lambda t: t[:, 1].contiguous())
+
+
+class StateView(torch.Tensor):
+    """Snapshot of one state attribute that writes in-place modifications back to the library (see ``_view``)."""
+    __torch_function__ = torch._C._disabled_torch_function_impl   # results of ordinary ops are plain tensors
+
+    @staticmethod
+    def wrap(data, env, name, readonly=False, post=None):
+        t = torch.Tensor._make_subclass(StateView, data)
+        t._env, t._name, t._readonly, t._post = env, name, readonly, post
+        return t
+
+    def _push(self):
+        if self._readonly:
+            raise RuntimeError(f"'{self._name}' is an output of the last step (read-only): writing it has no counterpart in the "
+                               "library state; set dof_pos / dof_vel / tip_positions / ... instead")
+        plain = self.as_subclass(torch.Tensor)
+        plain = self._post(plain) if self._post is not None else plain
+        n = self._env.num_envs
+        self._env.set_state_dict({self._name: plain.reshape(n) if plain.dim() == 2 and plain.shape[1] == 1
+                                  and self._name in self._env._STATE_FIELDS and self._env._STATE_FIELDS[self._name] == () else plain})
+
+    def __setitem__(self, key, value):
+        self.as_subclass(torch.Tensor).__setitem__(key, value)
+        self._push()
+
+
+def _write_through(name):
+    plain = getattr(torch.Tensor, name)
+
+    def method(self, *args, **kwargs):
+        plain(self.as_subclass(torch.Tensor), *args, **kwargs)
+        self._push()
+        return self
+    method.__name__ = name
+    return method
+
+
+for _m in ("copy_", "zero_", "fill_", "add_", "sub_", "mul_", "div_", "clamp_", "__iadd__", "__isub__", "__imul__", "__itruediv__"):
+    setattr(StateView, _m, _write_through(_m))
 
 
 _OBS_SCALING = {  # V5:246-266

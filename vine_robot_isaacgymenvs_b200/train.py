@@ -8,6 +8,7 @@ Checkpoints go to ``runs/<name>/nn/<name>.pth`` like rl_games' (train.py:148-163
 import json
 import os
 import sys
+import time
 
 import torch
 
@@ -66,7 +67,33 @@ def launch(overrides):
             sd["last_mean_rewards"] = mean_rew
             torch.save(sd, os.path.join(out_dir, name + ".pth"))
 
-    hist = agent.train(int(pc["max_epochs"]), log=print if rank == 0 else None,
+    # what rl_games' A2CBase writes per logged epoch (a2c_common.write_stats) + the reference's observer (train.py:145)
+    from .utils.rlgames_utils import RLGPUAlgoObserver, ScalarWriter
+    writer = ScalarWriter(os.path.join(exp_dir, "summaries")) if rank == 0 else ScalarWriter(None)
+    agent.writer, agent.games_to_track = writer, int(pc.get("games_to_track", 100))
+    observer = RLGPUAlgoObserver()
+    observer.after_init(agent)
+    t_start = time.perf_counter()
+
+    def log(line, st=None):
+        if rank != 0:
+            return
+        print(line)
+        if st is not None:
+            frame, ep, total = st["frames"], st["epoch"], time.perf_counter() - t_start
+            for tag, key in (("losses/a_loss", "a_loss"), ("losses/c_loss", "c_loss"), ("info/kl", "kl"), ("info/last_lr", "lr"),
+                             ("performance/step_inference_rl_update_fps", "fps_total")):
+                writer.add_scalar(tag, st[key], frame)
+            if st["episodes"] > 0:
+                for suffix, step in (("frame", frame), ("iter", ep), ("time", total)):
+                    writer.add_scalar(f"rewards/{suffix}", st["mean_return"], step)
+                    writer.add_scalar(f"episode_lengths/{suffix}", st["mean_length"], step)
+                writer.add_scalar("info/success_rate", st["success_rate"], frame)
+            writer.add_scalar("info/epochs", ep, frame)
+            observer.process_infos(env.extras if isinstance(env.extras, dict) else {}, None)
+            observer.after_print_stats(frame, ep, total)
+
+    hist = agent.train(int(pc["max_epochs"]), log=log,
                        on_epoch=on_epoch if (save_freq or save_best_after) else None)
     if rank == 0:
         os.makedirs(out_dir, exist_ok=True)
