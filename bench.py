@@ -357,12 +357,38 @@ def run_ours(args, rank, world, local_rank):
                                    "vine_policy_act (tcgen05)" if agent.fused else "torch"),
                 "collectives": "none" if world == 1 else "NCCL all-reduce: grads+KL per minibatch, running stats per iteration"}
 
+    # ---- HBM-bound PPO helper kernels (GAE 24 B per (t, env)), timed alone against the measured copy bandwidth ----
+    def measure_gae(num_envs, T=16, reps=200):
+        peaks_hbm = measured_peaks()[0]["hbm_gbs"]
+        f = lambda *sh: torch.rand(*sh, device=dev)  # noqa: E731
+        r, v, d, lv, ld = f(T, num_envs), f(T, num_envs), (f(T, num_envs) < 0.05).float(), f(num_envs), f(num_envs)
+        adv, ret = torch.empty(T, num_envs, device=dev), torch.empty(T, num_envs, device=dev)
+        p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        call = lambda: lib.vine_gae(p(r), p(v), p(d), p(lv), p(ld), T, num_envs, 0.99, 0.95, p(adv), p(ret), st)  # noqa: E731
+        for _ in range(5):
+            assert call() == 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            call()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = e0.elapsed_time(e1) / reps * 1e3
+        gbs = 24.0 * T * num_envs / (us * 1e-6) / 1e9
+        return {"kernel": "vine_gae_kernel", "num_envs": num_envs, "horizon": T, "us": us,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks_hbm, "unit": "GB/s", "frac": gbs / peaks_hbm,
+                             "note": "24 algorithmic B per (t, env); 25 MB at 65,536 envs fits the 126 MB L2 when timed back to back"
+                                     if num_envs * T * 24 < 126e6 else "24 algorithmic B per (t, env); larger than L2"}}
+
     ppo = None
     if not args.no_ppo:
         del env
         env = None
         torch.cuda.empty_cache()
         ppo = {"config": "BASELINE configs[1]: FSTR num_envs=4096 rollout+PPO",
+               "hbm_kernels": [measure_gae(65536), measure_gae(1 << 20)],
                "reference_network": measure_ppo(4096, args.ppo_iters, 5, []),
                "reference_network_torch_update": measure_ppo(4096, max(3, args.ppo_iters // 2), 3, [], fused_update=False),
                "mlp_only": measure_ppo(4096, args.ppo_iters, 5, ["train.params.network.rnn=null"]),

@@ -696,7 +696,8 @@ typedef struct VinePpoMinibatch {
   float* workspace;              /* [workspace_ctas][VINE_PPO_WS_FLOATS] gradient partials, 16-B aligned */
   float* state;                  /* device optimiser state, see above */
   float* debug_out;              /* NULL or [T*env_count, 4]: mu0, mu1, normalised value, neglogp per sample */
-  int32_t horizon, num_envs, env_begin, env_count, num_obs, workspace_ctas, adaptive_lr, reserved;
+  int32_t horizon, num_envs, env_begin, env_count, num_obs, workspace_ctas, adaptive_lr;
+  int32_t reserved;              /* 0; 2 selects two (instead of four) epilogue threads per row, an A/B switch for profiling */
   float e_clip, critic_coef, entropy_coef, bounds_loss_coef, kl_threshold, lr_min, lr_max, reserved_f;
   const float* dh3_ext;          /* NULL, or f32 [T*env_count, 64]: d(loss)/d(MLP output) supplied by the LSTM backward
                                     (vine_lstm_bwd_gemm); the heads and losses are skipped and the loss pointers may be
@@ -738,7 +739,14 @@ int vine_p2p_open(const void* ipc_handle, void** region);
 int vine_p2p_close(void* region);      /* a region obtained from vine_p2p_open */
 int vine_p2p_free(void* region);       /* a region obtained from vine_p2p_alloc */
 int vine_p2p_channel_create(void* const* regions, int world, int rank, int64_t count, void** channel);
+/* buf[i] <- sum over the ranks of buf[i] (f64, rank order) for a short vector, e.g. the running-statistics moments between
+ * vine_ppo_moments and vine_ppo_finalize; one single-block launch; the channel needs count >= 2 n */
+int vine_p2p_allreduce_f64(void* channel, double* buf, int n, void* stream);
 int vine_p2p_channel_status(const void* channel, uint32_t* exchanges_done, uint32_t* timed_out);   /* synchronises */
+/* mean ns per exchange seen by block 0 of the consumer kernel, then reset: out[0] = entry -> own flag stored at every peer,
+ * out[1 + r] = entry -> rank r's flag seen here, out[17] = entry -> last block of the consumer done, out[18] = entry -> block 0's
+ * sums ready; n_out >= 1 + VINE_P2P_MAX_WORLD (17) or 19.  Synchronises. */
+int vine_p2p_channel_timing(void* channel, double* out, int n_out);
 int vine_p2p_channel_destroy(void* channel);
 
 /* sizeof of the argument structs of the PPO entry points, in declaration order (VinePolicyAct = 0, VineRolloutPost,

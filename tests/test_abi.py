@@ -83,3 +83,12 @@ def test_product_never_imports_the_oracle():
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(RuntimeError, match="no CPU fallback|not found"):
         abi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_the_library_reads_no_environment_variable():
+    """Launch tuning goes through VineConfig / the argument structs, never through a hidden getenv channel behind the C ABI."""
+    import glob
+    import os
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vine_robot_isaacgymenvs_b200", "csrc")
+    for path in glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")) + glob.glob(os.path.join(csrc, "*.h")):
+        assert "getenv" not in open(path).read(), path

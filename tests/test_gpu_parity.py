@@ -235,10 +235,12 @@ def test_fused_step_single_step_parity(path, oracle_lib):
                                    atol=5e-3 if (contact_cfg or zoh) else 2e-4, err_msg=f"dof_vel step {t}")
         obs_gpu, obs_ref = env.obs_buf.cpu().numpy(), ora.obs
         scale = 1.0 + np.abs(obs_ref)
-        assert (np.abs(obs_gpu - obs_ref) / scale)[well].max() < (5e-2 if zoh else 2e-3), f"obs step {t}"
+        # measured (printed by test_gpu_presets_parity): free space max 1.5e-5, shelf 4.4e-5, pipe + DR 4.8e-4
+        assert (np.abs(obs_gpu - obs_ref) / scale)[well].max() < (5e-2 if zoh else (1e-3 if contact_cfg else 2e-4)), f"obs step {t}"
         clamp = od["obs"].cpu().numpy()
         assert np.array_equal(clamp, np.clip(obs_gpu, -5.0, 5.0))              # VT:374
-        np.testing.assert_allclose(rew.cpu().numpy()[same], ora.rew[same], rtol=1e-3, atol=2e-3)
+        np.testing.assert_allclose(rew.cpu().numpy()[same], ora.rew[same], rtol=1e-3 if (contact_cfg or zoh) else 1e-5,
+                                   atol=2e-3 if zoh else (5e-4 if contact_cfg else 1e-5))
         if int(g["reset_done_at"]) == t:
             ids = np.arange(0, n, 3)
             ora.reset_idx(ids)

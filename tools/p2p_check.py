@@ -24,9 +24,12 @@ def make_agent(extra, mode, rank, dev, n=4096):
     return PPOAgent(env, cfg["train"], device=dev, seed=42 + rank, use_graphs=True, grad_allreduce=mode)
 
 
+_ALL_REDUCE = dist.all_reduce
+
+
 def max_over_ranks(x, dev):
     t = torch.tensor([x], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    _ALL_REDUCE(t, op=dist.ReduceOp.MAX)
     return float(t)
 
 
@@ -38,14 +41,20 @@ def main():
     out = {"world": world}
     for name, extra in (("mlp", ["train.params.network.rnn=null"]), ("lstm", [])):
         res = {}
-        for mode in ("p2p", "nccl"):
-            agent = make_agent(extra, mode, rank, dev)
+        for mode in ("p2p", "nccl", "none"):
+            real_all_reduce = dist.all_reduce
+            if mode in ("none", "p2p_without_nccl_moments"):   # diagnosis only: "none" = no exchange at all (what unsynchronised GPUs
+                torch.distributed.all_reduce = lambda *a, **k: None   # would take); the other = p2p gradients, moments NOT reduced
+            agent = make_agent(extra, {"none": "nccl", "p2p_without_nccl_moments": "p2p"}.get(mode, mode), rank, dev)
             for _ in range(6):
                 agent.train_epoch()
             torch.cuda.synchronize()
             flat = torch.cat([p.detach().reshape(-1) for p in agent.model.parameters()])
             gathered = [torch.empty_like(flat) for _ in range(world)]
+            torch.distributed.all_reduce = real_all_reduce
             dist.all_gather(gathered, flat)
+            if mode in ("none", "p2p_without_nccl_moments"):
+                torch.distributed.all_reduce = lambda *a, **k: None
             identical = all(torch.equal(gathered[0], g) for g in gathered)
             st = agent.pop_stats()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -60,12 +69,19 @@ def main():
                 agent._g_update.replay()
             e1.record(); torch.cuda.synchronize()
             ms_upd = max_over_ranks(e0.elapsed_time(e1) / 20, dev)
+            e0.record()
+            for _ in range(20):
+                agent._g_rollout.replay()
+            e1.record(); torch.cuda.synchronize()
+            torch.distributed.all_reduce = real_all_reduce
+            ms_roll = max_over_ranks(e0.elapsed_time(e1) / 20, dev)
             res[mode] = {"params_bit_identical_across_ranks": bool(identical), "finite": bool(torch.isfinite(flat).all()),
-                         "kl": st["kl"], "a_loss": st["a_loss"], "c_loss": st["c_loss"], "ms_per_iteration": ms, "update_ms": ms_upd}
-            if mode == "p2p":
+                         "kl": st["kl"], "a_loss": st["a_loss"], "c_loss": st["c_loss"], "ms_per_iteration": ms, "update_ms": ms_upd, "rollout_ms": ms_roll}
+            if mode.startswith("p2p"):
+                res[mode]["exchange_timing"] = agent._p2p_mlp.timing()
                 seq, timed_out = agent._p2p_mlp.status()
                 res[mode].update({"exchanges": seq, "timed_out": timed_out})
-                assert identical and not timed_out, res
+                assert (identical or mode != "p2p") and not timed_out, res
             del agent
             torch.cuda.empty_cache()
         out[name] = res

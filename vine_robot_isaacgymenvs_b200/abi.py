@@ -139,7 +139,7 @@ EXPORTED_SYMBOLS = [
     "vine_mlp_pack", "vine_mlp_forward",
     "vine_ppo_num_params", "vine_ppo_max_ctas", "vine_ppo_minibatch", "vine_ppo_reduce", "vine_ppo_adam",
     "vine_p2p_alloc", "vine_p2p_open", "vine_p2p_close", "vine_p2p_free", "vine_p2p_channel_create", "vine_p2p_channel_status",
-    "vine_p2p_channel_destroy",
+    "vine_p2p_channel_timing", "vine_p2p_allreduce_f64", "vine_p2p_channel_destroy",
     "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
     "vine_lstm_cell_fwd", "vine_lstm_cell_bwd", "vine_lstm_pack", "vine_lstm_step", "vine_lstm_mask", "vine_lstm_head", "vine_lstm_head_train", "vine_lstm_cell_bwd_tiles", "vine_lstm_bwd_gemm",
     "vine_lstm_gather", "vine_abi_struct_size", "vine_lstm_num_params", "vine_lstm_wgrad", "vine_lstm_reduce", "vine_lstm_adam",
@@ -297,6 +297,8 @@ def _declare(lib):
     lib.vine_p2p_free.argtypes = [vp]
     lib.vine_p2p_channel_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
     lib.vine_p2p_channel_status.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.vine_p2p_channel_timing.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+    lib.vine_p2p_allreduce_f64.argtypes = [vp, vp, C.c_int, vp]
     lib.vine_p2p_channel_destroy.argtypes = [vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)

@@ -802,6 +802,7 @@ __global__ void __launch_bounds__(256) vine_lstm_reduce_kernel(const float* __re
     else if (q < 5 * HID + 5) flat[sg.ls + q - 5 * HID - 3] = hsum[HG_LS + q - 5 * HID - 3];
     else if (q < 5 * HID + 9) flat[PL + q - 5 * HID - 5] = hsum[HG_STATS + q - 5 * HID - 5];
   }
+  if (ch) p2p_producer_done(const_cast<VineP2PChannel*>(ch));
 }
 
 __global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scale, float* __restrict__ params, float* __restrict__ m,
@@ -810,17 +811,27 @@ __global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scal
   const int PL = lstm_num_params(O);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   // multi-GPU: wait for every rank's gradient buffer, then read the sum over the ranks instead of `flat` (vine_p2p.cuh)
-  const unsigned seq = ch ? p2p_exchange_begin(ch) : 0u;
-  auto grad = [&](int i) { return (ch ? p2p_sum(ch, seq, i) : flat[i]) * scale; };
+  __shared__ __align__(16) float s_g[256];
+  const unsigned seq = ch ? p2p_exchange_begin(ch, false) : 0u;   // vine_lstm_reduce has published this rank's flag
+  const int base = blockIdx.x * blockDim.x;
+  if (ch) p2p_sum_block(ch, seq, base, min((int)blockDim.x, PL + 4 - base), s_g);
   if (p == PL) {   // loss statistics + the KL that drives the adaptive learning rate (state layout: vine_ppo_adam)
-    for (int j = 0; j < 4; ++j) state[4 + j] += grad(PL + j);
+    float st4[4];
+    if (ch && PL - base + 4 <= (int)blockDim.x) {   // already in this block's sums
+      for (int j = 0; j < 4; ++j) st4[j] = s_g[PL - base + j];
+    } else if (ch) {
+      p2p_sum4(ch, seq, PL, st4);
+    } else {
+      st4[0] = flat[PL]; st4[1] = flat[PL + 1]; st4[2] = flat[PL + 2]; st4[3] = flat[PL + 3];
+    }
+    for (int j = 0; j < 4; ++j) state[4 + j] += st4[j] * scale;
     state[8] += 1.f;
-    state[2] = grad(PL + 2);
+    state[2] = st4[2] * scale;
     state[3] = 1.f;
   }
   if (p < PL) {
   const float lr = state[0], step = state[1];
-  const float g = grad(p);
+  const float g = (ch ? s_g[threadIdx.x] : flat[p]) * scale;
   const float mn = beta1 * m[p] + (1.f - beta1) * g;
   const float vn = beta2 * v[p] + (1.f - beta2) * g * g;
   m[p] = mn;

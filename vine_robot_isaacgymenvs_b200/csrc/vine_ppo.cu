@@ -18,6 +18,7 @@
 // + 32 B of rollout scalars in, nothing out.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -422,7 +423,7 @@ constexpr int RED_SLOTS = 64, RED_SPLIT = 4;
 __global__ void __launch_bounds__(RED_SLOTS* RED_SPLIT) vine_ppo_reduce_kernel(const float* __restrict__ ws, int n_partials, int O,
                                                                                float* __restrict__ flat, const float* __restrict__ logstd,
                                                                                float* __restrict__ logstd_old_out, const VineP2PChannel* ch) {
-  if (ch) flat = p2p_local_buffer(ch);   // multi-GPU: the sum goes straight into this rank's peer-visible buffer (vine_p2p.cuh)
+  if (ch) { flat = p2p_local_buffer(ch); p2p_producer_begin(const_cast<VineP2PChannel*>(ch)); }   // multi-GPU: the sum goes straight into this rank's peer-visible buffer (vine_p2p.cuh)
   // sigma half of dataset.update_mu_sigma: the log-std this minibatch was evaluated with becomes its rows' "old" one. Done
   // here because this launch sits between the last reader (the minibatch kernel) and the writer (Adam) of the parameter.
   if (logstd_old_out && blockIdx.x == 0 && threadIdx.x < 2) logstd_old_out[threadIdx.x] = logstd[threadIdx.x];
@@ -444,6 +445,7 @@ __global__ void __launch_bounds__(RED_SLOTS* RED_SPLIT) vine_ppo_reduce_kernel(c
     const int p = ws_to_param(w, O);
     if (p >= 0) flat[p] = part[0][lane] + part[1][lane] + part[2][lane] + part[3][lane];
   }
+  if (ch) p2p_producer_done(const_cast<VineP2PChannel*>(ch));
 }
 
 // torch.optim.Adam (no weight decay, no amsgrad) on the flat parameter vector + re-pack for the tensor cores
@@ -453,17 +455,27 @@ __global__ void vine_ppo_adam_kernel(const float* __restrict__ flat, float scale
   const int P = num_params(O);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   // multi-GPU: wait for every rank's gradient buffer, then read the sum over the ranks instead of `flat` (vine_p2p.cuh)
-  const unsigned seq = ch ? p2p_exchange_begin(ch) : 0u;
-  auto grad = [&](int i) { return (ch ? p2p_sum(ch, seq, i) : flat[i]) * scale; };
+  __shared__ __align__(16) float s_g[128];
+  const unsigned seq = ch ? p2p_exchange_begin(ch, false) : 0u;   // vine_ppo_reduce has published this rank's flag
+  const int base = blockIdx.x * blockDim.x;
+  if (ch) p2p_sum_block(ch, seq, base, min((int)blockDim.x, P + 4 - base), s_g);
   if (p == P && bookkeeping) {   // bookkeeping by exactly one thread
-    for (int j = 0; j < 4; ++j) state[ST_SUMS + j] += grad(P + j);
+    float st4[4];
+    if (ch && P - base + 4 <= (int)blockDim.x) {   // the statistics sit right behind the last parameters: already in this block's sums
+      for (int j = 0; j < 4; ++j) st4[j] = s_g[P - base + j];
+    } else if (ch) {
+      p2p_sum4(ch, seq, P, st4);
+    } else {
+      st4[0] = flat[P]; st4[1] = flat[P + 1]; st4[2] = flat[P + 2]; st4[3] = flat[P + 3];
+    }
+    for (int j = 0; j < 4; ++j) state[ST_SUMS + j] += st4[j] * scale;
     state[ST_COUNT] += 1.f;
-    state[ST_KL] = grad(P + 2);
+    state[ST_KL] = st4[2] * scale;
     state[ST_PENDING] = 1.f;
   }
   if (p < P) {
     const float lr = state[ST_LR], step = state[ST_STEP];
-    const float g = grad(p);
+    const float g = (ch ? s_g[threadIdx.x] : flat[p]) * scale;
     const float mn = beta1 * m[p] + (1.f - beta1) * g;
     const float vn = beta2 * v[p] + (1.f - beta2) * g * g;
     m[p] = mn;
@@ -510,10 +522,9 @@ int vine_ppo_minibatch(const VinePpoMinibatch* b, void* stream) {
     if (cudaFuncSetAttribute(vine_ppo_minibatch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(vine_ppo_minibatch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
       return VINE_ERR_CUDA;
-    const char* e = getenv("VINE_PPO_EPILOGUE_THREADS");   // A/B switch: 2 or 4 epilogue threads per row (default 4)
-    q4 = !(e && e[0] == '2');
     configured = dev;
   }
+  q4 = b->reserved != 2;   // VinePpoMinibatch.reserved: 2 = two epilogue threads per row (A/B switch), anything else four
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t B = (int64_t)b->horizon * b->env_count;
   const int64_t ntiles = (B + TILE - 1) / TILE;
@@ -559,7 +570,35 @@ int vine_ppo_adam(const float* flat, float grad_scale, float* params, float* exp
 // ------------------------------------------------------------------------------------------
 // peer-memory regions and channels of the gradient all-reduce (vine_p2p.cuh)
 // ------------------------------------------------------------------------------------------
-static size_t p2p_region_bytes(int64_t count) { return (size_t)VINE_P2P_FLAG_BYTES + 2u * (size_t)count * sizeof(float); }
+}  // extern "C"
+
+// In-place sum over the ranks of a SHORT f64 vector (the running-statistics moments of vine_ppo_moments: 2 O + 4 doubles) in one
+// single-block launch: producer and consumer of the exchange in one kernel (one block, so nothing has to be co-resident).
+// The doubles travel as their two 32-bit halves in a channel of 2 n floats; sums in rank order: bit-identical on all ranks.
+__global__ void __launch_bounds__(256) vine_p2p_allreduce_f64_kernel(VineP2PChannel* ch, double* __restrict__ buf, int n) {
+  float* mine = p2p_local_buffer(ch);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) reinterpret_cast<double*>(mine)[i] = buf[i];
+  __syncthreads();                                   // all of this block's stores precede thread r's system fence + flag store
+  const unsigned seq = p2p_exchange_begin(ch);
+  const int W = ch->world;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double acc = 0.0;
+    for (int r = 0; r < W; ++r) acc += __ldcv(reinterpret_cast<const double*>(p2p_buffer(ch, r, seq)) + i);
+    buf[i] = acc;
+  }
+  p2p_exchange_end(ch);
+}
+
+extern "C" {
+
+int vine_p2p_allreduce_f64(void* channel, double* buf, int n, void* stream) {
+  if (!channel || !buf || n < 1) return VINE_ERR_INVALID_ARG;
+  vine_p2p_allreduce_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((VineP2PChannel*)channel, buf, n);
+  return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
+}
+
+static int64_t p2p_padded(int64_t count) { return (count + 3) & ~(int64_t)3; }   // buffers are read with 128-bit loads
+static size_t p2p_region_bytes(int64_t count) { return (size_t)VINE_P2P_FLAG_BYTES + 2u * (size_t)p2p_padded(count) * sizeof(float); }
 
 int vine_p2p_alloc(int64_t count, void** region, void* ipc_handle_out) {
   if (count < 1 || !region || !ipc_handle_out) return VINE_ERR_INVALID_ARG;
@@ -592,7 +631,7 @@ int vine_p2p_channel_create(void* const* regions, int world, int rank, int64_t c
     if (!regions[r]) return VINE_ERR_INVALID_ARG;
     h.peer_base[r] = (unsigned long long)(uintptr_t)regions[r];
   }
-  h.world = world; h.rank = rank; h.count = count;
+  h.world = world; h.rank = rank; h.count = p2p_padded(count);
   void* d = nullptr;
   if (cudaMalloc(&d, sizeof(h)) != cudaSuccess) return VINE_ERR_CUDA;
   if (cudaMemcpy(d, &h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return VINE_ERR_CUDA; }
@@ -607,6 +646,27 @@ int vine_p2p_channel_status(const void* channel, uint32_t* seq, uint32_t* error)
   if (cudaMemcpy(&h, channel, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return VINE_ERR_CUDA;
   if (seq) *seq = h.seq;
   if (error) *error = h.error;
+  return VINE_OK;
+}
+
+// mean ns per exchange, as seen by block 0 of the consumer: [0] entry -> own flag stored at every peer, [1 + r] entry -> rank
+// r's flag seen here (r == own rank: the local store); resets the accumulators.  Synchronises the device.
+int vine_p2p_channel_timing(void* channel, double* out, int n_out) {
+  if (!channel || !out || n_out < 1 + VINE_P2P_MAX_RANKS) return VINE_ERR_INVALID_ARG;
+  VineP2PChannel h;
+  if (cudaMemcpy(&h, channel, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return VINE_ERR_CUDA;
+  const double n = h.t_n ? (double)h.t_n : 1.0;
+  out[0] = (double)h.t_signal / n;
+  for (int r = 0; r < VINE_P2P_MAX_RANKS; ++r) out[1 + r] = (double)h.t_wait[r] / n;
+  if (n_out >= 3 + VINE_P2P_MAX_RANKS) { out[1 + VINE_P2P_MAX_RANKS] = (double)h.t_kernel / n; out[2 + VINE_P2P_MAX_RANKS] = (double)h.t_loads / n; }
+  if (n_out >= 6 + VINE_P2P_MAX_RANKS) {
+    out[3 + VINE_P2P_MAX_RANKS] = (double)h.t_mb / n; out[4 + VINE_P2P_MAX_RANKS] = (double)h.t_prod / n; out[5 + VINE_P2P_MAX_RANKS] = (double)h.t_gap / n;
+  }
+  h.t_signal = 0; h.t_n = 0; h.t_kernel = 0; h.t_loads = 0; h.t_mb = 0; h.t_prod = 0; h.t_gap = 0; h.t_prev_end = 0;
+  for (int r = 0; r < VINE_P2P_MAX_RANKS; ++r) h.t_wait[r] = 0;
+  // only the accumulators are written back (seq / ticket belong to the kernels)
+  const size_t off = offsetof(VineP2PChannel, t_signal);   // t_signal .. the end: all timing fields
+  if (cudaMemcpy((char*)channel + off, (char*)&h + off, sizeof(h) - off, cudaMemcpyHostToDevice) != cudaSuccess) return VINE_ERR_CUDA;
   return VINE_OK;
 }
 

@@ -139,6 +139,17 @@ class P2PChannel:
         assert self.lib.vine_p2p_channel_status(self.ptr, C.byref(seq), C.byref(err)) == 0
         return int(seq.value), bool(err.value)
 
+    def timing(self):
+        """Mean microseconds per exchange since the last call, seen by block 0 of the consumer kernel: time to publish this
+        rank's flag, and per rank the time from the kernel's entry until that rank's flag was seen.  Synchronises."""
+        import ctypes as C
+        out = (C.c_double * 22)()
+        assert self.lib.vine_p2p_channel_timing(self.ptr, out, 22) == 0
+        return {"signal_us": out[0] / 1e3, "wait_us": [out[1 + r] / 1e3 for r in range(self.world)],
+                "sums_ready_us": out[18] / 1e3, "consumer_kernel_us": out[17] / 1e3,
+                "between_consumer_end_and_producer_entry_us": out[19] / 1e3, "producer_kernel_us": out[20] / 1e3,
+                "producer_end_to_consumer_entry_us": out[21] / 1e3}
+
     def close(self):
         if getattr(self, "ptr", None) is not None:
             torch.cuda.synchronize(self.device)

@@ -238,18 +238,19 @@ class PPOAgent:
         if grad_allreduce not in ("p2p", "nccl"):
             raise ValueError("grad_allreduce must be 'p2p' or 'nccl'")
         self.grad_allreduce = grad_allreduce if (self.world > 1 and self.fused_update) else "none"
-        self._p2p_mlp = self._p2p_lstm = None
+        self._p2p_mlp = self._p2p_lstm = self._p2p_moments = None
         if self.native_lstm:
             self._init_native_lstm(float(c["learning_rate"]))
         elif self.fused_update:
             self._init_fused_update(float(c["learning_rate"]))
+        else:
+            self.lr_t = torch.tensor(float(c["learning_rate"]), device=dev)   # device-side: no sync in the schedule
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t, eps=1e-8, capturable=True)
         if self.grad_allreduce == "p2p":
             self._p2p_mlp = vd.P2PChannel(self._lib, self._lib.vine_ppo_num_params(self.O) + 4, dev)
             if self.native_lstm:
                 self._p2p_lstm = vd.P2PChannel(self._lib, self._lib.vine_lstm_num_params(self.O) + 4, dev)
-        else:
-            self.lr_t = torch.tensor(float(c["learning_rate"]), device=dev)   # device-side: no sync in the schedule
-            self.opt = torch.optim.Adam(self.model.parameters(), lr=self.lr_t, eps=1e-8, capturable=True)
+            self._p2p_moments = vd.P2PChannel(self._lib, 2 * (2 * self.O + 4), dev)   # f64 moments as pairs of 32-bit halves
         T, n = self.T, self.n
         f = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
         self.b_obs, self.b_act, self.b_mu = f(T, n, self.O), f(T, n, self.A), f(T, n, self.A)
@@ -465,8 +466,7 @@ class PPOAgent:
                 normalize_advantage=int(self.normalize_advantage))
             self._mb_structs = True
         assert lib.vine_ppo_moments(C.byref(self._prologue), stream) == 0
-        if self.world > 1:
-            torch.distributed.all_reduce(self._moments)
+        self._allreduce_moments(stream)
         assert lib.vine_ppo_finalize(C.byref(self._prologue), stream) == 0
         self._logstd_old.copy_(self.model.sigma.expand_as(self._logstd_old))
         # per-row scalars of the loss, once per iteration: action(2), mu_old(2), neglogp_old, value_old, return, advantage
@@ -494,6 +494,17 @@ class PPOAgent:
                                          p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, 0, pm, stream) == 0
                 assert lib.vine_lstm_adam(p(path.flat_g_lstm), sc, p(self.flat_l), p(self.adam_ml), p(self.adam_vl), p(self._lpacked),
                                           p(self.ppo_state), self.O, 0.9, 0.999, 1e-8, pl, stream) == 0
+
+    def _allreduce_moments(self, stream):
+        """Sum over the ranks of the f64 running-statistics moments (observations, values, advantages), once per iteration:
+        over the peer-memory channel (one single-block launch) or, baseline, one NCCL all-reduce."""
+        if self.world == 1:
+            return
+        if self._p2p_moments is not None:
+            assert self._lib.vine_p2p_allreduce_f64(self._p2p_moments.ptr, C.c_void_p(self._moments.data_ptr()),
+                                                    self._moments.numel(), stream) == 0
+        else:
+            torch.distributed.all_reduce(self._moments)
 
     @torch.no_grad()
     def _refresh_fused(self, pack=False):
@@ -755,8 +766,7 @@ class PPOAgent:
                 normalize_advantage=int(self.normalize_advantage))
         # running statistics + normalised targets: f64 sufficient statistics, [one all-reduce], finalize
         assert lib.vine_ppo_moments(C.byref(self._prologue), stream) == 0
-        if self.world > 1:
-            torch.distributed.all_reduce(self._moments)
+        self._allreduce_moments(stream)
         assert lib.vine_ppo_finalize(C.byref(self._prologue), stream) == 0
         self._logstd_old.copy_(self.model.sigma.expand_as(self._logstd_old))
         if self._mb_structs is None:
