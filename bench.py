@@ -71,7 +71,7 @@ def measured_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.stop_flag, self.ok = [], False, True

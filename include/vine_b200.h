@@ -207,6 +207,9 @@ int vine_step(VineEnv* env, void* stream);
  * ranges covering 0..num_envs is bit-identical to one vine_step.
  */
 int vine_step_range(VineEnv* env, int64_t first, int64_t count, void* stream);
+/* Obstacle variants, routed step: how the last vine_step binned its envs -- out = {near (near pass), far (far pass), given up by
+ * the far pass and redone, 0}.  Zeros when the step is not routed.  Synchronises. */
+int vine_route_counts(VineEnv* env, int64_t out[4]);
 
 /*
  * reset_idx(env_ids) (V5:774-885) outside step, as VecTask.reset_done (VT:412-427)

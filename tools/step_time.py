@@ -26,3 +26,9 @@ for rep in range(3):
     torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1) / 40)
 print(f"{sys.argv[1]} n={n} {' '.join(sys.argv[3:])}: {best:.4f} ms/step  {n / best / 1e3:.4g} env-steps/s", flush=True)
+if any("CREATE_SHELF=True" in o or "CREATE_PIPE=True" in o for o in preset):
+    import ctypes as C
+    c = (C.c_int64 * 4)()
+    env._lib.vine_route_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    env._lib.vine_route_counts(env._h, c)
+    print(f"    routed: near pass {c[0]} envs ({100.0 * c[0] / n:.2f} %), far pass {c[1]}, given up and redone {c[2]} ({100.0 * c[2] / n:.3f} %)")

@@ -133,7 +133,7 @@ class VineSimulateIO(C.Structure):
 # every symbol include/vine_b200.h declares
 EXPORTED_SYMBOLS = [
     "vine_abi_version", "vine_config_defaults", "vine_num_observations", "vine_create",
-    "vine_destroy", "vine_last_error", "vine_bind_io", "vine_step", "vine_step_range", "vine_reset_idx",
+    "vine_destroy", "vine_last_error", "vine_bind_io", "vine_step", "vine_step_range", "vine_route_counts", "vine_reset_idx",
     "vine_get_state", "vine_set_state", "vine_set_debug_outputs", "vine_metrics", "vine_post_physics",
     "vine_pre_physics", "vine_actuation", "vine_simulate", "vine_philox_debug", "vine_gae",
     "vine_mlp_pack", "vine_mlp_forward",
@@ -252,6 +252,7 @@ def _declare(lib):
     lib.vine_bind_io.argtypes = [vp] + [vp] * 7
     lib.vine_step.argtypes = [vp, vp]
     lib.vine_step_range.argtypes = [vp, C.c_int64, C.c_int64, vp]
+    lib.vine_route_counts.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.vine_reset_idx.argtypes = [vp, vp, C.c_int64, vp]
     lib.vine_get_state.argtypes = [vp, C.POINTER(VineStateView), vp]
     lib.vine_set_state.argtypes = [vp, C.POINTER(VineStateView), vp]

@@ -1061,6 +1061,18 @@ int vine_step(VineEnv* env, void* stream) {
   return VINE_OK;
 }
 
+// counts of the last routed step: near and far envs as binned, and how many the far pass gave up (synchronises)
+int vine_route_counts(VineEnv* env, int64_t out[4]) {
+  if (!env || !out) return VINE_ERR_INVALID_ARG;
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if (!env->a.bin_cursor) return VINE_OK;
+  int32_t c[4];
+  CUDA_TRY(env, cudaDeviceSynchronize());
+  CUDA_TRY(env, cudaMemcpy(c, env->a.bin_cursor, sizeof(c), cudaMemcpyDeviceToHost));
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2];
+  return VINE_OK;
+}
+
 int vine_step_range(VineEnv* env, int64_t first, int64_t count, void* stream) {
   if (!env) return VINE_ERR_INVALID_ARG;
   if (!env->bound) { snprintf(env->err, 256, "vine_step_range: call vine_bind_io first"); return VINE_ERR_NOT_BOUND; }
