@@ -369,3 +369,27 @@ def test_state_attributes_write_through_like_the_reference_views():
         env.cart_positions[ids, 1] = 0.0
     kept = env.progress_buf > 0                       # an env reset in this step still shows the old episode's body position
     assert env.cart_positions.shape == (n, 3) and torch.equal(env.cart_positions[kept, 1], env.dof_pos[kept, 0])
+
+
+def test_route_counts_account_for_every_env():
+    """vine_route_counts: near + far == num_envs for a routed step, the redone envs are a subset of the far pass, and a step
+    that is not routed (free space, or binning off) reports zeros."""
+    import ctypes as C
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    n = 20000
+    counts = lambda env: (lambda c: (env._lib.vine_route_counts(env._h, c), list(c))[1])((C.c_int64 * 4)())  # noqa: E731
+    routed = vine.make(cfg=vcfg.compose(vcfg.SHELF_OVERRIDES + [f"num_envs={n}", "headless=True", "+task.sim.vine_contact.binning=2"]))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    seen_near = 0
+    for t in range(40):
+        act = torch.rand(n, 2, device="cuda", generator=g) * 2 - 1
+        act[: n // 2, 0] = -act[: n // 2, 0].abs(); act[: n // 2, 1] = act[: n // 2, 1].abs()
+        routed.step(act)
+        near, far, redone, _ = counts(routed)
+        assert near + far == n and 0 <= redone <= far
+        seen_near = max(seen_near, near)
+    assert seen_near > 0
+    free = vine.make(cfg=vcfg.compose(vcfg.FSTR_OVERRIDES + ["num_envs=256", "headless=True"]))
+    free.step(torch.zeros(256, 2, device="cuda"))
+    assert counts(free) == [0, 0, 0, 0]
