@@ -308,8 +308,17 @@ def run_ours(args, rank, world, local_rank):
         pcfg = (fstr_cfg(num_envs, devs + list(extra)) if preset is None else
                 vcfg.compose(preset + [f"num_envs={num_envs}", "headless=True"] + devs + list(extra)))
         penv = vine.make(cfg=pcfg, global_env_offset=rank * num_envs)
-        agent = PPOAgent(penv, pcfg["train"], device=dev, seed=42 + rank, use_graphs=use_graphs,
-                         use_fused_update=fused_update)
+        exchange = "none" if world == 1 else "p2p"
+        try:
+            agent = PPOAgent(penv, pcfg["train"], device=dev, seed=42 + rank, use_graphs=use_graphs, use_fused_update=fused_update)
+        except RuntimeError as err:   # no CUDA IPC / peer access on this box: every rank gets the same error (P2PChannel agrees first)
+            if "vine_p2p" not in str(err):
+                raise
+            exchange = "nccl (peer-memory channel unavailable: %s)" % str(err)[:120]
+            agent = PPOAgent(penv, pcfg["train"], device=dev, seed=42 + rank, use_graphs=use_graphs, use_fused_update=fused_update,
+                             grad_allreduce="nccl")
+        if world > 1 and not agent.fused_update:
+            exchange = "nccl"
         for _ in range(max(warmup, 3)):
             agent.train_epoch()
         barrier()
@@ -355,7 +364,10 @@ def run_ours(args, rank, world, local_rank):
                            else "torch autograd + cuBLAS/cuDNN + torch Adam"),
                 "policy_forward": ("vine_policy_act + vine_lstm_step/head (tcgen05)" if agent.native_lstm else
                                    "vine_policy_act (tcgen05)" if agent.fused else "torch"),
-                "collectives": "none" if world == 1 else "NCCL all-reduce: grads+KL per minibatch, running stats per iteration"}
+                "collectives": "none" if world == 1 else (
+                    "gradients + loss statistics per minibatch and running-statistics moments per iteration over NVLink peer memory "
+                    "inside the reduce / Adam kernels (csrc/vine_p2p.cuh); NCCL only for the start-up broadcast" if exchange == "p2p"
+                    else "NCCL all-reduce: grads+KL per minibatch, running stats per iteration [%s]" % exchange)}
 
     # ---- HBM-bound PPO helper kernels (GAE 24 B per (t, env)), timed alone against the measured copy bandwidth ----
     def measure_gae(num_envs, T=16, reps=200):

@@ -625,7 +625,6 @@ VDEV void observation_row(const VineParams& p, const PostIn& in, float raw[VINE_
 #pragma unroll
   for (int i = 0; i < 3; ++i) fdt[i] = div_rn(__fsub_rn(in.tip[i], in.prev_tip[i]), p.control_dt);  // V5:1348
   const int t = p.obs_type;
-  int k = 0;
 #pragma unroll
   for (int i = 0; i < VINE_MAX_OBS; ++i) raw[i] = 0.f;
   if (t == VINE_OBS_TIP_AND_CART_AND_OBJ_INFO) {
@@ -637,11 +636,9 @@ VDEV void observation_row(const VineParams& p, const PostIn& in, float raw[VINE_
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) raw[i] = in.q[i];
-  k = 6;
   if (t != VINE_OBS_POS_ONLY) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) raw[6 + i] = t == VINE_OBS_POS_AND_VEL ? in.qd[i] : (t == VINE_OBS_POS_AND_PREV_POS ? in.prev_q[i] : fdq[i]);
-    k = 12;
   }
   if (t == VINE_OBS_POS_ONLY) {
 #pragma unroll
@@ -657,7 +654,6 @@ VDEV void observation_row(const VineParams& p, const PostIn& in, float raw[VINE_
   }
   raw[24] = in.smoothed; raw[25] = in.prev_u_rail;
   if (t == VINE_OBS_POS_AND_FD_VEL_AND_OBJ_INFO) { raw[26] = in.obj[0]; raw[27] = in.obj[1]; }
-  (void)k;
 }
 
 // noise: [O] standard normals or nullptr

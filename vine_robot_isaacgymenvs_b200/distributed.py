@@ -110,6 +110,7 @@ class P2PChannel:
             handles = [mine]
         self._opened = []
         regions = (C.c_void_p * world)()
+        failed = None
         for r in range(world):
             if r == rank:
                 regions[r] = region.value
@@ -119,10 +120,20 @@ class P2PChannel:
             with torch.cuda.device(self.device):
                 rc = lib.vine_p2p_open(raw, C.byref(peer))
             if rc != 0:
-                raise RuntimeError(f"vine_p2p_open failed for rank {r} ({rc}): CUDA IPC / NVLink peer access is required "
-                                   "(one process per GPU on ONE node); pass grad_allreduce='nccl' to use NCCL instead")
+                failed = (r, rc)
+                break
             self._opened.append(peer)
             regions[r] = peer.value
+        if world > 1:   # every rank learns whether ALL mappings succeeded, so that all raise (or none): nobody is left at a barrier
+            ok = torch.tensor([0 if failed else 1], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0:
+                for peer in self._opened:
+                    lib.vine_p2p_close(peer)
+                lib.vine_p2p_free(region)
+                raise RuntimeError(("vine_p2p_open failed for rank %d (%d)" % failed if failed else "vine_p2p_open failed on another rank") +
+                                   ": CUDA IPC / NVLink peer access is required (one process per GPU on ONE node); pass "
+                                   "grad_allreduce='nccl' to use NCCL instead")
         ch = C.c_void_p()
         with torch.cuda.device(self.device):
             rc = lib.vine_p2p_channel_create(regions, world, rank, self.count, C.byref(ch))
