@@ -323,20 +323,25 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
   __shared__ ContactScratch s_contact[CONTACT ? BLOCK / 32 : 1];
   ContactScratch* cs = &s_contact[CONTACT ? threadIdx.x >> 5 : 0];
   const int64_t count = a.list_count ? (int64_t)*a.list_count : a.end - a.first;
-  // Listed launches (near / redo pass) hold nothing but envs with contact work, and the lanes of a warp wait for each other's
-  // narrow phases; when the list is short enough for the grid, each warp takes only 8 of them (lanes 0..7)
+  // Listed launches (near / redo pass) hold nothing but envs with contact work; when the list is short enough for the grid,
+  // each warp takes only 8 of them (lanes 0..7) and the other 24 lanes are ghosts = workers of the pooled narrow phase.
+  // (With a long list 32 envs per warp are faster: 16 -> +8 % / +24 %, 8 -> +22 % / +76 % step time, shelf / pipe at 1 M envs.)
   const int lanes = (CONTACT && a.list && count <= (int64_t)gridDim.x * 8) ? 8 : BLOCK;
   // grid-stride over the launch's slots: listed launches are sized without knowing the list length
 #pragma unroll 1
   for (int64_t base = (int64_t)blockIdx.x * lanes; base < count; base += (int64_t)gridDim.x * lanes) {
     const int64_t slot = base + threadIdx.x;
     const bool live = slot < count && (int)threadIdx.x < lanes;
-    const int64_t e = live ? slot_env(a, slot) : -1;
-    if (live) {
+    // Contact variant: the lanes of the warp that have no env of their own (tail of the launch; lanes 8..31 of a short listed
+    // launch) run along as ghosts on a copy of the warp's first env -- they never cull or touch, write nothing, and serve as
+    // workers of the warp's pooled narrow phase (contact_forces)
+    const bool ghost = CONTACT && !live;
+    const int64_t e = live ? slot_env(a, slot) : (ghost ? slot_env(a, base) : -1);
+    if (live || ghost) {
       EnvStep E; Dyn d;
       env_begin(p, a, e, E, d);
       Obstacles ob = {0, -1, 0.f, 0.f, 0.f, 0.f};
-      ContactCache cc = {0u, 1e30f, 0u};   // no candidate pairs yet: the first substep culls
+      ContactCache cc = {0u, ghost ? -1e30f : 1e30f, 0u};   // no candidate pairs yet: the first substep culls
       if (CONTACT) { const float4 s5 = a.S5[e]; build_obstacles(p, s5.x, s5.y, s5.z, s5.w, cs, ob); }
       const float m00 = fmaf(p.h, p.damping, p.mtot), m00inv = rcp_approx(m00);
       // ---- controlFrequencyInv x {forces, contact sample, simulate}  VT:338-356 ----
@@ -348,13 +353,15 @@ vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
         JointImp J;
         env_sim_step_begin(p, a, i, E, d, J);
 #pragma unroll 1
-        for (int s = 0; s < p.S; ++s) substep<CONTACT, float>(p, J, m00, m00inv, E.rail_force, ob, cs, cc, d, E.lip);
+        for (int s = 0; s < p.S; ++s) substep<CONTACT, float>(p, J, m00, m00inv, E.rail_force, ob, cs, cc, d, E.lip, ghost);
       }
-      env_end(p, a, e, E, d, s_obs + threadIdx.x * (VINE_MAX_OBS + 1));
-      if (CONTACT && a.near) a.near[e] = cc.seen != 0u;
+      if (!ghost) {
+        env_end(p, a, e, E, d, s_obs + threadIdx.x * (VINE_MAX_OBS + 1));
+        if (CONTACT && a.near) a.near[e] = cc.seen != 0u;
+      }
     }
     __syncthreads();
-    if (CONTACT && a.list) store_obs_rows_scattered(p, a, s_obs, e);
+    if (CONTACT && a.list) store_obs_rows_scattered(p, a, s_obs, live ? e : -1);
     else store_obs_block<BLOCK, BLOCK>(s_obs, p.O, a.first + base - (int64_t)blockIdx.x * BLOCK, a.end, p.clip_obs, a.obs, a.obs_clamped);   // unlisted: lanes == BLOCK
     __syncthreads();
   }
@@ -681,8 +688,10 @@ template <bool CONTACT>
 __global__ void __launch_bounds__(VINE_BLOCK) vine_simulate_kernel(const __grid_constant__ VineParams p, int64_t n, const VineSimulateIO io) {
   __shared__ ContactScratch s_contact[CONTACT ? VINE_BLOCK / 32 : 1];
   ContactScratch* cs = &s_contact[CONTACT ? threadIdx.x >> 5 : 0];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n) return;
+  const int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ghost = e0 >= n;                       // tail lanes run along on a copy of the last env (contact_forces needs whole warps)
+  if (ghost && !CONTACT) return;
+  const int64_t e = ghost ? n - 1 : e0;
   float q[6], qd[6], efforts[6];
   for (int i = 0; i < 6; ++i) { q[i] = io.dof_pos[6 * e + i]; qd[i] = io.dof_vel[6 * e + i]; efforts[i] = io.dof_efforts[6 * e + i]; }
   JointLaw law; joint_law_unscaled(law);
@@ -695,7 +704,7 @@ __global__ void __launch_bounds__(VINE_BLOCK) vine_simulate_kernel(const __grid_
   }
   const float u_use = io.u_fpam_to_use ? io.u_fpam_to_use[e] : 0.f;
   Obstacles ob = {0, -1, 0.f, 0.f, 0.f, 0.f};
-  ContactCache cc = {0u, 1e30f, 0u};
+  ContactCache cc = {0u, ghost ? -1e30f : 1e30f, 0u};
   if (CONTACT) build_obstacles(p, io.target_positions[3 * e + 1], io.target_positions[3 * e + 2],
                                io.object_info[2 * e], io.object_info[2 * e + 1], cs, ob);
   Dyn d; rel_to_abs(p, q, qd, d);
@@ -703,7 +712,8 @@ __global__ void __launch_bounds__(VINE_BLOCK) vine_simulate_kernel(const __grid_
   float lip = 0.f;
   const float m00 = fmaf(p.h, p.damping, p.mtot), m00inv = rcp_approx(m00);
 #pragma unroll 1
-  for (int s = 0; s < p.S; ++s) substep<CONTACT, float>(p, J, m00, m00inv, efforts[0], ob, cs, cc, d, lip);
+  for (int s = 0; s < p.S; ++s) substep<CONTACT, float>(p, J, m00, m00inv, efforts[0], ob, cs, cc, d, lip, ghost);
+  if (ghost) return;
   float ty, tz, vy, vz; tip_fk(d, ty, tz, vy, vz);
   abs_to_rel(d, q, qd);
   for (int i = 0; i < 6; ++i) { io.dof_pos[6 * e + i] = q[i]; io.dof_vel[6 * e + i] = qd[i]; }

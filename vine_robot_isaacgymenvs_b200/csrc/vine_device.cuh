@@ -138,9 +138,12 @@ VDEV float rail_controller(const VineParams& p, float cart_vel_y, float u_rail, 
 //   chain: joint positions / velocities, sin/cos and spin of the links of an env with candidate contacts, rewritten by
 //          that env's lane in the substeps in which it has any
 enum { CH_PY = 0, CH_PZ = 6, CH_VY = 12, CH_VZ = 18, CH_S = 24, CH_C = 29, CH_W = 34, CH_FIELDS = 39 };
+#define VINE_PAIR_PASS 64                   // (env, pair) work items the warp's narrow phase takes per pass
 struct ContactScratch {
   float rect[32][VINE_MAX_RECTS * 6 + 1];   // [lane][6 r + field]; odd row stride keeps the lanes on different banks
   float chain[CH_FIELDS][32];               // [field][lane]
+  float res[VINE_PAIR_PASS][3];             // net force (y, z) and torque about the proximal joint of a work item's pair
+  unsigned short item[VINE_PAIR_PASS];      // owner lane | pair bit << 5
 };
 // rectangle count and index of the sensing shelf_link rectangle (-1: none), the same for all envs; bounding box of this env's
 struct Obstacles { int n, lip; float lo_y, hi_y, lo_z, hi_z; };
@@ -379,28 +382,51 @@ VDEV float chain_obstacle_gap(const VineParams& p, const Obstacles& ob, const Dy
   return chain_obstacle_gap(p, ob, py, pz);
 }
 
-// all link-vs-obstacle contacts of one substep; adds generalized forces to f[6], returns |F_lip|
-VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScratch* cs, ContactCache& cc, const Dyn& d, float f[6]) {
-  cc.disp += chain_displacement_bound(p, d);
-  const bool stale = !(cc.disp <= p.cull_slack);
-  if (!stale && cc.pm == 0u) return 0.f;
+// net load of one candidate (link j, rectangle r) pair of the env published in column `owner` of the warp's scratch
+VDEV void pair_load(const VineParams& p, const ContactScratch* cs, int owner, int b, PairLoad& L) {
+  const int r = b / 5, j = b - 5 * r;
+  const float* R = cs->rect[owner] + 6 * r;
+  const float* ch = &cs->chain[j][owner];
+  const float jy = ch[32 * CH_PY], jz = ch[32 * CH_PZ], ty = ch[32 * (CH_PY + 1)], tz = ch[32 * (CH_PZ + 1)];
+  const float jvy = ch[32 * CH_VY], jvz = ch[32 * CH_VZ], S = ch[32 * CH_S], C = ch[32 * CH_C], w = ch[32 * CH_W];
+  const bool last = j == VINE_NL - 1;
+  L.fy = 0.f; L.fz = 0.f; L.t = 0.f;
+  // main cylinder URDF:95-99 as a capsule; the last link's capsules are shortened so that their caps end at the tip
+  capsule_rect(p, R, jy, jz, last ? fmaf(VINE_LINK_RADIUS, S, ty) : ty, last ? fmaf(-VINE_LINK_RADIUS, C, tz) : tz,
+               VINE_LINK_RADIUS, j == 0, last, jy, jz, jvy, jvz, w, L);
+  // FPAM cylinder URDF:110-114, offset along the link's local +y = (cos phi, sin phi)
+  const float oy = VINE_FPAM_OFFSET * C, oz = VINE_FPAM_OFFSET * S;
+  capsule_rect(p, R, jy + oy, jz + oz, ty + oy + (last ? VINE_FPAM_RADIUS * S : 0.f),
+               tz + oz - (last ? VINE_FPAM_RADIUS * C : 0.f), VINE_FPAM_RADIUS, true, true, jy, jz, jvy, jvz, w, L);
+}
 
+// All link-vs-obstacle contacts of one substep; adds generalized forces to f[6], returns |F_lip|.
+// Called by ALL 32 lanes of the warp together (`ghost` lanes carry no env of their own: tail lanes and, in short listed
+// launches, lanes 8..31).  The candidate pairs of the warp's envs are pooled into one work list and dealt out to the 32
+// lanes, so a warp does ceil(total pairs / 32) narrow-phase turns instead of max-over-lanes(pairs of one env) with most lanes
+// idle.  Every pair is evaluated by the same instruction sequence on the same published values whichever lane runs it, and each
+// env adds its pairs' loads in ascending pair order, so the result does not depend on who shares the warp.
+VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScratch* cs, ContactCache& cc, const Dyn& d, float f[6],
+                          bool ghost) {
   const int lane = threadIdx.x & 31;
+  if (!ghost) cc.disp += chain_displacement_bound(p, d);
+  const bool stale = !ghost && !(cc.disp <= p.cull_slack);
   float py[VINE_NL + 1], pz[VINE_NL + 1];
-  py[0] = d.x[0]; pz[0] = VINE_PIVOT_Z;
+  if (stale || cc.pm != 0u) {     // joint positions: for the cull, the published chain and the lever arms of the pairs' loads
+    py[0] = d.x[0]; pz[0] = VINE_PIVOT_Z;
 #pragma unroll
-  for (int j = 0; j < VINE_NL; ++j) {
-    py[j + 1] = fmaf(-VINE_LINK_LEN, d.S[j], py[j]); pz[j + 1] = fmaf(VINE_LINK_LEN, d.C[j], pz[j]);
+    for (int j = 0; j < VINE_NL; ++j) {
+      py[j + 1] = fmaf(-VINE_LINK_LEN, d.S[j], py[j]); pz[j + 1] = fmaf(VINE_LINK_LEN, d.C[j], pz[j]);
+    }
   }
-  const float* R = cs->rect[lane];
   if (stale) {
     const float gap = chain_obstacle_gap(p, ob, py, pz);
     if (gap > 0.f) { cc.pm = 0u; cc.disp = -gap; }
-    else { cc.pm = cull_pairs(p, ob, R, py, pz); cc.disp = 0.f; cc.seen |= cc.pm | 0x80000000u; }   // bit 31: the boxes overlapped
-    if (cc.pm == 0u) return 0.f;
+    else { cc.pm = cull_pairs(p, ob, cs->rect[lane], py, pz); cc.disp = 0.f; cc.seen |= cc.pm | 0x80000000u; }   // bit 31: the boxes overlapped
   }
-  // publish this env's chain in its column of the warp's scratch: the narrow phase picks its link by a run-time index
-  {
+  const unsigned pm = ghost ? 0u : cc.pm;
+  if (__ballot_sync(0xffffffffu, pm != 0u) == 0u) return 0.f;   // nobody in the warp has a candidate pair (uniform)
+  if (pm) {   // publish this env's chain in its column of the warp's scratch: a pair's link is picked by a run-time index
     float* ch = &cs->chain[0][lane];
     float vy = d.v[0], vz = 0.f;
     ch[32 * CH_PY] = py[0]; ch[32 * CH_PZ] = pz[0]; ch[32 * CH_VY] = vy; ch[32 * CH_VZ] = vz;
@@ -413,35 +439,56 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScrat
       ch[32 * (CH_S + j)] = d.S[j]; ch[32 * (CH_C + j)] = d.C[j]; ch[32 * (CH_W + j)] = d.v[j + 1];
     }
   }
-  float lfy = 0.f, lfz = 0.f;
-  unsigned pm = cc.pm;
-#pragma unroll 1
-  while (pm) {
-    const int b = __ffs(pm) - 1;
-    pm &= pm - 1;
-    const int r = b / 5, j = b - 5 * r;
-    const float* ch = &cs->chain[j][lane];
-    const float jy = ch[32 * CH_PY], jz = ch[32 * CH_PZ], ty = ch[32 * (CH_PY + 1)], tz = ch[32 * (CH_PZ + 1)];
-    const float jvy = ch[32 * CH_VY], jvz = ch[32 * CH_VZ], S = ch[32 * CH_S], C = ch[32 * CH_C], w = ch[32 * CH_W];
-    const bool last = j == VINE_NL - 1;
-    PairLoad L = {0.f, 0.f, 0.f};
-    // main cylinder URDF:95-99 as a capsule; the last link's capsules are shortened so that their caps end at the tip
-    capsule_rect(p, R + 6 * r, jy, jz, last ? fmaf(VINE_LINK_RADIUS, S, ty) : ty, last ? fmaf(-VINE_LINK_RADIUS, C, tz) : tz,
-                 VINE_LINK_RADIUS, j == 0, last, jy, jz, jvy, jvz, w, L);
-    // FPAM cylinder URDF:110-114, offset along the link's local +y = (cos phi, sin phi)
-    const float oy = VINE_FPAM_OFFSET * C, oz = VINE_FPAM_OFFSET * S;
-    capsule_rect(p, R + 6 * r, jy + oy, jz + oz, ty + oy + (last ? VINE_FPAM_RADIUS * S : 0.f),
-                 tz + oz - (last ? VINE_FPAM_RADIUS * C : 0.f), VINE_FPAM_RADIUS, true, true, jy, jz, jvy, jvz, w, L);
-    if (L.fy != 0.f || L.fz != 0.f) {
-      // generalized forces: Q_y = F;  Q_j = T_j;  Q_m = (p_{m+1} - p_m) x F for the links m < j below the contact
-      f[0] += L.fy;
+  // positions of the lanes' pairs in the warp's work list: inclusive prefix sum of the pair counts
+  const int cnt = __popc(pm);
+  int incl = cnt;
 #pragma unroll
-      for (int m = 0; m < VINE_NL; ++m) {
-        const float q = m == j ? L.t : (py[m + 1] - py[m]) * L.fz - (pz[m + 1] - pz[m]) * L.fy;
-        if (m <= j) f[m + 1] += q;
-      }
-      if (r == ob.lip) { lfy -= L.fy; lfz -= L.fz; }
+  for (int off = 1; off < 32; off <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int next = incl - cnt;          // index of this env's next pair that has not been dealt out / added yet
+  unsigned todo = pm, toadd = pm;
+  int next_add = next;
+  float lfy = 0.f, lfz = 0.f;
+#pragma unroll 1
+  for (int base = 0; base < total; base += VINE_PAIR_PASS) {
+    while (todo && next < base + VINE_PAIR_PASS) {          // this env's pairs that fall into this pass
+      const int b = __ffs(todo) - 1;
+      todo &= todo - 1;
+      cs->item[next - base] = (unsigned short)(lane | (b << 5));
+      ++next;
     }
+    __syncwarp();
+    const int n_pass = min(VINE_PAIR_PASS, total - base);
+#pragma unroll 1
+    for (int i = lane; i < n_pass; i += 32) {               // the narrow phase, one pair per lane and turn
+      const int it = cs->item[i];
+      PairLoad L;
+      pair_load(p, cs, it & 31, it >> 5, L);
+      cs->res[i][0] = L.fy; cs->res[i][1] = L.fz; cs->res[i][2] = L.t;
+    }
+    __syncwarp();
+    while (toadd && next_add < base + VINE_PAIR_PASS) {     // each env adds its own pairs' loads, in ascending pair order
+      const int b = __ffs(toadd) - 1;
+      toadd &= toadd - 1;
+      const float* rs = cs->res[next_add - base];
+      ++next_add;
+      const float Lfy = rs[0], Lfz = rs[1], Lt = rs[2];
+      if (Lfy != 0.f || Lfz != 0.f) {
+        const int r = b / 5, j = b - 5 * r;
+        // generalized forces: Q_y = F;  Q_j = T_j;  Q_m = (p_{m+1} - p_m) x F for the links m < j below the contact
+        f[0] += Lfy;
+#pragma unroll
+        for (int m = 0; m < VINE_NL; ++m) {
+          const float q = m == j ? Lt : (py[m + 1] - py[m]) * Lfz - (pz[m + 1] - pz[m]) * Lfy;
+          if (m <= j) f[m + 1] += q;
+        }
+        if (r == ob.lip) { lfy -= Lfy; lfz -= Lfz; }
+      }
+    }
+    __syncwarp();
   }
   // |F_lip| is zero in almost every substep, and sqrt's zero argument sends the warp through its slow-path subroutine
   const float l2 = lfy * lfy + lfz * lfz;
@@ -501,7 +548,7 @@ VDEV void pack2(const JointImp& A, const JointImp& B, JointImpT<float2>& J) {
 // m00 = M_tot + h D (cart row of the system matrix), m00inv its reciprocal: the same for every env and substep.
 template <bool CONTACT, typename T>
 VDEV void substep(const VineParams& p, const JointImpT<T>& J, float m00, float m00inv, T rail_force, const Obstacles& ob,
-                  ContactScratch* cs, ContactCache& cc, DynT<T>& d, float& lip) {
+                  ContactScratch* cs, ContactCache& cc, DynT<T>& d, float& lip, bool ghost = false) {
   typedef Ops<T> O;
   T a[VINE_NL], b[VINE_NL], As[VINE_NL], Bs[VINE_NL];
 #pragma unroll
@@ -538,7 +585,7 @@ VDEV void substep(const VineParams& p, const JointImpT<T>& J, float m00, float m
       tn = t;
     }
   }
-  if constexpr (CONTACT) lip = contact_forces(p, ob, cs, cc, d, f);
+  if constexpr (CONTACT) lip = contact_forces(p, ob, cs, cc, d, f, ghost);   // ghost: a lane without an env of its own (see there)
   // lower triangle of the SPD system matrix; rows/cols: 0 = cart, 1..5 = links
   T M[6][6];
 #pragma unroll
