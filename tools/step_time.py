@@ -9,14 +9,32 @@ from vine_robot_isaacgymenvs_b200 import config as vcfg  # noqa: E402
 
 preset = getattr(vcfg, sys.argv[1])
 n = int(sys.argv[2])
-env = vine.make(cfg=vcfg.compose(preset + [f"num_envs={n}", "headless=True"] + sys.argv[3:]))
+env = vine.make(cfg=vcfg.compose(preset + [f"num_envs={n}", "headless=True"] + [a for a in sys.argv[3:] if a != "--graph"]))
 g = torch.Generator(device="cuda").manual_seed(0)
 acts = [torch.rand(n, 2, device="cuda", generator=g) * 2 - 1 for _ in range(8)]
 for t in range(40):
     env.step(acts[t % 8])
 torch.cuda.synchronize()
 best = 1e9
-for rep in range(3):
+if "--graph" in sys.argv:   # like bench.py: the steps captured into one CUDA graph, replayed
+    extra_note = " [graph replay]"
+    st = torch.cuda.Stream()
+    g2 = torch.cuda.CUDAGraph()
+    import ctypes as C
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(g2, stream=st):
+            for t in range(40):
+                env._bind(acts[t % 8])
+                env._check(env._lib.vine_step(env._h, C.c_void_p(st.cuda_stream)))
+    torch.cuda.synchronize()
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(st):
+            e0.record(); g2.replay(); e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / 40)
+    env._bind()
+for rep in range(0 if "--graph" in sys.argv else 3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(40):

@@ -57,6 +57,7 @@ struct VineEnv {
   // into the caller's stream with the two events, so the whole step stays one capturable unit of the caller's stream)
   cudaStream_t side;
   cudaEvent_t ev_fork, ev_join;
+  int prio_hi;
   char err[256];
 };
 
@@ -853,6 +854,7 @@ int vine_create(const VineConfig* cfg, int64_t num_envs, int64_t global_env_offs
     if (e == cudaSuccess) {   // the near pass (few, slow warps) gets its blocks placed ahead of the far pass's: it then runs beside it
       int lo = 0, hi = 0;
       cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      env->prio_hi = hi;
       e = cudaStreamCreateWithPriority(&env->side, cudaStreamNonBlocking, hi);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&env->ev_fork, cudaEventDisableTiming);
@@ -1050,7 +1052,15 @@ int vine_step(VineEnv* env, void* stream) {
       CUDA_TRY(env, cudaStreamWaitEvent(env->side, env->ev_fork, 0));
       StepArgs nr = a;
       nr.list = a.perm; nr.list_count = a.bin_cursor; nr.list_reversed = 0;
-      vine_step_kernel<true><<<listed_grid(a.n, 148 * 12), VINE_BLOCK_CONTACT, 0, env->side>>>(env->p, nr);
+      {   // the priority travels as a launch attribute too: a captured graph keeps it on the kernel node (a stream's priority alone
+          // is not recorded, and without it the far pass's blocks are placed first and the near pass starts when they drain)
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(listed_grid(a.n, 148 * 12)); lc.blockDim = dim3(VINE_BLOCK_CONTACT); lc.stream = env->side;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributePriority; at[0].val.priority = env->prio_hi;
+        lc.attrs = at; lc.numAttrs = 1;
+        CUDA_TRY(env, cudaLaunchKernelEx(&lc, vine_step_kernel<true>, env->p, nr));
+      }
       CUDA_TRY(env, cudaEventRecord(env->ev_join, env->side));
       StepArgs fr = a;
       fr.list = a.perm; fr.list_count = a.bin_cursor; fr.list_reversed = 1;
