@@ -158,14 +158,17 @@ def test_long_random_rollout_stays_physical():
 def test_contact_configs_at_baseline_sizes_are_deterministic_shard_invariant_and_physical(preset, n):
     """BASELINE configs[2] / configs[3] at their full env counts, through size-independent properties: bit-identical
     reruns, bit-identical under 4-way sharding by global env id (the 8-GPU layout of configs[3]), finite and bounded
-    state after a random rollout that pushes half the envs into the obstacles. At 131072 envs the whole-batch launches bin
-    the envs by contact candidates (vine_bin_kernel) while the four 32768-env shards step in identity order, so the same
-    comparison pins the binned launch bit for bit against the unbinned one."""
+    state after a random rollout that pushes half the envs into the obstacles. At 131072 envs the whole batches are ROUTED
+    (vine_bin_kernel -> near pass || far pass -> redo pass, forced with sim.vine_contact.binning=2) while the four 32768-env
+    shards step as single launches in identity order, so the same comparison pins the routed step bit for bit against the
+    single launch of the contact variant."""
     import vine_robot_isaacgymenvs_b200 as vine
     from vine_robot_isaacgymenvs_b200 import config as vcfg
     ov = getattr(vcfg, preset) + ["headless=True", "task.env.maxEpisodeLength=40"]
-    make = lambda m, off=0: vine.make(cfg=vcfg.compose(ov + [f"num_envs={m}"]), global_env_offset=off)  # noqa: E731
-    whole, again = make(n), make(n)
+    make = lambda m, off=0, route=0: vine.make(  # noqa: E731
+        cfg=vcfg.compose(ov + [f"num_envs={m}", f"+task.sim.vine_contact.binning={route}"]), global_env_offset=off)
+    route = 2 if n >= 131072 else 1
+    whole, again = make(n, route=route), make(n, route=route)
     shards = [make(n // 4, k * (n // 4)) for k in range(4)]
     g = torch.Generator(device="cuda").manual_seed(11)
     early_resets = 0
@@ -218,14 +221,15 @@ def test_routed_obstacle_step_equals_the_single_launch_bit_for_bit(preset, n):
 
 
 def test_binned_contact_launch_with_a_ragged_tail_equals_unbinned_shards():
-    """98,341 envs (not a multiple of the warp or of the 1024-env binning block) step through the binned launch; two shards
-    below the binning threshold cover the same global env ids in identity order. Bit-identical outputs and state."""
+    """98,341 envs (not a multiple of the warp or of the 1024-env binning block) step through the routed step; two shards
+    stepping as single launches cover the same global env ids in identity order. Bit-identical outputs and state."""
     import vine_robot_isaacgymenvs_b200 as vine
     from vine_robot_isaacgymenvs_b200 import config as vcfg
     n, n0 = 98304 + 37, 49152
     ov = vcfg.SHELF_OVERRIDES + ["headless=True", "task.env.maxEpisodeLength=30"]
-    make = lambda m, off=0: vine.make(cfg=vcfg.compose(ov + [f"num_envs={m}"]), global_env_offset=off)  # noqa: E731
-    whole, lo, hi = make(n), make(n0), make(n - n0, n0)
+    make = lambda m, off=0, route=0: vine.make(  # noqa: E731
+        cfg=vcfg.compose(ov + [f"num_envs={m}", f"+task.sim.vine_contact.binning={route}"]), global_env_offset=off)
+    whole, lo, hi = make(n, route=2), make(n0), make(n - n0, n0)
     g = torch.Generator(device="cuda").manual_seed(5)
     for t in range(45):
         act = torch.rand(n, 2, device="cuda", generator=g) * 2.4 - 1.2
