@@ -335,23 +335,34 @@ constexpr int HG_LNG = 0, HG_LNB = HID, HG_WH = 2 * HID, HG_BH = 5 * HID, HG_LS 
 constexpr int HG_FLOATS = 5 * HID + 16;
 static_assert(HG_FLOATS == VINE_LSTM_HEAD_GRAD_FLOATS, "header constant out of date");
 
+// Latency, not arithmetic, bounds this kernel (≈350 warp-instructions per row in four dependent butterfly rounds): every
+// warp keeps HT_ROWS rows in flight, the parameters live in shared memory (conflict-free float4 columns) instead of 40
+// registers, and only A_j[k] = sum_rows d_j yh[k] (j = mu0, mu1, v) is accumulated per lane — the gradients of the
+// LayerNorm gain/bias and of the head weights are linear in those sums and are assembled once per block at the end.
+constexpr int HT_ROWS = 2;
+
 __global__ void __launch_bounds__(256, 2) vine_lstm_head_train_kernel(const VineLstmHeadTrain a) {
   __shared__ float red[HG_FLOATS];
+  __shared__ float4 prm[5][2][32];   // g, b, w0, w1, w2: [array][half of the lane's 8 units][lane]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const uint8_t* P = reinterpret_cast<const uint8_t*>(a.params);
-  const float* lng = reinterpret_cast<const float*>(P + LP_LNG) + 8 * lane;
-  const float* lnb = reinterpret_cast<const float*>(P + LP_LNB) + 8 * lane;
-  const float* wh = reinterpret_cast<const float*>(P + LP_WH) + 8 * lane;
-  const float* bh = reinterpret_cast<const float*>(P + LP_BH);
-  float g[8], b[8], w0[8], w1[8], w2[8];
-  float ag[8], ab[8], aw0[8], aw1[8], aw2[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    g[k] = lng[k], b[k] = lnb[k], w0[k] = wh[k], w1[k] = wh[HID + k], w2[k] = wh[2 * HID + k];
-    ag[k] = ab[k] = aw0[k] = aw1[k] = aw2[k] = 0.f;
+  for (int i = threadIdx.x; i < 5 * 64; i += blockDim.x) {
+    const int arr = i / 64, r = i % 64, l = r >> 1, half = r & 1;
+    const float* src = arr == 0 ? reinterpret_cast<const float*>(P + LP_LNG)
+                     : arr == 1 ? reinterpret_cast<const float*>(P + LP_LNB)
+                                : reinterpret_cast<const float*>(P + LP_WH) + (arr - 2) * HID;
+    prm[arr][half][l] = *reinterpret_cast<const float4*>(src + 8 * l + 4 * half);
   }
-  float sc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // lane 0: dbh[3], dlogstd[2], a_loss, c_loss, kl, b_loss
+  for (int i = threadIdx.x; i < HG_FLOATS; i += blockDim.x) red[i] = 0.f;
+  const float* bh = reinterpret_cast<const float*>(P + LP_BH);
+  const float bh0_ = bh[0], bh1_ = bh[1], bh2_ = bh[2];
+  float A[3][8];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) A[j][k] = 0.f;
+  float sc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dbh[3], dlogstd[2], a_loss, c_loss, kl, b_loss (same in every lane)
   const float ls0 = a.logstd[0], ls1 = a.logstd[1], lso0 = a.logstd_old[0], lso1 = a.logstd_old[1];
   const float sig0 = __expf(ls0), sig1 = __expf(ls1), sigo0 = __expf(lso0), sigo1 = __expf(lso1);
   // sigma is a parameter, not a per-row quantity: every division of the row math below is by one of these constants, so the
@@ -360,166 +371,234 @@ __global__ void __launch_bounds__(256, 2) vine_lstm_head_train_kernel(const Vine
   // rl_games policy_kl(p0 = current policy, p1 = the policy the rows were last evaluated with), as in vine_ppo_minibatch_kernel
   const float klc0 = __logf(sigo0 / sig0 + 1e-5f) - 0.5f, klc1 = __logf(sigo1 / sig1 + 1e-5f) - 0.5f;
   const float klq0 = 1.f / (2.f * (sigo0 * sigo0 + 1e-5f)), klq1 = 1.f / (2.f * (sigo1 * sigo1 + 1e-5f));
-  for (int64_t s = warp0; s < a.n; s += nwarps) {
-    const int64_t tile = s / TILE;
-    const int row = (int)(s % TILE), unit = 8 * lane;
-    const size_t off = ((size_t)tile * 2 + unit / UK) * TILE_BYTES + tile_offset(row, unit % UK, UK);
-    const uint4 hv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.hh) + off);
-    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-    float h[8], yh[8];
+  const float lo = 1.f - a.e_clip, hi = 1.f + a.e_clip;
+  __syncthreads();
+  auto load8 = [&](int arr, float* v) {
+    const float4 x = prm[arr][0][lane], y = prm[arr][1][lane];
+    v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w, v[4] = y.x, v[5] = y.y, v[6] = y.z, v[7] = y.w;
+  };
+  for (int64_t s0 = warp0; s0 < a.n; s0 += HT_ROWS * nwarps) {
+    int64_t srow[HT_ROWS];
+    bool ok[HT_ROWS];
+    size_t off[HT_ROWS];
+    uint4 hv[HT_ROWS];
+    float4 q0[HT_ROWS], q1[HT_ROWS];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = unpack_bf16(hw[k]);
-      h[2 * k] = f.x, h[2 * k + 1] = f.y;
+    for (int r = 0; r < HT_ROWS; ++r) {   // every load of the rows in flight is issued before anything waits on one
+      const int64_t s = s0 + r * nwarps;
+      ok[r] = s < a.n;
+      srow[r] = ok[r] ? s : s0;
+      const int64_t tile = srow[r] / TILE;
+      const int row = (int)(srow[r] % TILE), unit = 8 * lane;
+      off[r] = ((size_t)tile * 2 + unit / UK) * TILE_BYTES + tile_offset(row, unit % UK, UK);
+      hv[r] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(a.hh) + off[r]));
+      const float4* q = reinterpret_cast<const float4*>(a.scalars + 8 * srow[r]);
+      q0[r] = __ldg(q), q1[r] = __ldg(q + 1);
     }
-    float sm = 0.f;
+    float yh[HT_ROWS][8], rstd[HT_ROWS], mean[HT_ROWS], sq[HT_ROWS];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sm += h[k];
-    const float mean = wsum(sm) * (1.f / HID);
-    float sq = 0.f;
+    for (int r = 0; r < HT_ROWS; ++r) {
+      const uint32_t hw[4] = {hv[r].x, hv[r].y, hv[r].z, hv[r].w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sq += (h[k] - mean) * (h[k] - mean);
-    const float rstd = rsqrtf(wsum(sq) * (1.f / HID) + 1e-5f);
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      yh[k] = (h[k] - mean) * rstd;
-      const float y = fmaf(yh[k], g[k], b[k]);
-      d0 = fmaf(y, w0[k], d0), d1 = fmaf(y, w1[k], d1), d2 = fmaf(y, w2[k], d2);
-    }
-    const float mu0 = wsum(d0) + bh[0], mu1 = wsum(d1) + bh[1], v = wsum(d2) + bh[2];
-    // ---- PPO losses and their gradient with respect to (mu0, mu1, v); every lane computes the same numbers ----
-    const float* q = a.scalars + 8 * s;
-    const float4 q0 = *reinterpret_cast<const float4*>(q), q1 = *reinterpret_cast<const float4*>(q + 4);
-    const float act0 = q0.x, act1 = q0.y, muo0 = q0.z, muo1 = q0.w, nlpo = q1.x, vo = q1.y, ret = q1.z, adv = q1.w;
-    const float e0 = (act0 - mu0) * inv_sig0, e1 = (act1 - mu1) * inv_sig1;
-    const float nlp = 0.5f * (e0 * e0 + e1 * e1) + 1.8378770664093453f + ls0 + ls1;
-    const float ratio = __expf(nlpo - nlp);
-    const float lo = 1.f - a.e_clip, hi = 1.f + a.e_clip;
-    const float t1 = -adv * ratio, t2 = -adv * fminf(fmaxf(ratio, lo), hi);
-    const bool inside = ratio >= lo && ratio <= hi;
-    const float g_nlp = ((inside || t1 > t2) ? -adv : 0.f) * (-ratio);
-    float dmu0 = g_nlp * (-e0 * inv_sig0), dmu1 = g_nlp * (-e1 * inv_sig1);
-    const float dls0 = g_nlp * (1.f - e0 * e0) - a.entropy_coef, dls1 = g_nlp * (1.f - e1 * e1) - a.entropy_coef;
-    const float dvo = v - vo, vclip = vo + fminf(fmaxf(dvo, -a.e_clip), a.e_clip);
-    const float r1 = v - ret, r2 = vclip - ret, c1 = r1 * r1, c2 = r2 * r2;
-    const float pass2 = (fabsf(dvo) <= a.e_clip) ? 1.f : 0.f;
-    const float dvc = c1 > c2 ? 2.f * r1 : (c2 > c1 ? 2.f * r2 * pass2 : r1 + r2 * pass2);
-    float dv = 0.5f * a.critic_coef * dvc;
-    const float bh0 = fmaxf(mu0 - 1.1f, 0.f), bl0 = fminf(mu0 + 1.1f, 0.f), bh1 = fmaxf(mu1 - 1.1f, 0.f), bl1 = fminf(mu1 + 1.1f, 0.f);
-    dmu0 += a.bounds_loss_coef * 2.f * (bh0 + bl0);
-    dmu1 += a.bounds_loss_coef * 2.f * (bh1 + bl1);
-    const float m0 = mu0 - muo0, m1 = mu1 - muo1;
-    const float kl = klc0 + (sig0 * sig0 + m0 * m0) * klq0 + klc1 + (sig1 * sig1 + m1 * m1) * klq1;
-    dmu0 *= a.inv_B, dmu1 *= a.inv_B, dv *= a.inv_B;
-    if (lane == 0) {
-      if (a.mu_writeback) {   // dataset.update_mu_sigma: row s = [step l][chunk c][env e] of the minibatch -> row (c L + l, e0 + e) of [T, N, 8]
-        const int64_t per_step = a.wb_chunks * a.wb_env_count;
-        const int64_t l = s / per_step, rem = s - l * per_step, c = rem / a.wb_env_count, e = rem - c * a.wb_env_count;
-        float* dst = a.mu_writeback + ((c * a.wb_seq_len + l) * a.wb_num_envs + a.wb_env_begin + e) * 8 + 2;
-        *reinterpret_cast<float2*>(dst) = make_float2(mu0, mu1);
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16(hw[k]);
+        yh[r][2 * k] = f.x, yh[r][2 * k + 1] = f.y;
       }
+      mean[r] = ((yh[r][0] + yh[r][1]) + (yh[r][2] + yh[r][3])) + ((yh[r][4] + yh[r][5]) + (yh[r][6] + yh[r][7]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < HT_ROWS; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+    for (int r = 0; r < HT_ROWS; ++r) {
+      mean[r] *= (1.f / HID);
+      float t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) yh[r][k] -= mean[r], t[k] = yh[r][k] * yh[r][k];
+      sq[r] = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < HT_ROWS; ++r) sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], o);
+    float d[HT_ROWS][3];
+    {
+      float g[8], b[8], w0[8], w1[8], w2[8];
+      load8(0, g), load8(1, b), load8(2, w0), load8(3, w1), load8(4, w2);
+#pragma unroll
+      for (int r = 0; r < HT_ROWS; ++r) {
+        rstd[r] = rsqrtf(sq[r] * (1.f / HID) + 1e-5f);   // torch.nn.LayerNorm: biased variance, eps 1e-5
+        d[r][0] = d[r][1] = d[r][2] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          yh[r][k] *= rstd[r];
+          const float y = fmaf(yh[r][k], g[k], b[k]);
+          d[r][0] = fmaf(y, w0[k], d[r][0]), d[r][1] = fmaf(y, w1[k], d[r][1]), d[r][2] = fmaf(y, w2[k], d[r][2]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < HT_ROWS; ++r)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) d[r][j] += __shfl_xor_sync(0xffffffffu, d[r][j], o);
+    // ---- PPO losses and their gradient with respect to (mu0, mu1, v); every lane computes the same numbers ----
+    float gr[HT_ROWS][3];
+#pragma unroll
+    for (int r = 0; r < HT_ROWS; ++r) {
+      const float mu0 = d[r][0] + bh0_, mu1 = d[r][1] + bh1_, v = d[r][2] + bh2_;
+      const float act0 = q0[r].x, act1 = q0[r].y, muo0 = q0[r].z, muo1 = q0[r].w, nlpo = q1[r].x, vo = q1[r].y, ret = q1[r].z, adv = q1[r].w;
+      const float e0 = (act0 - mu0) * inv_sig0, e1 = (act1 - mu1) * inv_sig1;
+      const float nlp = 0.5f * (e0 * e0 + e1 * e1) + 1.8378770664093453f + ls0 + ls1;
+      const float ratio = __expf(nlpo - nlp);
+      const float t1 = -adv * ratio, t2 = -adv * fminf(fmaxf(ratio, lo), hi);
+      const bool inside = ratio >= lo && ratio <= hi;
+      const float g_nlp = ((inside || t1 > t2) ? -adv : 0.f) * (-ratio);
+      float dmu0 = g_nlp * (-e0 * inv_sig0), dmu1 = g_nlp * (-e1 * inv_sig1);
+      const float dls0 = g_nlp * (1.f - e0 * e0) - a.entropy_coef, dls1 = g_nlp * (1.f - e1 * e1) - a.entropy_coef;
+      const float dvo = v - vo, vclip = vo + fminf(fmaxf(dvo, -a.e_clip), a.e_clip);
+      const float r1 = v - ret, r2 = vclip - ret, c1 = r1 * r1, c2 = r2 * r2;
+      const float pass2 = (fabsf(dvo) <= a.e_clip) ? 1.f : 0.f;
+      const float dvc = c1 > c2 ? 2.f * r1 : (c2 > c1 ? 2.f * r2 * pass2 : r1 + r2 * pass2);
+      float dv = 0.5f * a.critic_coef * dvc;
+      const float bh0 = fmaxf(mu0 - 1.1f, 0.f), bl0 = fminf(mu0 + 1.1f, 0.f), bh1 = fmaxf(mu1 - 1.1f, 0.f), bl1 = fminf(mu1 + 1.1f, 0.f);
+      dmu0 += a.bounds_loss_coef * 2.f * (bh0 + bl0);
+      dmu1 += a.bounds_loss_coef * 2.f * (bh1 + bl1);
+      const float m0 = mu0 - muo0, m1 = mu1 - muo1;
+      const float kl = klc0 + (sig0 * sig0 + m0 * m0) * klq0 + klc1 + (sig1 * sig1 + m1 * m1) * klq1;
+      const float w = ok[r] ? a.inv_B : 0.f;   // a row past the end contributes nothing
+      dmu0 *= w, dmu1 *= w, dv *= w;
+      gr[r][0] = dmu0, gr[r][1] = dmu1, gr[r][2] = dv;
       sc[0] += dmu0, sc[1] += dmu1, sc[2] += dv;
-      sc[3] += dls0 * a.inv_B, sc[4] += dls1 * a.inv_B;
-      sc[5] += fmaxf(t1, t2) * a.inv_B, sc[6] += fmaxf(c1, c2) * a.inv_B, sc[7] += kl * a.inv_B;
-      sc[8] += (bh0 * bh0 + bl0 * bl0 + bh1 * bh1 + bl1 * bl1) * a.inv_B;
-      if (a.debug_out) {
-        float* d = a.debug_out + 4 * s;
-        d[0] = mu0, d[1] = mu1, d[2] = v, d[3] = nlp;
+      sc[3] += dls0 * w, sc[4] += dls1 * w;
+      sc[5] += fmaxf(t1, t2) * w, sc[6] += fmaxf(c1, c2) * w, sc[7] += kl * w;
+      sc[8] += (bh0 * bh0 + bl0 * bl0 + bh1 * bh1 + bl1 * bl1) * w;
+      if (lane == 0 && ok[r]) {
+        const int64_t s = srow[r];
+        if (a.mu_writeback) {   // dataset.update_mu_sigma: row s = [step l][chunk c][env e] of the minibatch -> row (c L + l, e0 + e) of [T, N, 8]
+          const int64_t per_step = a.wb_chunks * a.wb_env_count;
+          const int64_t l = s / per_step, rem = s - l * per_step, c = rem / a.wb_env_count, e = rem - c * a.wb_env_count;
+          float* dst = a.mu_writeback + ((c * a.wb_seq_len + l) * a.wb_num_envs + a.wb_env_begin + e) * 8 + 2;
+          *reinterpret_cast<float2*>(dst) = make_float2(mu0, mu1);
+        }
+        if (a.debug_out) {
+          float* dd = a.debug_out + 4 * s;
+          dd[0] = mu0, dd[1] = mu1, dd[2] = v, dd[3] = nlp;
+        }
       }
     }
     // ---- backward: heads -> LayerNorm -> dh ----
-    float dyh[8], s1 = 0.f, s2 = 0.f;
+    float dyh[HT_ROWS][8], s1[HT_ROWS], s2[HT_ROWS];
+    {
+      float g[8], w0[8], w1[8], w2[8];
+      load8(0, g), load8(2, w0), load8(3, w1), load8(4, w2);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float dy = dmu0 * w0[k] + dmu1 * w1[k] + dv * w2[k];
-      const float y = fmaf(yh[k], g[k], b[k]);
-      ag[k] = fmaf(dy, yh[k], ag[k]);
-      ab[k] += dy;
-      aw0[k] = fmaf(dmu0, y, aw0[k]), aw1[k] = fmaf(dmu1, y, aw1[k]), aw2[k] = fmaf(dv, y, aw2[k]);
-      dyh[k] = dy * g[k];
-      s1 += dyh[k], s2 = fmaf(dyh[k], yh[k], s2);
+      for (int r = 0; r < HT_ROWS; ++r) {
+        s1[r] = s2[r] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float dy = fmaf(gr[r][0], w0[k], fmaf(gr[r][1], w1[k], gr[r][2] * w2[k]));
+          A[0][k] = fmaf(gr[r][0], yh[r][k], A[0][k]);
+          A[1][k] = fmaf(gr[r][1], yh[r][k], A[1][k]);
+          A[2][k] = fmaf(gr[r][2], yh[r][k], A[2][k]);
+          dyh[r][k] = dy * g[k];
+          s1[r] += dyh[r][k], s2[r] = fmaf(dyh[r][k], yh[r][k], s2[r]);
+        }
+      }
     }
-    const float mean1 = wsum(s1) * (1.f / HID), mean2 = wsum(s2) * (1.f / HID);
-    uint32_t o[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      o[k] = pack_bf16(rstd * (dyh[2 * k] - mean1 - yh[2 * k] * mean2), rstd * (dyh[2 * k + 1] - mean1 - yh[2 * k + 1] * mean2));
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.dh) + off) = make_uint4(o[0], o[1], o[2], o[3]);
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < HT_ROWS; ++r) {
+        s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
+        s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+      }
+#pragma unroll
+    for (int r = 0; r < HT_ROWS; ++r) {
+      const float mean1 = s1[r] * (1.f / HID), mean2 = s2[r] * (1.f / HID);
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        o[k] = pack_bf16(rstd[r] * (dyh[r][2 * k] - mean1 - yh[r][2 * k] * mean2),
+                         rstd[r] * (dyh[r][2 * k + 1] - mean1 - yh[r][2 * k + 1] * mean2));
+      if (ok[r]) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.dh) + off[r]) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
-  // ---- combine the 8 warps of the block, then one atomic per slot ----
-  for (int i = threadIdx.x; i < HG_FLOATS; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  for (int w = 0; w < 8; ++w) {
-    if (warp == w) {
+  // ---- the parameter gradients from the sums: with y = yh g + b and dy = sum_j d_j w_j,
+  //        d(gain)[k] = sum_j w_j[k] A_j[k]     d(bias)[k] = sum_j w_j[k] S_j     d(w_j)[k] = g[k] A_j[k] + b[k] S_j
+  //      (S_j = sum_rows d_j = sc[0..2]); the 8 warps of the block take turns on the block's partial in shared memory ----
+  {
+    float g[8], b[8], w0[8], w1[8], w2[8];
+    load8(0, g), load8(1, b), load8(2, w0), load8(3, w1), load8(4, w2);
+    for (int w = 0; w < 8; ++w) {
+      if (warp == w) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        red[HG_LNG + 8 * lane + k] += ag[k];
-        red[HG_LNB + 8 * lane + k] += ab[k];
-        red[HG_WH + 8 * lane + k] += aw0[k];
-        red[HG_WH + HID + 8 * lane + k] += aw1[k];
-        red[HG_WH + 2 * HID + 8 * lane + k] += aw2[k];
+        for (int k = 0; k < 8; ++k) {
+          red[HG_LNG + 8 * lane + k] += fmaf(w0[k], A[0][k], fmaf(w1[k], A[1][k], w2[k] * A[2][k]));
+          red[HG_LNB + 8 * lane + k] += fmaf(w0[k], sc[0], fmaf(w1[k], sc[1], w2[k] * sc[2]));
+          red[HG_WH + 8 * lane + k] += fmaf(g[k], A[0][k], b[k] * sc[0]);
+          red[HG_WH + HID + 8 * lane + k] += fmaf(g[k], A[1][k], b[k] * sc[1]);
+          red[HG_WH + 2 * HID + 8 * lane + k] += fmaf(g[k], A[2][k], b[k] * sc[2]);
+        }
+        if (lane == 0) {
+          red[HG_BH] += sc[0], red[HG_BH + 1] += sc[1], red[HG_BH + 2] += sc[2];
+          red[HG_LS] += sc[3], red[HG_LS + 1] += sc[4];
+          red[HG_STATS] += sc[5], red[HG_STATS + 1] += sc[6], red[HG_STATS + 2] += sc[7], red[HG_STATS + 3] += sc[8];
+        }
       }
-      if (lane == 0) {
-        red[HG_BH] += sc[0], red[HG_BH + 1] += sc[1], red[HG_BH + 2] += sc[2];
-        red[HG_LS] += sc[3], red[HG_LS + 1] += sc[4];
-        red[HG_STATS] += sc[5], red[HG_STATS + 1] += sc[6], red[HG_STATS + 2] += sc[7], red[HG_STATS + 3] += sc[8];
-      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   for (int i = threadIdx.x; i < HG_FLOATS; i += blockDim.x) a.grads[(size_t)blockIdx.x * HG_FLOATS + i] = red[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Backward of the cell (pointwise) on the tile layouts: block = (tile, group of 8 hidden units), thread = sequence row.
+// Backward of the cell (pointwise) on the tile layouts.
 //   dh = dh_out + dh_rec ;  dc = dc_next + dh o (1 - tanh^2 c) ;  dG = (dc g i(1-i), dc c_in f(1-f), dc i (1-g^2), dh tanh(c) o(1-o))
 //   dc_prev = dc f nd          (c_in = nd c_prev; dh_rec arrives already masked from vine_lstm_bwd_gemm)
-__global__ void __launch_bounds__(TILE) vine_lstm_cell_bwd_tiles_kernel(const VineLstmCellBwd a) {
-  const int tile = blockIdx.x, ug = blockIdx.y, row = threadIdx.x;
+// Thread mapping: block = (tile, piece of 16 hidden units), 512 threads; the four threads of a sequence row are neighbouring
+// lanes (4 hidden units each) and a warp covers 8 consecutive rows, so a warp's loads fall into 8 (row-major f32 cell
+// arrays) or 2 (row-blocked bf16 tiles) 128-byte lines instead of 32.
+constexpr int CB_THREADS = 4 * TILE;
+
+__global__ void __launch_bounds__(CB_THREADS) vine_lstm_cell_bwd_tiles_kernel(const VineLstmCellBwd a) {
+  const int tile = blockIdx.x, piece = blockIdx.y, row = threadIdx.x >> 2, q = threadIdx.x & 3;
   const int64_t s = (int64_t)tile * TILE + row;
   if (s >= a.n) return;
-  const int piece = ug >> 1, sub = ug & 1, unit0 = 8 * ug;
+  const int col = 4 * q, unit0 = 16 * piece + col;
   const uint8_t* at = reinterpret_cast<const uint8_t*>(a.act) + ((size_t)tile * NPIECE + piece) * ACT_BYTES;
   uint8_t* dg = reinterpret_cast<uint8_t*>(a.dg) + ((size_t)tile * NPIECE + piece) * ACT_BYTES;
-  float gi[8], gf[8], gg[8], go[8];
-  auto ld8 = [&](const uint8_t* p, float (&o)[8]) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 f = unpack_bf16(w[k]);
-      o[2 * k] = f.x, o[2 * k + 1] = f.y;
-    }
+  auto ld4 = [&](const uint8_t* p, float (&o)[4]) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 f0 = unpack_bf16(v.x), f1 = unpack_bf16(v.y);
+    o[0] = f0.x, o[1] = f0.y, o[2] = f1.x, o[3] = f1.y;
   };
-  ld8(at + tile_offset(row, 8 * sub, PIECE_ROWS), gi);
-  ld8(at + tile_offset(row, 16 + 8 * sub, PIECE_ROWS), gf);
-  ld8(at + tile_offset(row, 32 + 8 * sub, PIECE_ROWS), gg);
-  ld8(at + tile_offset(row, 48 + 8 * sub, PIECE_ROWS), go);
+  auto ldf4 = [&](const float* p, float (&o)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+  };
+  float gi[4], gf[4], gg[4], go[4], dh[4], cp[4], cc[4], dc[4] = {0.f, 0.f, 0.f, 0.f};
+  ld4(at + tile_offset(row, col, PIECE_ROWS), gi);
+  ld4(at + tile_offset(row, 16 + col, PIECE_ROWS), gf);
+  ld4(at + tile_offset(row, 32 + col, PIECE_ROWS), gg);
+  ld4(at + tile_offset(row, 48 + col, PIECE_ROWS), go);
   const size_t hoff = ((size_t)tile * 2 + unit0 / UK) * TILE_BYTES + tile_offset(row, unit0 % UK, UK);
-  float dh[8], dr[8];
-  ld8(reinterpret_cast<const uint8_t*>(a.dh) + hoff, dh);
+  ld4(reinterpret_cast<const uint8_t*>(a.dh) + hoff, dh);
   if (a.dh_rec) {
-    ld8(reinterpret_cast<const uint8_t*>(a.dh_rec) + hoff, dr);
+    float dr[4];
+    ld4(reinterpret_cast<const uint8_t*>(a.dh_rec) + hoff, dr);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dh[k] += dr[k];
+    for (int k = 0; k < 4; ++k) dh[k] += dr[k];
   }
-  const float m = a.not_done ? a.not_done[s] : 1.f;
-  float cp[8], cc[8], dc[8];
-  auto ldf8 = [&](const float* p, float (&o)[8]) {
-    const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
-    o[0] = v0.x, o[1] = v0.y, o[2] = v0.z, o[3] = v0.w, o[4] = v1.x, o[5] = v1.y, o[6] = v1.z, o[7] = v1.w;
-  };
-  ldf8(a.c_prev + s * HID + unit0, cp);
-  ldf8(a.c + s * HID + unit0, cc);
-  if (a.dc_next) ldf8(a.dc_next + s * HID + unit0, dc);
-  else {
+  const float m = a.not_done ? __ldg(a.not_done + s) : 1.f;
+  ldf4(a.c_prev + s * HID + unit0, cp);
+  ldf4(a.c + s * HID + unit0, cc);
+  if (a.dc_next) ldf4(a.dc_next + s * HID + unit0, dc);
+  float di[4], df[4], dgg[4], dob[4], dcp[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dc[k] = 0.f;
-  }
-  float di[8], df[8], dgg[8], dob[8], dcp[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < 4; ++k) {
     const float t = tanh_(cc[k]);
     const float d = fmaf(dh[k] * go[k], 1.f - t * t, dc[k]);
     di[k] = d * gg[k] * gi[k] * (1.f - gi[k]);
@@ -528,16 +607,12 @@ __global__ void __launch_bounds__(TILE) vine_lstm_cell_bwd_tiles_kernel(const Vi
     dob[k] = dh[k] * t * go[k] * (1.f - go[k]);
     dcp[k] = d * gf[k] * m;
   }
-  auto st8 = [&](uint8_t* p, const float (&v)[8]) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-  };
-  st8(dg + tile_offset(row, 8 * sub, PIECE_ROWS), di);
-  st8(dg + tile_offset(row, 16 + 8 * sub, PIECE_ROWS), df);
-  st8(dg + tile_offset(row, 32 + 8 * sub, PIECE_ROWS), dgg);
-  st8(dg + tile_offset(row, 48 + 8 * sub, PIECE_ROWS), dob);
-  float* o = a.dc_prev + s * HID + unit0;
-  *reinterpret_cast<float4*>(o) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
-  *reinterpret_cast<float4*>(o + 4) = make_float4(dcp[4], dcp[5], dcp[6], dcp[7]);
+  auto st4 = [&](uint8_t* p, const float (&v)[4]) { *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3])); };
+  st4(dg + tile_offset(row, col, PIECE_ROWS), di);
+  st4(dg + tile_offset(row, 16 + col, PIECE_ROWS), df);
+  st4(dg + tile_offset(row, 32 + col, PIECE_ROWS), dgg);
+  st4(dg + tile_offset(row, 48 + col, PIECE_ROWS), dob);
+  *reinterpret_cast<float4*>(a.dc_prev + s * HID + unit0) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -781,15 +856,19 @@ __global__ void __launch_bounds__(256) vine_lstm_reduce_kernel(const float* __re
       p = sg.whh + tr * HID + (part - 1) * UK + f;
     }
     if (p >= 0) {
-      float acc0 = 0.f, acc1 = 0.f;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // fixed order: split k goes to accumulator k % 4
       int k = 0;
-      for (; k + 1 < splits; k += 2) {
-        acc0 += ws[(size_t)k * SLOTS + w];
-        acc1 += ws[(size_t)(k + 1) * SLOTS + w];
+      for (; k + 3 < splits; k += 4) {   // four independent loads in flight per thread
+        const float v0 = __ldg(ws + (size_t)k * SLOTS + w), v1 = __ldg(ws + (size_t)(k + 1) * SLOTS + w),
+                    v2 = __ldg(ws + (size_t)(k + 2) * SLOTS + w), v3 = __ldg(ws + (size_t)(k + 3) * SLOTS + w);
+        acc0 += v0, acc1 += v1, acc2 += v2, acc3 += v3;
       }
-      if (k < splits) acc0 += ws[(size_t)k * SLOTS + w];
-      flat[p] = acc0 + acc1;
-      if (p2 >= 0) flat[p2] = acc0 + acc1;
+      if (k < splits) acc0 += __ldg(ws + (size_t)k * SLOTS + w);
+      if (k + 1 < splits) acc1 += __ldg(ws + (size_t)(k + 1) * SLOTS + w);
+      if (k + 2 < splits) acc2 += __ldg(ws + (size_t)(k + 2) * SLOTS + w);
+      const float total = (acc0 + acc1) + (acc2 + acc3);
+      flat[p] = total;
+      if (p2 >= 0) flat[p2] = total;
     }
   } else {
     const int q = w - SLOTS;   // LayerNorm, heads, logstd, statistics
@@ -873,19 +952,24 @@ __global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scal
 // tiles of every sequence (saved at the chunk starts of the rollout).
 __global__ void __launch_bounds__(256) vine_lstm_gather_kernel(const VineLstmGather a) {
   const int64_t S = (int64_t)a.chunks * a.env_count;
-  const int64_t rows = (int64_t)a.seq_len * S;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int W = a.num_obs + 8 + 1;
-  if (i < rows * W) {                       // one element of (obs | scalars | not_done) per thread
-    const int64_t r = i / W;
-    const int c = (int)(i % W);
-    const int t = (int)(r / S);
-    const int64_t sq = r % S;
-    const int ck = (int)(sq / a.env_count), e = a.env_begin + (int)(sq % a.env_count);
+  // one piece of (obs | scalars | not_done) per thread: obs in float2 pieces when the width is even (8-byte aligned rows),
+  // scalars as two float4, not_done as one float; the host checked that rows * pieces fits 32 bits
+  const bool even = (a.num_obs & 1) == 0;
+  const unsigned OP = even ? a.num_obs / 2 : a.num_obs, W = OP + 3;
+  const unsigned rows = (unsigned)(a.seq_len * S);
+  if (i < (int64_t)rows * W) {
+    const unsigned iu = (unsigned)i, r = iu / W, c = iu - r * W, Su = (unsigned)S, t = r / Su, sq = r - t * Su;
+    const unsigned ck = sq / (unsigned)a.env_count, e = (unsigned)a.env_begin + (sq - ck * (unsigned)a.env_count);
     const int64_t src = ((int64_t)ck * a.seq_len + t) * a.num_envs + e;
-    if (c < a.num_obs) a.mb_obs[r * a.num_obs + c] = a.obs[src * a.num_obs + c];
-    else if (c < a.num_obs + 8) a.mb_scalars[r * 8 + (c - a.num_obs)] = a.scalars[src * 8 + (c - a.num_obs)];
-    else a.mb_not_done[r] = a.not_done[src];
+    if (c < OP) {
+      if (even) reinterpret_cast<float2*>(a.mb_obs + (int64_t)r * a.num_obs)[c] = __ldg(reinterpret_cast<const float2*>(a.obs + src * a.num_obs) + c);
+      else a.mb_obs[(int64_t)r * a.num_obs + c] = __ldg(a.obs + src * a.num_obs + c);
+    } else if (c < OP + 2) {
+      reinterpret_cast<float4*>(a.mb_scalars + (int64_t)r * 8)[c - OP] = __ldg(reinterpret_cast<const float4*>(a.scalars + src * 8) + (c - OP));
+    } else {
+      a.mb_not_done[r] = __ldg(a.not_done + src);
+    }
   }
   // initial state: thread -> one 16-byte chunk (8 hidden units) of one sequence
   const int64_t nchunks = S * (HID / 8);
@@ -957,8 +1041,8 @@ int vine_lstm_mask(const void* hh, const float* not_done, int64_t n, void* hm, v
 
 int vine_lstm_cell_bwd_tiles(const VineLstmCellBwd* a, void* stream) {
   if (!a || !a->act || !a->c_prev || !a->c || !a->dh || !a->dg || !a->dc_prev || a->n <= 0) return VINE_ERR_INVALID_ARG;
-  const dim3 grid((unsigned)((a->n + TILE - 1) / TILE), HID / 8);
-  vine_lstm_cell_bwd_tiles_kernel<<<grid, TILE, 0, (cudaStream_t)stream>>>(*a);
+  const dim3 grid((unsigned)((a->n + TILE - 1) / TILE), NPIECE);
+  vine_lstm_cell_bwd_tiles_kernel<<<grid, CB_THREADS, 0, (cudaStream_t)stream>>>(*a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -999,7 +1083,9 @@ int vine_lstm_gather(const VineLstmGather* a, void* stream) {
       a->env_begin + a->env_count > a->num_envs || a->num_envs % TILE || a->env_count % TILE || a->env_begin % TILE || a->num_obs < 1)
     return VINE_ERR_INVALID_ARG;
   const int64_t S = (int64_t)a->chunks * a->env_count, rows = (int64_t)a->seq_len * S;
-  int64_t work = rows * (a->num_obs + 9);
+  const int64_t pieces = ((a->num_obs & 1) ? a->num_obs : a->num_obs / 2) + 3;
+  if (rows * pieces >= (int64_t)1 << 31) return VINE_ERR_INVALID_ARG;
+  int64_t work = rows * pieces;
   if (S * (HID / 8) > work) work = S * (HID / 8);
   vine_lstm_gather_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
