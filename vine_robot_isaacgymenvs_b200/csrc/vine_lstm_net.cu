@@ -83,8 +83,14 @@ __global__ void vine_lstm_pack_kernel(const float* __restrict__ w_ih, const floa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoid_(float x) { return fast_rcp(1.f + fast_exp(-x)); }
-__device__ __forceinline__ float tanh_(float x) { return 1.f - 2.f * fast_rcp(1.f + fast_exp(2.f * x)); }   // +-1 at +-inf
+// One MUFU each (tanh.approx.f32, max relative error 2^-11: below the bf16 rounding of every stored gate / hidden value;
+// exp + reciprocal cost two per function, and the cell epilogue evaluates five per hidden unit).
+__device__ __forceinline__ float tanh_(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_(float x) { return fmaf(tanh_(0.5f * x), 0.5f, 0.5f); }
 
 // CTA = (tile of 128 sequences, half of the hidden units).  A = [U | HM] (96 KB) stays resident; the CTA's 8 weight pieces
 // (16 hidden units x 4 gates each, 48 KB: W_ih piece + the two W_hh half pieces) stream through a 2-stage ring of bulk copies;
@@ -101,7 +107,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) vine_lstm_step_kernel(const V
   const int tile = blockIdx.x;
   const int PIECES_PER_CTA = NPIECE / (int)gridDim.y;                // gridDim.y = 2 (8 pieces) or 4 (4 pieces: small batches)
   const uint32_t bar0 = smem_u32(smem + SO_BAR);
-  const uint32_t bar_a = bar0;                                       // A + bias landed
+  const uint32_t bar_a = bar0, bar_hm = bar0 + 72u;                  // U + bias landed | HM landed
   auto full = [&](int st) { return bar0 + 8u + 8u * st; };           // ring stage filled
   auto done = [&](int st) { return bar0 + 24u + 8u * st; };          // ring stage consumed by the tensor core
   auto acc_full = [&](int b) { return bar0 + 40u + 8u * b; };        // accumulator buffer complete
@@ -111,6 +117,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) vine_lstm_step_kernel(const V
   const int piece0 = (int)blockIdx.y * PIECES_PER_CTA, hf = piece0 / (NPIECE / 2);
   if (tid == 0) {
     mbar_init(bar_a, 1);
+    mbar_init(bar_hm, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(full(i), 1); mbar_init(done(i), 1); mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -132,11 +139,13 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) vine_lstm_step_kernel(const V
         bulk_g2s(dst + PIECE_BYTES, P + LP_WHH + (size_t)(piece0 + p) * PIECE_BYTES, PIECE_BYTES, full(st));
         bulk_g2s(dst + 2 * PIECE_BYTES, P + LP_WHH + (size_t)(NPIECE + piece0 + p) * PIECE_BYTES, PIECE_BYTES, full(st));
       };
-      mbar_expect_tx(bar_a, 3 * TILE_BYTES + PIECES_PER_CTA * 256);
+      // K-chunked operand barriers: the first MMAs (U columns) start after U + the first weight piece, not after all 192 KB
+      mbar_expect_tx(bar_a, TILE_BYTES + PIECES_PER_CTA * 256);
       bulk_g2s(smem_u32(smem + SO_U), reinterpret_cast<const uint8_t*>(a.u) + (size_t)tile * TILE_BYTES, TILE_BYTES, bar_a);
-      bulk_g2s(smem_u32(smem + SO_HM), reinterpret_cast<const uint8_t*>(a.hm) + (size_t)tile * 2 * TILE_BYTES, 2 * TILE_BYTES, bar_a);
       bulk_g2s(smem_u32(smem + SO_BIAS), P + LP_BIAS + (size_t)piece0 * PIECE_ROWS * 4, PIECES_PER_CTA * 256, bar_a);
       load_b(0, 0);
+      mbar_expect_tx(bar_hm, 2 * TILE_BYTES);
+      bulk_g2s(smem_u32(smem + SO_HM), reinterpret_cast<const uint8_t*>(a.hm) + (size_t)tile * 2 * TILE_BYTES, 2 * TILE_BYTES, bar_hm);
       load_b(1, 1);
       mbar_wait(bar_a, 0);
       const uint32_t idesc = instr_desc(PIECE_ROWS, false, false);
@@ -150,6 +159,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) vine_lstm_step_kernel(const V
         fence_after_sync();
         const uint32_t base = smem_u32(smem + SO_RING + st * RING_STAGE), acc = tmem + 64u * st;
         mma_sequence(acc, aU, k_major(base, UK), idesc, 96 / 16, false);
+        if (p == 0) {
+          mbar_wait(bar_hm, 0);
+          fence_after_sync();
+        }
         mma_sequence(acc, aH0, k_major(base + PIECE_BYTES, UK), idesc, UK / 16, true);
         mma_sequence(acc, aH1, k_major(base + 2 * PIECE_BYTES, UK), idesc, UK / 16, true);
         mma_commit(acc_full(st));
