@@ -157,6 +157,15 @@ typedef struct VineEnv VineEnv;
 /* Version of this header the library was built against. */
 int vine_abi_version(void);
 
+/*
+ * Programmatic dependent launch (process-wide, default OFF): when on, the short dependent kernels of the PPO iteration and
+ * the single-launch env step are launched with cudaLaunchAttributeProgrammaticStreamSerialization and begin with
+ * griddepcontrol.wait, so that a kernel's launch latency overlaps the tail of its predecessor in the stream (memory semantics
+ * unchanged: nothing is read or written before the predecessors have completed).  0 = plain stream-ordered launches.
+ * Returns the previous setting.  Launches already captured in a CUDA graph keep the mode they were captured with.
+ */
+int vine_set_programmatic_launch(int enabled);
+
 /* Fill `cfg` with the defaults of cfg/task/Vine5LinkMovingBase.yaml (YT:7-134). */
 int vine_config_defaults(VineConfig* cfg);
 

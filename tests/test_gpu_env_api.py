@@ -397,3 +397,38 @@ def test_route_counts_account_for_every_env():
     free = vine.make(cfg=vcfg.compose(vcfg.FSTR_OVERRIDES + ["num_envs=256", "headless=True"]))
     free.step(torch.zeros(256, 2, device="cuda"))
     assert counts(free) == [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("preset", ["FSTR_OVERRIDES", "SHELF_OVERRIDES"])
+def test_programmatic_dependent_launch_changes_nothing_but_the_launch(preset):
+    """vine_set_programmatic_launch(1): the step kernels are launched with the programmatic-stream-serialization attribute and
+    begin with griddepcontrol.wait; outputs and state over 60 back-to-back steps (resets included) must equal the plain
+    stream-ordered launches bit for bit, eagerly and from a captured graph."""
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import abi, config as vcfg
+    lib = abi.load_library()
+    ov = getattr(vcfg, preset) + ["headless=True", "task.env.maxEpisodeLength=25", "num_envs=4096"]
+    plain, pdl = vine.make(cfg=vcfg.compose(ov)), vine.make(cfg=vcfg.compose(ov))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    acts = [torch.rand(4096, 2, device="cuda", generator=g) * 2 - 1 for _ in range(60)]
+    assert lib.vine_set_programmatic_launch(0) == 0          # the library default
+    for a in acts[:30]:
+        plain.step(a)
+    assert lib.vine_set_programmatic_launch(1) == 0
+    try:
+        for a in acts[:30]:
+            pdl.step(a)
+        graph = pdl.capture_graph() if hasattr(pdl, "capture_graph") else None
+    finally:
+        assert lib.vine_set_programmatic_launch(0) == 1
+    for a in acts[30:]:
+        plain.step(a)
+        if graph is not None:
+            pdl.actions.copy_(a)
+            graph.replay()
+        else:
+            pdl.step(a)
+    torch.cuda.synchronize()
+    for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf"):
+        assert torch.equal(getattr(plain, name), getattr(pdl, name)), name
+    assert torch.equal(plain.dof_pos, pdl.dof_pos) and torch.equal(plain.dof_vel, pdl.dof_vel)

@@ -1,5 +1,5 @@
 """Time one PPO iteration of the reference network (MLP -> LSTM 256 -> LayerNorm) at FSTR, N envs, CUDA-graph replay:
-python tools/ppo_time.py [N] [--mlp]
+python tools/ppo_time.py [N] [--mlp] [--no-pdl]
 Prints ms per iteration / rollout / update (CUDA events, best of 3 x 20)."""
 import sys
 
@@ -13,6 +13,8 @@ from vine_robot_isaacgymenvs_b200.ppo.ppo import PPOAgent  # noqa: E402
 args = [a for a in sys.argv[1:]]
 n = int(args[0]) if args and args[0].isdigit() else 4096
 extra = ["train.params.network.rnn=null"] if "--mlp" in args else []
+if "--no-pdl" in args:
+    PPOAgent.PDL_MAX_ENVS = 0
 cfg = vcfg.compose(vcfg.FSTR_OVERRIDES + [f"num_envs={n}", "headless=True"] + extra)
 env = vine.make(cfg=cfg)
 agent = PPOAgent(env, cfg["train"], device="cuda:0", seed=42, use_graphs=True, use_fused_update=True)

@@ -142,7 +142,7 @@ EXPORTED_SYMBOLS = [
     "vine_p2p_channel_timing", "vine_p2p_allreduce_f64", "vine_p2p_channel_destroy",
     "vine_policy_act", "vine_rollout_post", "vine_ppo_moments", "vine_ppo_finalize",
     "vine_lstm_cell_fwd", "vine_lstm_cell_bwd", "vine_lstm_pack", "vine_lstm_step", "vine_lstm_mask", "vine_lstm_head", "vine_lstm_head_train", "vine_lstm_cell_bwd_tiles", "vine_lstm_bwd_gemm",
-    "vine_lstm_gather", "vine_abi_struct_size", "vine_lstm_num_params", "vine_lstm_wgrad", "vine_lstm_reduce", "vine_lstm_adam",
+    "vine_set_programmatic_launch", "vine_lstm_gather", "vine_abi_struct_size", "vine_lstm_num_params", "vine_lstm_wgrad", "vine_lstm_reduce", "vine_lstm_adam",
 ]
 METRIC_SUMS, METRIC_MAXES = 45, 30
 METRIC_SCALARS = ["dist_tip_to_target", "target_reached", "limit_hit", "tip_limit_hit", "abs_tip_y", "tip_z", "tip_velocities",
@@ -283,6 +283,7 @@ def _declare(lib):
     lib.vine_lstm_bwd_gemm.argtypes = [C.POINTER(VineLstmBwdGemm), vp]
     lib.vine_lstm_gather.argtypes = [C.POINTER(VineLstmGather), vp]
     lib.vine_abi_struct_size.argtypes = [C.c_int]
+    lib.vine_set_programmatic_launch.argtypes = [C.c_int]
     lib.vine_lstm_num_params.argtypes = [C.c_int]
     lib.vine_lstm_wgrad.argtypes = [C.POINTER(VineLstmWgrad), vp]
     lib.vine_lstm_reduce.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp]

@@ -9,7 +9,7 @@ import subprocess
 _DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_DIR, "csrc")
 SOURCES = ["vine_b200.cu", "vine_mlp.cu", "vine_ppo.cu", "vine_rollout.cu", "vine_lstm.cu", "vine_lstm_net.cu"]
-HEADERS = ["vine_device.cuh", "vine_params.h", "vine_umma.cuh", "vine_mlp_common.cuh", "vine_p2p.cuh", os.path.join("..", "..", "include", "vine_b200.h")]
+HEADERS = ["vine_device.cuh", "vine_params.h", "vine_umma.cuh", "vine_mlp_common.cuh", "vine_p2p.cuh", "vine_launch.cuh", os.path.join("..", "..", "include", "vine_b200.h")]
 OUT = os.path.join(CSRC, "libvine_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

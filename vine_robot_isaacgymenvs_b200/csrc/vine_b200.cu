@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "vine_device.cuh"
+#include "vine_launch.cuh"
 
 #define VINE_BLOCK 128
 #ifndef VINE_STEP_MIN_BLOCKS
@@ -319,6 +320,7 @@ __device__ __forceinline__ int64_t slot_env(const StepArgs& a, int64_t slot) {
 template <bool CONTACT>
 __global__ void __launch_bounds__(CONTACT ? VINE_BLOCK_CONTACT : VINE_BLOCK, CONTACT ? VINE_STEP_MIN_BLOCKS_CONTACT : VINE_STEP_MIN_BLOCKS)
 vine_step_kernel(const __grid_constant__ VineParams p, const StepArgs a) {
+  vine_launch::grid_dependency_sync();
   constexpr int BLOCK = CONTACT ? VINE_BLOCK_CONTACT : VINE_BLOCK;
   __shared__ float s_obs[BLOCK * (VINE_MAX_OBS + 1)];
   __shared__ ContactScratch s_contact[CONTACT ? BLOCK / 32 : 1];
@@ -741,6 +743,7 @@ __global__ void vine_gae_kernel(const float* __restrict__ rewards, const float* 
                                 const float* __restrict__ dones, const float* __restrict__ last_values,
                                 const float* __restrict__ last_dones, int64_t T, int64_t N, float gamma, float gt,
                                 float* __restrict__ adv, float* __restrict__ ret) {
+  vine_launch::grid_dependency_sync();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
   float nextv = last_values[e], nonterm = __fsub_rn(1.0f, last_dones[e]), lastgaelam = 0.f;
@@ -766,6 +769,12 @@ static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + b
 extern "C" {
 
 int vine_abi_version(void) { return VINE_ABI_VERSION; }
+
+int vine_set_programmatic_launch(int enabled) {
+  const int before = vine_launch::programmatic_launch_enabled();
+  vine_launch::programmatic_launch_enabled() = enabled ? 1 : 0;
+  return before;
+}
 
 int vine_config_defaults(VineConfig* c) {  // YT:7-134
   if (!c) return VINE_ERR_INVALID_ARG;
@@ -1018,7 +1027,7 @@ static void launch_free_step(const VineEnv* env, const StepArgs& a, cudaStream_t
   if (env->cfg.step_kernel_variant == VINE_STEP_KERNEL_TWO_ENVS_PACKED)
     vine_step2_kernel<<<grid_for(count, 2 * VINE_BLOCK2), VINE_BLOCK2, 0, st>>>(env->p, a);
   else
-    vine_step_kernel<false><<<grid_for(count, VINE_BLOCK), VINE_BLOCK, 0, st>>>(env->p, a);
+    vine_launch::launch(vine_step_kernel<false>, grid_for(count, VINE_BLOCK), VINE_BLOCK, 0, st, env->p, a);
 }
 
 // Routed step of the obstacle variants (contact_binning != 0), per control step:
@@ -1072,7 +1081,7 @@ int vine_step(VineEnv* env, void* stream) {
       vine_step_kernel<true><<<listed_grid(a.n, 148 * 6), VINE_BLOCK_CONTACT, 0, st>>>(env->p, rd);
     } else {
       a.perm = nullptr;
-      vine_step_kernel<true><<<grid_for(a.n, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, st>>>(env->p, a);
+      vine_launch::launch(vine_step_kernel<true>, grid_for(a.n, VINE_BLOCK_CONTACT), VINE_BLOCK_CONTACT, 0, st, env->p, a);
     }
   } else {
     launch_free_step(env, env->a, st);

@@ -24,6 +24,7 @@
 #include "vine_device.cuh"
 #include "vine_p2p.cuh"
 #include "vine_mlp_common.cuh"
+#include "vine_launch.cuh"
 
 namespace {
 using namespace vine_mlp;
@@ -102,6 +103,7 @@ constexpr int STEP_SMEM = SO_BAR + 128;
 constexpr int STEP_THREADS = THREADS + 32;
 
 __global__ void __launch_bounds__(STEP_THREADS, 1) vine_lstm_step_kernel(const VineLstmStep a) {
+  vine_launch::grid_dependency_sync();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) vine_lstm_step_kernel(const V
 
 // h tile rows -> masked copy (rollout: the done flag of the env step arrives after the LSTM step has run)
 __global__ void vine_lstm_mask_kernel(const uint8_t* __restrict__ hh, const float* __restrict__ not_done, int64_t n, uint8_t* __restrict__ hm) {
+  vine_launch::grid_dependency_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte chunk (8 hidden units of one row)
   const int64_t chunks = ((n + TILE - 1) / TILE) * 2 * (TILE_BYTES / 16);
   if (i >= chunks) return;
@@ -281,6 +284,7 @@ __device__ __forceinline__ float wsum(float v) {
 }
 
 __global__ void __launch_bounds__(256) vine_lstm_head_kernel(const VineLstmHead a) {
+  vine_launch::grid_dependency_sync();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const uint8_t* P = reinterpret_cast<const uint8_t*>(a.params);
@@ -355,6 +359,7 @@ static_assert(HG_FLOATS == VINE_LSTM_HEAD_GRAD_FLOATS, "header constant out of d
 constexpr int HT_ROWS = 2;
 
 __global__ void __launch_bounds__(256, 2) vine_lstm_head_train_kernel(const VineLstmHeadTrain a) {
+  vine_launch::grid_dependency_sync();
   __shared__ float red[HG_FLOATS];
   __shared__ float4 prm[5][2][32];   // g, b, w0, w1, w2: [array][half of the lane's 8 units][lane]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -577,6 +582,7 @@ __global__ void __launch_bounds__(256, 2) vine_lstm_head_train_kernel(const Vine
 constexpr int CB_THREADS = 4 * TILE;
 
 __global__ void __launch_bounds__(CB_THREADS) vine_lstm_cell_bwd_tiles_kernel(const VineLstmCellBwd a) {
+  vine_launch::grid_dependency_sync();
   const int tile = blockIdx.x, piece = blockIdx.y, row = threadIdx.x >> 2, q = threadIdx.x & 3;
   const int64_t s = (int64_t)tile * TILE + row;
   if (s >= a.n) return;
@@ -639,6 +645,7 @@ constexpr int BG_SMEM = BG_BAR + 128;
 constexpr uint32_t BG_TM_DU = 0, BG_TM_DH = 64;
 
 __global__ void __launch_bounds__(THREADS, 1) vine_lstm_bwd_gemm_kernel(const VineLstmBwdGemm a) {
+  vine_launch::grid_dependency_sync();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
   const int tile = blockIdx.x, part = blockIdx.y;          // part 0: d U(:, 0:64) and d HM half 0;  part 1: d HM half 1
@@ -743,6 +750,7 @@ constexpr int WG_SMEM = WG_BAR + 128;
 constexpr int WG_BLOCKS = 12, WG_BLOCK_FLOATS = TILE * 256;
 
 __global__ void __launch_bounds__(THREADS, 1) vine_lstm_wgrad_kernel(const VineLstmWgrad a) {
+  vine_launch::grid_dependency_sync();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
   const int blk = blockIdx.x, sp = blockIdx.y, part = blk >> 2, nq = blk & 3;
@@ -836,6 +844,7 @@ __host__ __device__ inline LstmSeg lstm_segments(int O) {
 
 // sum of the head kernel's per-block partials: block = 4 slots, thread = every 128th partial
 __global__ void __launch_bounds__(128) vine_lstm_head_sum_kernel(const float* __restrict__ hg, int parts, float* __restrict__ out) {
+  vine_launch::grid_dependency_sync();
   __shared__ float red[4][4];
   const int slot0 = blockIdx.x * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -853,6 +862,7 @@ __global__ void __launch_bounds__(128) vine_lstm_head_sum_kernel(const float* __
 // scattered write to the slot's parameter; the parameters fed by the head kernel come from the summed head buffer.
 __global__ void __launch_bounds__(256) vine_lstm_reduce_kernel(const float* __restrict__ ws, int splits, const float* __restrict__ hsum, int O,
                                                                float* __restrict__ flat, const VineP2PChannel* ch) {
+  vine_launch::grid_dependency_sync();
   if (ch) flat = p2p_local_buffer(ch);   // multi-GPU: straight into this rank's peer-visible buffer (vine_p2p.cuh)
   const LstmSeg sg = lstm_segments(O);
   const int PL = sg.end;
@@ -900,6 +910,7 @@ __global__ void __launch_bounds__(256) vine_lstm_reduce_kernel(const float* __re
 __global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scale, float* __restrict__ params, float* __restrict__ m,
                                       float* __restrict__ v, uint8_t* __restrict__ packed, float* __restrict__ state, int O, float beta1,
                                       float beta2, float eps, VineP2PChannel* ch) {
+  vine_launch::grid_dependency_sync();
   const int PL = lstm_num_params(O);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   // multi-GPU: wait for every rank's gradient buffer, then read the sum over the ranks instead of `flat` (vine_p2p.cuh)
@@ -964,6 +975,7 @@ __global__ void vine_lstm_adam_kernel(const float* __restrict__ flat, float scal
 // [T, N] rollout buffers (observations, loss scalars, not_done), the initial cell state and the masked initial hidden-state
 // tiles of every sequence (saved at the chunk starts of the rollout).
 __global__ void __launch_bounds__(256) vine_lstm_gather_kernel(const VineLstmGather a) {
+  vine_launch::grid_dependency_sync();
   const int64_t S = (int64_t)a.chunks * a.env_count;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   // one piece of (obs | scalars | not_done) per thread: obs in float2 pieces when the width is even (8-byte aligned rows),
@@ -1041,21 +1053,21 @@ int vine_lstm_step(const VineLstmStep* a, void* stream) {
   }
   const unsigned tiles = (unsigned)((a->n + TILE - 1) / TILE);
   const dim3 grid(tiles, tiles * 2 <= 74 ? 4 : 2);   // small batches (rollout): 4 CTAs per tile to fill more SMs
-  vine_lstm_step_kernel<<<grid, STEP_THREADS, STEP_SMEM, (cudaStream_t)stream>>>(*a);
+  vine_launch::launch(vine_lstm_step_kernel, grid, STEP_THREADS, STEP_SMEM, (cudaStream_t)stream, *a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
 int vine_lstm_mask(const void* hh, const float* not_done, int64_t n, void* hm, void* stream) {
   if (!hh || !not_done || !hm || n <= 0) return VINE_ERR_INVALID_ARG;
   const int64_t chunks = ((n + TILE - 1) / TILE) * 2 * (TILE_BYTES / 16);
-  vine_lstm_mask_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)hh, not_done, n, (uint8_t*)hm);
+  vine_launch::launch(vine_lstm_mask_kernel, (unsigned)((chunks + 255) / 256), 256, 0, (cudaStream_t)stream, (const uint8_t*)hh, not_done, n, (uint8_t*)hm);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
 int vine_lstm_cell_bwd_tiles(const VineLstmCellBwd* a, void* stream) {
   if (!a || !a->act || !a->c_prev || !a->c || !a->dh || !a->dg || !a->dc_prev || a->n <= 0) return VINE_ERR_INVALID_ARG;
   const dim3 grid((unsigned)((a->n + TILE - 1) / TILE), NPIECE);
-  vine_lstm_cell_bwd_tiles_kernel<<<grid, CB_THREADS, 0, (cudaStream_t)stream>>>(*a);
+  vine_launch::launch(vine_lstm_cell_bwd_tiles_kernel, grid, CB_THREADS, 0, (cudaStream_t)stream, *a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -1069,7 +1081,7 @@ int vine_lstm_bwd_gemm(const VineLstmBwdGemm* a, void* stream) {
       return VINE_ERR_CUDA;
     configured = dev;
   }
-  vine_lstm_bwd_gemm_kernel<<<dim3((unsigned)((a->n + TILE - 1) / TILE), 2), THREADS, BG_SMEM, (cudaStream_t)stream>>>(*a);
+  vine_launch::launch(vine_lstm_bwd_gemm_kernel, dim3((unsigned)((a->n + TILE - 1) / TILE), 2), THREADS, BG_SMEM, (cudaStream_t)stream, *a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -1100,7 +1112,7 @@ int vine_lstm_gather(const VineLstmGather* a, void* stream) {
   if (rows * pieces >= (int64_t)1 << 31) return VINE_ERR_INVALID_ARG;
   int64_t work = rows * pieces;
   if (S * (HID / 8) > work) work = S * (HID / 8);
-  vine_lstm_gather_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
+  vine_launch::launch(vine_lstm_gather_kernel, (unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream, *a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -1117,7 +1129,7 @@ int vine_lstm_wgrad(const VineLstmWgrad* a, void* stream) {
       return VINE_ERR_CUDA;
     configured = dev;
   }
-  vine_lstm_wgrad_kernel<<<dim3(WG_BLOCKS, (unsigned)a->splits), THREADS, WG_SMEM, (cudaStream_t)stream>>>(*a);
+  vine_launch::launch(vine_lstm_wgrad_kernel, dim3(WG_BLOCKS, (unsigned)a->splits), THREADS, WG_SMEM, (cudaStream_t)stream, *a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -1129,11 +1141,11 @@ int vine_lstm_reduce(const float* workspace, int splits, float* head_grads, int 
   const int n = lstm_num_params(num_obs) + 4;
   // the per-block partials of the head kernel are summed in parallel into the extra row [VINE_LSTM_HEAD_GRAD_PARTS]
   float* hsum = head_grads + (size_t)VINE_LSTM_HEAD_GRAD_PARTS * HG_FLOATS;
-  vine_lstm_head_sum_kernel<<<HG_FLOATS / 4, 128, 0, (cudaStream_t)stream>>>(head_grads, head_parts, hsum);
+  vine_launch::launch(vine_lstm_head_sum_kernel, HG_FLOATS / 4, 128, 0, (cudaStream_t)stream, (const float*)head_grads, head_parts, hsum);
   const int threads = WG_BLOCKS * WG_BLOCK_FLOATS + 5 * HID + 9;
   (void)n;
-  vine_lstm_reduce_kernel<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, splits, hsum, num_obs, flat,
-                                                                                   (const VineP2PChannel*)p2p_channel);
+  vine_launch::launch(vine_lstm_reduce_kernel, (threads + 255) / 256, 256, 0, (cudaStream_t)stream, workspace, splits, (const float*)hsum, num_obs, flat,
+                      (const VineP2PChannel*)p2p_channel);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -1141,8 +1153,8 @@ int vine_lstm_adam(const float* flat, float grad_scale, float* params, float* ex
                    int num_obs, float beta1, float beta2, float eps, void* p2p_channel, void* stream) {
   if ((!flat && !p2p_channel) || !params || !exp_avg || !exp_avg_sq || !packed || !state || num_obs < 1 || num_obs >= K1) return VINE_ERR_INVALID_ARG;
   const int n = lstm_num_params(num_obs) + 1;
-  vine_lstm_adam_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(flat, grad_scale, params, exp_avg, exp_avg_sq, (uint8_t*)packed,
-                                                                         state, num_obs, beta1, beta2, eps, (VineP2PChannel*)p2p_channel);
+  vine_launch::launch(vine_lstm_adam_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, flat, grad_scale, params, exp_avg, exp_avg_sq, (uint8_t*)packed,
+                      state, num_obs, beta1, beta2, eps, (VineP2PChannel*)p2p_channel);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -1151,7 +1163,7 @@ int vine_lstm_head_train(const VineLstmHeadTrain* a, void* stream) {
     return VINE_ERR_INVALID_ARG;
   int64_t blocks = (a->n + 7) / 8;
   if (blocks > 296) blocks = 296;   // 2 resident blocks per SM (128 registers per thread), one wave; <= VINE_LSTM_HEAD_GRAD_PARTS
-  vine_lstm_head_train_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+  vine_launch::launch(vine_lstm_head_train_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, *a);
   return cudaGetLastError() == cudaSuccess ? (int)blocks : VINE_ERR_CUDA;   // number of gradient partials written
 }
 
@@ -1160,7 +1172,7 @@ int vine_lstm_head(const VineLstmHead* a, void* stream) {
   if (a->actions && !a->logstd) return VINE_ERR_INVALID_ARG;
   int64_t blocks = (a->n + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  vine_lstm_head_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+  vine_launch::launch(vine_lstm_head_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, *a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 

@@ -24,6 +24,7 @@
 
 #include "vine_mlp_common.cuh"
 #include "vine_p2p.cuh"
+#include "vine_launch.cuh"
 
 namespace {
 using namespace vine_mlp;
@@ -68,6 +69,7 @@ struct MbArgs {
 // accumulator; with Q = 4 the SM has 4 warps per sub-partition to hide the TMEM/shared-memory latencies of the epilogues.
 template <int Q>
 __global__ void __launch_bounds__(128 * Q, 1) vine_ppo_minibatch_kernel(const MbArgs a) {
+  vine_launch::grid_dependency_sync();
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int C128 = 128 / Q, C64 = 64 / Q;
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, part = tid >> 7;
@@ -423,6 +425,7 @@ constexpr int RED_SLOTS = 64, RED_SPLIT = 4;
 __global__ void __launch_bounds__(RED_SLOTS* RED_SPLIT) vine_ppo_reduce_kernel(const float* __restrict__ ws, int n_partials, int O,
                                                                                float* __restrict__ flat, const float* __restrict__ logstd,
                                                                                float* __restrict__ logstd_old_out, const VineP2PChannel* ch) {
+  vine_launch::grid_dependency_sync();
   if (ch) { flat = p2p_local_buffer(ch); p2p_producer_begin(const_cast<VineP2PChannel*>(ch)); }   // multi-GPU: the sum goes straight into this rank's peer-visible buffer (vine_p2p.cuh)
   // sigma half of dataset.update_mu_sigma: the log-std this minibatch was evaluated with becomes its rows' "old" one. Done
   // here because this launch sits between the last reader (the minibatch kernel) and the writer (Adam) of the parameter.
@@ -452,6 +455,7 @@ __global__ void __launch_bounds__(RED_SLOTS* RED_SPLIT) vine_ppo_reduce_kernel(c
 __global__ void vine_ppo_adam_kernel(const float* __restrict__ flat, float scale, float* __restrict__ params, float* __restrict__ m,
                                      float* __restrict__ v, uint8_t* __restrict__ packed, float* __restrict__ state, int O,
                                      float beta1, float beta2, float eps, int bookkeeping, VineP2PChannel* ch) {
+  vine_launch::grid_dependency_sync();
   const int P = num_params(O);
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   // multi-GPU: wait for every rank's gradient buffer, then read the sum over the ranks instead of `flat` (vine_p2p.cuh)
@@ -539,8 +543,8 @@ int vine_ppo_minibatch(const VinePpoMinibatch* b, void* stream) {
   a.T = b->horizon, a.N = b->num_envs, a.e0 = b->env_begin, a.E = b->env_count, a.O = b->num_obs;
   a.e_clip = b->e_clip, a.critic_coef = b->critic_coef, a.entropy_coef = b->entropy_coef, a.bounds_coef = b->bounds_loss_coef;
   a.inv_B = 1.0f / (float)B, a.kl_threshold = b->kl_threshold, a.lr_min = b->lr_min, a.lr_max = b->lr_max, a.adaptive = b->adaptive_lr;
-  if (q4) vine_ppo_minibatch_kernel<4><<<grid, 512, SMEM_BYTES, (cudaStream_t)stream>>>(a);
-  else vine_ppo_minibatch_kernel<2><<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  if (q4) vine_launch::launch(vine_ppo_minibatch_kernel<4>, grid, 512, SMEM_BYTES, (cudaStream_t)stream, a);
+  else vine_launch::launch(vine_ppo_minibatch_kernel<2>, grid, 256, SMEM_BYTES, (cudaStream_t)stream, a);
   if (cudaGetLastError() != cudaSuccess) return VINE_ERR_CUDA;
   return grid;   // number of gradient partials written (>= 1)
 }
@@ -550,8 +554,8 @@ int vine_ppo_reduce(const float* workspace, int n_partials, int num_obs, float* 
   if (!workspace || (!flat && !p2p_channel) || n_partials < 1 || num_obs < 1 || num_obs >= K1 || (logstd_old_out && !logstd))
     return VINE_ERR_INVALID_ARG;
   const int slots = WS_STATS + 8;
-  vine_ppo_reduce_kernel<<<(slots + RED_SLOTS - 1) / RED_SLOTS, RED_SLOTS * RED_SPLIT, 0, (cudaStream_t)stream>>>(
-      workspace, n_partials, num_obs, flat, logstd, logstd_old_out, (const VineP2PChannel*)p2p_channel);
+  vine_launch::launch(vine_ppo_reduce_kernel, (slots + RED_SLOTS - 1) / RED_SLOTS, RED_SLOTS * RED_SPLIT, 0, (cudaStream_t)stream,
+                      workspace, n_partials, num_obs, flat, logstd, logstd_old_out, (const VineP2PChannel*)p2p_channel);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -560,9 +564,8 @@ int vine_ppo_adam(const float* flat, float grad_scale, float* params, float* exp
   if ((!flat && !p2p_channel) || !params || !exp_avg || !exp_avg_sq || !packed || !state || num_obs < 1 || num_obs >= K1)
     return VINE_ERR_INVALID_ARG;
   const int n = num_params(num_obs) + 1;
-  vine_ppo_adam_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(flat, grad_scale, params, exp_avg, exp_avg_sq,
-                                                                         (uint8_t*)packed, state, num_obs, beta1, beta2, eps,
-                                                                         bookkeeping, (VineP2PChannel*)p2p_channel);
+  vine_launch::launch(vine_ppo_adam_kernel, (n + 127) / 128, 128, 0, (cudaStream_t)stream, flat, grad_scale, params, exp_avg, exp_avg_sq,
+                      (uint8_t*)packed, state, num_obs, beta1, beta2, eps, bookkeeping, (VineP2PChannel*)p2p_channel);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 

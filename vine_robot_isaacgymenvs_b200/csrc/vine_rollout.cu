@@ -15,6 +15,7 @@
 
 #include "vine_device.cuh"
 #include "vine_mlp_common.cuh"
+#include "vine_launch.cuh"
 
 namespace {
 using namespace vine_mlp;
@@ -24,6 +25,7 @@ constexpr int ACT_SMEM_BYTES = OFF_BAR + 64;
 constexpr uint32_t VINE_SITE_POLICY = 16;   // Philox "site" of the policy's action noise (env sites: vine_params.h:20)
 
 __global__ void __launch_bounds__(THREADS, 1) vine_policy_act_kernel(const VinePolicyAct a) {
+  vine_launch::grid_dependency_sync();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
   const uint32_t bar_w = smem_u32(smem + OFF_BAR), bar_mma = bar_w + 8;
@@ -140,6 +142,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 __global__ void __launch_bounds__(256) vine_rollout_post_kernel(const VineRolloutPost a) {
+  vine_launch::grid_dependency_sync();
   __shared__ double red[8][4];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -278,7 +281,7 @@ int vine_policy_act(const VinePolicyAct* a, void* stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t ntiles = (a->n + TILE - 1) / TILE;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  vine_policy_act_kernel<<<grid, THREADS, ACT_SMEM_BYTES, (cudaStream_t)stream>>>(*a);
+  vine_launch::launch(vine_policy_act_kernel, grid, THREADS, ACT_SMEM_BYTES, (cudaStream_t)stream, *a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
@@ -295,7 +298,7 @@ int vine_rollout_post(const VineRolloutPost* a, void* stream) {
   if (!a || !a->rewards || !a->resets || !a->timeouts || !a->values || !a->shaped_rewards || !a->dones_next || !a->ep_return ||
       !a->ep_length || !a->ep_stats || a->n <= 0)
     return VINE_ERR_INVALID_ARG;
-  vine_rollout_post_kernel<<<(unsigned)((a->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
+  vine_launch::launch(vine_rollout_post_kernel, (unsigned)((a->n + 255) / 256), 256, 0, (cudaStream_t)stream, *a);
   return cudaGetLastError() == cudaSuccess ? VINE_OK : VINE_ERR_CUDA;
 }
 
