@@ -311,18 +311,18 @@ __global__ void __launch_bounds__(256) vine_lstm_head_kernel(const VineLstmHead 
       const float2 f = unpack_bf16(hw[k]);
       h[2 * k] = f.x, h[2 * k + 1] = f.y;
     }
-    float sm = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sm += h[k];
+    // same summation order as vine_lstm_head_train_kernel: the first training pass reproduces the rollout's mu bit for bit
+    const float sm = ((h[0] + h[1]) + (h[2] + h[3])) + ((h[4] + h[5]) + (h[6] + h[7]));
     const float mean = wsum(sm) * (1.f / HID);
-    float sq = 0.f;
+    float t[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sq += (h[k] - mean) * (h[k] - mean);
+    for (int k = 0; k < 8; ++k) h[k] -= mean, t[k] = h[k] * h[k];
+    const float sq = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
     const float rstd = rsqrtf(wsum(sq) * (1.f / HID) + 1e-5f);     // torch.nn.LayerNorm: biased variance, eps 1e-5
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float y = fmaf((h[k] - mean) * rstd, g[k], b[k]);
+      const float y = fmaf(h[k] * rstd, g[k], b[k]);
       d0 = fmaf(y, w0[k], d0), d1 = fmaf(y, w1[k], d1), d2 = fmaf(y, w2[k], d2);
     }
     const float mu0 = wsum(d0) + bh[0], mu1 = wsum(d1) + bh[1], v = wsum(d2) + bh[2];
