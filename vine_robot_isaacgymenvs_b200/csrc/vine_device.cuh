@@ -439,16 +439,17 @@ VDEV float contact_forces(const VineParams& p, const Obstacles& ob, ContactScrat
       ch[32 * (CH_S + j)] = d.S[j]; ch[32 * (CH_C + j)] = d.C[j]; ch[32 * (CH_W + j)] = d.v[j + 1];
     }
   }
-  // positions of the lanes' pairs in the warp's work list: inclusive prefix sum of the pair counts
+  // positions of the lanes' pairs in the warp's work list: exclusive prefix sum of the pair counts (< 32 each), bit plane by
+  // bit plane with five independent ballots instead of a five-step shuffle scan (a dependent chain of ~150 cycles)
   const int cnt = __popc(pm);
-  int incl = cnt;
+  const unsigned below = (1u << lane) - 1u;
+  int next = 0, total = 0;        // next: index of this env's next pair that has not been dealt out / added yet
 #pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, off);
-    if (lane >= off) incl += t;
+  for (int k = 0; k < 5; ++k) {
+    const unsigned plane = __ballot_sync(0xffffffffu, (cnt >> k) & 1);
+    next += __popc(plane & below) << k;
+    total += __popc(plane) << k;
   }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  int next = incl - cnt;          // index of this env's next pair that has not been dealt out / added yet
   unsigned todo = pm, toadd = pm;
   int next_add = next;
   float lfy = 0.f, lfz = 0.f;
