@@ -277,3 +277,91 @@ def test_penalty_force_law_on_a_face(oracle_lib):
         _, _, lip = _simulate(O, vc, q, qd, np.zeros((1, 6)), target=target, obj=obj)
         forces.append(lip[0])
     assert forces[0] > k * pen * 0.99 and abs(forces[1] - forces[0]) < 2e-3 * forces[0], forces
+
+
+# ---------------------------------------------------------------------------------------------- the torque law's time semantics
+def _reference_sampled_law(O, q0, qd0, u, span, K, damping=2e-2):
+    """The reference's force semantics to the letter (V5:1053-1098 + VT:346-356): joint torques computed from the current state
+    by oracle_actuation, then held for one sim step -- with the sim step shortened to dt / K (one integrator substep per
+    sample), for `span` reference sim steps.  The rail force is zeroed: only the joint law is under test."""
+    dt = 0.00833 / K
+    vc = _free_cfg(O, zoh=True, damping=damping, dt=dt, substeps=1)
+    f = np.float32
+    q, qd = q0[None].copy(), qd0[None].copy()
+    for _ in range(span * K):
+        io = {"dof_pos": np.ascontiguousarray(q, f), "dof_vel": np.ascontiguousarray(qd, f), "cart_vel_y": np.ascontiguousarray(qd[:, 0], f),
+              "u_rail_velocity": np.ascontiguousarray(qd[:, 0], f), "u_fpam_to_use": np.full(1, u, f), "prev_cart_vel": np.ascontiguousarray(qd[:, 0], f),
+              "prev_cart_vel_error": np.zeros(1, f), "dynamics_scaling": None, "accel_scaling": None,
+              "dof_efforts": np.zeros((1, 6), f), "prev_cart_vel_out": np.zeros(1, f), "prev_cart_vel_error_out": np.zeros(1, f)}
+        O.call_io("oracle_actuation", vc, 1, abi.VineActuationIO, io)
+        eff = io["dof_efforts"].astype(np.float64)
+        eff[:, 0] = 0.0
+        q, qd, _ = _simulate(O, vc, q, qd, eff)
+    return q[0], qd[0]
+
+
+def test_implicit_torque_law_is_the_small_dt_limit_of_the_references_sampled_law(oracle_lib):
+    """The reference evaluates tau_j = -(K_j q_j + C_j qd_j + b_j + B_j u) once per sim step and PhysX holds it for dt = 8.33 ms.
+    On this rigid-body model that sampled law is unstable at the reference's dt (explicit damping on 5-gram links: DESIGN.md
+    section 4; the step_zoh fixture pins only two steps), so the shipped default integrates the law inside the solver
+    (TORQUE_LAW_INTEGRATION: implicit).  This anchors WHAT the implicit mode integrates: shorten the sampling period of the
+    reference's own semantics to dt / K and its trajectory converges, first order in 1 / K, to the implicit integration of the
+    same time span -- the implicit law is the reference's law with the sampling artefact removed, not a different law."""
+    rng = np.random.default_rng(11)
+    span = 2                                                        # two reference sim steps = 16.7 ms
+    for case in range(2):
+        q0 = np.concatenate([rng.uniform(-0.1, 0.1, 1), rng.normal(0, 0.1, 5)]).astype(np.float32).astype(np.float64)
+        qd0 = np.concatenate([rng.normal(0, 0.2, 1), rng.normal(0, 0.5, 5)]).astype(np.float32).astype(np.float64)
+        u = float(rng.uniform(0.2, 2.0))
+        # implicit integration, fine substeps (its own discretisation error is O(h) too: take it far below the samples')
+        vc_i = _free_cfg(oracle_lib, zoh=False, substeps=4000)
+        qi, qdi = q0[None].copy(), qd0[None].copy()
+        for _ in range(span):
+            qi, qdi, _ = _simulate(oracle_lib, vc_i, qi, qdi, np.zeros((1, 6)), u=np.full(1, u))
+        errs = []
+        for K in (250, 500, 1000):
+            q, qd = _reference_sampled_law(oracle_lib, q0, qd0, u, span, K)
+            assert np.isfinite(q).all() and np.isfinite(qd).all(), K
+            errs.append((np.abs(q - qi[0]).max(), np.abs(qd - qdi[0]).max()))
+        errs = np.array(errs)
+        moved = max(np.abs(qi[0] - q0).max(), 1e-3)
+        print(f"\n[anchor] torque-law semantics case {case}: sampled law at dt/250, /500, /1000 vs implicit: |dq| {errs[:, 0]}, |dqd| {errs[:, 1]} "
+              f"(moved {moved:.3f} rad)")
+        assert errs[-1, 0] < 2e-2 * moved and errs[-1, 1] < 5e-2 * max(np.abs(qdi).max(), 0.5), errs   # converged to the implicit trajectory
+        ratio = errs[0, 1] / errs[2, 1]
+        assert 2.5 < ratio < 6.0, (ratio, errs)                     # first order: quartering the period quarters the error
+        # and the shipped step (dt, 10 substeps) integrates the same law: within its own O(h) of the fine solution
+        vc_s = _free_cfg(oracle_lib, zoh=False, substeps=10)
+        qs, qds = q0[None].copy(), qd0[None].copy()
+        for _ in range(span):
+            qs, qds, _ = _simulate(oracle_lib, vc_s, qs, qds, np.zeros((1, 6)), u=np.full(1, u))
+        assert np.abs(qs[0] - qi[0]).max() < 0.1 * moved + 1e-3, (qs, qi)
+
+
+def test_references_sampled_law_is_unstable_at_the_references_own_dt(oracle_lib):
+    """The other half of the argument: the same semantics at K = 1 (dt = 8.33 ms, the reference's substeps) blows up within a few
+    sim steps from a gentle start -- which is why `zoh` is an opt-in mode and not the default."""
+    q0 = np.array([0.0, 0.05, -0.03, 0.02, 0.04, -0.02]); qd0 = np.zeros(6)
+    vc = _free_cfg(oracle_lib, zoh=True, substeps=10)
+    f = np.float32
+    q, qd = q0[None].copy(), qd0[None].copy()
+    peak = 0.0
+    for _ in range(12):
+        io = {"dof_pos": np.ascontiguousarray(q, f), "dof_vel": np.ascontiguousarray(qd, f), "cart_vel_y": np.ascontiguousarray(qd[:, 0], f),
+              "u_rail_velocity": np.ascontiguousarray(qd[:, 0], f), "u_fpam_to_use": np.full(1, 1.0, f), "prev_cart_vel": np.ascontiguousarray(qd[:, 0], f),
+              "prev_cart_vel_error": np.zeros(1, f), "dynamics_scaling": None, "accel_scaling": None,
+              "dof_efforts": np.zeros((1, 6), f), "prev_cart_vel_out": np.zeros(1, f), "prev_cart_vel_error_out": np.zeros(1, f)}
+        oracle_lib.call_io("oracle_actuation", vc, 1, abi.VineActuationIO, io)
+        eff = io["dof_efforts"].astype(np.float64); eff[:, 0] = 0.0
+        q, qd, _ = _simulate(oracle_lib, vc, q, qd, eff)
+        if not np.isfinite(qd).all():
+            peak = np.inf
+            break
+        peak = max(peak, float(np.abs(qd[0, 1:]).max()))
+    vc_i = _free_cfg(oracle_lib, zoh=False, substeps=10)
+    qi, qdi, peak_i = q0[None].copy(), qd0[None].copy(), 0.0
+    for _ in range(12):
+        qi, qdi, _ = _simulate(oracle_lib, vc_i, qi, qdi, np.zeros((1, 6)), u=np.full(1, 1.0))
+        peak_i = max(peak_i, float(np.abs(qdi[0, 1:]).max()))
+    print(f"\n[anchor] 12 sim steps from rest near equilibrium: peak joint speed sampled-at-dt {peak:.3g} rad/s, implicit {peak_i:.3g} rad/s")
+    assert peak_i < 20.0 and peak > 50.0 * max(peak_i, 1.0), (peak, peak_i)   # beyond anything physical and still growing
