@@ -1,5 +1,5 @@
 """Time one PPO iteration of the reference network (MLP -> LSTM 256 -> LayerNorm) at FSTR, N envs, CUDA-graph replay:
-python tools/ppo_time.py [N] [--mlp] [--no-pdl]
+python tools/ppo_time.py [N] [--mlp] [--no-pdl] [--no-arena] [--pad K]
 Prints ms per iteration / rollout / update (CUDA events, best of 3 x 20)."""
 import sys
 
@@ -15,6 +15,14 @@ n = int(args[0]) if args and args[0].isdigit() else 4096
 extra = ["train.params.network.rnn=null"] if "--mlp" in args else []
 if "--no-pdl" in args:
     PPOAgent.PDL_MAX_ENVS = 0
+if "--no-arena" in args:
+    from vine_robot_isaacgymenvs_b200.ppo.lstm_native import NativeLstmPath
+    NativeLstmPath.ARENA = False
+if "--pad" in args:   # perturb the caching allocator's placement of the agent's buffers (placement-sensitivity experiment)
+    k = int(args[args.index("--pad") + 1])
+    _g = torch.Generator().manual_seed(k)
+    _pads = [torch.empty(int(torch.randint(1, 64, (1,), generator=_g)) * 524288 + 512 * k, dtype=torch.uint8, device="cuda") for _ in range(k)]
+    del _pads[::2]
 cfg = vcfg.compose(vcfg.FSTR_OVERRIDES + [f"num_envs={n}", "headless=True"] + extra)
 env = vine.make(cfg=cfg)
 agent = PPOAgent(env, cfg["train"], device="cuda:0", seed=42, use_graphs=True, use_fused_update=True)

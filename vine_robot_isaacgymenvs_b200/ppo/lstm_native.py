@@ -21,28 +21,46 @@ def _ptr(t, off_elems=0):
 
 
 class NativeLstmPath:
+    ARENA = True
+
     def __init__(self, num_obs, seq_len, num_seqs, device, hyper, wgrad_splits=12):
         assert num_seqs % 128 == 0, "sequences per minibatch must be a multiple of the 128-row tile"
         self.lib = abi.load_library()
         self.O, self.L, self.S, self.dev = num_obs, seq_len, num_seqs, device
         self.tiles = num_seqs // 128
         L, S, tl = seq_len, num_seqs, self.tiles
-        bf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=device)  # noqa: E731
-        f32 = lambda *s: torch.zeros(*s, device=device)  # noqa: E731
+        # every activation / scratch buffer of the path is a view into ONE allocation (ARENA): their relative placement then
+        # does not depend on what the caching allocator freed before the agent was built
+        elems = lambda s: int(torch.Size(s).numel())  # noqa: E731
+        sizes = {"bf": 2 * (elems((L, tl, TB)) + 4 * elems((L, tl, 2, TB)) + 2 * elems((L, tl, 16, AB))),
+                 "f32": 4 * (elems((L, S, 256)) + 3 * elems((S, 256)) + elems((L, S, 64)))}
+        self._arena = torch.zeros(sizes["bf"] + sizes["f32"] + 64 * 4096, dtype=torch.uint8, device=device) if self.ARENA else None
+        self._arena_off = 0
+
+        def alloc(shape, dtype):
+            if self._arena is None:
+                return torch.zeros(*shape, dtype=dtype, device=device)
+            nbytes = elems(shape) * torch.empty(0, dtype=dtype).element_size()
+            off = self._arena_off
+            self._arena_off = (off + nbytes + 4095) & ~4095
+            assert self._arena_off <= self._arena.numel()
+            return self._arena[off:off + nbytes].view(dtype).view(*shape)
+        bf = lambda *s: alloc(s, torch.bfloat16)  # noqa: E731
+        f32 = lambda *s: alloc(s, torch.float32)  # noqa: E731
         self.U, self.HM, self.HH = bf(L, tl, TB), bf(L, tl, 2, TB), bf(L, tl, 2, TB)
         self.ACT, self.DG = bf(L, tl, 16, AB), bf(L, tl, 16, AB)
         self.DH, self.DHREC = bf(L, tl, 2, TB), bf(L, tl, 2, TB)
         self.Cs, self.C0 = f32(L, S, 256), f32(S, 256)
         self.DC = [f32(S, 256), f32(S, 256)]
         self.DH3 = f32(L, S, 64)
-        self.head_grads = f32(abi.LSTM_HEAD_GRAD_PARTS + 1, abi.LSTM_HEAD_GRAD_FLOATS)   # + 1 row: their sum
+        self.head_grads = torch.zeros(abi.LSTM_HEAD_GRAD_PARTS + 1, abi.LSTM_HEAD_GRAD_FLOATS, device=device)   # + 1 row: their sum
         self.splits = min(wgrad_splits, L * tl)
-        self.wg_ws = f32(self.splits, abi.LSTM_WGRAD_BLOCK_FLOATS)
+        self.wg_ws = torch.zeros(self.splits, abi.LSTM_WGRAD_BLOCK_FLOATS, device=device)
         self.mlp_ctas = self.lib.vine_ppo_max_ctas()
         self.mlp_ws = torch.empty(self.mlp_ctas, abi.PPO_WS_FLOATS, device=device)
         self.P_mlp, self.P_lstm = self.lib.vine_ppo_num_params(num_obs), self.lib.vine_lstm_num_params(num_obs)
         # both gradient vectors (+ 4 loss statistics each) in ONE buffer: one all-reduce per minibatch across ranks
-        self.flat_g = f32(self.P_mlp + 4 + self.P_lstm + 4)
+        self.flat_g = torch.zeros(self.P_mlp + 4 + self.P_lstm + 4, device=device)
         self.flat_g_mlp, self.flat_g_lstm = self.flat_g[:self.P_mlp + 4], self.flat_g[self.P_mlp + 4:]
         self.hyper = hyper
         self._stream = lambda: C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
