@@ -432,3 +432,41 @@ def test_programmatic_dependent_launch_changes_nothing_but_the_launch(preset):
     for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf"):
         assert torch.equal(getattr(plain, name), getattr(pdl, name)), name
     assert torch.equal(plain.dof_pos, pdl.dof_pos) and torch.equal(plain.dof_vel, pdl.dof_vel)
+
+
+@pytest.mark.parametrize("preset", ["FSTR_OVERRIDES", "SHELF_OVERRIDES", "PIPE_DR_OVERRIDES"], ids=["fstr", "shelf_routed", "pipe_dr_routed"])
+def test_million_env_batch_equals_its_eight_shards_by_checksum(preset):
+    """The bench's full size (1,048,576 envs on one GPU: one launch in free space, the routed near/far/redo step with obstacles)
+    against the 8-GPU layout of the same global env ids (eight 131,072-env handles with global_env_offset, single launches):
+    a checksum of checksums -- the integer sums of the raw bits of obs / rew / reset / progress of the shards add up to the
+    whole batch's, at several steps of a rollout with resets and contacts.  (Sums of bit patterns are order independent, so
+    the comparison needs no concatenation of 1 M-row buffers; any differing element changes them.)"""
+    import vine_robot_isaacgymenvs_b200 as vine
+    from vine_robot_isaacgymenvs_b200 import config as vcfg
+    n, parts = 1 << 20, 8
+    ov = getattr(vcfg, preset) + ["headless=True", "task.env.maxEpisodeLength=30"]
+    whole = vine.make(cfg=vcfg.compose(ov + [f"num_envs={n}"]))
+    shards = [vine.make(cfg=vcfg.compose(ov + [f"num_envs={n // parts}"]), global_env_offset=k * (n // parts)) for k in range(parts)]
+
+    def checksum(env):
+        f = lambda t: int(t.contiguous().view(torch.int32).to(torch.int64).sum())  # noqa: E731
+        return (f(env.obs_buf), f(env.rew_buf), int(env.reset_buf.sum()), int(env.progress_buf.sum()), int(env.timeout_buf.sum()))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(45):
+        act = torch.rand(n, 2, device="cuda", generator=g) * 2.4 - 1.2
+        act[: n // 2, 1] = act[: n // 2, 1].abs()
+        whole.step(act)
+        for k, sh in enumerate(shards):
+            sh.step(act[k * (n // parts):(k + 1) * (n // parts)])
+        if t in (0, 1, 14, 31, 44):
+            total = [sum(c) for c in zip(*[checksum(sh) for sh in shards])]
+            assert list(checksum(whole)) == total, (preset, t)
+    assert int(whole.reset_buf.sum()) > 0 and bool(torch.isfinite(whole.obs_buf).all())
+    if preset != "FSTR_OVERRIDES":
+        from vine_robot_isaacgymenvs_b200 import abi
+        import ctypes as C
+        counts = (C.c_int64 * 4)()
+        lib = abi.load_library()
+        lib.vine_route_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        assert lib.vine_route_counts(whole._h, counts) == 0
+        assert counts[0] > 0 and counts[0] + counts[1] == n, list(counts)      # the whole batch really took the routed step
