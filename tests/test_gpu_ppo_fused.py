@@ -140,6 +140,29 @@ def test_fused_minibatch_gradients_match_autograd(T, N, e0, E, O):
     assert float(state[1]) == 1.0   # the kernel counted one optimiser step
 
 
+def test_minibatch_gradient_at_the_baseline_size_is_the_mean_of_its_halves():
+    """BASELINE configs[1] at its full size (16 x 4096 rows, minibatch 32768 = horizon x 2048 envs) through a size-independent
+    property instead of a 32768-row autograd reference: the loss is a mean over rows, so the gradient and the four loss statistics
+    of a minibatch are the mean of those of its two env-halves (different tiles, different CTAs, different TMEM accumulation
+    chains); tolerance 2e-5 of the gradient's norm (f32 accumulation order), against 3e-2 for the bf16 forward vs autograd."""
+    lib = abi.load_library()
+    T, N, O = 16, 4096, 18
+    W, buf, mean, inv_std, logstd_old = make_problem(T, N, O, seed=123)
+    outs = {}
+    for name, (e0, E) in {"whole": (0, 2048), "a": (0, 1024), "b": (1024, 1024)}.items():
+        flat, _, _, out, _, n_part = run_kernel(lib, W, buf, mean, inv_std, logstd_old, e0, E, HYP, O, T, N, debug=False)
+        outs[name] = out.double()
+        assert torch.isfinite(out).all() and n_part > 0
+    P = lib.vine_ppo_num_params(O)
+    mean_of_halves = 0.5 * (outs["a"] + outs["b"])
+    g, h = outs["whole"][:P], mean_of_halves[:P]
+    assert float(g.norm()) > 1e-3
+    assert float((g - h).norm() / g.norm()) < 2e-5, float((g - h).norm() / g.norm())
+    for j, k in enumerate(["a_loss", "c_loss", "kl", "b_loss"]):
+        w, m = float(outs["whole"][P + j]), float(mean_of_halves[P + j])
+        assert abs(w - m) <= 1e-5 * max(abs(w), 1e-3), (k, w, m)
+
+
 def test_adam_kernel_matches_torch_adam_and_repacks_the_weights():
     lib = abi.load_library()
     T, N, O = 16, 512, 18
