@@ -271,3 +271,31 @@ def test_gae_matches_oracle(lib, oracle_lib):
     torch.cuda.synchronize()
     assert np.array_equal(adv.cpu().numpy(), adv_ref)
     assert np.array_equal(ret.cpu().numpy(), ret_ref)
+
+
+def test_gae_at_a_million_envs_is_column_independent_and_bit_exact_on_slices(lib, oracle_lib):
+    """The scaling sweep's size (16 x 1,048,576) through size-independent properties: every env's column depends on that column
+    only, so (i) random 4096-column slices recomputed by the oracle equal the full launch's columns bit for bit, (ii) the full
+    launch equals two half launches on the column halves (strided views copied out), (iii) returns == advantages + values."""
+    T, N = 16, 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(5)
+    r, v = torch.randn(T, N, device="cuda", generator=g), torch.randn(T, N, device="cuda", generator=g)
+    d = (torch.rand(T, N, device="cuda", generator=g) < 0.1).float()
+    lv, ld = torch.randn(N, device="cuda", generator=g), (torch.rand(N, device="cuda", generator=g) < 0.1).float()
+    p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+
+    def run(r_, v_, d_, lv_, ld_):
+        adv, ret = torch.zeros_like(r_), torch.zeros_like(r_)
+        assert lib.vine_gae(p(r_), p(v_), p(d_), p(lv_), p(ld_), T, r_.shape[1], 0.99, 0.95, p(adv), p(ret), None) == 0
+        return adv, ret
+    adv, ret = run(r, v, d, lv, ld)
+    torch.cuda.synchronize()
+    assert torch.equal(ret, adv + v)
+    for lo in (0, 333_333, N - 4096):
+        sl = slice(lo, lo + 4096)
+        a_ref, r_ref = oracle_lib.gae(*(x[:, sl].contiguous().cpu().numpy() for x in (r, v, d)), lv[sl].cpu().numpy(), ld[sl].cpu().numpy(), 0.99, 0.95)
+        assert np.array_equal(adv[:, sl].cpu().numpy(), a_ref) and np.array_equal(ret[:, sl].cpu().numpy(), r_ref), lo
+    h = N // 2
+    for sl in (slice(0, h), slice(h, N)):
+        a2, r2 = run(*(x[:, sl].contiguous() for x in (r, v, d)), lv[sl].contiguous(), ld[sl].contiguous())
+        assert torch.equal(a2, adv[:, sl]) and torch.equal(r2, ret[:, sl])
